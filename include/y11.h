@@ -1,0 +1,189 @@
+/*
+ * y11.h - C ABI of liby11_b200.so: the B200 (sm_100a) YOLO11 detection hot path.
+ *
+ * The reference (t0saki/YOLO-Infer) is pure Python and has no FFI of its own: its boundary for this
+ * path is the Python class core.model.YOLO11Model (reference core/model.py:29-295) which forwards
+ * `predict` to the un-vendored ultralytics engine (core/model.py:118-133).  The entry points below
+ * are what a ctypes binding behind that class calls; each cites the reference /
+ * upstream-ultralytics step it replaces (SURVEY.md section 8a row numbers in brackets).
+ *
+ * Conventions: plain C, no torch types.  Every tensor pointer is a DEVICE pointer owned by the
+ * caller (PyTorch on the Python side); every call takes the CUDA stream to launch on; return value
+ * 0 = ok, negative = error (text via y11_last_error()); nothing throws across the ABI.  Handles are
+ * not thread-safe (the Python side holds the same per-model lock the reference's predictor has).
+ *
+ * Activation layout everywhere: NHWC bf16, a "view" = (base pointer, pixel stride in channels
+ * `c_total`, first channel `c_off`, channel count) so that concat / chunk / split of the reference
+ * network (ultralytics Concat, C3k2.chunk, C2PSA.split) are pure address arithmetic.
+ */
+#ifndef Y11_H_
+#define Y11_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define Y11_ABI_VERSION 1
+
+typedef struct y11_engine* y11_handle;
+typedef struct y11_plan_s* y11_plan;
+typedef void* y11_stream; /* cudaStream_t */
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+int y11_abi_version(void);
+const char* y11_last_error(void);
+/* One engine per device.  Replaces the device placement of reference core/model.py:110-112. */
+int y11_create(y11_handle* out, int device);
+void y11_destroy(y11_handle h);
+
+/* ---- (1) letterbox preprocess  [a4: ultralytics LetterBox + BasePredictor.preprocess] -------- */
+typedef struct {
+  const uint8_t* src; /* device, BGR uint8 HWC */
+  int32_t h0, w0;     /* source size */
+  int32_t pitch;      /* source row pitch in bytes */
+  int32_t new_h, new_w; /* resized (unpadded) size; == h0,w0 -> pure copy */
+  int32_t top, left;  /* placement on the HxW canvas; border value 114 */
+} y11_image;
+/* images: DEVICE array of B descriptors.  out: bf16 NHWC [B,H,W,3], RGB, value/255.
+ * Bilinear arithmetic is bit-identical to cv2.resize(INTER_LINEAR) on uint8 (11-bit fixed point,
+ * 2x-downscale area fast path), then exact fp32 /255 and round-to-nearest-even to bf16. */
+int y11_letterbox(y11_handle h, const y11_image* images, int B, int H, int W, void* out_bf16_nhwc, y11_stream s);
+/* Same resize/pad, uint8 BGR HWC out (parity tests against cv2 bit for bit). */
+int y11_letterbox_u8(y11_handle h, const y11_image* images, int B, int H, int W, uint8_t* out_u8_hwc, y11_stream s);
+/* Tensor sources [a3: LoadTensor]: fp32 NCHW [B,3,H,W] / divisor -> bf16 NHWC (divisor = 255 when max>1, else 1). */
+int y11_nchw_f32_to_nhwc_bf16(y11_handle h, const float* in, int B, int H, int W, float divisor, void* out, y11_stream s);
+
+/* ---- (2) network plan  [a6-a12: DetectionModel._predict_once over fused Conv/C3k2/SPPF/C2PSA/Detect] */
+typedef struct {
+  void* ptr;        /* base of the NHWC buffer */
+  int32_t c_total;  /* pixel stride in channels */
+  int32_t c_off;    /* first channel of the view */
+  int32_t c;        /* channels in the view (multiple of 16 for tensor-core convs) */
+} y11_view;
+
+enum { Y11_ACT_NONE = 0, Y11_ACT_SILU = 1 };
+enum { Y11_IMPL_TCGEN05 = 0, Y11_IMPL_SIMT_DEBUG = 1 };
+
+/* Dense conv k in {1,3}, stride in {1,2}, pad k/2, BN folded  [a7 Conv.forward_fuse]:
+ *   out = act(conv(in, w) + bias) (+ res)
+ * w: bf16 [cout][k*k*cin] with K ordered (kh, kw, cin); bias: fp32 [cout].
+ * out may be bf16 (default) or fp32 (out_f32 != 0, used for the Detect logits). */
+typedef struct {
+  y11_view in, out, res; /* res.ptr == NULL -> no residual; res may alias out (in-place residual) */
+  const void* w;
+  const float* bias;
+  int32_t B, Hin, Win, Hout, Wout;
+  int32_t k, stride, act, out_f32;
+  int32_t impl; /* Y11_IMPL_TCGEN05 (product) | Y11_IMPL_SIMT_DEBUG (bring-up cross-check only) */
+} y11_conv_desc;
+
+/* Stem conv: 3 -> cout, 3x3 stride 2, input is the dense 3-channel bf16 NHWC letterbox output. */
+typedef struct {
+  const void* in; /* bf16 [B,Hin,Win,3] */
+  y11_view out;
+  const void* w;  /* bf16 [cout][27], K ordered (kh, kw, c) */
+  const float* bias;
+  int32_t B, Hin, Win, Hout, Wout;
+} y11_stem_desc;
+
+/* Depthwise 3x3 stride 1 pad 1  [a7 DWConv, Attention.pe]: out = act(dw(in)+bias) (+ res).
+ * w: bf16 [9][c] tap-major. */
+typedef struct {
+  y11_view in, out, res;
+  const void* w;
+  const float* bias;
+  int32_t B, H, W, act;
+} y11_dwconv_desc;
+
+/* SPPF pools  [a9]: io view holds 4*c channels; [0,c) is cv1's output, the op writes
+ * maxpool5, maxpool5^2, maxpool5^3 (stride 1, pad 2) into [c,2c), [2c,3c), [3c,4c). */
+typedef struct {
+  y11_view io;
+  int32_t B, H, W, c;
+} y11_sppf_desc;
+
+/* nn.Upsample(2,'nearest') into a channel slice  [a11]. in: [B,H,W], out: [B,2H,2W]. */
+typedef struct {
+  y11_view in, out;
+  int32_t B, H, W;
+} y11_upsample_desc;
+
+/* PSA attention core  [a10 Attention.forward between qkv and pe/proj]:
+ * qkv view channels = [Q: heads*kd | K: heads*kd | V: heads*hd] (the qkv conv's output channels are
+ * permuted into this order at weight-packing time); out[b, n, h*hd + d] =
+ * sum_m softmax_m(scale * q[b,n,h,:] . k[b,m,h,:]) * v[b,m,h,d]. */
+typedef struct {
+  y11_view qkv, out;
+  int32_t B, N, heads, kd, hd;
+  float scale;
+} y11_attn_desc;
+
+int y11_plan_create(y11_handle h, y11_plan* out);
+void y11_plan_destroy(y11_plan p);
+int y11_plan_add_conv(y11_plan p, const y11_conv_desc* d);
+int y11_plan_add_stem(y11_plan p, const y11_stem_desc* d);
+int y11_plan_add_dwconv(y11_plan p, const y11_dwconv_desc* d);
+int y11_plan_add_sppf(y11_plan p, const y11_sppf_desc* d);
+int y11_plan_add_upsample(y11_plan p, const y11_upsample_desc* d);
+int y11_plan_add_attention(y11_plan p, const y11_attn_desc* d);
+int y11_plan_num_ops(y11_plan p);
+/* kernels launched by one y11_plan_run (for bench.py's gpu_launches). */
+int y11_plan_num_launches(y11_plan p);
+/* Enqueue every op on `s` (capturable in a CUDA graph). */
+int y11_plan_run(y11_plan p, y11_stream s);
+/* Run ops [first, last) only. */
+int y11_plan_run_range(y11_plan p, int first, int last, y11_stream s);
+/* Run with a CUDA-event pair around every op; ms_per_op has y11_plan_num_ops entries. Synchronises. */
+int y11_plan_run_timed(y11_plan p, y11_stream s, float* ms_per_op);
+/* FLOPs (2*MAC) of op i as launched; 0 for non-conv ops. */
+double y11_plan_op_flops(y11_plan p, int i);
+
+/* ---- (3) Detect decode + NMS  [a12 Detect._inference/DFL/dist2bbox, a13 non_max_suppression,
+ *          a14 torchvision.ops.nms, a15 scale_boxes+clip_boxes] -------------------------------- */
+typedef struct {
+  const float* head[3]; /* per level fp32 [B, H_l*W_l, 64+nc]: 64 DFL logits then nc class logits */
+  int32_t hl[3], wl[3];
+  float stride[3];
+  int32_t nl, B, nc;
+} y11_head_desc;
+
+typedef struct {
+  float conf;        /* candidate iff score > (float)conf */
+  double iou;        /* suppress iff (double)iou_f32 > iou   (torchvision CPU semantics) */
+  int32_t max_det;   /* 300 */
+  int32_t max_nms;   /* 30000 */
+  int32_t max_wh;    /* 7680: class offset for class-aware NMS */
+  int32_t agnostic;
+  int32_t multi_label;
+} y11_nms_params;
+
+/* Dense decode only: y fp32 [B, 4+nc, A] exactly as Detect._inference returns it (parity tests). */
+int y11_decode_dense(y11_handle h, const y11_head_desc* hd, float* y, y11_stream s);
+
+/* Workspace bytes y11_detect_postprocess needs for (B, A, nc, multi_label). */
+size_t y11_postprocess_workspace(int B, int A, int nc, int multi_label, int max_nms);
+
+/* Fused path: decode -> conf threshold -> ordered compaction (warp-ballot prefix sums) -> stable
+ * score sort -> class-aware IoU NMS (bitmask tiles + warp sweep) -> max_det cut -> scale_boxes+clip.
+ * scale: per image [gain, pad_x, pad_y, w0, h0] fp32 (DEVICE, [B,5]); NULL = no rescale/clip.
+ * out_det: fp32 [B, max_det, 6] = x1,y1,x2,y2,conf,cls; out_count: int32 [B];
+ * out_ncand (optional, may be NULL): int32 [B] candidates above conf before NMS. */
+int y11_detect_postprocess(y11_handle h, const y11_head_desc* hd, const y11_nms_params* p, const float* scale,
+                           float* out_det, int32_t* out_count, int32_t* out_ncand, void* workspace,
+                           size_t workspace_bytes, y11_stream s);
+
+/* NMS only, batched, on caller-provided candidates (the bit-exact test against torchvision.ops.nms):
+ * boxes fp32 [B, K, 4] xyxy (class offset NOT yet applied), scores fp32 [B,K], cls fp32 [B,K],
+ * n int32 [B] valid candidates per image.  keep: int32 [B, max_det] candidate indices in score order. */
+int y11_nms_batched(y11_handle h, const float* boxes, const float* scores, const float* cls, const int32_t* n,
+                    int B, int K, const y11_nms_params* p, int32_t* keep, int32_t* keep_count, void* workspace,
+                    size_t workspace_bytes, y11_stream s);
+size_t y11_nms_workspace(int B, int K);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* Y11_H_ */

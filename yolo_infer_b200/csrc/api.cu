@@ -1,0 +1,206 @@
+// C ABI plumbing of liby11_b200: engine lifecycle, error string, and the op-list "plan" executor that replays
+// the fused YOLO11 network (built once per (model, B, H, W) by the Python host from the reference topology,
+// see yolo_infer_b200/network.py) as a fixed sequence of kernel launches on the caller's stream.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "ops.h"
+
+static thread_local char g_err[1024] = "";
+
+void y11_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* y11_last_error(void) { return g_err; }
+extern "C" int y11_abi_version(void) { return Y11_ABI_VERSION; }
+
+extern "C" int y11_create(y11_handle* out, int device) {
+  Y11_REQUIRE(out, "y11_create: null out");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  Y11_REQUIRE(e == cudaSuccess && count > 0, "y11_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  Y11_REQUIRE(device >= 0 && device < count, "y11_create: device %d out of range (%d devices)", device, count);
+  Y11_CHECK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  Y11_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  Y11_REQUIRE(prop.major == 10, "y11_create: device %d is sm_%d%d; liby11_b200 contains sm_100a code only", device, prop.major, prop.minor);
+  y11_engine* eng = new y11_engine();
+  eng->device = device;
+  eng->num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    delete eng;
+    y11_set_error("y11_create: cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+    return -2;
+  }
+  eng->encode_tiled = reinterpret_cast<y11_encode_tiled_fn>(fn);
+  Y11_CHECK_CUDA(cudaMalloc(&eng->dev_error_flag, sizeof(int)));
+  Y11_CHECK_CUDA(cudaMemset(eng->dev_error_flag, 0, sizeof(int)));
+  *out = eng;
+  return 0;
+}
+
+extern "C" void y11_destroy(y11_handle h) {
+  if (!h) return;
+  cudaFree(h->dev_error_flag);
+  delete h;
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+enum OpKind { OP_CONV_TC, OP_CONV_SIMT, OP_STEM, OP_DWCONV, OP_SPPF, OP_UPSAMPLE, OP_ATTN };
+
+struct PlanOp {
+  OpKind kind;
+  ConvTcLaunch tc;  // OP_CONV_TC
+  union {
+    y11_conv_desc conv;
+    y11_stem_desc stem;
+    y11_dwconv_desc dw;
+    y11_sppf_desc sppf;
+    y11_upsample_desc up;
+    y11_attn_desc attn;
+  } d;
+  double flops;
+};
+
+struct y11_plan_s {
+  y11_engine* eng;
+  std::vector<PlanOp*> ops;
+  cudaEvent_t* events = nullptr;
+  int n_events = 0;
+};
+
+extern "C" int y11_plan_create(y11_handle h, y11_plan* out) {
+  Y11_REQUIRE(h && out, "y11_plan_create: null argument");
+  y11_plan_s* p = new y11_plan_s();
+  p->eng = h;
+  *out = p;
+  return 0;
+}
+
+extern "C" void y11_plan_destroy(y11_plan p) {
+  if (!p) return;
+  for (PlanOp* op : p->ops) delete op;
+  for (int i = 0; i < p->n_events; ++i) cudaEventDestroy(p->events[i]);
+  delete[] p->events;
+  delete p;
+}
+
+static PlanOp* new_op(OpKind k) {
+  PlanOp* op = new PlanOp();
+  std::memset(static_cast<void*>(op), 0, sizeof(PlanOp));
+  op->kind = k;
+  return op;
+}
+
+extern "C" int y11_plan_add_conv(y11_plan p, const y11_conv_desc* d) {
+  Y11_REQUIRE(p && d, "plan_add_conv: null argument");
+  Y11_REQUIRE(d->in.ptr && d->out.ptr && d->w && d->bias, "plan_add_conv: null tensor");
+  PlanOp* op = new_op(d->impl == Y11_IMPL_SIMT_DEBUG ? OP_CONV_SIMT : OP_CONV_TC);
+  op->d.conv = *d;
+  op->flops = 2.0 * d->B * d->Hout * d->Wout * (double)d->out.c * d->in.c * d->k * d->k;
+  if (op->kind == OP_CONV_TC) {
+    if (int e = conv_tc_prepare(p->eng, d, &op->tc)) { delete op; return e; }
+  }
+  p->ops.push_back(op);
+  return 0;
+}
+
+extern "C" int y11_plan_add_stem(y11_plan p, const y11_stem_desc* d) {
+  Y11_REQUIRE(p && d && d->in && d->out.ptr && d->w && d->bias, "plan_add_stem: null argument");
+  Y11_REQUIRE(d->out.c_off % 8 == 0 && d->out.c_total % 8 == 0, "plan_add_stem: output alignment");
+  PlanOp* op = new_op(OP_STEM);
+  op->d.stem = *d;
+  op->flops = 2.0 * d->B * d->Hout * d->Wout * (double)d->out.c * 27;
+  p->ops.push_back(op);
+  return 0;
+}
+
+extern "C" int y11_plan_add_dwconv(y11_plan p, const y11_dwconv_desc* d) {
+  Y11_REQUIRE(p && d && d->in.ptr && d->out.ptr && d->w && d->bias, "plan_add_dwconv: null argument");
+  PlanOp* op = new_op(OP_DWCONV);
+  op->d.dw = *d;
+  op->flops = 2.0 * d->B * d->H * d->W * (double)d->in.c * 9;
+  p->ops.push_back(op);
+  return 0;
+}
+
+extern "C" int y11_plan_add_sppf(y11_plan p, const y11_sppf_desc* d) {
+  Y11_REQUIRE(p && d && d->io.ptr, "plan_add_sppf: null argument");
+  PlanOp* op = new_op(OP_SPPF);
+  op->d.sppf = *d;
+  p->ops.push_back(op);
+  return 0;
+}
+
+extern "C" int y11_plan_add_upsample(y11_plan p, const y11_upsample_desc* d) {
+  Y11_REQUIRE(p && d && d->in.ptr && d->out.ptr, "plan_add_upsample: null argument");
+  PlanOp* op = new_op(OP_UPSAMPLE);
+  op->d.up = *d;
+  p->ops.push_back(op);
+  return 0;
+}
+
+extern "C" int y11_plan_add_attention(y11_plan p, const y11_attn_desc* d) {
+  Y11_REQUIRE(p && d && d->qkv.ptr && d->out.ptr, "plan_add_attention: null argument");
+  PlanOp* op = new_op(OP_ATTN);
+  op->d.attn = *d;
+  op->flops = 2.0 * d->B * d->heads * (double)d->N * d->N * (d->kd + d->hd);
+  p->ops.push_back(op);
+  return 0;
+}
+
+extern "C" int y11_plan_num_ops(y11_plan p) { return p ? (int)p->ops.size() : 0; }
+extern "C" int y11_plan_num_launches(y11_plan p) { return p ? (int)p->ops.size() : 0; }  // one kernel per op
+extern "C" double y11_plan_op_flops(y11_plan p, int i) { return (p && i >= 0 && i < (int)p->ops.size()) ? p->ops[i]->flops : 0.0; }
+
+static int run_op(const PlanOp* op, cudaStream_t s) {
+  switch (op->kind) {
+    case OP_CONV_TC: return conv_tc_launch(&op->tc, s);
+    case OP_CONV_SIMT: return conv_simt_launch(&op->d.conv, s);
+    case OP_STEM: return stem_launch(&op->d.stem, s);
+    case OP_DWCONV: return dwconv_launch(&op->d.dw, s);
+    case OP_SPPF: return sppf_launch(&op->d.sppf, s);
+    case OP_UPSAMPLE: return upsample_launch(&op->d.up, s);
+    case OP_ATTN: return attention_launch(&op->d.attn, s);
+  }
+  return -1;
+}
+
+extern "C" int y11_plan_run_range(y11_plan p, int first, int last, y11_stream s) {
+  Y11_REQUIRE(p && first >= 0 && last <= (int)p->ops.size() && first <= last, "plan_run_range: bad range");
+  for (int i = first; i < last; ++i)
+    if (int e = run_op(p->ops[i], static_cast<cudaStream_t>(s))) return e;
+  return 0;
+}
+
+extern "C" int y11_plan_run(y11_plan p, y11_stream s) { return y11_plan_run_range(p, 0, p ? (int)p->ops.size() : 0, s); }
+
+extern "C" int y11_plan_run_timed(y11_plan p, y11_stream s_, float* ms_per_op) {
+  Y11_REQUIRE(p && ms_per_op, "plan_run_timed: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(s_);
+  const int n = (int)p->ops.size();
+  if (p->n_events < n + 1) {
+    for (int i = 0; i < p->n_events; ++i) cudaEventDestroy(p->events[i]);
+    delete[] p->events;
+    p->events = new cudaEvent_t[n + 1];
+    p->n_events = n + 1;
+    for (int i = 0; i <= n; ++i) Y11_CHECK_CUDA(cudaEventCreate(&p->events[i]));
+  }
+  Y11_CHECK_CUDA(cudaEventRecord(p->events[0], s));
+  for (int i = 0; i < n; ++i) {
+    if (int e = run_op(p->ops[i], s)) return e;
+    Y11_CHECK_CUDA(cudaEventRecord(p->events[i + 1], s));
+  }
+  Y11_CHECK_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < n; ++i) Y11_CHECK_CUDA(cudaEventElapsedTime(&ms_per_op[i], p->events[i], p->events[i + 1]));
+  return 0;
+}

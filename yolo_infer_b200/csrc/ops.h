@@ -1,0 +1,46 @@
+// Internal (non-ABI) declarations shared by the .cu translation units of liby11_b200.
+#pragma once
+#include "common.cuh"
+
+// ---- tcgen05 implicit-GEMM conv (conv_tc.cu) ---------------------------------------------------
+struct ConvTcMaps {
+  CUtensorMap a[4];  // activation views: [0] for stride 1; [ph*2+pw] parity sub-grids for stride 2
+  CUtensorMap b;     // packed weights [cout][k*k*cin]
+};
+
+struct ConvTcParams {
+  int32_t Tw, Th, Tn;                 // spatial tile of output pixels, Tw*Th*Tn <= 128 GEMM rows
+  int32_t tiles_w, tiles_h, tiles_n;  // spatial tile grid
+  int32_t n_tiles;                    // Cout tiles of BN columns
+  int32_t BN, Cc, chunks_per_tap, taps, ksize, stride, stages, tmem_cols;
+  uint32_t a_slot, b_slot, tx_bytes, sbo, layout_type;
+  int32_t B, Hout, Wout, cout, cin;
+  void* out;
+  int32_t out_ct, out_co, out_f32;
+  const void* res;
+  int32_t res_ct, res_co;
+  const float* bias;
+  int32_t act;
+  int* err_flag;
+};
+
+struct ConvTcLaunch {
+  ConvTcMaps maps;
+  ConvTcParams p;
+  unsigned grid;
+  unsigned smem_bytes;
+  double flops;
+};
+
+int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* out);
+int conv_tc_launch(const ConvTcLaunch* l, cudaStream_t s);
+
+// ---- CUDA-core kernels (conv_simt.cu) ------------------------------------------------------------
+int conv_simt_launch(const y11_conv_desc* d, cudaStream_t s);  // bring-up cross-check only
+int stem_launch(const y11_stem_desc* d, cudaStream_t s);
+int dwconv_launch(const y11_dwconv_desc* d, cudaStream_t s);
+int sppf_launch(const y11_sppf_desc* d, cudaStream_t s);
+int upsample_launch(const y11_upsample_desc* d, cudaStream_t s);
+
+// ---- attention.cu --------------------------------------------------------------------------------
+int attention_launch(const y11_attn_desc* d, cudaStream_t s);

@@ -1,0 +1,533 @@
+// Detect-head post-processing on device:
+//   decode  : DFL softmax-expectation -> dist2bbox against anchor points -> x stride; class sigmoid
+//             (ultralytics Detect._inference / DFL / make_anchors / dist2bbox, ~12 ATen kernels)
+//   compact : `score > conf` candidates in ANCHOR ORDER via warp ballots + prefix sums (two passes, no staging)
+//             (ultralytics non_max_suppression's boolean-mask indexing, which syncs the host per image)
+//   sort    : stable descending by score (unique 64-bit keys (~score, index), bitonic)
+//   nms     : class-aware greedy IoU NMS, bit-exact with torchvision.ops.nms CPU semantics: 256x256 bitmask
+//             tiles + a warp-level suppression sweep over the bit rows; a candidate is tested only against the
+//             boxes kept so far, so work is K*kept instead of K^2 and stops at max_det
+//   output  : [:max_det], scale_boxes + clip_boxes fused into the write.
+// All boxes/score arithmetic that feeds a comparison uses explicit round-to-nearest intrinsics so that nvcc
+// cannot contract it into FMAs (the reference computes every step as a separate fp32 op).
+#include <math.h>
+
+#include "ops.h"
+
+using namespace y11;
+
+namespace {
+
+constexpr int kChunk = 256;        // anchors per CTA in decode/compaction
+constexpr int kNmsThreads = 1024;  // sort + nms CTA
+constexpr int kTile = 256;         // candidates per NMS tile
+constexpr int kSmemKeys = 16384;   // sort in shared memory up to this many keys (128 KB)
+
+struct HeadParams {
+  const float* head[3];
+  int hl[3], wl[3];
+  int off[4];  // anchor offset per level
+  float stride[3];
+  int nl, B, nc, A, no;
+};
+
+struct AnchorOut {
+  float cx, cy, w, h;  // Detect output box (pixels of the network input)
+  float score;         // best class score (single-label)
+  int cls;
+  int npass;           // classes with score > conf (multi-label)
+};
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// Whole warp decodes ONE anchor; every lane returns the same box; class scores stay distributed:
+// sc[j] = sigmoid of class (j*32 + lane) or -1.
+template <int NCJ>
+__device__ __forceinline__ void warp_decode(const HeadParams& hp, int b, int a, int lane, float& cx, float& cy, float& w, float& h,
+                                            float (&sc)[NCJ]) {
+  int l = 0;
+  if (hp.nl > 1 && a >= hp.off[1]) l = 1;
+  if (hp.nl > 2 && a >= hp.off[2]) l = 2;
+  const int i = a - hp.off[l];
+  const int wl = hp.wl[l];
+  const float ax = (float)(i % wl) + 0.5f, ay = (float)(i / wl) + 0.5f;
+  const float* row = hp.head[l] + ((size_t)b * hp.hl[l] * wl + i) * hp.no;
+  float d[2];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {  // lanes 0-15: side 2*half, lanes 16-31: side 2*half+1
+    const float v = __ldg(row + half * 32 + lane);
+    float mx = v;
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e = expf(v - mx);
+    float den = e, num = e * (float)(lane & 15);
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+      den += __shfl_xor_sync(0xffffffffu, den, o);
+      num += __shfl_xor_sync(0xffffffffu, num, o);
+    }
+    d[half] = __fdiv_rn(num, den);
+  }
+  const float dl = __shfl_sync(0xffffffffu, d[0], 0), dt = __shfl_sync(0xffffffffu, d[0], 16);
+  const float dr = __shfl_sync(0xffffffffu, d[1], 0), db = __shfl_sync(0xffffffffu, d[1], 16);
+  const float x1 = __fsub_rn(ax, dl), y1 = __fsub_rn(ay, dt), x2 = __fadd_rn(ax, dr), y2 = __fadd_rn(ay, db);
+  const float st = hp.stride[l];
+  cx = __fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.0f), st);
+  cy = __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.0f), st);
+  w = __fmul_rn(__fsub_rn(x2, x1), st);
+  h = __fmul_rn(__fsub_rn(y2, y1), st);
+#pragma unroll
+  for (int j = 0; j < NCJ; ++j) {
+    const int c = j * 32 + lane;
+    sc[j] = c < hp.nc ? sigmoidf_acc(__ldg(row + 64 + c)) : -1.0f;
+  }
+}
+
+constexpr int kNcj = 4;  // up to 128 classes
+
+__global__ void __launch_bounds__(256) decode_dense_kernel(HeadParams hp, float* __restrict__ y) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int a0 = blockIdx.x * kChunk + warp * 32;
+  float* yb = y + (size_t)b * (4 + hp.nc) * hp.A;
+  for (int k = 0; k < 32; ++k) {
+    const int a = a0 + k;
+    if (a >= hp.A) break;
+    float cx, cy, w, h, sc[kNcj];
+    warp_decode<kNcj>(hp, b, a, lane, cx, cy, w, h, sc);
+    if (lane == 0) {
+      yb[a] = cx; yb[(size_t)hp.A + a] = cy; yb[2 * (size_t)hp.A + a] = w; yb[3 * (size_t)hp.A + a] = h;
+    }
+#pragma unroll
+    for (int j = 0; j < kNcj; ++j) {
+      const int c = j * 32 + lane;
+      if (c < hp.nc) yb[(size_t)(4 + c) * hp.A + a] = sc[j];
+    }
+  }
+}
+
+// MODE 0: count candidates per chunk.  MODE 1: write candidates at chunk_off + in-chunk prefix (anchor order).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+decode_compact_kernel(HeadParams hp, float conf, int multi_label, int cap, int nchunks, int* __restrict__ chunk_cnt,
+                      const int* __restrict__ chunk_off, float4* __restrict__ cbox, float* __restrict__ cscore, float* __restrict__ ccls) {
+  __shared__ int s_warp[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int a0 = blockIdx.x * kChunk + warp * 32;
+  // pass A: every lane ends up owning anchor a0+lane
+  float mcx = 0, mcy = 0, mw = 0, mh = 0, mscore = -1.f;
+  int mcls = 0, mcnt = 0;
+  for (int k = 0; k < 32; ++k) {
+    const int a = a0 + k;
+    if (a >= hp.A) break;
+    float cx, cy, w, h, sc[kNcj];
+    warp_decode<kNcj>(hp, b, a, lane, cx, cy, w, h, sc);
+    int npass = 0;
+    float best = -1.f;
+    int bcls = 0;
+    if (multi_label) {
+#pragma unroll
+      for (int j = 0; j < kNcj; ++j) npass += __popc(__ballot_sync(0xffffffffu, sc[j] > conf));
+    } else {
+#pragma unroll
+      for (int j = 0; j < kNcj; ++j)
+        if (sc[j] > best) { best = sc[j]; bcls = j * 32 + lane; }  // strict > keeps the first (lowest) class on ties
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, bcls, o);
+        if (ob > best || (ob == best && oc < bcls)) { best = ob; bcls = oc; }
+      }
+      npass = best > conf ? 1 : 0;
+    }
+    if (lane == k) { mcx = cx; mcy = cy; mw = w; mh = h; mscore = best; mcls = bcls; mcnt = npass; }
+  }
+  // in-warp exclusive prefix of counts
+  int incl = mcnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
+  if (lane == 0) s_warp[warp] = wtotal;
+  __syncthreads();
+  if (MODE == 0) {
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int i = 0; i < 8; ++i) t += s_warp[i];
+      chunk_cnt[b * nchunks + blockIdx.x] = t;
+    }
+    return;
+  }
+  int base = chunk_off[b * nchunks + blockIdx.x];
+  for (int i = 0; i < warp; ++i) base += s_warp[i];
+  const int pos = base + incl - mcnt;
+  const size_t ob = (size_t)b * cap;
+  if (!multi_label) {
+    if (mcnt && pos < cap) {
+      // xywh2xyxy exactly as the reference: wh/2 first, then xy -/+ it
+      const float hw = __fdiv_rn(mw, 2.0f), hh = __fdiv_rn(mh, 2.0f);
+      cbox[ob + pos] = make_float4(__fsub_rn(mcx, hw), __fsub_rn(mcy, hh), __fadd_rn(mcx, hw), __fadd_rn(mcy, hh));
+      cscore[ob + pos] = mscore;
+      ccls[ob + pos] = (float)mcls;
+    }
+    return;
+  }
+  // multi-label: decode again and emit (anchor, class) pairs in (anchor, class) order
+  for (int k = 0; k < 32; ++k) {
+    const int a = a0 + k;
+    if (a >= hp.A) break;
+    const int pk = __shfl_sync(0xffffffffu, pos, k), nk = __shfl_sync(0xffffffffu, mcnt, k);
+    if (nk == 0) continue;
+    float cx, cy, w, h, sc[kNcj];
+    warp_decode<kNcj>(hp, b, a, lane, cx, cy, w, h, sc);
+    const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+    const float4 bx = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+    int before = 0;
+#pragma unroll
+    for (int j = 0; j < kNcj; ++j) {
+      const unsigned m = __ballot_sync(0xffffffffu, sc[j] > conf);
+      if (sc[j] > conf) {
+        const int p = pk + before + __popc(m & ((1u << lane) - 1u));
+        if (p < cap) { cbox[ob + p] = bx; cscore[ob + p] = sc[j]; ccls[ob + p] = (float)(j * 32 + lane); }
+      }
+      before += __popc(m);
+    }
+  }
+}
+
+// exclusive scan of chunk counts, one CTA per image
+__global__ void __launch_bounds__(1024) scan_chunks_kernel(const int* __restrict__ chunk_cnt, int* __restrict__ chunk_off, int nchunks,
+                                                           int cap, int* __restrict__ ncand, int* __restrict__ ncand_raw) {
+  __shared__ int s[1024];
+  const int b = blockIdx.x;
+  int carry = 0;
+  for (int c0 = 0; c0 < nchunks; c0 += 1024) {
+    const int i = c0 + threadIdx.x;
+    const int v = i < nchunks ? chunk_cnt[b * nchunks + i] : 0;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+      __syncthreads();
+      s[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nchunks) chunk_off[b * nchunks + i] = carry + s[threadIdx.x] - v;
+    carry += s[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    ncand[b] = min(carry, cap);
+    if (ncand_raw) ncand_raw[b] = carry;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ sort + NMS
+__device__ __forceinline__ float iou_rn(const float4 a, float aarea, const float4 b, float barea) {
+  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y), xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter));
+}
+
+struct NmsArgs {
+  const float4* cbox;    // [B, cap] xyxy without class offset
+  const float* cscore;   // [B, cap]
+  const float* ccls;     // [B, cap]
+  const int* ncand;      // [B]
+  unsigned long long* keys;  // [B, keys_stride] scratch (used when n > kSmemKeys)
+  float4* kbox;          // [B, max_det] kept boxes (with class offset)
+  float* karea;          // [B, max_det]
+  int cap, keys_stride;
+  float iou_thr;         // largest float <= (double) iou: ovr_f32 > thr  <=>  (double)ovr_f32 > iou
+  float class_offset;    // max_wh, or 0 when agnostic
+  int max_det, max_nms;
+  const float* scale;    // [B,5] gain,pad_x,pad_y,w0,h0 or nullptr
+  float* out_det;        // [B, max_det, 6] or nullptr
+  int* out_keep;         // [B, max_det] or nullptr
+  int* out_count;        // [B]
+};
+
+__global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
+  extern __shared__ unsigned long long s_keys[];
+  __shared__ float4 t_box[kTile];
+  __shared__ float t_area[kTile];
+  __shared__ int t_idx[kTile];
+  __shared__ unsigned long long t_mask[kTile][kTile / 64];
+  __shared__ unsigned int t_dead[kTile / 32];
+  __shared__ int s_nk;
+
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const size_t ob = (size_t)b * g.cap;
+  const int n = min(g.ncand[b], g.cap);
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  unsigned long long* keys = (np2 <= kSmemKeys) ? s_keys : g.keys + (size_t)b * g.keys_stride;
+
+  // 1. keys: descending score, ascending index on ties == stable descending sort of the anchor-ordered list
+  for (int i = tid; i < np2; i += kNmsThreads) {
+    unsigned long long k = ~0ull;
+    if (i < n) {
+      unsigned u = __float_as_uint(g.cscore[ob + i]);
+      u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // monotone map float -> unsigned
+      k = ((unsigned long long)(~u) << 32) | (unsigned)i;
+    }
+    keys[i] = k;
+  }
+  __syncthreads();
+  // 2. bitonic sort, ascending keys
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (np2 >> 1); t += kNmsThreads) {
+        const int i = 2 * j * (t / j) + (t % j);
+        const int l = i + j;
+        const unsigned long long x = keys[i], y = keys[l];
+        const bool up = (i & k) == 0;
+        if ((x > y) == up) { keys[i] = y; keys[l] = x; }
+      }
+      __syncthreads();
+    }
+  }
+  // 3. greedy NMS over score order, 256 candidates per tile
+  const int K = min(n, g.max_nms);
+  float4* kbox = g.kbox + (size_t)b * g.max_det;
+  float* karea = g.karea + (size_t)b * g.max_det;
+  if (tid == 0) s_nk = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < K; c0 += kTile) {
+    const int nk0 = s_nk;
+    if (nk0 >= g.max_det) break;
+    const int cnt = min(kTile, K - c0);
+    if (tid < kTile) {
+      if (tid < cnt) {
+        const int idx = (int)(keys[c0 + tid] & 0xffffffffu);
+        float4 bx = g.cbox[ob + idx];
+        const float off = __fmul_rn(g.ccls[ob + idx], g.class_offset);
+        bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off); bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
+        t_box[tid] = bx;
+        t_area[tid] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+        t_idx[tid] = idx;
+      }
+      if (tid < kTile / 32) t_dead[tid] = 0u;
+    }
+    __syncthreads();
+    {
+      const int c = tid & (kTile - 1), part = tid >> 8;  // 4 threads per candidate
+      if (c < cnt) {
+        // (a) against boxes kept by earlier tiles
+        const float4 bx = t_box[c];
+        const float ar = t_area[c];
+        bool dead = false;
+        for (int k = part; k < nk0 && !dead; k += kNmsThreads / kTile) dead = iou_rn(kbox[k], karea[k], bx, ar) > g.iou_thr;
+        if (dead) atomicOr(&t_dead[c >> 5], 1u << (c & 31));
+        // (b) bit row of this tile: later candidates j this one would suppress
+        unsigned long long bits = 0ull;
+        const int j0 = part * 64;
+        for (int j = max(j0, c + 1); j < min(j0 + 64, cnt); ++j)
+          if (iou_rn(bx, ar, t_box[j], t_area[j]) > g.iou_thr) bits |= 1ull << (j - j0);
+        t_mask[c][part] = bits;
+      }
+    }
+    __syncthreads();
+    // (c) warp-level sweep: lane w (< 4) owns word w of the `removed` bitset
+    if (tid < 32) {
+      const int lane = tid;
+      unsigned long long removed = ~0ull, todo = 0ull;
+      if (lane < kTile / 64) {
+        const unsigned long long dead = (unsigned long long)t_dead[2 * lane] | ((unsigned long long)t_dead[2 * lane + 1] << 32);
+        const int lo = lane * 64;
+        const unsigned long long valid = cnt >= lo + 64 ? ~0ull : (cnt > lo ? ((1ull << (cnt - lo)) - 1ull) : 0ull);
+        removed = dead | ~valid;
+        todo = valid;
+      }
+      int nk = nk0;
+      while (nk < g.max_det) {
+        const unsigned long long avail = ~removed & todo;
+        const unsigned have = __ballot_sync(0xffffffffu, avail != 0ull);
+        if (!have) break;
+        const int wsel = __ffs(have) - 1;
+        const int bit = __ffsll((long long)__shfl_sync(0xffffffffu, avail, wsel)) - 1;
+        const int c = wsel * 64 + bit;
+        if (lane < kTile / 64) removed |= t_mask[c][lane];
+        if (lane == wsel) todo &= ~((2ull << bit) - 1ull);  // bits <= c are settled
+        if (lane > wsel && lane < kTile / 64) { /* later words untouched */ }
+        if (lane < wsel) todo = 0ull;
+        if (lane == 0) {
+          kbox[nk] = t_box[c];
+          karea[nk] = t_area[c];
+          const int idx = t_idx[c];
+          if (g.out_keep) g.out_keep[(size_t)b * g.max_det + nk] = idx;
+          if (g.out_det) {
+            float4 bx = g.cbox[ob + idx];
+            if (g.scale) {
+              const float* sc = g.scale + (size_t)b * 5;
+              const float gain = sc[0], px = sc[1], py = sc[2], w0 = sc[3], h0 = sc[4];
+              bx.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.x, px), gain), 0.f), w0);
+              bx.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.y, py), gain), 0.f), h0);
+              bx.z = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.z, px), gain), 0.f), w0);
+              bx.w = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.w, py), gain), 0.f), h0);
+            }
+            float* o = g.out_det + ((size_t)b * g.max_det + nk) * 6;
+            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+            o[4] = g.cscore[ob + idx];
+            o[5] = g.ccls[ob + idx];
+          }
+        }
+        ++nk;
+      }
+      if (lane == 0) s_nk = nk;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) g.out_count[b] = s_nk;
+}
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int next_pow2(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+int fill_head(const y11_head_desc* hd, HeadParams* hp) {
+  Y11_REQUIRE(hd->nl >= 1 && hd->nl <= 3, "postprocess: nl=%d", hd->nl);
+  Y11_REQUIRE(hd->nc >= 1 && hd->nc <= 32 * kNcj, "postprocess: nc=%d unsupported (max %d)", hd->nc, 32 * kNcj);
+  int off = 0;
+  for (int l = 0; l < 3; ++l) {
+    hp->head[l] = l < hd->nl ? hd->head[l] : nullptr;
+    hp->hl[l] = l < hd->nl ? hd->hl[l] : 0;
+    hp->wl[l] = l < hd->nl ? hd->wl[l] : 1;
+    hp->stride[l] = l < hd->nl ? hd->stride[l] : 0.f;
+    hp->off[l] = off;
+    off += hp->hl[l] * (l < hd->nl ? hd->wl[l] : 0);
+  }
+  hp->off[3] = off;
+  hp->nl = hd->nl; hp->B = hd->B; hp->nc = hd->nc; hp->A = off; hp->no = 64 + hd->nc;
+  return 0;
+}
+
+float thr_round_down(double iou) {
+  float f = (float)iou;
+  if ((double)f > iou) f = nextafterf(f, -INFINITY);
+  return f;
+}
+
+struct Workspace {
+  float4* cbox; float* cscore; float* ccls; int* chunk_cnt; int* chunk_off; int* ncand;
+  unsigned long long* keys; float4* kbox; float* karea;
+  int cap, keys_stride, nchunks;
+  size_t total;
+};
+
+int candidate_cap(int A, int nc, int multi_label) {
+  if (!multi_label) return A;
+  const long long full = (long long)A * nc;
+  return (int)(full < (1ll << 17) ? full : (1ll << 17));
+}
+
+void carve(Workspace* w, void* base, int B, int cap, int nchunks, int kept_cap) {
+  size_t o = 0;
+  char* p = static_cast<char*>(base);
+  auto take = [&](size_t bytes) { char* r = p ? p + o : nullptr; o += align_up(bytes); return r; };
+  w->cap = cap; w->nchunks = nchunks; w->keys_stride = next_pow2(cap);
+  w->cbox = (float4*)take((size_t)B * cap * 16);
+  w->cscore = (float*)take((size_t)B * cap * 4);
+  w->ccls = (float*)take((size_t)B * cap * 4);
+  w->chunk_cnt = (int*)take((size_t)B * nchunks * 4);
+  w->chunk_off = (int*)take((size_t)B * nchunks * 4);
+  w->ncand = (int*)take((size_t)B * 4);
+  w->keys = (unsigned long long*)take(w->keys_stride > kSmemKeys ? (size_t)B * w->keys_stride * 8 : 0);
+  w->kbox = (float4*)take((size_t)B * kept_cap * 16);
+  w->karea = (float*)take((size_t)B * kept_cap * 4);
+  w->total = o;
+}
+
+int launch_sort_nms(const NmsArgs& a, int B, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    Y11_CHECK_CUDA(cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemKeys * 8));
+    attr_set = true;
+  }
+  const int np2 = next_pow2(a.cap);
+  const size_t smem = (size_t)(np2 <= kSmemKeys ? np2 : 0) * 8;
+  sort_nms_kernel<<<B, kNmsThreads, smem, s>>>(a);
+  Y11_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int y11_decode_dense(y11_handle, const y11_head_desc* hd, float* y, y11_stream s) {
+  HeadParams hp;
+  if (int e = fill_head(hd, &hp)) return e;
+  dim3 grid((unsigned)y11_ceil_div(hp.A, kChunk), (unsigned)hp.B);
+  decode_dense_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(s)>>>(hp, y);
+  Y11_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" size_t y11_postprocess_workspace(int B, int A, int nc, int multi_label, int max_nms) {
+  (void)max_nms;
+  Workspace w;
+  const int cap = candidate_cap(A, nc, multi_label);
+  carve(&w, nullptr, B, cap, y11_ceil_div(A, kChunk), cap);
+  return w.total;
+}
+
+extern "C" int y11_detect_postprocess(y11_handle, const y11_head_desc* hd, const y11_nms_params* p, const float* scale, float* out_det,
+                                      int32_t* out_count, int32_t* out_ncand, void* workspace, size_t workspace_bytes, y11_stream s_) {
+  cudaStream_t s = static_cast<cudaStream_t>(s_);
+  HeadParams hp;
+  if (int e = fill_head(hd, &hp)) return e;
+  Y11_REQUIRE(p->max_det >= 1, "postprocess: max_det=%d", p->max_det);
+  const int cap = candidate_cap(hp.A, hp.nc, p->multi_label);
+  Y11_REQUIRE(p->max_det <= cap, "postprocess: max_det=%d exceeds candidate capacity %d", p->max_det, cap);
+  const int nchunks = y11_ceil_div(hp.A, kChunk);
+  Workspace w;
+  carve(&w, workspace, hp.B, cap, nchunks, cap);
+  Y11_REQUIRE(workspace && workspace_bytes >= w.total, "postprocess: workspace %zu < required %zu", workspace_bytes, w.total);
+  dim3 grid((unsigned)nchunks, (unsigned)hp.B);
+  decode_compact_kernel<0><<<grid, 256, 0, s>>>(hp, p->conf, p->multi_label, cap, nchunks, w.chunk_cnt, w.chunk_off, w.cbox, w.cscore, w.ccls);
+  scan_chunks_kernel<<<hp.B, 1024, 0, s>>>(w.chunk_cnt, w.chunk_off, nchunks, cap, w.ncand, out_ncand);
+  decode_compact_kernel<1><<<grid, 256, 0, s>>>(hp, p->conf, p->multi_label, cap, nchunks, w.chunk_cnt, w.chunk_off, w.cbox, w.cscore, w.ccls);
+  Y11_CHECK_CUDA(cudaGetLastError());
+  NmsArgs a;
+  a.cbox = w.cbox; a.cscore = w.cscore; a.ccls = w.ccls; a.ncand = w.ncand; a.keys = w.keys; a.kbox = w.kbox; a.karea = w.karea;
+  a.cap = cap; a.keys_stride = w.keys_stride;
+  a.iou_thr = thr_round_down(p->iou);
+  a.class_offset = p->agnostic ? 0.0f : (float)p->max_wh;
+  a.max_det = p->max_det; a.max_nms = p->max_nms;
+  a.scale = scale; a.out_det = out_det; a.out_keep = nullptr; a.out_count = out_count;
+  return launch_sort_nms(a, hp.B, s);
+}
+
+extern "C" size_t y11_nms_workspace(int B, int K) {
+  const int np2 = next_pow2(K);
+  return align_up(np2 > kSmemKeys ? (size_t)B * np2 * 8 : 0) + align_up((size_t)B * K * 16) + align_up((size_t)B * K * 4) + 1024;
+}
+
+extern "C" int y11_nms_batched(y11_handle, const float* boxes, const float* scores, const float* cls, const int32_t* n, int B, int K,
+                               const y11_nms_params* p, int32_t* keep, int32_t* keep_count, void* workspace, size_t workspace_bytes,
+                               y11_stream s_) {
+  Y11_REQUIRE(K >= 1 && p->max_det >= 1 && p->max_det <= K, "nms: need 1 <= max_det (%d) <= K (%d)", p->max_det, K);
+  Y11_REQUIRE(workspace && workspace_bytes >= y11_nms_workspace(B, K), "nms: workspace too small");
+  const int np2 = next_pow2(K);
+  char* wp = static_cast<char*>(workspace);
+  NmsArgs a;
+  a.keys = reinterpret_cast<unsigned long long*>(wp);
+  wp += align_up(np2 > kSmemKeys ? (size_t)B * np2 * 8 : 0);
+  a.kbox = reinterpret_cast<float4*>(wp);
+  wp += align_up((size_t)B * K * 16);
+  a.karea = reinterpret_cast<float*>(wp);
+  a.cbox = reinterpret_cast<const float4*>(boxes); a.cscore = scores; a.ccls = cls; a.ncand = n;
+  a.cap = K; a.keys_stride = np2;
+  a.iou_thr = thr_round_down(p->iou);
+  a.class_offset = p->agnostic ? 0.0f : (float)p->max_wh;
+  a.max_det = p->max_det; a.max_nms = p->max_nms;
+  a.scale = nullptr; a.out_det = nullptr; a.out_keep = keep; a.out_count = keep_count;
+  return launch_sort_nms(a, B, static_cast<cudaStream_t>(s_));
+}

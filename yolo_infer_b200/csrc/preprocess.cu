@@ -1,0 +1,155 @@
+// Letterbox preprocessing: BGR uint8 HWC frames -> resized (cv2 INTER_LINEAR semantics), centred on a 114-grey
+// H x W canvas, BGR->RGB, /255, bf16 NHWC - ONE kernel, replacing the reference's per-image CPU chain
+// cv2.resize + cv2.copyMakeBorder + np.stack + [..., ::-1] + transpose + torch.from_numpy + .to(device)
+// + .float() + /255  (ultralytics LetterBox.__call__ + BasePredictor.preprocess).
+//
+// The bilinear arithmetic is the exact integer pipeline OpenCV uses for uint8 (oracle/letterbox_ref.py restates
+// and pins it bit-for-bit against cv2): 11-bit fixed-point taps, horizontal pass in int32, vertical pass
+// ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2, and the 2x-downscale INTER_AREA fast path.
+//
+// HBM-bound: algorithmic bytes/image = h0*w0*3 (read) + H*W*3*2 (write).  One thread produces 4 consecutive
+// output pixels (12 channel values = 24 B of bf16, written as three 8-byte stores); consecutive threads cover
+// consecutive pixels, so both the source gathers and the stores of a warp are contiguous.
+#include "ops.h"
+
+using namespace y11;
+
+namespace {
+
+struct Taps {
+  int i0, i1;
+  int c0, c1;
+};
+
+// horizontal tap (clamped index, clamped weight)
+__device__ __forceinline__ Taps tap_x(int d, double scale, int src) {
+  float f = (float)(((double)d + 0.5) * scale - 0.5);
+  int s = (int)floorf(f);
+  f -= (float)s;
+  if (s < 0) { f = 0.f; s = 0; }
+  if (s >= src - 1) { f = 0.f; s = src - 1; }
+  Taps t;
+  t.i0 = s;
+  t.i1 = min(s + 1, src - 1);
+  t.c0 = __float2int_rn((1.f - f) * 2048.f);
+  t.c1 = __float2int_rn(f * 2048.f);
+  return t;
+}
+// vertical tap (weights NOT clamped, rows clamped)
+__device__ __forceinline__ Taps tap_y(int d, double scale, int src) {
+  float f = (float)(((double)d + 0.5) * scale - 0.5);
+  const int s = (int)floorf(f);
+  f -= (float)s;
+  Taps t;
+  t.i0 = min(max(s, 0), src - 1);
+  t.i1 = min(max(s + 1, 0), src - 1);
+  t.c0 = __float2int_rn((1.f - f) * 2048.f);
+  t.c1 = __float2int_rn(f * 2048.f);
+  return t;
+}
+
+template <bool kU8Out>
+__global__ void __launch_bounds__(256) letterbox_kernel(const y11_image* __restrict__ images, int H, int W, void* __restrict__ out) {
+  const int quads = W / 4;
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= quads * H) return;
+  const int b = blockIdx.y;
+  const y11_image im = images[b];
+  const int y = qi / quads, x0 = (qi % quads) * 4;
+  uint8_t px[12];  // 4 pixels, BGR as in the source
+  const int yy = y - im.top;
+  const bool row_in = yy >= 0 && yy < im.new_h;
+  const bool identity = im.new_h == im.h0 && im.new_w == im.w0;
+  const bool area2 = im.h0 == 2 * im.new_h && im.w0 == 2 * im.new_w;
+  Taps ty = {0, 0, 0, 0};
+  if (row_in && !identity && !area2) ty = tap_y(yy, (double)im.h0 / im.new_h, im.h0);
+  const double sx = (double)im.w0 / im.new_w;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int xx = x0 + i - im.left;
+    if (!row_in || xx < 0 || xx >= im.new_w) {
+      px[3 * i] = px[3 * i + 1] = px[3 * i + 2] = 114;
+    } else if (identity) {
+      const uint8_t* sp = im.src + (size_t)yy * im.pitch + (size_t)xx * 3;
+      px[3 * i] = __ldg(sp); px[3 * i + 1] = __ldg(sp + 1); px[3 * i + 2] = __ldg(sp + 2);
+    } else if (area2) {
+      const uint8_t* r0 = im.src + (size_t)(2 * yy) * im.pitch + (size_t)(2 * xx) * 3;
+      const uint8_t* r1 = r0 + im.pitch;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        px[3 * i + c] = (uint8_t)(((int)__ldg(r0 + c) + (int)__ldg(r0 + 3 + c) + (int)__ldg(r1 + c) + (int)__ldg(r1 + 3 + c) + 2) >> 2);
+    } else {
+      const Taps tx = tap_x(xx, sx, im.w0);
+      const uint8_t* r0 = im.src + (size_t)ty.i0 * im.pitch;
+      const uint8_t* r1 = im.src + (size_t)ty.i1 * im.pitch;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int s0 = (int)__ldg(r0 + tx.i0 * 3 + c) * tx.c0 + (int)__ldg(r0 + tx.i1 * 3 + c) * tx.c1;
+        const int s1 = (int)__ldg(r1 + tx.i0 * 3 + c) * tx.c0 + (int)__ldg(r1 + tx.i1 * 3 + c) * tx.c1;
+        int v = (((ty.c0 * (s0 >> 4)) >> 16) + ((ty.c1 * (s1 >> 4)) >> 16) + 2) >> 2;
+        px[3 * i + c] = (uint8_t)min(max(v, 0), 255);
+      }
+    }
+  }
+  const size_t opix = ((size_t)b * H + y) * W + x0;
+  if (kU8Out) {
+    uint32_t* op = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(out) + opix * 3);  // 12-byte aligned group
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      op[i] = (uint32_t)px[4 * i] | ((uint32_t)px[4 * i + 1] << 8) | ((uint32_t)px[4 * i + 2] << 16) | ((uint32_t)px[4 * i + 3] << 24);
+  } else {
+    float f[12];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // BGR -> RGB, exact fp32 division as the reference does
+      f[3 * i + 0] = __fdiv_rn((float)px[3 * i + 2], 255.0f);
+      f[3 * i + 1] = __fdiv_rn((float)px[3 * i + 1], 255.0f);
+      f[3 * i + 2] = __fdiv_rn((float)px[3 * i + 0], 255.0f);
+    }
+    uint2* op = reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + opix * 3);  // 24-byte group, 8-byte aligned
+#pragma unroll
+    for (int i = 0; i < 3; ++i) op[i] = make_uint2(pack_bf16x2(f[4 * i], f[4 * i + 1]), pack_bf16x2(f[4 * i + 2], f[4 * i + 3]));
+  }
+}
+
+// fp32 NCHW (tensor sources) -> bf16 NHWC with a divisor; 4 pixels per thread like above
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, int HW, float divisor, __nv_bfloat16* __restrict__ out) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= HW / 4) return;
+  const int b = blockIdx.y;
+  const float* ip = in + (size_t)b * 3 * HW + (size_t)qi * 4;
+  const float4 r = __ldg(reinterpret_cast<const float4*>(ip));
+  const float4 g = __ldg(reinterpret_cast<const float4*>(ip + HW));
+  const float4 bl = __ldg(reinterpret_cast<const float4*>(ip + 2 * (size_t)HW));
+  const float f[12] = {r.x, g.x, bl.x, r.y, g.y, bl.y, r.z, g.z, bl.z, r.w, g.w, bl.w};
+  uint2* op = reinterpret_cast<uint2*>(out + ((size_t)b * HW + (size_t)qi * 4) * 3);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    op[i] = make_uint2(pack_bf16x2(__fdiv_rn(f[4 * i], divisor), __fdiv_rn(f[4 * i + 1], divisor)), pack_bf16x2(__fdiv_rn(f[4 * i + 2], divisor), __fdiv_rn(f[4 * i + 3], divisor)));
+}
+
+}  // namespace
+
+static int letterbox_common(const y11_image* images, int B, int H, int W, void* out, bool u8, cudaStream_t s) {
+  Y11_REQUIRE(W % 4 == 0 && B > 0 && H > 0, "letterbox: W must be a multiple of 4 (got %d)", W);
+  dim3 grid((unsigned)((W / 4 * H + 255) / 256), (unsigned)B);
+  if (u8)
+    letterbox_kernel<true><<<grid, 256, 0, s>>>(images, H, W, out);
+  else
+    letterbox_kernel<false><<<grid, 256, 0, s>>>(images, H, W, out);
+  Y11_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int y11_letterbox(y11_handle, const y11_image* images, int B, int H, int W, void* out, y11_stream s) {
+  return letterbox_common(images, B, H, W, out, false, static_cast<cudaStream_t>(s));
+}
+extern "C" int y11_letterbox_u8(y11_handle, const y11_image* images, int B, int H, int W, uint8_t* out, y11_stream s) {
+  return letterbox_common(images, B, H, W, out, true, static_cast<cudaStream_t>(s));
+}
+extern "C" int y11_nchw_f32_to_nhwc_bf16(y11_handle, const float* in, int B, int H, int W, float divisor, void* out, y11_stream s) {
+  Y11_REQUIRE((H * W) % 4 == 0, "nchw->nhwc: H*W must be a multiple of 4");
+  dim3 grid((unsigned)((H * W / 4 + 255) / 256), (unsigned)B);
+  nchw_to_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(s)>>>(in, H * W, divisor, static_cast<__nv_bfloat16*>(out));
+  Y11_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
