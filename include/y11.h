@@ -144,10 +144,11 @@ double y11_plan_op_flops(y11_plan p, int i);
 /* ---- (3) Detect decode + NMS  [a12 Detect._inference/DFL/dist2bbox, a13 non_max_suppression,
  *          a14 torchvision.ops.nms, a15 scale_boxes+clip_boxes] -------------------------------- */
 typedef struct {
-  const float* head[3]; /* per level fp32 [B, H_l*W_l, 64+nc]: 64 DFL logits then nc class logits */
+  const float* head[3]; /* per level fp32 [B, H_l*W_l, row_stride]: 64 DFL logits then nc class logits */
   int32_t hl[3], wl[3];
   float stride[3];
   int32_t nl, B, nc;
+  int32_t row_stride; /* floats per anchor row, >= 64+nc (64 + nc rounded up to 16 when nc % 16 != 0) */
 } y11_head_desc;
 
 typedef struct {

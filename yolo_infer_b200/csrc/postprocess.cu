@@ -406,7 +406,8 @@ int fill_head(const y11_head_desc* hd, HeadParams* hp) {
     off += hp->hl[l] * (l < hd->nl ? hd->wl[l] : 0);
   }
   hp->off[3] = off;
-  hp->nl = hd->nl; hp->B = hd->B; hp->nc = hd->nc; hp->A = off; hp->no = 64 + hd->nc;
+  hp->nl = hd->nl; hp->B = hd->B; hp->nc = hd->nc; hp->A = off; hp->no = hd->row_stride;
+  Y11_REQUIRE(hd->row_stride >= 64 + hd->nc, "postprocess: row_stride %d < 64+nc", hd->row_stride);
   return 0;
 }
 

@@ -1,0 +1,398 @@
+"""The engine object that sits where ``ultralytics.YOLO`` sits in the reference (core/model.py:110: ``self.model``).
+
+``YOLO(path).predict(source, **kw)`` reproduces the reference's detect path: source loaders ->
+letterbox preprocess -> fused network -> Detect decode -> NMS -> scale_boxes -> ``Results`` - with every
+arithmetic step executed by liby11_b200.so on an sm_100 GPU.  There is no CPU fallback: constructing the
+engine without a B200-class device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import math
+import threading
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _cabi as cabi
+from . import topology as T
+from .network import CompiledNet, pack_weights
+from .results import Results
+
+logger = logging.getLogger(__name__)
+
+PREDICT_DEFAULTS = dict(conf=0.25, iou=0.7, max_det=300, imgsz=640, rect=True, agnostic_nms=False, classes=None,
+                        half=False, verbose=True, save=False, show=False, stream=False, batch=1, device=None,
+                        multi_label=False, max_nms=30000)
+
+
+def letterbox_geometry(h0: int, w0: int, new_shape: Tuple[int, int], auto: bool, stride: int = 32):
+    """ultralytics LetterBox geometry (center, scaleup): returns new_w, new_h, top, left, H, W."""
+    r = min(new_shape[0] / h0, new_shape[1] / w0)
+    new_w, new_h = int(round(w0 * r)), int(round(h0 * r))
+    dw, dh = new_shape[1] - new_w, new_shape[0] - new_h
+    if auto:
+        dw, dh = dw % stride, dh % stride
+    dw, dh = dw / 2, dh / 2
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    return new_w, new_h, top, left, new_h + top + bottom, new_w + left + right
+
+
+def scale_geometry(net_hw: Tuple[int, int], orig_hw: Tuple[int, int]):
+    """ultralytics scale_boxes geometry: gain, pad_x, pad_y."""
+    gain = min(net_hw[0] / orig_hw[0], net_hw[1] / orig_hw[1])
+    pad_x = round((net_hw[1] - orig_hw[1] * gain) / 2 - 0.1)
+    pad_y = round((net_hw[0] - orig_hw[0] * gain) / 2 - 0.1)
+    return gain, pad_x, pad_y
+
+
+class DetectionNet:
+    """What ``YOLO.model`` is in the reference (an nn.Module there): parameter access for get_model_info
+    (/root/reference/core/model.py:237-247) and eval() for the benchmark (benchmarks/speed_benchmark.py:323)."""
+
+    def __init__(self, scale: str, nc: int, state_dict: Dict[str, torch.Tensor], names: Dict[int, str]):
+        self.scale, self.nc, self.names = scale, nc, names
+        self._sd = {k: v for k, v in state_dict.items() if not k.endswith("num_batches_tracked")}
+        shapes = T.param_shapes(scale, nc)
+        missing = sorted(set(shapes) - set(self._sd))
+        if missing:
+            raise KeyError(f"state_dict is missing {len(missing)} tensors, e.g. {missing[:3]}")
+        for k, s in shapes.items():
+            if tuple(self._sd[k].shape) != s:
+                raise ValueError(f"{k}: shape {tuple(self._sd[k].shape)} != expected {s}")
+        self.training = False
+        self.stride = torch.tensor([float(s) for s in T.STRIDES])
+        self._params = None
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return dict(self._sd)
+
+    def named_parameters(self):
+        if self._params is None:
+            self._params = {k: torch.nn.Parameter(v, requires_grad=not k.startswith("model.23.dfl"))
+                            for k, v in self._sd.items() if T.is_learnable(k)}
+        return iter(self._params.items())
+
+    def parameters(self):
+        return (p for _, p in self.named_parameters())
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("yolo_infer_b200 is an inference path; training is out of scope (SURVEY.md section 2 #8)")
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def fuse(self):
+        return self
+
+
+def _load_state_dict(path: Path):
+    obj = torch.load(str(path), map_location="cpu", weights_only=True)
+    if isinstance(obj, dict) and "state_dict" in obj:
+        return obj["state_dict"], obj.get("scale"), obj.get("names"), obj.get("nc")
+    if isinstance(obj, dict) and all(isinstance(v, torch.Tensor) for v in obj.values()):
+        return obj, None, None, None
+    raise ValueError(f"{path}: expected a plain state_dict (ultralytics key names, see SURVEY.md A.4); pickled "
+                     "ultralytics model objects cannot be read without ultralytics")
+
+
+def infer_scale(sd: Dict[str, torch.Tensor]) -> str:
+    c0 = sd["model.0.conv.weight"].shape[0]
+    deep = "model.2.m.1.cv1.conv.weight" in sd  # depth 1.0 -> two inner blocks
+    return {16: "n", 32: "s", 96: "x"}.get(c0) or ("l" if deep else "m")
+
+
+class YOLO:
+    """Drop-in for the subset of ``ultralytics.YOLO`` the reference uses on the detect path."""
+
+    def __init__(self, model: Union[str, Path] = "yolo11n.yaml", task: Optional[str] = "detect", verbose: bool = False,
+                 init: str = "default", seed: int = 0):
+        if task not in (None, "detect"):
+            raise NotImplementedError(f"task={task!r}: only 'detect' is on the B200 hot path (SURVEY.md section 8)")
+        self.task = "detect"
+        self.ckpt_path = str(model)
+        p = Path(str(model))
+        stem = p.stem.lower()
+        names = None
+        nc = 80
+        if p.suffix in (".yaml", ".yml"):
+            if not (stem.startswith("yolo11") and len(stem) >= 7 and stem[6] in T.SCALES):
+                raise ValueError(f"{model}: expected yolo11{{n,s,m,l,x}}.yaml")
+            scale = stem[6]
+            sd = T.default_state_dict(scale, nc, seed)
+        elif p.suffix in (".pt", ".pth"):
+            if p.exists():
+                sd, scale, names, nc_ = _load_state_dict(p)
+                scale = scale or infer_scale(sd)
+                nc = nc_ or sd["model.23.cv3.0.2.weight"].shape[0]
+            elif stem.startswith("yolo11") and len(stem) >= 7 and stem[6] in T.SCALES:
+                # the reference would download pretrained weights here (core/model.py:106-110); there is no network
+                logger.warning("%s not found and cannot be downloaded offline: using random-init %s.yaml weights", model, stem[:7])
+                scale = stem[6]
+                sd = T.default_state_dict(scale, nc, seed)
+            else:
+                raise FileNotFoundError(str(model))
+        else:
+            raise ValueError(f"unsupported model file {model!r}")
+        self.scale = scale
+        self.nc = nc
+        self.names: Dict[int, str] = names or {i: f"{i}" for i in range(nc)}
+        self.model = DetectionNet(scale, nc, sd, self.names)
+        self.overrides: Dict[str, object] = {}
+        self.device: Optional[torch.device] = None
+        self._engine = C.c_void_p()
+        self._packed = None
+        self._nets: Dict[Tuple[int, int, int], CompiledNet] = {}
+        self._lock = threading.Lock()
+        self._ws: Dict[Tuple, torch.Tensor] = {}
+        self._lib = None
+        self.conv_impl = cabi.IMPL_TCGEN05
+        self.last_speed: Dict[str, float] = {}
+
+    # ---- construction from an in-memory state_dict (tests, bench) -----------------------------------
+    @classmethod
+    def from_state_dict(cls, sd: Dict[str, torch.Tensor], scale: Optional[str] = None, nc: int = 80) -> "YOLO":
+        self = cls.__new__(cls)
+        YOLO.__init__(self, f"yolo11{scale or infer_scale(sd)}.yaml")
+        self.nc = nc
+        self.model = DetectionNet(self.scale, nc, {k: v.detach().clone() for k, v in sd.items()}, self.names)
+        return self
+
+    # ---- device ---------------------------------------------------------------------------------
+    def to(self, device) -> "YOLO":
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError(f"device={device!r}: yolo_infer_b200 runs on sm_100 GPUs only - there is no CPU fallback "
+                               "(the reference's CPU path is kept only as the test oracle under oracle/)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("CUDA device requested but none is visible; yolo_infer_b200 has no CPU fallback")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if self.device == dev and self._engine:
+            return self
+        self._release()
+        self.device = dev
+        self._lib = cabi.load()
+        with torch.cuda.device(dev):
+            cabi.check(self._lib.y11_create(C.byref(self._engine), dev.index), "y11_create")
+            self._packed = pack_weights(self.scale, self.nc, self.model.state_dict(), dev)
+        return self
+
+    def cuda(self) -> "YOLO":
+        return self.to("cuda")
+
+    def eval(self) -> "YOLO":
+        return self
+
+    def fuse(self) -> "YOLO":
+        return self
+
+    def _release(self):
+        self._nets.clear()
+        self._ws.clear()
+        if self._engine and self._lib is not None:
+            self._lib.y11_destroy(self._engine)
+        self._engine = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _ensure_device(self, device=None):
+        if device is not None:
+            self.to(device)
+        elif not self._engine:
+            self.to("cuda")
+
+    def compiled(self, B: int, H: int, W: int) -> CompiledNet:
+        key = (B, H, W)
+        net = self._nets.get(key)
+        if net is None:
+            with torch.cuda.device(self.device):
+                net = CompiledNet(self._engine, self.scale, self.nc, self._packed, B, H, W, self.device, self.conv_impl)
+            self._nets[key] = net
+        return net
+
+    def _workspace(self, key, nbytes: int) -> torch.Tensor:
+        t = self._ws.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+            self._ws[key] = t
+        return t
+
+    # ---- stages (each is one or a few kernel launches through the C ABI) -----------------------------
+    def preprocess_images(self, net: CompiledNet, frames: Sequence[torch.Tensor], geoms) -> None:
+        """frames: device uint8 HWC BGR tensors; writes net.input (bf16 NHWC RGB /255)."""
+        arr = (cabi.Image * len(frames))()
+        for i, (f, g) in enumerate(zip(frames, geoms)):
+            new_w, new_h, top, left, _, _ = g
+            arr[i] = cabi.Image(f.data_ptr(), f.shape[0], f.shape[1], f.stride(0), new_h, new_w, top, left)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        dev = self._workspace(("img_desc", len(frames)), host.numel())
+        dev[: host.numel()].copy_(host, non_blocking=False)
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        cabi.check(self._lib.y11_letterbox(self._engine, dev.data_ptr(), len(frames), net.H, net.W, net.input.data_ptr(),
+                                           C.c_void_p(s)), "y11_letterbox")
+
+    def preprocess_tensor(self, net: CompiledNet, x: torch.Tensor, divisor: float) -> None:
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        cabi.check(self._lib.y11_nchw_f32_to_nhwc_bf16(self._engine, x.data_ptr(), net.B, net.H, net.W, divisor,
+                                                       net.input.data_ptr(), C.c_void_p(s)), "y11_nchw_f32_to_nhwc_bf16")
+
+    def forward(self, net: CompiledNet) -> None:
+        net.run(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def postprocess(self, net: CompiledNet, scale_rows: Optional[torch.Tensor], conf: float, iou: float, max_det: int,
+                    agnostic: bool = False, multi_label: bool = False, max_nms: int = 30000):
+        """-> (det fp32 [B,max_det,6], count int32 [B], ncand int32 [B]) device tensors."""
+        B = net.B
+        nbytes = self._lib.y11_postprocess_workspace(B, net.A, self.nc, int(multi_label), max_nms)
+        ws = self._workspace(("post", B, net.A, multi_label), nbytes)
+        okey = ("post_out", B, max_det)
+        out = self._ws.get(okey)
+        if out is None:
+            out = (torch.zeros((B, max_det, 6), dtype=torch.float32, device=self.device),
+                   torch.zeros((B,), dtype=torch.int32, device=self.device),
+                   torch.zeros((B,), dtype=torch.int32, device=self.device))
+            self._ws[okey] = out
+        det, count, ncand = out
+        hd = net.head_desc()
+        p = cabi.NmsParams(conf, iou, max_det, max_nms, 7680, int(agnostic), int(multi_label))
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        cabi.check(self._lib.y11_detect_postprocess(self._engine, C.byref(hd), C.byref(p),
+                                                    scale_rows.data_ptr() if scale_rows is not None else None,
+                                                    det.data_ptr(), count.data_ptr(), ncand.data_ptr(), ws.data_ptr(),
+                                                    ws.numel(), C.c_void_p(s)), "y11_detect_postprocess")
+        return det, count, ncand
+
+    # ---- sources ----------------------------------------------------------------------------------
+    @staticmethod
+    def _load_sources(source) -> Tuple[List[np.ndarray], List[str]]:
+        import cv2
+        items = source if isinstance(source, (list, tuple)) else [source]
+        imgs, paths = [], []
+        for i, it in enumerate(items):
+            if isinstance(it, (str, Path)):
+                im = cv2.imread(str(it))  # BGR, as ultralytics LoadImagesAndVideos does
+                if im is None:
+                    raise FileNotFoundError(f"cannot read image {it}")
+                imgs.append(im)
+                paths.append(str(it))
+            elif isinstance(it, np.ndarray):
+                if it.ndim != 3 or it.shape[2] != 3 or it.dtype != np.uint8:
+                    raise ValueError(f"ndarray source must be HxWx3 uint8 BGR, got {it.shape} {it.dtype}")
+                imgs.append(np.ascontiguousarray(it))
+                paths.append(f"image{i}.jpg")
+            else:
+                raise TypeError(f"unsupported source element {type(it)}")
+        return imgs, paths
+
+    # ---- predict ----------------------------------------------------------------------------------
+    def predict(self, source=None, stream: bool = False, **kwargs) -> List[Results]:
+        args = {**PREDICT_DEFAULTS, **self.overrides, **kwargs}
+        unknown = set(kwargs) - set(PREDICT_DEFAULTS)
+        if unknown:
+            logger.debug("predict: ignoring unsupported kwargs %s", sorted(unknown))
+        if args["half"]:
+            logger.debug("half=True: the B200 path always computes in bf16 with fp32 accumulation")
+        if source is None:
+            raise ValueError("predict: source is required")
+        self._ensure_device(args["device"])
+        imgsz = args["imgsz"]
+        new_shape = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        with self._lock, torch.cuda.device(self.device), torch.inference_mode():
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            if isinstance(source, torch.Tensor) and source.is_floating_point():
+                # LoadTensor semantics: whole tensor is one batch; /255 only if max > 1
+                x = source
+                if x.ndim == 3:
+                    x = x[None]
+                if x.ndim != 4 or x.shape[1] != 3 or x.shape[2] % 32 or x.shape[3] % 32:
+                    raise ValueError(f"tensor source must be [B,3,H,W] with H,W % 32 == 0, got {tuple(x.shape)}")
+                x = x.to(self.device, torch.float32, non_blocking=True).contiguous()
+                divisor = 255.0 if float(x.max()) > 1.0 + torch.finfo(torch.float32).eps else 1.0
+                B, _, H, W = x.shape
+                net = self.compiled(B, H, W)
+                self.preprocess_tensor(net, x, divisor)
+                orig_shapes = [(H, W)] * B
+                paths = [f"image{i}.jpg" for i in range(B)]
+                orig_imgs: List[Optional[np.ndarray]] = [None] * B
+            else:
+                if isinstance(source, torch.Tensor):  # device-resident uint8 frames [B,H,W,3] BGR (zero-copy path)
+                    if source.dtype != torch.uint8 or source.ndim != 4 or source.shape[-1] != 3:
+                        raise ValueError("uint8 tensor source must be [B,H,W,3] BGR")
+                    frames = [f for f in source.to(self.device).contiguous()]
+                    paths = [f"image{i}.jpg" for i in range(len(frames))]
+                    orig_imgs = [None] * len(frames)
+                else:
+                    imgs, paths = self._load_sources(source)
+                    frames = [torch.from_numpy(im).pin_memory().to(self.device, non_blocking=True) for im in imgs]
+                    orig_imgs = list(imgs)
+                orig_shapes = [(int(f.shape[0]), int(f.shape[1])) for f in frames]
+                auto = bool(args["rect"]) and len(set(orig_shapes)) == 1
+                geoms = [letterbox_geometry(h, w, new_shape, auto) for h, w in orig_shapes]
+                H, W = geoms[0][4], geoms[0][5]
+                B = len(frames)
+                net = self.compiled(B, H, W)
+                self.preprocess_images(net, frames, geoms)
+            ev[1].record()
+            self.forward(net)
+            ev[2].record()
+            rows = []
+            for (h0, w0) in orig_shapes:
+                gain, px, py = scale_geometry((H, W), (h0, w0))
+                rows.append([gain, float(px), float(py), float(w0), float(h0)])
+            scale_rows = torch.tensor(rows, dtype=torch.float32).to(self.device, non_blocking=True)
+            det, count, ncand = self.postprocess(net, scale_rows, float(args["conf"]), float(args["iou"]), int(args["max_det"]),
+                                                 bool(args["agnostic_nms"]), bool(args["multi_label"]), int(args["max_nms"]))
+            ev[3].record()
+            counts = count.cpu().tolist()  # one small D2H; also the sync point of the call
+            speed = {"preprocess": ev[0].elapsed_time(ev[1]) / B, "inference": ev[1].elapsed_time(ev[2]) / B,
+                     "postprocess": ev[2].elapsed_time(ev[3]) / B}
+            self.last_speed = speed
+            det = det.clone()
+            results = []
+            classes = args["classes"]
+            for i in range(B):
+                d = det[i, : counts[i]]
+                if classes is not None:
+                    keep = torch.isin(d[:, 5].long(), torch.as_tensor(list(classes), device=d.device))
+                    d = d[keep]
+                results.append(Results(orig_imgs[i], paths[i], self.names, d, orig_shapes[i], dict(speed)))
+        if args["verbose"]:
+            logger.info("%d image(s) %dx%d: %.2f ms pre, %.2f ms inference, %.2f ms post per image", B, H, W,
+                        speed["preprocess"], speed["inference"], speed["postprocess"])
+        return results
+
+    __call__ = predict
+
+    # ---- out-of-scope surface: fail loudly, never silently fall back -----------------------------------
+    def val(self, *a, **k):
+        raise NotImplementedError("val: forward + multi-label NMS are available via predict(multi_label=True, conf=0.001, "
+                                  "iou=0.6); dataset loading and mAP maths are a 'next' row (SURVEY.md section 8f)")
+
+    def train(self, *a, **k):
+        raise NotImplementedError("training is out of scope for the B200 inference path (SURVEY.md section 2 #8)")
+
+    def export(self, *a, **k):
+        raise NotImplementedError("export is out of scope: the B200 path is not a TensorRT/ONNX export")
+
+    def save(self, path: Union[str, Path]):
+        torch.save({"state_dict": self.model.state_dict(), "scale": self.scale, "nc": self.nc, "names": self.names}, str(path))
+
+    def info(self, *a, **k):
+        n = T.count_parameters(self.scale, self.nc)
+        return {"scale": self.scale, "parameters": n}

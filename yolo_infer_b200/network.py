@@ -1,0 +1,368 @@
+"""Host-side compiler: YOLO11 topology + state_dict -> BN-folded bf16 weights + an op list for liby11_b200.
+
+Replaces what the reference gets from ultralytics ``AutoBackend(fuse=True)`` + ``DetectionModel._predict_once``
+(SURVEY.md section 8a rows a5, a6): Conv+BN are folded offline (W' = W*g/sqrt(v+eps), b' = beta - mu*g/sqrt(v+eps)),
+weights are packed K-major (kh, kw, cin) in bf16, and the 24-layer graph is flattened into one launch per fused op.
+Concat / chunk / split never copy: producers write straight into channel slices of the consumer's buffer.
+
+PyTorch is used for device memory only (buffers are torch tensors kept alive by the CompiledNet); every
+computation is a kernel of liby11_b200.so reached through the C ABI in include/y11.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _cabi as cabi
+from . import topology as T
+
+BN_EPS = 1e-3
+
+
+def pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+@dataclass
+class PackedConv:
+    w: torch.Tensor          # bf16 [cout_p, k*k*cin_p]  (dense) | [9, c] (depthwise) | [cout, 27] (stem)
+    b: torch.Tensor          # fp32 [cout_p]
+    c1: int
+    c2: int
+    k: int
+    s: int
+    act: int
+    depthwise: bool = False
+
+
+def fold(sd: Dict[str, torch.Tensor], cp: T.ConvParam) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 folded (weight [c2, c1/g, k, k], bias [c2])."""
+    if cp.bn:
+        w = sd[f"{cp.prefix}.conv.weight"].float()
+        scale = sd[f"{cp.prefix}.bn.weight"].float() / torch.sqrt(sd[f"{cp.prefix}.bn.running_var"].float() + BN_EPS)
+        b = sd[f"{cp.prefix}.bn.bias"].float() - sd[f"{cp.prefix}.bn.running_mean"].float() * scale
+        return w * scale.view(-1, 1, 1, 1), b
+    return sd[f"{cp.prefix}.weight"].float(), sd[f"{cp.prefix}.bias"].float()
+
+
+def qkv_permutation(c: int, heads: int, kd: int, hd: int) -> torch.Tensor:
+    """Row order that turns ultralytics' per-head [q|k|v] qkv channels into [Q all heads | K all heads | V all heads]."""
+    per = 2 * kd + hd
+    q = [h * per + i for h in range(heads) for i in range(kd)]
+    k = [h * per + kd + i for h in range(heads) for i in range(kd)]
+    v = [h * per + 2 * kd + i for h in range(heads) for i in range(hd)]
+    return torch.tensor(q + k + v, dtype=torch.long)
+
+
+def pack_weights(scale: str, nc: int, sd: Dict[str, torch.Tensor], device) -> Dict[str, PackedConv]:
+    packed: Dict[str, PackedConv] = {}
+    for cp in T.conv_params(scale, nc):
+        w, b = fold(sd, cp)
+        if cp.prefix.endswith("attn.qkv"):
+            c = cp.c1
+            heads = c // 64
+            hd = c // heads
+            perm = qkv_permutation(c, heads, int(hd * 0.5), hd)
+            w, b = w[perm], b[perm]
+        act = cabi.ACT_SILU if cp.act else cabi.ACT_NONE
+        if cp.g > 1:  # depthwise
+            assert cp.g == cp.c1 == cp.c2 and cp.k == 3
+            wp = w.view(cp.c2, 9).t().contiguous()  # [9, c] tap-major
+            packed[cp.prefix] = PackedConv(wp.to(device, torch.bfloat16), b.to(device).contiguous(), cp.c1, cp.c2, 3, 1, act, True)
+        elif cp.c1 == 3:  # stem
+            wp = w.permute(0, 2, 3, 1).reshape(cp.c2, 27).contiguous()
+            packed[cp.prefix] = PackedConv(wp.to(device, torch.bfloat16), b.to(device).contiguous(), 3, cp.c2, 3, 2, act)
+        else:
+            c1p, c2p = pad16(cp.c1), pad16(cp.c2)
+            wp = torch.zeros(c2p, cp.k, cp.k, c1p)
+            wp[: cp.c2, :, :, : cp.c1] = w.permute(0, 2, 3, 1)
+            bp = torch.zeros(c2p)
+            bp[: cp.c2] = b
+            packed[cp.prefix] = PackedConv(wp.view(c2p, -1).to(device, torch.bfloat16).contiguous(), bp.to(device), c1p, c2p,
+                                           cp.k, cp.s, act)
+    return packed
+
+
+@dataclass
+class V:
+    """A channel-slice view of an NHWC buffer."""
+    t: torch.Tensor
+    off: int
+    c: int
+
+    @property
+    def H(self):
+        return self.t.shape[1]
+
+    @property
+    def W(self):
+        return self.t.shape[2]
+
+    def sub(self, off: int, c: int) -> "V":
+        assert off + c <= self.c
+        return V(self.t, self.off + off, c)
+
+    def cview(self) -> cabi.View:
+        return cabi.View(self.t.data_ptr(), self.t.shape[-1], self.off, self.c)
+
+
+@dataclass
+class OpRecord:
+    kind: str
+    name: str
+    flops: float = 0.0
+    bytes_algo: float = 0.0   # algorithmic HBM bytes: unique input + weights + output
+
+
+class CompiledNet:
+    """One (scale, B, H, W) instance: owns activation buffers, the plan handle and the head tensors."""
+
+    def __init__(self, engine, scale: str, nc: int, packed: Dict[str, PackedConv], B: int, H: int, W: int, device,
+                 conv_impl: int = cabi.IMPL_TCGEN05):
+        assert H % 32 == 0 and W % 32 == 0, "network input must be a multiple of 32"
+        self.lib = cabi.load()
+        self.engine = engine
+        self.scale, self.nc, self.B, self.H, self.W, self.device = scale, nc, B, H, W, device
+        self.packed = packed
+        self.conv_impl = conv_impl
+        self.buffers: List[torch.Tensor] = []
+        self.ops: List[OpRecord] = []
+        self.plan = C.c_void_p()
+        cabi.check(self.lib.y11_plan_create(engine, C.byref(self.plan)), "y11_plan_create")
+        self.input = self._alloc(H, W, 3)                      # bf16 NHWC, written by the letterbox kernel
+        self.no = 64 + pad16(nc)
+        self.head: List[torch.Tensor] = []
+        self._build()
+        self.A = sum(h.shape[1] * h.shape[2] for h in self.head)
+
+    def __del__(self):
+        try:
+            if self.plan:
+                self.lib.y11_plan_destroy(self.plan)
+                self.plan = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- buffers ------------------------------------------------------------------------------
+    def _alloc(self, h: int, w: int, c: int, dtype=torch.bfloat16) -> torch.Tensor:
+        t = torch.zeros((self.B, h, w, c), dtype=dtype, device=self.device)
+        self.buffers.append(t)
+        return t
+
+    def _new(self, h: int, w: int, c: int) -> V:
+        cp = pad16(c)
+        return V(self._alloc(h, w, cp), 0, cp)
+
+    # ---- op emitters --------------------------------------------------------------------------
+    def _conv(self, name: str, x: V, out: V, res: Optional[V] = None, out_f32: bool = False):
+        pc = self.packed[name]
+        assert not pc.depthwise
+        assert x.c == pc.c1, (name, x.c, pc.c1)
+        assert out.c == pc.c2, (name, out.c, pc.c2)
+        d = cabi.ConvDesc()
+        d.inp, d.out = x.cview(), out.cview()
+        d.res = res.cview() if res is not None else cabi.NULL_VIEW
+        d.w, d.bias = pc.w.data_ptr(), pc.b.data_ptr()
+        d.B, d.Hin, d.Win, d.Hout, d.Wout = self.B, x.H, x.W, out.H, out.W
+        d.k, d.stride, d.act, d.out_f32, d.impl = pc.k, pc.s, pc.act, int(out_f32), self.conv_impl
+        cabi.check(self.lib.y11_plan_add_conv(self.plan, C.byref(d)), f"plan_add_conv({name})")
+        px = self.B * out.H * out.W
+        self.ops.append(OpRecord("conv", name, 2.0 * px * pc.c2 * pc.c1 * pc.k * pc.k,
+                                 self.B * x.H * x.W * pc.c1 * 2 + pc.w.numel() * 2 + px * pc.c2 * (4 if out_f32 else 2)
+                                 + (px * pc.c2 * 2 if res is not None else 0)))
+
+    def _dw(self, name: str, x: V, out: V, res: Optional[V] = None):
+        pc = self.packed[name]
+        assert pc.depthwise and x.c == pc.c1 == out.c
+        d = cabi.DwConvDesc()
+        d.inp, d.out = x.cview(), out.cview()
+        d.res = res.cview() if res is not None else cabi.NULL_VIEW
+        d.w, d.bias = pc.w.data_ptr(), pc.b.data_ptr()
+        d.B, d.H, d.W, d.act = self.B, x.H, x.W, pc.act
+        cabi.check(self.lib.y11_plan_add_dwconv(self.plan, C.byref(d)), f"plan_add_dwconv({name})")
+        px = self.B * x.H * x.W
+        self.ops.append(OpRecord("dwconv", name, 2.0 * px * pc.c1 * 9, px * pc.c1 * 2 * (3 if res is not None else 2)))
+
+    # ---- modules ------------------------------------------------------------------------------
+    def _bottleneck(self, p: str, x: V, out: V, e: float):
+        hidden = self._new(x.H, x.W, int(out.c * e))
+        self._conv(f"{p}.cv1", x, hidden)
+        self._conv(f"{p}.cv2", hidden, out, res=x)  # shortcut: c1 == c2 everywhere in YOLO11
+
+    def _c3k(self, p: str, x: V, out: V):
+        c_ = int(out.c * 0.5)
+        z = self._new(x.H, x.W, 2 * c_)
+        t0 = self._new(x.H, x.W, c_)
+        self._conv(f"{p}.cv1", x, t0)
+        t1 = self._new(x.H, x.W, c_)
+        self._bottleneck(f"{p}.m.0", t0, t1, 1.0)
+        self._bottleneck(f"{p}.m.1", t1, z.sub(0, c_), 1.0)
+        self._conv(f"{p}.cv2", x, z.sub(c_, c_))
+        self._conv(f"{p}.cv3", z, out)
+
+    def _c3k2(self, sp: T.LayerSpec, x: V, out: V):
+        p = f"model.{sp.index}"
+        c = int(sp.c2 * sp.e)
+        y = self._new(x.H, x.W, (2 + sp.n) * c)
+        self._conv(f"{p}.cv1", x, y.sub(0, 2 * c))
+        for j in range(sp.n):
+            src, dst = y.sub((1 + j) * c, c), y.sub((2 + j) * c, c)
+            if sp.c3k:
+                self._c3k(f"{p}.m.{j}", src, dst)
+            else:
+                self._bottleneck(f"{p}.m.{j}", src, dst, 0.5)
+        self._conv(f"{p}.cv2", y, out)
+
+    def _sppf(self, sp: T.LayerSpec, x: V, out: V):
+        p = f"model.{sp.index}"
+        c_ = sp.c1 // 2
+        s = self._new(x.H, x.W, 4 * c_)
+        self._conv(f"{p}.cv1", x, s.sub(0, c_))
+        d = cabi.SppfDesc(s.cview(), self.B, x.H, x.W, c_)
+        cabi.check(self.lib.y11_plan_add_sppf(self.plan, C.byref(d)), "plan_add_sppf")
+        self.ops.append(OpRecord("sppf", p + ".pool", 0.0, self.B * x.H * x.W * c_ * 2 * 4))
+        self._conv(f"{p}.cv2", s, out)
+
+    def _c2psa(self, sp: T.LayerSpec, x: V, out: V):
+        p = f"model.{sp.index}"
+        c = int(sp.c1 * 0.5)
+        heads = c // 64
+        hd = c // heads
+        kd = int(hd * 0.5)
+        pbuf = self._new(x.H, x.W, 2 * c)
+        self._conv(f"{p}.cv1", x, pbuf)
+        b = pbuf.sub(c, c)
+        n_tok = x.H * x.W
+        for j in range(sp.n):
+            q = self._new(x.H, x.W, c + 2 * heads * kd)
+            self._conv(f"{p}.m.{j}.attn.qkv", b, q)
+            o = self._new(x.H, x.W, c)
+            d = cabi.AttnDesc(q.cview(), o.cview(), self.B, n_tok, heads, kd, hd, float(kd ** -0.5))
+            cabi.check(self.lib.y11_plan_add_attention(self.plan, C.byref(d)), "plan_add_attention")
+            self.ops.append(OpRecord("attention", f"{p}.m.{j}.attn", 2.0 * self.B * heads * n_tok * n_tok * (kd + hd),
+                                     self.B * n_tok * (q.c + c) * 2))
+            t = self._new(x.H, x.W, c)
+            self._dw(f"{p}.m.{j}.attn.pe", q.sub(2 * heads * kd, c), t, res=o)
+            self._conv(f"{p}.m.{j}.attn.proj", t, b, res=b)        # x = x + attn(x), in place on the b slice
+            f = self._new(x.H, x.W, 2 * c)
+            self._conv(f"{p}.m.{j}.ffn.0", b, f)
+            self._conv(f"{p}.m.{j}.ffn.1", f, b, res=b)            # x = x + ffn(x)
+        self._conv(f"{p}.cv2", pbuf, out)
+
+    def _upsample(self, x: V, out: V):
+        d = cabi.UpsampleDesc(x.cview(), out.cview(), self.B, x.H, x.W)
+        cabi.check(self.lib.y11_plan_add_upsample(self.plan, C.byref(d)), "plan_add_upsample")
+        self.ops.append(OpRecord("upsample", "upsample", 0.0, self.B * x.H * x.W * x.c * 2 * 5))
+
+    def _detect(self, sp: T.LayerSpec, xs: List[V]):
+        p = f"model.{sp.index}"
+        c2, c3 = T.detect_dims(sp.ch_in, self.nc)
+        for l, x in enumerate(xs):
+            head = self._alloc(x.H, x.W, self.no, torch.float32)
+            self.head.append(head)
+            t1 = self._new(x.H, x.W, c2)
+            t2 = self._new(x.H, x.W, c2)
+            self._conv(f"{p}.cv2.{l}.0", x, t1)
+            self._conv(f"{p}.cv2.{l}.1", t1, t2)
+            self._conv(f"{p}.cv2.{l}.2", t2, V(head, 0, 64), out_f32=True)
+            u1 = self._new(x.H, x.W, x.c)
+            u2 = self._new(x.H, x.W, c3)
+            u3 = self._new(x.H, x.W, c3)
+            u4 = self._new(x.H, x.W, c3)
+            self._dw(f"{p}.cv3.{l}.0.0", x, u1)
+            self._conv(f"{p}.cv3.{l}.0.1", u1, u2)
+            self._dw(f"{p}.cv3.{l}.1.0", u2, u3)
+            self._conv(f"{p}.cv3.{l}.1.1", u3, u4)
+            self._conv(f"{p}.cv3.{l}.2", u4, V(head, 64, pad16(self.nc)), out_f32=True)
+
+    # ---- graph ----------------------------------------------------------------------------------
+    def _build(self):
+        specs = T.layer_specs(self.scale)
+        H, W = self.H, self.W
+        # where each layer's output lives: concat consumers own the storage, producers write into slices
+        concat_of: Dict[int, Tuple[int, int]] = {}   # producer layer -> (concat layer, channel offset)
+        for sp in specs:
+            if sp.kind == "Concat":
+                off = 0
+                for src in sp.frm:
+                    concat_of[src] = (sp.index, off)
+                    off += specs[src].c2
+        cat_buf: Dict[int, V] = {}
+        outs: Dict[int, V] = {}
+        hw: Dict[int, Tuple[int, int]] = {}
+
+        def out_view(sp: T.LayerSpec, h: int, w: int) -> V:
+            if sp.index in concat_of:
+                ci, off = concat_of[sp.index]
+                if ci not in cat_buf:
+                    cat_buf[ci] = self._new(h, w, specs[ci].c2)
+                return cat_buf[ci].sub(off, sp.c2)
+            return self._new(h, w, sp.c2)
+
+        for sp in specs:
+            if sp.kind == "Conv":
+                if sp.index == 0:
+                    h, w = H // 2, W // 2
+                    o = out_view(sp, h, w)
+                    pc = self.packed["model.0"]
+                    d = cabi.StemDesc(self.input.data_ptr(), o.cview(), pc.w.data_ptr(), pc.b.data_ptr(), self.B, H, W, h, w)
+                    cabi.check(self.lib.y11_plan_add_stem(self.plan, C.byref(d)), "plan_add_stem")
+                    self.ops.append(OpRecord("stem", "model.0", 2.0 * self.B * h * w * sp.c2 * 27,
+                                             self.B * (H * W * 3 * 2 + h * w * sp.c2 * 2)))
+                else:
+                    x = outs[sp.frm[0]]
+                    h, w = (x.H + 1) // 2, (x.W + 1) // 2
+                    o = out_view(sp, h, w)
+                    self._conv(f"model.{sp.index}", x, o)
+            elif sp.kind in ("C3k2", "SPPF", "C2PSA"):
+                x = outs[sp.frm[0]]
+                o = out_view(sp, x.H, x.W)
+                {"C3k2": self._c3k2, "SPPF": self._sppf, "C2PSA": self._c2psa}[sp.kind](sp, x, o)
+            elif sp.kind == "Upsample":
+                x = outs[sp.frm[0]]
+                o = out_view(sp, 2 * x.H, 2 * x.W)
+                self._upsample(x, o)
+            elif sp.kind == "Concat":
+                o = cat_buf[sp.index]
+            elif sp.kind == "Detect":
+                self._detect(sp, [outs[i] for i in sp.frm])
+                o = None
+            outs[sp.index] = o
+        self.layer_out = outs
+        self.n_ops = self.lib.y11_plan_num_ops(self.plan)
+        self.n_launches = self.lib.y11_plan_num_launches(self.plan)
+        assert self.n_ops == len(self.ops)
+
+    # ---- execution ------------------------------------------------------------------------------
+    def run(self, stream: int) -> None:
+        cabi.check(self.lib.y11_plan_run(self.plan, C.c_void_p(stream)), "y11_plan_run")
+
+    def run_timed(self, stream: int) -> List[float]:
+        ms = (C.c_float * self.n_ops)()
+        cabi.check(self.lib.y11_plan_run_timed(self.plan, C.c_void_p(stream), ms), "y11_plan_run_timed")
+        return list(ms)
+
+    def head_desc(self) -> cabi.HeadDesc:
+        hd = cabi.HeadDesc()
+        for l, h in enumerate(self.head):
+            hd.head[l] = h.data_ptr()
+            hd.hl[l], hd.wl[l] = h.shape[1], h.shape[2]
+            hd.stride[l] = float(T.STRIDES[l])
+        hd.nl, hd.B, hd.nc, hd.row_stride = len(self.head), self.B, self.nc, self.no
+        return hd
+
+    def raw_head(self) -> torch.Tensor:
+        """[B, 64+nc, A] fp32 in ultralytics' layout (test helper; a torch view/permute, not a kernel)."""
+        parts = []
+        for h in self.head:
+            x = torch.cat((h[..., :64], h[..., 64:64 + self.nc]), -1)
+            parts.append(x.reshape(self.B, -1, 64 + self.nc))
+        return torch.cat(parts, 1).permute(0, 2, 1).contiguous()
+
+    @property
+    def conv_flops(self) -> float:
+        return sum(o.flops for o in self.ops if o.kind in ("conv", "stem", "dwconv"))

@@ -1,0 +1,129 @@
+"""Results / Boxes containers with the layout the reference's consumers read.
+
+The reference receives these objects from ultralytics (engine/results.py, un-vendored) and touches exactly:
+``results[0].boxes`` (len, truthiness, iteration -> 1-row Boxes), ``boxes.xyxy[i].cpu().numpy()``,
+``boxes.conf[i]``, ``boxes.cls[i]``, ``result.names[class_id]``
+(/root/reference/utils/visualization.py:52-74, /root/reference/demos/detection_demo.py:96-132,
+SURVEY.md section 8b).  Layout: ``data`` float32 [n, 6] = x1, y1, x2, y2 (original-image pixels, clipped), conf, cls;
+rows sorted by confidence descending; n <= max_det.  Tensors stay on the device they were produced on.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterator, Optional, Tuple
+
+import numpy as np
+import torch
+
+
+class Boxes:
+    def __init__(self, data: torch.Tensor, orig_shape: Tuple[int, int]):
+        if data.ndim == 1:
+            data = data[None, :]
+        assert data.shape[-1] == 6, f"expected [n,6] boxes, got {tuple(data.shape)}"
+        self.data = data
+        self.orig_shape = tuple(orig_shape)
+        self.is_track = False
+        self.id = None
+
+    # ---- the accessors the reference reads ------------------------------------------------------
+    @property
+    def xyxy(self) -> torch.Tensor:
+        return self.data[:, :4]
+
+    @property
+    def conf(self) -> torch.Tensor:
+        return self.data[:, -2]
+
+    @property
+    def cls(self) -> torch.Tensor:
+        return self.data[:, -1]
+
+    # ---- derived layouts (ultralytics API) --------------------------------------------------------
+    @property
+    def xywh(self) -> torch.Tensor:
+        b = self.xyxy
+        out = torch.empty_like(b)
+        out[:, 0] = (b[:, 0] + b[:, 2]) / 2
+        out[:, 1] = (b[:, 1] + b[:, 3]) / 2
+        out[:, 2] = b[:, 2] - b[:, 0]
+        out[:, 3] = b[:, 3] - b[:, 1]
+        return out
+
+    def _norm(self, b: torch.Tensor) -> torch.Tensor:
+        h, w = self.orig_shape
+        out = b.clone()
+        out[:, [0, 2]] /= w
+        out[:, [1, 3]] /= h
+        return out
+
+    @property
+    def xyxyn(self) -> torch.Tensor:
+        return self._norm(self.xyxy)
+
+    @property
+    def xywhn(self) -> torch.Tensor:
+        return self._norm(self.xywh)
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    def __len__(self) -> int:
+        return int(self.data.shape[0])
+
+    def __getitem__(self, idx) -> "Boxes":
+        return Boxes(self.data[idx], self.orig_shape)
+
+    def __iter__(self) -> Iterator["Boxes"]:
+        for i in range(len(self)):
+            yield self[i]
+
+    def cpu(self) -> "Boxes":
+        return Boxes(self.data.cpu(), self.orig_shape)
+
+    def numpy(self) -> "Boxes":
+        b = Boxes.__new__(Boxes)
+        b.data, b.orig_shape, b.is_track, b.id = self.data.cpu().numpy(), self.orig_shape, False, None
+        return b
+
+    def cuda(self) -> "Boxes":
+        return Boxes(self.data.cuda(), self.orig_shape)
+
+    def to(self, *a, **k) -> "Boxes":
+        return Boxes(self.data.to(*a, **k), self.orig_shape)
+
+    def __repr__(self) -> str:
+        return f"Boxes(n={len(self)}, orig_shape={self.orig_shape}, device={getattr(self.data, 'device', 'numpy')})"
+
+
+class Results:
+    def __init__(self, orig_img: Optional[np.ndarray], path: str, names: Dict[int, str], boxes: torch.Tensor,
+                 orig_shape: Tuple[int, int], speed: Optional[Dict[str, float]] = None):
+        self.orig_img = orig_img
+        self.orig_shape = tuple(orig_shape)
+        self.path = path
+        self.names = names
+        self.boxes = Boxes(boxes, self.orig_shape)
+        self.masks = None
+        self.probs = None
+        self.keypoints = None
+        self.obb = None
+        self.speed = speed or {"preprocess": None, "inference": None, "postprocess": None}
+
+    def __len__(self) -> int:
+        return len(self.boxes)
+
+    def cpu(self) -> "Results":
+        r = Results(self.orig_img, self.path, self.names, self.boxes.data.cpu(), self.orig_shape, self.speed)
+        return r
+
+    def to(self, *a, **k) -> "Results":
+        return Results(self.orig_img, self.path, self.names, self.boxes.data.to(*a, **k), self.orig_shape, self.speed)
+
+    def summary(self):
+        d = self.boxes.data.cpu().tolist()
+        return [{"name": self.names[int(r[5])], "class": int(r[5]), "confidence": r[4],
+                 "box": {"x1": r[0], "y1": r[1], "x2": r[2], "y2": r[3]}} for r in d]
+
+    def __repr__(self) -> str:
+        return f"Results(path={self.path!r}, orig_shape={self.orig_shape}, boxes={len(self.boxes)})"
