@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py - end-to-end detection throughput of the B200 YOLO11 path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--model n|s|m|l|x] [--batch 64] [--imgsz 640]
+  python bench.py --impl reference ...     # the reference's CPU path (oracle restatement), same metric/config
+  torchrun --nproc-per-node N bench.py --gpus N ...   # one rank per GPU, image-sharded (weak scaling)
+
+A "step" = one pass of the hot path over one batch of synthetic frames per GPU:
+  letterbox preprocess (u8 HWC -> bf16 NHWC) -> fused YOLO11 forward -> decode -> NMS -> max_det results.
+`value`  : images/s with the uint8 frames already resident in HBM (CUDA-event timed, max over ranks).
+`e2e`    : images/s through the public API (`YOLO.predict`) from pinned HOST frames, H2D + result D2H inside the timing.
+`roofline`: conv FLOPs (dense tcgen05 convs) / time spent in conv_tc_kernel launches, vs MEASURED_PEAKS bf16 peak.
+`cpu_baseline`: the oracle (reference CPU path restated) on the host cores, bounded sample (rank 0, N=1 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "end-to-end images/sec @640 (letterbox+forward+decode+NMS)"
+UNIT = "images/s"
+CONF, IOU, MAX_DET = 0.25, 0.7, 300   # the reference benchmark's thresholds (ultralytics predict defaults)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="n", help="YOLO11 scale; default = BASELINE.json configs[1] (YOLO11n)")
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--imgsz", type=int, default=640)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-batch", type=int, default=16, help="images per step of the CPU reference arm (bounded sample)")
+    ap.add_argument("--per-op", action="store_true", help="also print a per-op time table to stderr")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "tflops_burst": d.get("bf16_tflops", 1590.0),
+                "tflops_sustained": d.get("bf16_tflops_sustained", 1400.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def synth_frames(batch: int, imgsz: int, seed: int):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (batch, imgsz, imgsz, 3), generator=g, dtype=torch.uint8)
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arms
+def cpu_reference_arm(args, sd, steps: int, warmup: int, batch: int):
+    """The reference's own CPU implementation of the path = oracle/ (ultralytics-on-torch-CPU restated; ultralytics itself
+    is not installable here).  All host threads; returns (images/s, ms/step, cores, sample description)."""
+    import numpy as np
+    import torch
+    from oracle import pipeline_ref as P
+    from oracle import yolo11_ref as R
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = R.DetectionModel(args.model)
+    model.load_state_dict(sd, strict=False)
+    model.eval().fuse()
+    frames = synth_frames(batch, args.imgsz, 1234).numpy()
+    imgs = [np.ascontiguousarray(f) for f in frames]
+    kw = dict(conf=CONF, iou=IOU, max_det=MAX_DET, imgsz=args.imgsz)
+    for _ in range(warmup):
+        P.predict(model, imgs, **kw)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        P.predict(model, imgs, **kw)
+        ts.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(ts) / len(ts)
+    return batch / (ms / 1e3), ms, cores, f"{steps} x predict({batch} frames {args.imgsz}x{args.imgsz}), fused fp32, torch {torch.__version__} CPU"
+
+
+def weights_for(args):
+    """Synthetic weights: variance-conditioned on the GPU (engine.condition_synthetic_weights) for our arm; the reference
+    arm has no GPU dependency and uses the oracle's own calibrated init."""
+    from yolo_infer_b200 import topology as T
+    return T.synthetic_state_dict(args.model, 80, seed=0)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import yolo11_ref as R
+    ref = R.build(args.model, init="calibrated", seed=0)
+    sd = ref.state_dict()
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    ips, ms, cores, sample = cpu_reference_arm(args, sd, steps, warmup, args.ref_batch)
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"YOLO11{args.model} detect {args.imgsz}x{args.imgsz}, CPU reference path, {args.ref_batch} frames/step "
+                                   f"(bounded sample of the batch-{args.batch}/GPU workload)", "conf": CONF, "iou": IOU, "max_det": MAX_DET},
+            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from yolo_infer_b200 import _cabi as cabi
+    from yolo_infer_b200.engine import YOLO, letterbox_geometry, scale_geometry
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch with torchrun for --gpus > 1 (one rank per GPU)")
+    assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU arm)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, S = args.batch, args.imgsz
+    eng = YOLO.from_state_dict(weights_for(args), args.model).to(dev)
+    eng.condition_synthetic_weights((S, S), batch=2, seed=0)
+    net = eng.compiled(B, S, S)
+    stream = torch.cuda.current_stream(dev)
+
+    # inputs: NROT distinct device-resident uint8 batches (> L2) rotated between steps
+    NROT = 4
+    host_batches = [synth_frames(B, S, 1000 * rank + i).pin_memory() for i in range(NROT)]
+    dev_batches = [hb.to(dev) for hb in host_batches]
+    geoms = [letterbox_geometry(S, S, (S, S), True)] * B
+    gain, px, py = scale_geometry((S, S), (S, S))
+    scale_rows = torch.tensor([[gain, px, py, S, S]] * B, dtype=torch.float32, device=dev)
+
+    def step_resident(i: int):
+        eng.preprocess_images(net, list(dev_batches[i % NROT]), geoms)
+        eng.forward(net)
+        return eng.postprocess(net, scale_rows, CONF, IOU, MAX_DET)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        det, cnt, ncand = step_resident(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record(stream)
+        for i in range(args.steps):
+            det, cnt, ncand = step_resident(i)
+        e1.record(stream)
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t) / args.steps
+    value = world * B / (ms_step / 1e3)
+    mean_cand = float(ncand.float().mean())
+    mean_det = float(cnt.float().mean())
+
+    # ---- e2e through the public API from pinned host frames (H2D + D2H inside the timed region) ----
+    def step_e2e(i: int):
+        res = eng.predict(host_batches[i % NROT], conf=CONF, iou=IOU, max_det=MAX_DET, imgsz=S, verbose=False)
+        return [r.boxes.data.cpu() for r in res]
+
+    for i in range(min(args.warmup, 3)):
+        step_e2e(i)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        out = step_e2e(i)
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    t2 = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / (float(t2) / 1e3)
+    d2h = sum(o.numel() * 4 for o in out) + B * 4
+
+    # ---- per-op timing (CUDA events around every launch) for the roofline of the dominant kernel ----
+    per_op = None
+    for _ in range(3):
+        eng.preprocess_images(net, list(dev_batches[0]), geoms)
+        ms = net.run_timed(stream.cuda_stream)
+        per_op = ms if per_op is None else [a + b for a, b in zip(per_op, ms)]
+    per_op = [m / 3 for m in per_op]
+    conv_ms = sum(m for m, o in zip(per_op, net.ops) if o.kind == "conv")
+    conv_flops = sum(o.flops for o in net.ops if o.kind == "conv")
+    all_ms = sum(per_op)
+    pk = peaks()
+    achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    n_conv = sum(1 for o in net.ops if o.kind == "conv")
+    roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tflops_sustained"], "traffic": None,
+            "kernel": f"conv_tc_kernel ({n_conv} launches/step, {conv_ms:.3f} ms of {all_ms:.3f} ms network time)",
+            "peak_source": f"{pk['source']} sustained bf16 (burst {pk['tflops_burst']})",
+            "whole_path_conv_frac": (value / world) * (net.conv_flops / B) / (pk["tflops_sustained"] * 1e12)}
+    if args.per_op and rank == 0:
+        rows = sorted(zip(per_op, net.ops), key=lambda r: -r[0])
+        for m, o in rows[:40]:
+            tf = o.flops / (m / 1e3) / 1e12 if m > 0 else 0
+            gb = o.bytes_algo / (m / 1e3) / 1e9 if m > 0 else 0
+            print(f"{m:8.4f} ms  {o.kind:9s} {o.name:28s} {tf:8.1f} TFLOP/s {gb:8.1f} GB/s(algo)", file=sys.stderr)
+        print(f"network total {all_ms:.3f} ms; conv {conv_ms:.3f} ms; step {ms_step:.3f} ms", file=sys.stderr)
+
+    launches_per_step = 1 + net.n_launches + 4   # letterbox + plan + (count, scan, write, sort+nms)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"YOLO11{args.model} detect, {S}x{S}, batch {B}/GPU, synthetic uint8 frames, random-init "
+                                   f"variance-conditioned weights", "global_batch": B * world, "parallelism": f"image-sharded x{world}",
+                       "conf": CONF, "iou": IOU, "max_det": MAX_DET, "mean_candidates_per_image": mean_cand,
+                       "mean_detections_per_image": mean_det,
+                       "l2_policy": f"{NROT} rotating input batches ({NROT * B * S * S * 3 / 1e6:.0f} MB) + "
+                                    f"{sum(b.numel() * b.element_size() for b in net.buffers) / 1e9:.2f} GB of activations per step (> 126 MB L2)"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * S * 3, "d2h_bytes_per_step": d2h,
+                    "api": "YOLO.predict(pinned uint8 [B,H,W,3] host tensor) -> List[Results] -> .cpu()", "steps": e2e_steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roof}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sd = {k: v.cpu() for k, v in eng.model.state_dict().items()}
+        ips, ms, cores, sample = cpu_reference_arm(args, sd, steps=2, warmup=1, batch=min(16, B))
+        line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    else:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,4 +39,10 @@ det = R.Detect(nc=80, ch=(16, 16, 16))
 feats = [torch.randn(2, 144, h, w, generator=g) * 2 for (h, w) in [(8, 12), (4, 6), (2, 3)]]
 y = det.decode(feats)
 np.savez_compressed(OUT / "decode_small.npz", f0=feats[0].numpy(), f1=feats[1].numpy(), f2=feats[2].numpy(), y=y.numpy())
+ref_img = Path("/root/reference/image.jpg")
+if ref_img.exists():  # only in the build container; the committed small copy is what travels
+    import cv2
+    im = cv2.imread(str(ref_img))
+    small = cv2.resize(im, (480, 320), interpolation=cv2.INTER_AREA)
+    cv2.imwrite(str(OUT / "image_small.jpg"), small, [cv2.IMWRITE_JPEG_QUALITY, 90])
 print("golden fixtures written to", OUT)

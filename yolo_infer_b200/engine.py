@@ -277,6 +277,69 @@ class YOLO:
                                                     ws.numel(), C.c_void_p(s)), "y11_detect_postprocess")
         return det, count, ncand
 
+    # ---- synthetic-weight conditioning (benchmarks without checkpoints) ----------------------------------
+    def condition_synthetic_weights(self, hw: Tuple[int, int] = (640, 640), batch: int = 2, seed: int = 0, iters: int = 3,
+                                    act_rms: float = 1.0, box_std: float = 3.0, cls_std: float = 1.1) -> Dict[str, float]:
+        """Rescale each conv (its BN gamma, or the plain conv weight) so activations stay O(1) on random frames.
+
+        Random-init YOLO11 weights either collapse or explode through ~90 layers, which would make the decode/NMS stages
+        of a benchmark meaningless (zero or 8400 candidates per image).  This walks the plan in execution order; for conv
+        i it runs ops [0, i] on seeded uint8 frames, measures the rms (std for the two logit convs) of the op's output
+        buffer and scales that conv's packed weights towards the target, `iters` times.  The per-conv factors are then
+        written into the model's state_dict (so the oracle can load the very same weights) and everything is re-packed.
+        Uses the engine's own kernels plus torch reductions at init time only - nothing here is on the predict path.
+        """
+        self._ensure_device()
+        H, W = hw
+        with torch.cuda.device(self.device), torch.inference_mode():
+            net = self.compiled(batch, H, W)
+            g = torch.Generator().manual_seed(seed)
+            frames = torch.randint(0, 256, (batch, H, W, 3), generator=g, dtype=torch.uint8).to(self.device)
+            geoms = [letterbox_geometry(H, W, (H, W), False)] * batch
+            self.preprocess_images(net, list(frames), geoms)
+            s = torch.cuda.current_stream(self.device).cuda_stream
+            factors: Dict[str, float] = {}
+            for i, op in enumerate(net.ops):
+                in_place = op.name.endswith(("attn.proj", "ffn.1"))  # out aliases the residual: must run exactly once
+                if op.kind not in ("conv", "dwconv", "stem") or op.name not in self._packed or in_place:
+                    net.run_range(i, i + 1, s)
+                    continue
+                pc = self._packed[op.name]
+                v = op.out
+                is_logit = op.name.endswith((".cv2.0.2", ".cv2.1.2", ".cv2.2.2", ".cv3.0.2", ".cv3.1.2", ".cv3.2.2"))
+                target = act_rms if not is_logit else (cls_std if ".cv3." in op.name else box_std)
+                total = 1.0
+                for _ in range(iters):
+                    net.run_range(i, i + 1, s)
+                    out = v.t[..., v.off:v.off + v.c].float()
+                    if is_logit:
+                        cur = float((out - out.mean((0, 1, 2), keepdim=True)).std())
+                    else:  # residual adds are part of the signal the next layer sees, so they stay in
+                        cur = float(out.pow(2).mean().sqrt())
+                    if not math.isfinite(cur) or cur <= 0:
+                        break
+                    f = min(max(target / cur, 0.05), 20.0)
+                    pc.w.mul_(f)
+                    if not is_logit:
+                        pc.b.mul_(f)
+                    total *= f
+                net.run_range(i, i + 1, s)
+                factors[op.name] = total
+            torch.cuda.synchronize(self.device)
+        sd = self.model.state_dict()
+        for cp in T.conv_params(self.scale, self.nc):
+            f = factors.get(cp.prefix, 1.0)
+            if cp.bn:
+                sd[f"{cp.prefix}.bn.weight"] = sd[f"{cp.prefix}.bn.weight"] * f
+                sd[f"{cp.prefix}.bn.bias"] = sd[f"{cp.prefix}.bn.bias"] * f
+            else:
+                sd[f"{cp.prefix}.weight"] = sd[f"{cp.prefix}.weight"] * f
+        self.model = DetectionNet(self.scale, self.nc, sd, self.names)
+        self._nets.clear()
+        with torch.cuda.device(self.device):
+            self._packed = pack_weights(self.scale, self.nc, sd, self.device)
+        return factors
+
     # ---- sources ----------------------------------------------------------------------------------
     @staticmethod
     def _load_sources(source) -> Tuple[List[np.ndarray], List[str]]:

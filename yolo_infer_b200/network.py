@@ -116,6 +116,7 @@ class OpRecord:
     name: str
     flops: float = 0.0
     bytes_algo: float = 0.0   # algorithmic HBM bytes: unique input + weights + output
+    out: object = None  # where the op writes (used by weight conditioning and debugging)
 
 
 class CompiledNet:
@@ -173,7 +174,7 @@ class CompiledNet:
         px = self.B * out.H * out.W
         self.ops.append(OpRecord("conv", name, 2.0 * px * pc.c2 * pc.c1 * pc.k * pc.k,
                                  self.B * x.H * x.W * pc.c1 * 2 + pc.w.numel() * 2 + px * pc.c2 * (4 if out_f32 else 2)
-                                 + (px * pc.c2 * 2 if res is not None else 0)))
+                                 + (px * pc.c2 * 2 if res is not None else 0), out))
 
     def _dw(self, name: str, x: V, out: V, res: Optional[V] = None):
         pc = self.packed[name]
@@ -185,7 +186,7 @@ class CompiledNet:
         d.B, d.H, d.W, d.act = self.B, x.H, x.W, pc.act
         cabi.check(self.lib.y11_plan_add_dwconv(self.plan, C.byref(d)), f"plan_add_dwconv({name})")
         px = self.B * x.H * x.W
-        self.ops.append(OpRecord("dwconv", name, 2.0 * px * pc.c1 * 9, px * pc.c1 * 2 * (3 if res is not None else 2)))
+        self.ops.append(OpRecord("dwconv", name, 2.0 * px * pc.c1 * 9, px * pc.c1 * 2 * (3 if res is not None else 2), out))
 
     # ---- modules ------------------------------------------------------------------------------
     def _bottleneck(self, p: str, x: V, out: V, e: float):
@@ -312,7 +313,7 @@ class CompiledNet:
                     d = cabi.StemDesc(self.input.data_ptr(), o.cview(), pc.w.data_ptr(), pc.b.data_ptr(), self.B, H, W, h, w)
                     cabi.check(self.lib.y11_plan_add_stem(self.plan, C.byref(d)), "plan_add_stem")
                     self.ops.append(OpRecord("stem", "model.0", 2.0 * self.B * h * w * sp.c2 * 27,
-                                             self.B * (H * W * 3 * 2 + h * w * sp.c2 * 2)))
+                                             self.B * (H * W * 3 * 2 + h * w * sp.c2 * 2), o))
                 else:
                     x = outs[sp.frm[0]]
                     h, w = (x.H + 1) // 2, (x.W + 1) // 2
@@ -340,6 +341,9 @@ class CompiledNet:
     # ---- execution ------------------------------------------------------------------------------
     def run(self, stream: int) -> None:
         cabi.check(self.lib.y11_plan_run(self.plan, C.c_void_p(stream)), "y11_plan_run")
+
+    def run_range(self, first: int, last: int, stream: int) -> None:
+        cabi.check(self.lib.y11_plan_run_range(self.plan, first, last, C.c_void_p(stream)), "y11_plan_run_range")
 
     def run_timed(self, stream: int) -> List[float]:
         ms = (C.c_float * self.n_ops)()

@@ -215,3 +215,33 @@ def default_state_dict(scale: str, nc: int = 80, seed: int = 0) -> Dict[str, tor
 
 def anchors_for(h: int, w: int) -> int:
     return sum((h // s) * (w // s) for s in STRIDES)
+
+
+def synthetic_state_dict(scale: str, nc: int = 80, seed: int = 0, gain: float = 2.4, cls_prior: float = 0.01,
+                         cls_gain: float = 1.6, box_gain: float = 3.0) -> Dict[str, torch.Tensor]:
+    """Data-free, variance-preserving random weights for benchmarks (bench.py, smoke()).
+
+    ultralytics-style default init collapses activations to ~1e-9 and produces zero detections, which
+    would make the decode/NMS stages of a benchmark trivially cheap.  Here conv W ~ N(0, gain/fan_in) with `gain` chosen
+    so the second moment survives SiLU, BN is the identity, the class bias is logit(cls_prior) and the last-layer gains
+    make a few hundred to a few thousand of the 8400 anchors clear conf 0.25 with peaky DFL bins.
+    """
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for cp in conv_params(scale, nc):
+        fan_in = cp.c1 // cp.g * cp.k * cp.k
+        std = math.sqrt((gain if cp.act else 1.0) / fan_in)
+        w = torch.randn((cp.c2, cp.c1 // cp.g, cp.k, cp.k), generator=g) * std
+        if cp.bn:
+            sd[f"{cp.prefix}.conv.weight"] = w
+            sd[f"{cp.prefix}.bn.weight"] = torch.ones(cp.c2)
+            sd[f"{cp.prefix}.bn.bias"] = torch.zeros(cp.c2)
+            sd[f"{cp.prefix}.bn.running_mean"] = torch.zeros(cp.c2)
+            sd[f"{cp.prefix}.bn.running_var"] = torch.ones(cp.c2)
+        else:
+            is_cls = ".cv3." in cp.prefix
+            sd[f"{cp.prefix}.weight"] = w * (cls_gain if is_cls else box_gain)
+            sd[f"{cp.prefix}.bias"] = (torch.full((cp.c2,), math.log(cls_prior / (1 - cls_prior))) if is_cls
+                                       else torch.randn(cp.c2, generator=g) * 0.5)
+    sd["model.23.dfl.conv.weight"] = torch.arange(REG_MAX, dtype=torch.float32).view(1, REG_MAX, 1, 1)
+    return sd
