@@ -403,14 +403,21 @@ def conv_flops(model: DetectionModel, h: int = 640, w: int = 640) -> int:
 
 @torch.no_grad()
 def calibrated_init(model: DetectionModel, seed: int = 0, calib_hw: Tuple[int, int] = (640, 640),
-                    cls_prior: float = 0.01, cls_gain: float = 1.0, box_gain: float = 3.0) -> DetectionModel:
-    """Deterministic, well-conditioned random weights shared by oracle and CUDA path (SURVEY §0.4, §8d).
+                    cls_prior: float = 0.01, cls_gain: float = 1.0, box_gain: float = 3.0,
+                    gamma: Tuple[float, float] = (0.2, 0.5), beta: Tuple[float, float] = (1.5, 0.3)) -> DetectionModel:
+    """Deterministic, well-conditioned random weights shared by oracle and CUDA path (SURVEY section 0.4, section 8d).
 
-    ultralytics' default init collapses activations (~1e-9 by P5) and yields zero detections, so
-    parity tests use: conv W ~ N(0, 1/fan_in); BN gamma ~ U(0.5,1.5), beta ~ N(0,0.3); BN running
-    statistics := the statistics the layer actually sees on a seeded random batch (one train-mode
-    pass with momentum 1), which keeps every activation O(1); Detect cls bias = logit(cls_prior),
-    last-conv gains chosen so that hundreds of anchors clear conf 0.25 and DFL bins are peaky.
+    ultralytics' default init collapses activations (~1e-9 by P5) and yields zero detections, so parity tests use:
+    conv W ~ N(0, 1/fan_in); BN gamma ~ U(gamma), beta ~ N(beta); BN running statistics := the statistics the layer
+    actually sees on a seeded random batch (one train-mode pass with momentum 1), which keeps every activation O(1);
+    Detect cls bias = logit(cls_prior); last-conv gains chosen so that hundreds of anchors clear conf 0.25 and DFL bins
+    are peaky.
+
+    Why gamma is small and beta positive: with gamma ~ U(.5,1.5), beta ~ 0 a random SiLU network is in the chaotic phase
+    - a 2^-9 perturbation (one bf16 rounding) is amplified ~50x by the time it reaches the head, so an fp32 run and ANY
+    16-bit run of the same network differ by 15-25 % (measured: bf16-emulating oracle vs fp32 oracle, box logits), which
+    says nothing about kernel correctness.  gamma ~ U(.2,.5), beta ~ N(1.5,.3) keeps the perturbation growth per layer
+    ~1, so the remaining fp32-vs-bf16 difference is the accumulated storage rounding of ~40 sequential layers (~1 %).
     """
     g = torch.Generator().manual_seed(seed)
     for m in model.modules():
@@ -418,8 +425,8 @@ def calibrated_init(model: DetectionModel, seed: int = 0, calib_hw: Tuple[int, i
             fan_in = m.in_channels // m.groups * m.kernel_size[0] * m.kernel_size[1]
             m.weight.copy_(torch.randn(m.weight.shape, generator=g) * (1.0 / fan_in) ** 0.5)
         elif isinstance(m, nn.BatchNorm2d):
-            m.weight.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
-            m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.3)
+            m.weight.copy_(torch.rand(m.weight.shape, generator=g) * (gamma[1] - gamma[0]) + gamma[0])
+            m.bias.copy_(torch.randn(m.bias.shape, generator=g) * beta[1] + beta[0])
     det: Detect = model.model[-1]
     for a, b in zip(det.cv2, det.cv3):
         a[-1].weight.mul_(box_gain)
@@ -439,6 +446,25 @@ def calibrated_init(model: DetectionModel, seed: int = 0, calib_hw: Tuple[int, i
     for m, mom in moms.items():
         m.momentum = mom
     return model
+
+
+def emulate_bf16_storage(fused: DetectionModel) -> DetectionModel:
+    """Turn a FUSED oracle model into the fp32-accumulate / bf16-storage network the B200 path computes:
+    conv weights rounded to bf16 once; every Conv output, every residual sum (Bottleneck, PSABlock) rounded to bf16,
+    exactly the places where the CUDA path writes an activation tensor to HBM.  The Detect logits stay fp32 (the last
+    1x1 convs of the head write fp32 on the GPU).  Used by tests to separate kernel arithmetic (must agree to <= 1e-2)
+    from the storage-format noise floor that any bf16 implementation has against an fp32 run."""
+    def rq(t):
+        return t.to(torch.bfloat16).float()
+
+    for m in fused.modules():
+        if isinstance(m, nn.Conv2d) and not (m.out_channels == 1 and m.in_channels == 16):
+            m.weight.data = rq(m.weight.data)
+    for m in fused.modules():
+        if isinstance(m, (Conv, Bottleneck, PSABlock)):
+            m.register_forward_hook(lambda mod, inp, out: rq(out))
+    fused.register_forward_pre_hook(lambda mod, inp: (rq(inp[0]),))
+    return fused
 
 
 def build(scale: str = "n", nc: int = 80, init: str = "calibrated", seed: int = 0) -> DetectionModel:

@@ -292,7 +292,7 @@ def test_nms_keep_set_bit_exact_vs_torchvision(ctx, K, clustered):
     for iou in (0.45, 0.7, 0.6):
         want = torchvision.ops.nms(boxes + cls[:, None] * 7680, scores, iou)
         keep, cnt = nms_gpu(ctx, boxes[None].to(ctx.dev), scores[None].to(ctx.dev), cls[None].to(ctx.dev),
-                            torch.tensor([K], dtype=torch.int32, device=ctx.dev), iou, K)
+                            torch.tensor([K], dtype=torch.int32, device=ctx.dev), iou, K, max_nms=1 << 30)
         assert cnt[0].item() == want.numel()
         assert keep[0, :cnt[0]].tolist() == want.tolist()
 

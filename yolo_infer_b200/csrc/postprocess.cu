@@ -454,7 +454,8 @@ int launch_sort_nms(const NmsArgs& a, int B, cudaStream_t s) {
     attr_set = true;
   }
   const int np2 = next_pow2(a.cap);
-  const size_t smem = (size_t)(np2 <= kSmemKeys ? np2 : 0) * 8;
+  // the kernel sorts in shared memory whenever THIS image's count fits, whatever the capacity is
+  const size_t smem = (size_t)(np2 <= kSmemKeys ? np2 : kSmemKeys) * 8;
   sort_nms_kernel<<<B, kNmsThreads, smem, s>>>(a);
   Y11_CHECK_CUDA(cudaGetLastError());
   return 0;
