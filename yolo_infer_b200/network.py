@@ -116,7 +116,9 @@ class OpRecord:
     name: str
     flops: float = 0.0
     bytes_algo: float = 0.0   # algorithmic HBM bytes: unique input + weights + output
-    out: object = None  # where the op writes (used by weight conditioning and debugging)
+    out: object = None  # where the op writes (used by weight conditioning and the per-layer parity test)
+    inp: object = None
+    res: object = None
 
 
 class CompiledNet:
@@ -174,7 +176,7 @@ class CompiledNet:
         px = self.B * out.H * out.W
         self.ops.append(OpRecord("conv", name, 2.0 * px * pc.c2 * pc.c1 * pc.k * pc.k,
                                  self.B * x.H * x.W * pc.c1 * 2 + pc.w.numel() * 2 + px * pc.c2 * (4 if out_f32 else 2)
-                                 + (px * pc.c2 * 2 if res is not None else 0), out))
+                                 + (px * pc.c2 * 2 if res is not None else 0), out, x, res))
 
     def _dw(self, name: str, x: V, out: V, res: Optional[V] = None):
         pc = self.packed[name]
@@ -186,7 +188,7 @@ class CompiledNet:
         d.B, d.H, d.W, d.act = self.B, x.H, x.W, pc.act
         cabi.check(self.lib.y11_plan_add_dwconv(self.plan, C.byref(d)), f"plan_add_dwconv({name})")
         px = self.B * x.H * x.W
-        self.ops.append(OpRecord("dwconv", name, 2.0 * px * pc.c1 * 9, px * pc.c1 * 2 * (3 if res is not None else 2), out))
+        self.ops.append(OpRecord("dwconv", name, 2.0 * px * pc.c1 * 9, px * pc.c1 * 2 * (3 if res is not None else 2), out, x, res))
 
     # ---- modules ------------------------------------------------------------------------------
     def _bottleneck(self, p: str, x: V, out: V, e: float):
