@@ -279,7 +279,8 @@ class YOLO:
 
     # ---- synthetic-weight conditioning (benchmarks without checkpoints) ----------------------------------
     def condition_synthetic_weights(self, hw: Tuple[int, int] = (640, 640), batch: int = 2, seed: int = 0, iters: int = 3,
-                                    act_rms: float = 1.0, box_std: float = 3.0, cls_std: float = 1.1) -> Dict[str, float]:
+                                    act_rms: float = 1.0, box_std: float = 3.0, cls_std: float = 1.1,
+                                    cls_prior: float = 0.01) -> Dict[str, float]:
         """Rescale each conv (its BN gamma, or the plain conv weight) so activations stay O(1) on random frames.
 
         Random-init YOLO11 weights either collapse or explode through ~90 layers, which would make the decode/NMS stages
@@ -299,6 +300,7 @@ class YOLO:
             self.preprocess_images(net, list(frames), geoms)
             s = torch.cuda.current_stream(self.device).cuda_stream
             factors: Dict[str, float] = {}
+            bias_shift: Dict[str, torch.Tensor] = {}
             for i, op in enumerate(net.ops):
                 in_place = op.name.endswith(("attn.proj", "ffn.1"))  # out aliases the residual: must run exactly once
                 if op.kind not in ("conv", "dwconv", "stem") or op.name not in self._packed or in_place:
@@ -324,6 +326,14 @@ class YOLO:
                         pc.b.mul_(f)
                     total *= f
                 net.run_range(i, i + 1, s)
+                if is_logit and ".cv3." in op.name:
+                    # class logits: centre every channel on logit(prior) (random weights on positive-mean inputs give each
+                    # class its own offset of ~+-2, which would push most anchors over conf 0.25)
+                    out = v.t[..., v.off:v.off + self.nc].float()
+                    shift = math.log(cls_prior / (1 - cls_prior)) - out.mean((0, 1, 2))
+                    pc.b[: self.nc].add_(shift)
+                    bias_shift[op.name] = shift.cpu()
+                    net.run_range(i, i + 1, s)
                 factors[op.name] = total
             torch.cuda.synchronize(self.device)
         sd = self.model.state_dict()
@@ -334,6 +344,8 @@ class YOLO:
                 sd[f"{cp.prefix}.bn.bias"] = sd[f"{cp.prefix}.bn.bias"] * f
             else:
                 sd[f"{cp.prefix}.weight"] = sd[f"{cp.prefix}.weight"] * f
+                if cp.prefix in bias_shift:
+                    sd[f"{cp.prefix}.bias"] = sd[f"{cp.prefix}.bias"] + bias_shift[cp.prefix]
         self.model = DetectionNet(self.scale, self.nc, sd, self.names)
         self._nets.clear()
         with torch.cuda.device(self.device):
