@@ -204,7 +204,11 @@ def run_ours(args):
     def step_resident(i: int):
         eng.preprocess_images(net, list(dev_batches[i % NROT]), geoms)
         eng.forward(net)
-        return eng.postprocess(net, scale_rows, CONF, IOU, MAX_DET)
+        det, cnt, ncand = eng.postprocess(net, scale_rows, CONF, IOU, MAX_DET)
+        if world > 1:  # the only collective of the path: gather the fixed-shape results (461 KB/rank) so every rank,
+            from yolo_infer_b200.parallel import gather_detections  # hence rank 0, holds the whole global batch
+            gather_detections(det, cnt)
+        return det, cnt, ncand
 
     def barrier():
         if world > 1:

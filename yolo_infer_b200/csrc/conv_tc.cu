@@ -1,32 +1,62 @@
-// Implicit-GEMM convolution on Blackwell 5th-gen tensor cores (tcgen05.mma, TMEM accumulator, TMA operands).
+// Implicit-GEMM convolution on Blackwell 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA in AND out).
 //
 // Replaces, for every dense conv of the fused YOLO11 network, what the reference executes as
 // ultralytics Conv.forward_fuse -> torch conv2d (+SiLU) (+ Bottleneck/PSABlock residual add) (+ Concat copy)
 // (SURVEY.md section 8a rows a6-a8, a11).
 //
 // GEMM view (NHWC bf16 activations, fp32 accumulation):
-//   M = output pixels   : one CTA owns a 128-row tile = a Tw x Th x Tn box of (w, h, image)
-//   N = output channels : BN <= 128 columns per CTA, accumulator = 128 lanes x BN fp32 columns of TMEM
+//   M = output pixels   : a tile is 128 rows = a Tw x Th x Tn box of (w, h, image), chosen per layer to waste few rows
+//   N = output channels : BN <= 128 columns per tile; accumulator = 128 TMEM lanes x BN fp32 columns
 //   K = (kh, kw, cin)   : one pipeline stage = one filter tap x Cc (16/32/64) input channels
 // The A operand is never materialised (no im2col buffer): for each tap the TMA engine loads the SHIFTED
 // Tw x Th x Tn x Cc box of the input straight into the canonical K-major swizzled smem layout UMMA reads;
 // rows/cols outside the image are zero-filled by TMA, which is exactly the conv zero padding.  Stride-2
 // convs address four parity sub-grids of the input (one tensor map each) so they are shifted boxes too.
-// Epilogue (4 warps, one TMEM lane quadrant each): tcgen05.ld -> +bias -> SiLU -> +residual -> bf16/fp32
-// -> written at a channel offset of the destination buffer (this is how Concat/chunk cost nothing).
 //
-// Warp roles: warp0 = TMA producer (1 elected lane), warp1 = MMA issuer (1 elected lane),
-//             warps2-5 = epilogue; warp2 also owns TMEM alloc/dealloc.
+// v2 (round 1, after the first ncu pass showed the one-tile-per-CTA version latency bound - profiles/r01_summary.md):
+//   * PERSISTENT: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...; barrier init / TMEM alloc / tensor-map
+//     prefetch are paid once per SM instead of once per 128 pixels, and the TMA producer runs ahead across tile borders.
+//   * TWO TMEM accumulator stages: the MMA warp starts tile i+1 while the epilogue drains tile i.
+//   * 8 epilogue warps (2 per TMEM lane quadrant, each pair splits the columns) so SiLU/bias/convert has 2 warps/SMSP.
+//   * Epilogue writes through swizzled shared-memory staging + TMA STORE (cp.async.bulk.tensor ... global.shared::cta):
+//     full-sector writes at the channel offset of the destination view (this is how Concat/chunk cost nothing), and
+//     ragged tiles are clipped by the TMA unit instead of per-thread predicates.
+//
+// Warp roles (320 threads): warp0 = TMA producer (1 lane), warp1 = MMA issuer (1 lane), warps2-9 = epilogue;
+// warp2 also owns TMEM alloc/dealloc.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "ops.h"
 
 namespace {
 
-constexpr int kThreads = 192;
-constexpr int kMaxStages = 8;
-constexpr uint32_t kHeaderBytes = 256;  // mbarriers + tmem pointer
+constexpr int kThreads = 320;
+constexpr int kEpiWarps = 8;
+constexpr int kMaxStages = 32;           // small-channel layers have 5-9 KB stages: bytes in flight, not stage count, hide latency
+constexpr uint32_t kHeaderBytes = 1024;  // mbarriers + tmem pointer
+constexpr uint32_t kSmemBudget = 200 * 1024;
+
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 __global__ void __launch_bounds__(kThreads)
 conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcParams p) {
@@ -36,31 +66,30 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   const uint32_t tiles_base = (smem_base + kHeaderBytes + 1023u) & ~1023u;
   const uint32_t full_bar = smem_base;                    // kMaxStages x 8 B
   const uint32_t empty_bar = smem_base + 8 * kMaxStages;  // kMaxStages x 8 B
-  const uint32_t acc_bar = smem_base + 16 * kMaxStages;
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_raw + 16 * kMaxStages + 8);
+  const uint32_t accf_bar = smem_base + 16 * kMaxStages;  // 2 x 8 B  accumulator full  (MMA -> epilogue)
+  const uint32_t acce_bar = accf_bar + 16;                // 2 x 8 B  accumulator empty (epilogue -> MMA)
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_raw + 16 * kMaxStages + 32);
+  const uint32_t stage_bytes = p.a_slot + p.b_slot;
+  const uint32_t staging_base = tiles_base + p.stages * stage_bytes;  // 2 groups x 2 buffers x stg_bytes
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile coordinates: Cout tile fastest so CTAs sharing an activation tile are launched together (L2 reuse)
-  int t = blockIdx.x;
-  const int nt = t % p.n_tiles; t /= p.n_tiles;
-  const int tw_i = t % p.tiles_w; t /= p.tiles_w;
-  const int th_i = t % p.tiles_h; t /= p.tiles_h;
-  const int tn_i = t;
-  const int w0 = tw_i * p.Tw, h0 = th_i * p.Th, n0 = tn_i * p.Tn;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
     }
-    mbar_init(acc_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(accf_bar + 8 * a, 1);
+      mbar_init(acce_bar + 8 * a, kEpiWarps);
+    }
     mbar_fence_init();
   }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a[0]);
     prefetch_tmap(&maps.b);
+    prefetch_tmap(&maps.out);
     if (p.stride == 2) {
       prefetch_tmap(&maps.a[1]);
       prefetch_tmap(&maps.a[2]);
@@ -74,34 +103,42 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = *tmem_ptr_smem;
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t acc_stride = p.tmem_cols >> 1;  // column offset of accumulator stage 1
 
   const int k_iters = p.taps * p.chunks_per_tap;
-  const uint32_t stage_bytes = p.a_slot + p.b_slot;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------------ TMA producer
       int it = 0;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        int mi = 0, cw, ch;
-        if (p.ksize == 1) {
-          cw = w0; ch = h0;
-        } else if (p.stride == 1) {
-          cw = w0 + tap % 3 - 1; ch = h0 + tap / 3 - 1;
-        } else {
-          const int kh = tap / 3, kw = tap % 3;
-          mi = ((kh == 1) ? 0 : 2) + ((kw == 1) ? 0 : 1);  // input row 2*oy+kh-1 has parity (kh != 1)
-          cw = w0 - (kw == 0); ch = h0 - (kh == 0);
-        }
-        for (int c = 0; c < p.chunks_per_tap; ++c, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(empty_bar + 8 * s, ph ^ 1, p.err_flag, 101);
-          mbar_expect_tx(full_bar + 8 * s, p.tx_bytes);
-          const uint32_t a_dst = tiles_base + s * stage_bytes;
-          tma_load_4d(a_dst, &maps.a[mi], full_bar + 8 * s, c * p.Cc, cw, ch, n0);
-          tma_load_2d(a_dst + p.a_slot, &maps.b, full_bar + 8 * s, tap * p.cin + c * p.Cc, nt * p.BN);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int nt = t % p.n_tiles; t /= p.n_tiles;
+        const int w0 = (t % p.tiles_w) * p.Tw; t /= p.tiles_w;
+        const int h0 = (t % p.tiles_h) * p.Th; t /= p.tiles_h;
+        const int n0 = t * p.Tn;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          int mi = 0, cw, ch;
+          if (p.ksize == 1) {
+            cw = w0; ch = h0;
+          } else if (p.stride == 1) {
+            cw = w0 + tap % 3 - 1; ch = h0 + tap / 3 - 1;
+          } else {
+            const int kh = tap / 3, kw = tap % 3;
+            mi = ((kh == 1) ? 0 : 2) + ((kw == 1) ? 0 : 1);  // input row 2*oy+kh-1 has parity (kh != 1)
+            cw = w0 - (kw == 0); ch = h0 - (kh == 0);
+          }
+          for (int c = 0; c < p.chunks_per_tap; ++c, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            mbar_wait(empty_bar + 8 * s, ph ^ 1, p.err_flag, 101);
+            mbar_expect_tx(full_bar + 8 * s, p.tx_bytes);
+            const uint32_t a_dst = tiles_base + s * stage_bytes;
+            tma_load_4d(a_dst, &maps.a[mi], full_bar + 8 * s, c * p.Cc, cw, ch, n0);
+            tma_load_2d(a_dst + p.a_slot, &maps.b, full_bar + 8 * s, tap * p.cin + c * p.Cc, nt * p.BN);
+          }
         }
       }
     }
@@ -110,37 +147,62 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       // ------------------------------------------------------------------ MMA issuer
       const uint32_t idesc = make_idesc_bf16_m128(p.BN);
       const int kk_n = p.Cc / 16;
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(full_bar + 8 * s, ph, p.err_flag, 102);
+      int it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        const int as = ti & 1;
+        const uint32_t aph = (ti >> 1) & 1;
+        mbar_wait(acce_bar + 8 * as, aph ^ 1, p.err_flag, 104);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t a_src = tiles_base + s * stage_bytes;
-        const uint64_t ad = make_umma_desc(a_src, p.sbo, p.layout_type);
-        const uint64_t bd = make_umma_desc(a_src + p.a_slot, p.sbo, p.layout_type);
-        for (int kk = 0; kk < kk_n; ++kk)  // +32 B (= 16 bf16 of K) inside the swizzle row per UMMA
-          umma_bf16(tmem_acc, ad + 2 * kk, bd + 2 * kk, idesc, (it | kk) != 0);
-        umma_commit(empty_bar + 8 * s);  // frees the smem slot once these MMAs retire
+        const uint32_t tmem_acc = tmem_base + as * acc_stride;
+        for (int k = 0; k < k_iters; ++k, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(full_bar + 8 * s, ph, p.err_flag, 102);
+          tc_fence_after();
+          const uint32_t a_src = tiles_base + s * stage_bytes;
+          const uint64_t ad = make_umma_desc(a_src, p.sbo, p.layout_type);
+          const uint64_t bd = make_umma_desc(a_src + p.a_slot, p.sbo, p.layout_type);
+          for (int kk = 0; kk < kk_n; ++kk)  // +32 B (= 16 bf16 of K) inside the swizzle row per UMMA
+            umma_bf16(tmem_acc, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0);
+          umma_commit(empty_bar + 8 * s);  // frees the smem slot once these MMAs retire
+        }
+        umma_commit(accf_bar + 8 * as);  // accumulator complete
       }
-      umma_commit(acc_bar);  // accumulator complete
     }
   } else {
-    // -------------------------------------------------------------------- epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // -------------------------------------------------------------------- epilogue (warps 2..9)
+    const int ew = warp - 2;
+    const int grp = ew >> 2;  // two groups of 4 warps; group g takes 16-column chunks g, g+2, ...
+    const int q = warp & 3;   // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;
     const int tw = r % p.Tw, th = (r / p.Tw) % p.Th, tn = r / (p.Tw * p.Th);
-    const int ow = w0 + tw, oh = h0 + th, on = n0 + tn;
-    const bool valid = (r < p.Tw * p.Th * p.Tn) && ow < p.Wout && oh < p.Hout && on < p.B;
-    const size_t pix = (static_cast<size_t>(on) * p.Hout + oh) * p.Wout + ow;
-    mbar_wait(acc_bar, 0, p.err_flag, 103);
-    tc_fence_after();
-    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(taddr + c0, v);
-      tmem_ld_wait();
-      const int n = nt * p.BN + c0;
-      if (valid && n < p.cout) {
+    const bool leader = (ew & 3) == 0 && lane == 0;
+    const uint32_t esz = p.out_f32 ? 4u : 2u;
+    const uint32_t pitch = 16u * esz;                      // staging row pitch: 32 B (bf16) / 64 B (fp32)
+    const uint32_t swz = (r / (128u / pitch)) & (pitch / 16u - 1u);  // TMA SWIZZLE_32B / _64B pattern for row r
+    const uint32_t stg_bytes = 128u * pitch;
+    const uint32_t stg0 = staging_base + grp * 2 * stg_bytes;
+    const uint32_t row_addr = r * pitch;
+    const int n_chunks = p.BN / 16;
+    int ti = 0, ci = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      int t = tile;
+      const int nt = t % p.n_tiles; t /= p.n_tiles;
+      const int w0 = (t % p.tiles_w) * p.Tw; t /= p.tiles_w;
+      const int h0 = (t % p.tiles_h) * p.Th; t /= p.tiles_h;
+      const int n0 = t * p.Tn;
+      const int ow = w0 + tw, oh = h0 + th, on = n0 + tn;
+      const bool valid = (r < p.Tw * p.Th * p.Tn) && ow < p.Wout && oh < p.Hout && on < p.B;
+      const size_t pix = (static_cast<size_t>(on) * p.Hout + oh) * p.Wout + ow;
+      const int as = ti & 1;
+      mbar_wait(accf_bar + 8 * as, (ti >> 1) & 1, p.err_flag, 103);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+      for (int c = grp; c < n_chunks; c += 2, ++ci) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c * 16, v);
+        tmem_ld_wait();
+        const int n = nt * p.BN + c * 16;
         float f[16];
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
@@ -155,7 +217,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = silu(f[i]);
         }
-        if (p.res) {
+        if (p.res && valid) {
           const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ct + p.res_co + n);
           const uint4 r0 = rp[0], r1 = rp[1];
           const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -165,30 +227,44 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
             f[2 * i + 1] += bf16_hi(rr[i]);
           }
         }
+        const uint32_t dst = stg0 + (ci & 1) * stg_bytes + row_addr;
         if (p.out_f32) {
-          float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + pix * p.out_ct + p.out_co + n);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          for (int i = 0; i < 4; ++i)
+            st_shared_v4(dst + ((i ^ swz) << 4), __float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]),
+                         __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3]));
         } else {
-          uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix * p.out_ct + p.out_co + n);
-          op[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-          op[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+          st_shared_v4(dst + ((0u ^ swz) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                       pack_bf16x2(f[6], f[7]));
+          st_shared_v4(dst + ((1u ^ swz) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                       pack_bf16x2(f[14], f[15]));
+        }
+        fence_async_smem();              // my generic-proxy smem writes -> visible to the TMA (async proxy)
+        if (leader) bulk_wait_read0();   // the previous store of this group has finished READING its (other) buffer
+        named_bar_sync(1 + grp, 128);    // all 128 rows of this chunk are staged; other buffer is free for the next chunk
+        if (leader) {
+          tma_store_4d(&maps.out, stg0 + (ci & 1) * stg_bytes, n, w0, h0, n0);
+          bulk_commit();
         }
       }
+      // all tcgen05.ld of this accumulator stage have completed (wait::ld above): hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce_bar + 8 * as);
     }
+    if (leader) bulk_wait_all();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_acc, p.tmem_cols);
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-int encode_map(y11_engine* eng, CUtensorMap* m, int rank, void* base, const cuuint64_t* gdim, const cuuint64_t* gstr,
-               const cuuint32_t* box, CUtensorMapSwizzle swz) {
+int encode_map(y11_engine* eng, CUtensorMap* m, CUtensorMapDataType dt, int rank, void* base, const cuuint64_t* gdim,
+               const cuuint64_t* gstr, const cuuint32_t* box, CUtensorMapSwizzle swz) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = eng->encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, gdim, gstr, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = eng->encode_tiled(m, dt, rank, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     y11_set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u", (int)r, rank,
                   (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)(rank > 2 ? gdim[2] : 0),
@@ -257,12 +333,19 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
   p.tx_bytes = (uint32_t)(p.Tw * p.Th * p.Tn) * swz_bytes + (uint32_t)bn * swz_bytes;
   const int k_iters = p.taps * p.chunks_per_tap;
   const uint32_t stage = p.a_slot + p.b_slot;
-  int stages = (int)((96u * 1024u) / stage);
-  stages = std::max(2, std::min(std::min(stages, kMaxStages), k_iters));
-  if (stages < 1) stages = 1;
-  p.stages = stages;
+  const uint32_t staging = 4u * 128u * (d->out_f32 ? 64u : 32u);
+  // persistent CTAs per SM: TMEM (512 columns) and shared memory are split between them
+  // (measured on B200, YOLO11s batch 64: conv time 5.25 / 3.78 / 3.65 / 3.88 ms for 1 / 2 / 3 / 4 CTAs per SM - several
+  //  independent TMA->MMA->epilogue chains per SM hide the per-tile latencies better than one deep pipeline)
+  int cps = 3;
+  if (const char* e = getenv("Y11_CTAS_PER_SM")) cps = std::max(1, std::min(4, atoi(e)));
   int cols = 32;
-  while (cols < bn) cols *= 2;
+  while (cols < 2 * bn) cols *= 2;
+  while (cps > 1 && cps * cols > 512) --cps;
+  const uint32_t budget = (cps == 1 ? kSmemBudget : (220u * 1024u) / cps - 2048u);
+  int stages = (int)((budget - kHeaderBytes - 1024u - staging) / stage);
+  stages = std::max(2, std::min(stages, kMaxStages));
+  p.stages = stages;
   p.tmem_cols = cols;
   p.B = d->B; p.Hout = d->Hout; p.Wout = d->Wout; p.cout = cout;
   p.out = d->out.ptr; p.out_ct = d->out.c_total; p.out_co = d->out.c_off; p.out_f32 = d->out_f32;
@@ -274,10 +357,11 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
   const size_t ct = d->in.c_total;
   __nv_bfloat16* in_base = static_cast<__nv_bfloat16*>(d->in.ptr) + d->in.c_off;
   const cuuint32_t box[4] = {(cuuint32_t)p.Cc, (cuuint32_t)p.Tw, (cuuint32_t)p.Th, (cuuint32_t)p.Tn};
+  const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   if (d->stride == 1) {
     const cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
     const cuuint64_t gstr[3] = {ct * 2, ct * 2 * d->Win, ct * 2 * d->Win * d->Hin};
-    if (int e = encode_map(eng, &L->maps.a[0], 4, in_base, gdim, gstr, box, swz)) return e;
+    if (int e = encode_map(eng, &L->maps.a[0], bf, 4, in_base, gdim, gstr, box, swz)) return e;
     L->maps.a[1] = L->maps.a[2] = L->maps.a[3] = L->maps.a[0];
   } else {
     for (int ph = 0; ph < 2; ++ph)
@@ -286,7 +370,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
                                     (cuuint64_t)d->B};
         const cuuint64_t gstr[3] = {ct * 2 * 2, ct * 2 * d->Win * 2, ct * 2 * d->Win * d->Hin};
         __nv_bfloat16* base = in_base + ((size_t)ph * d->Win + pw) * ct;
-        if (int e = encode_map(eng, &L->maps.a[ph * 2 + pw], 4, base, gdim, gstr, box, swz)) return e;
+        if (int e = encode_map(eng, &L->maps.a[ph * 2 + pw], bf, 4, base, gdim, gstr, box, swz)) return e;
       }
   }
   {
@@ -294,14 +378,28 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
     const cuuint64_t gdim[2] = {K, (cuuint64_t)cout};
     const cuuint64_t gstr[1] = {K * 2};
     const cuuint32_t bbox[2] = {(cuuint32_t)p.Cc, (cuuint32_t)bn};
-    if (int e = encode_map(eng, &L->maps.b, 2, const_cast<void*>(d->w), gdim, gstr, bbox, swz)) return e;
+    if (int e = encode_map(eng, &L->maps.b, bf, 2, const_cast<void*>(d->w), gdim, gstr, bbox, swz)) return e;
   }
-  L->grid = (unsigned)(p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles);
-  L->smem_bytes = kHeaderBytes + 1024u + (unsigned)stages * stage;
+  {
+    // output view: 16-channel boxes (32 B bf16 / 64 B fp32 per pixel), swizzled staging, clipped at the tensor edge
+    const size_t esz = d->out_f32 ? 4 : 2;
+    const size_t oct = d->out.c_total;
+    char* obase = static_cast<char*>(d->out.ptr) + (size_t)d->out.c_off * esz;
+    const cuuint64_t gdim[4] = {(cuuint64_t)cout, (cuuint64_t)d->Wout, (cuuint64_t)d->Hout, (cuuint64_t)d->B};
+    const cuuint64_t gstr[3] = {oct * esz, oct * esz * d->Wout, oct * esz * d->Wout * d->Hout};
+    const cuuint32_t obox[4] = {16u, (cuuint32_t)p.Tw, (cuuint32_t)p.Th, (cuuint32_t)p.Tn};
+    if (int e = encode_map(eng, &L->maps.out, d->out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : bf, 4, obase, gdim, gstr, obox,
+                           d->out_f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B))
+      return e;
+  }
+  const unsigned total_tiles = (unsigned)(p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles);
+  L->grid = std::min(total_tiles, (unsigned)(eng->num_sms * cps));
+  L->smem_bytes = kHeaderBytes + 1024u + (unsigned)stages * stage + staging;
   L->flops = 2.0 * d->B * d->Hout * d->Wout * (double)cout * cin * p.taps;
+  (void)k_iters;
   static bool attr_set = false;
   if (!attr_set) {
-    Y11_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    Y11_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
   return 0;

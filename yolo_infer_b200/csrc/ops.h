@@ -6,6 +6,7 @@
 struct ConvTcMaps {
   CUtensorMap a[4];  // activation views: [0] for stride 1; [ph*2+pw] parity sub-grids for stride 2
   CUtensorMap b;     // packed weights [cout][k*k*cin]
+  CUtensorMap out;   // output view, 16-channel boxes (TMA store)
 };
 
 struct ConvTcParams {
