@@ -49,74 +49,118 @@ int conv_simt_launch(const y11_conv_desc* d, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// stem: 3 -> COUT, 3x3 stride 2 pad 1, +bias, SiLU.  One thread = one output pixel x all COUT channels
-// (accumulators in registers), input rows staged in shared memory as fp32, weights broadcast from smem.
+// stem: 3 -> COUT, 3x3 stride 2 pad 1, +bias, SiLU (CUDA cores: K = 27 is too thin for an MMA tile).
+// Register blocked: one thread owns P output pixels x all COUT channels, so every broadcast weight load from shared
+// memory feeds 4*P FMAs (v1, 1 pixel per thread, was LDS-issue bound: 0.70 ms for YOLO11s batch 64).  A CTA covers
+// TX*P consecutive pixels of one output row; thread tx owns pixels tx, tx+TX, ... (adjacent lanes -> adjacent pixels).
+// The three input rows are staged with 16-byte loads (v2 staged 2 bytes at a time and was 3x slower than v1).
 // ------------------------------------------------------------------------------------------------
-constexpr int kStemPix = 128;  // output pixels (along W) per CTA
-
-template <int COUT>
-__global__ void __launch_bounds__(kStemPix) stem_kernel(y11_stem_desc d) {
-  __shared__ float s_in[3][(2 * kStemPix + 1) * 3];
-  __shared__ float s_w[27][COUT];
-  __shared__ float s_b[COUT];
-  const int tiles_w = (d.Wout + kStemPix - 1) / kStemPix;
+template <int COUT, int P>
+__global__ void __launch_bounds__(128) stem_kernel(y11_stem_desc d, int TX, int tiles_w) {
+  extern __shared__ float s_dyn[];
+  float* s_w = s_dyn;                  // [27][COUT]
+  float* s_b = s_w + 27 * COUT;        // [COUT]
+  float* s_in = s_b + COUT;            // [3][(2*TX*P+1)*3]
+  const int span = TX * P;
+  const int row_f = (2 * span + 1) * 3;
   const int tile = blockIdx.x % tiles_w;
   const int oh = (blockIdx.x / tiles_w) % d.Hout;
   const int n = blockIdx.x / (tiles_w * d.Hout);
-  const int ow0 = tile * kStemPix;
+  const int ow0 = tile * span;
+  const int nt = blockDim.x;
   const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(d.w);
-  for (int i = threadIdx.x; i < 27 * COUT; i += kStemPix) s_w[i % 27][i / 27] = __bfloat162float(w[i]);  // w is [COUT][27]
-  for (int i = threadIdx.x; i < COUT; i += kStemPix) s_b[i] = d.bias[i];
-  const __nv_bfloat16* in = static_cast<const __nv_bfloat16*>(d.in);
+  for (int i = threadIdx.x; i < 27 * COUT; i += nt) s_w[(i % 27) * COUT + i / 27] = __bfloat162float(w[i]);  // w is [COUT][27]
+  for (int i = threadIdx.x; i < COUT; i += nt) s_b[i] = d.bias[i];
+  for (int i = threadIdx.x; i < 3 * row_f; i += nt) s_in[i] = 0.f;
+  __syncthreads();
   const int iw0 = 2 * ow0 - 1;
-  constexpr int kRow = (2 * kStemPix + 1) * 3;
+  const int e_lo = max(iw0, 0) * 3, e_hi = min(iw0 + 2 * span + 1, d.Win) * 3;  // bf16 elements of the input row we need
+  const int v_lo = e_lo / 8, v_hi = (e_hi + 7) / 8;                             // 16-byte chunks (rows are 16-byte aligned)
   for (int r = 0; r < 3; ++r) {
     const int ih = 2 * oh + r - 1;
-    const bool row_ok = ih >= 0 && ih < d.Hin;
-    const __nv_bfloat16* rp = in + ((size_t)n * d.Hin + (row_ok ? ih : 0)) * d.Win * 3;
-    for (int i = threadIdx.x; i < kRow; i += kStemPix) {
-      const int iw = iw0 + i / 3;
-      float v = 0.f;
-      if (row_ok && iw >= 0 && iw < d.Win) v = __bfloat162float(rp[(size_t)iw * 3 + i % 3]);
-      s_in[r][i] = v;
+    if (ih < 0 || ih >= d.Hin) continue;
+    const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(d.in) + ((size_t)n * d.Hin + ih) * d.Win * 3);
+    float* dst = s_in + r * row_f - iw0 * 3;
+    for (int v = v_lo + threadIdx.x; v < v_hi; v += nt) {
+      const uint4 u = __ldg(rp + v);
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int e = v * 8 + 2 * t;
+        if (e >= e_lo && e < e_hi) dst[e] = bf16_lo(uu[t]);
+        if (e + 1 >= e_lo && e + 1 < e_hi) dst[e + 1] = bf16_hi(uu[t]);
+      }
     }
   }
   __syncthreads();
-  const int ow = ow0 + threadIdx.x;
-  if (ow >= d.Wout) return;
-  float acc[COUT];
+  const int tx = threadIdx.x;
+  if (tx >= TX) return;
+  float acc[P][COUT];
 #pragma unroll
-  for (int c = 0; c < COUT; ++c) acc[c] = s_b[c];
+  for (int q = 0; q < P; ++q)
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[q][c] = s_b[c];
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
     for (int j = 0; j < 9; ++j) {  // j = kw*3 + c
-      const float x = s_in[kh][threadIdx.x * 6 + j];
+      float x[P];
 #pragma unroll
-      for (int c = 0; c < COUT; ++c) acc[c] = fmaf(x, s_w[kh * 9 + j][c], acc[c]);
+      for (int q = 0; q < P; ++q) x[q] = s_in[kh * row_f + (tx + q * TX) * 6 + j];
+      const float4* wr = reinterpret_cast<const float4*>(s_w + (kh * 9 + j) * COUT);
+#pragma unroll
+      for (int c4 = 0; c4 < COUT / 4; ++c4) {
+        const float4 ww = wr[c4];
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+          acc[q][4 * c4 + 0] = fmaf(x[q], ww.x, acc[q][4 * c4 + 0]);
+          acc[q][4 * c4 + 1] = fmaf(x[q], ww.y, acc[q][4 * c4 + 1]);
+          acc[q][4 * c4 + 2] = fmaf(x[q], ww.z, acc[q][4 * c4 + 2]);
+          acc[q][4 * c4 + 3] = fmaf(x[q], ww.w, acc[q][4 * c4 + 3]);
+        }
+      }
     }
   }
-  const size_t pix = ((size_t)n * d.Hout + oh) * d.Wout + ow;
-  uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(d.out.ptr) + pix * d.out.c_total + d.out.c_off);
 #pragma unroll
-  for (int c = 0; c < COUT; c += 8) {
-    op[c / 8] = make_uint4(pack_bf16x2(silu(acc[c]), silu(acc[c + 1])), pack_bf16x2(silu(acc[c + 2]), silu(acc[c + 3])),
-                           pack_bf16x2(silu(acc[c + 4]), silu(acc[c + 5])), pack_bf16x2(silu(acc[c + 6]), silu(acc[c + 7])));
+  for (int q = 0; q < P; ++q) {
+    const int ow = ow0 + tx + q * TX;
+    if (ow >= d.Wout) continue;
+    const size_t pix = ((size_t)n * d.Hout + oh) * d.Wout + ow;
+    uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(d.out.ptr) + pix * d.out.c_total + d.out.c_off);
+#pragma unroll
+    for (int c = 0; c < COUT; c += 8) {
+      op[c / 8] = make_uint4(pack_bf16x2(silu(acc[q][c]), silu(acc[q][c + 1])), pack_bf16x2(silu(acc[q][c + 2]), silu(acc[q][c + 3])),
+                             pack_bf16x2(silu(acc[q][c + 4]), silu(acc[q][c + 5])), pack_bf16x2(silu(acc[q][c + 6]), silu(acc[q][c + 7])));
+    }
   }
 }
 
-int stem_launch(const y11_stem_desc* d, cudaStream_t s) {
-  const int tiles_w = (d->Wout + kStemPix - 1) / kStemPix;
-  const unsigned grid = (unsigned)(tiles_w * d->Hout * d->B);
-  switch (d->out.c) {
-    case 16: stem_kernel<16><<<grid, kStemPix, 0, s>>>(*d); break;
-    case 32: stem_kernel<32><<<grid, kStemPix, 0, s>>>(*d); break;
-    case 64: stem_kernel<64><<<grid, kStemPix, 0, s>>>(*d); break;
-    case 96: stem_kernel<96><<<grid, kStemPix, 0, s>>>(*d); break;
-    default: y11_set_error("stem: unsupported cout %d", d->out.c); return -1;
+template <int COUT, int P>
+static int stem_launch_t(const y11_stem_desc* d, cudaStream_t s) {
+  Y11_REQUIRE(d->Win % 8 == 0, "stem: input width must be a multiple of 8 (got %d)", d->Win);
+  const int nblk = y11_ceil_div(d->Wout, P * 128);
+  const int TX = y11_ceil_div(d->Wout, P * nblk);
+  const int threads = (TX + 31) / 32 * 32;
+  const size_t smem = (size_t)(27 * COUT + COUT + 3 * (2 * TX * P + 1) * 3) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    Y11_CHECK_CUDA(cudaFuncSetAttribute(stem_kernel<COUT, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
   }
+  Y11_REQUIRE(smem <= 64 * 1024, "stem: row too wide for shared memory");
+  stem_kernel<COUT, P><<<(unsigned)(nblk * d->Hout * d->B), threads, smem, s>>>(*d, TX, nblk);
   Y11_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+int stem_launch(const y11_stem_desc* d, cudaStream_t s) {
+  switch (d->out.c) {
+    case 16: return stem_launch_t<16, 4>(d, s);
+    case 32: return stem_launch_t<32, 4>(d, s);
+    case 64: return stem_launch_t<64, 2>(d, s);
+    case 96: return stem_launch_t<96, 1>(d, s);
+    default: y11_set_error("stem: unsupported cout %d", d->out.c); return -1;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

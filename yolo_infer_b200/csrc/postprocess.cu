@@ -12,13 +12,15 @@
 // cannot contract it into FMAs (the reference computes every step as a separate fp32 op).
 #include <math.h>
 
+#include <algorithm>
+
 #include "ops.h"
 
 using namespace y11;
 
 namespace {
 
-constexpr int kChunk = 256;        // anchors per CTA in decode/compaction
+constexpr int kChunk = 64;         // anchors per CTA in decode/compaction (4 lanes per anchor, 256 threads)
 constexpr int kNmsThreads = 1024;  // sort + nms CTA
 constexpr int kTile = 256;         // candidates per NMS tile
 constexpr int kSmemKeys = 16384;   // sort in shared memory up to this many keys (128 KB)
@@ -29,129 +31,135 @@ struct HeadParams {
   int off[4];  // anchor offset per level
   float stride[3];
   int nl, B, nc, A, no;
-};
-
-struct AnchorOut {
-  float cx, cy, w, h;  // Detect output box (pixels of the network input)
-  float score;         // best class score (single-label)
-  int cls;
-  int npass;           // classes with score > conf (multi-label)
+  int cls_per_lane;  // classes scanned by each of the 4 lanes of an anchor: multiple of 4, 4*cls_per_lane >= nc
 };
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
-// Whole warp decodes ONE anchor; every lane returns the same box; class scores stay distributed:
-// sc[j] = sigmoid of class (j*32 + lane) or -1.
-template <int NCJ>
-__device__ __forceinline__ void warp_decode(const HeadParams& hp, int b, int a, int lane, float& cx, float& cy, float& w, float& h,
-                                            float (&sc)[NCJ]) {
+// ---- decode building blocks: FOUR lanes cooperate on one anchor ------------------------------------------------
+// lane `sub` (0..3) owns DFL side `sub` (l,t,r,b: 16 logits = 64 contiguous bytes) and a contiguous quarter of the
+// class logits.  Every helper below is used by the dense kernel (tests) AND the compaction kernels, so both produce
+// bit-identical boxes and scores.
+struct AnchorRef {
+  const float* row;
+  float ax, ay, stride;
+};
+
+__device__ __forceinline__ AnchorRef anchor_ref(const HeadParams& hp, int b, int a) {
   int l = 0;
   if (hp.nl > 1 && a >= hp.off[1]) l = 1;
   if (hp.nl > 2 && a >= hp.off[2]) l = 2;
   const int i = a - hp.off[l];
   const int wl = hp.wl[l];
-  const float ax = (float)(i % wl) + 0.5f, ay = (float)(i / wl) + 0.5f;
-  const float* row = hp.head[l] + ((size_t)b * hp.hl[l] * wl + i) * hp.no;
-  float d[2];
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {  // lanes 0-15: side 2*half, lanes 16-31: side 2*half+1
-    const float v = __ldg(row + half * 32 + lane);
-    float mx = v;
-#pragma unroll
-    for (int o = 8; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const float e = expf(v - mx);
-    float den = e, num = e * (float)(lane & 15);
-#pragma unroll
-    for (int o = 8; o >= 1; o >>= 1) {
-      den += __shfl_xor_sync(0xffffffffu, den, o);
-      num += __shfl_xor_sync(0xffffffffu, num, o);
-    }
-    d[half] = __fdiv_rn(num, den);
-  }
-  const float dl = __shfl_sync(0xffffffffu, d[0], 0), dt = __shfl_sync(0xffffffffu, d[0], 16);
-  const float dr = __shfl_sync(0xffffffffu, d[1], 0), db = __shfl_sync(0xffffffffu, d[1], 16);
-  const float x1 = __fsub_rn(ax, dl), y1 = __fsub_rn(ay, dt), x2 = __fadd_rn(ax, dr), y2 = __fadd_rn(ay, db);
-  const float st = hp.stride[l];
-  cx = __fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.0f), st);
-  cy = __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.0f), st);
-  w = __fmul_rn(__fsub_rn(x2, x1), st);
-  h = __fmul_rn(__fsub_rn(y2, y1), st);
-#pragma unroll
-  for (int j = 0; j < NCJ; ++j) {
-    const int c = j * 32 + lane;
-    sc[j] = c < hp.nc ? sigmoidf_acc(__ldg(row + 64 + c)) : -1.0f;
-  }
+  AnchorRef r;
+  r.row = hp.head[l] + ((size_t)b * hp.hl[l] * wl + i) * hp.no;
+  r.ax = (float)(i % wl) + 0.5f;
+  r.ay = (float)(i / wl) + 0.5f;
+  r.stride = hp.stride[l];
+  return r;
 }
 
-constexpr int kNcj = 4;  // up to 128 classes
+// softmax expectation over the 16 bins of one side (ultralytics DFL: softmax then conv with arange(16))
+__device__ __forceinline__ float dfl_side(const float* p) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+  float mx = v[0];
+#pragma unroll
+  for (int i = 1; i < 16; ++i) mx = fmaxf(mx, v[i]);
+  float den = 0.f, num = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float e = expf(v[i] - mx);
+    den += e;
+    num = fmaf(e, (float)i, num);
+  }
+  return __fdiv_rn(num, den);
+}
+
+// all 4 lanes of the anchor's group call this (gmask = the group's lanes); returns cx,cy,w,h in every lane
+__device__ __forceinline__ float4 decode_box(const AnchorRef& ar, int sub, int lane, unsigned gmask) {
+  const float d = dfl_side(ar.row + 16 * sub);
+  const int g0 = lane & ~3;
+  const float dl = __shfl_sync(gmask, d, g0), dt = __shfl_sync(gmask, d, g0 + 1);
+  const float dr = __shfl_sync(gmask, d, g0 + 2), db = __shfl_sync(gmask, d, g0 + 3);
+  const float x1 = __fsub_rn(ar.ax, dl), y1 = __fsub_rn(ar.ay, dt), x2 = __fadd_rn(ar.ax, dr), y2 = __fadd_rn(ar.ay, db);
+  return make_float4(__fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.0f), ar.stride), __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.0f), ar.stride),
+                     __fmul_rn(__fsub_rn(x2, x1), ar.stride), __fmul_rn(__fsub_rn(y2, y1), ar.stride));
+}
+
+// xywh2xyxy exactly as the reference: wh/2 first, then xy -/+ it
+__device__ __forceinline__ float4 xywh2xyxy_rn(float4 b) {
+  const float hw = __fdiv_rn(b.z, 2.0f), hh = __fdiv_rn(b.w, 2.0f);
+  return make_float4(__fsub_rn(b.x, hw), __fsub_rn(b.y, hh), __fadd_rn(b.x, hw), __fadd_rn(b.y, hh));
+}
 
 __global__ void __launch_bounds__(256) decode_dense_kernel(HeadParams hp, float* __restrict__ y) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, sub = threadIdx.x & 3;
   const int b = blockIdx.y;
-  const int a0 = blockIdx.x * kChunk + warp * 32;
+  const int a = blockIdx.x * kChunk + (threadIdx.x >> 2);
+  if (a >= hp.A) return;  // whole 4-lane groups leave together
+  const unsigned gmask = 0xFu << (lane & ~3);
+  const AnchorRef ar = anchor_ref(hp, b, a);
+  const float4 box = decode_box(ar, sub, lane, gmask);
   float* yb = y + (size_t)b * (4 + hp.nc) * hp.A;
-  for (int k = 0; k < 32; ++k) {
-    const int a = a0 + k;
-    if (a >= hp.A) break;
-    float cx, cy, w, h, sc[kNcj];
-    warp_decode<kNcj>(hp, b, a, lane, cx, cy, w, h, sc);
-    if (lane == 0) {
-      yb[a] = cx; yb[(size_t)hp.A + a] = cy; yb[2 * (size_t)hp.A + a] = w; yb[3 * (size_t)hp.A + a] = h;
-    }
-#pragma unroll
-    for (int j = 0; j < kNcj; ++j) {
-      const int c = j * 32 + lane;
-      if (c < hp.nc) yb[(size_t)(4 + c) * hp.A + a] = sc[j];
-    }
-  }
+  const float bx[4] = {box.x, box.y, box.z, box.w};
+  yb[(size_t)sub * hp.A + a] = bx[sub];
+  for (int c = sub; c < hp.nc; c += 4) yb[(size_t)(4 + c) * hp.A + a] = sigmoidf_acc(__ldg(ar.row + 64 + c));
 }
 
-// MODE 0: count candidates per chunk.  MODE 1: write candidates at chunk_off + in-chunk prefix (anchor order).
+// MODE 0: count candidates per 64-anchor chunk.  MODE 1: write candidates at chunk_off + in-chunk prefix (anchor order).
+// Only the class logits are read to decide candidacy (sigmoid is monotone: max score = sigmoid(max logit)); the DFL
+// softmaxes (64 expf per anchor) run for candidates only, in MODE 1.
 template <int MODE>
 __global__ void __launch_bounds__(256)
-decode_compact_kernel(HeadParams hp, float conf, int multi_label, int cap, int nchunks, int* __restrict__ chunk_cnt,
+decode_compact_kernel(HeadParams hp, float conf, float logit_lo, int multi_label, int cap, int nchunks, int* __restrict__ chunk_cnt,
                       const int* __restrict__ chunk_off, float4* __restrict__ cbox, float* __restrict__ cscore, float* __restrict__ ccls) {
   __shared__ int s_warp[8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = threadIdx.x & 3;
   const int b = blockIdx.y;
-  const int a0 = blockIdx.x * kChunk + warp * 32;
-  // pass A: every lane ends up owning anchor a0+lane
-  float mcx = 0, mcy = 0, mw = 0, mh = 0, mscore = -1.f;
-  int mcls = 0, mcnt = 0;
-  for (int k = 0; k < 32; ++k) {
-    const int a = a0 + k;
-    if (a >= hp.A) break;
-    float cx, cy, w, h, sc[kNcj];
-    warp_decode<kNcj>(hp, b, a, lane, cx, cy, w, h, sc);
-    int npass = 0;
-    float best = -1.f;
-    int bcls = 0;
-    if (multi_label) {
+  const int a = blockIdx.x * kChunk + (threadIdx.x >> 2);
+  const bool in_range = a < hp.A;
+  const unsigned gmask = 0xFu << (lane & ~3);
+  AnchorRef ar;
+  ar.row = nullptr; ar.ax = ar.ay = ar.stride = 0.f;
+  if (in_range) ar = anchor_ref(hp, b, a);
+  // ---- class scan: this lane's quarter of the classes
+  const int q = hp.cls_per_lane;  // multiple of 4, 4*q >= nc
+  const int c0 = sub * q;
+  float best = -INFINITY;
+  unsigned mask = 0u;  // multi-label: bit j set <=> class c0+j passes
+  if (in_range) {
+    for (int j = 0; j < q; j += 4) {
+      if (c0 + j >= hp.nc) break;
+      const float4 t = __ldg(reinterpret_cast<const float4*>(ar.row + 64 + c0 + j));
+      const float v[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-      for (int j = 0; j < kNcj; ++j) npass += __popc(__ballot_sync(0xffffffffu, sc[j] > conf));
-    } else {
-#pragma unroll
-      for (int j = 0; j < kNcj; ++j)
-        if (sc[j] > best) { best = sc[j]; bcls = j * 32 + lane; }  // strict > keeps the first (lowest) class on ties
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oc = __shfl_xor_sync(0xffffffffu, bcls, o);
-        if (ob > best || (ob == best && oc < bcls)) { best = ob; bcls = oc; }
+      for (int k = 0; k < 4; ++k) {
+        if (c0 + j + k < hp.nc) {
+          best = fmaxf(best, v[k]);
+          if (multi_label && v[k] > logit_lo && sigmoidf_acc(v[k]) > conf) mask |= 1u << (j + k);
+        }
       }
-      npass = best > conf ? 1 : 0;
     }
-    if (lane == k) { mcx = cx; mcy = cy; mw = w; mh = h; mscore = best; mcls = bcls; mcnt = npass; }
   }
-  // in-warp exclusive prefix of counts
-  int incl = mcnt;
+  best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 1));
+  best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 2));
+  const float score = in_range ? sigmoidf_acc(best) : -1.f;
+  int mycnt;  // per lane: multi-label -> my passing classes; single-label -> leader lane carries the anchor's flag
+  if (multi_label) mycnt = __popc(mask);
+  else mycnt = (sub == 0 && score > conf) ? 1 : 0;
+  // ---- in-warp inclusive scan, warp totals, chunk base
+  int incl = mycnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const int v = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += v;
   }
-  const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
-  if (lane == 0) s_warp[warp] = wtotal;
+  if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
   if (MODE == 0) {
     if (threadIdx.x == 0) {
@@ -161,40 +169,42 @@ decode_compact_kernel(HeadParams hp, float conf, int multi_label, int cap, int n
     }
     return;
   }
-  int base = chunk_off[b * nchunks + blockIdx.x];
-  for (int i = 0; i < warp; ++i) base += s_warp[i];
-  const int pos = base + incl - mcnt;
+  int pos = chunk_off[b * nchunks + blockIdx.x] + incl - mycnt;
+  for (int i = 0; i < warp; ++i) pos += s_warp[i];
   const size_t ob = (size_t)b * cap;
-  if (!multi_label) {
-    if (mcnt && pos < cap) {
-      // xywh2xyxy exactly as the reference: wh/2 first, then xy -/+ it
-      const float hw = __fdiv_rn(mw, 2.0f), hh = __fdiv_rn(mh, 2.0f);
-      cbox[ob + pos] = make_float4(__fsub_rn(mcx, hw), __fsub_rn(mcy, hh), __fadd_rn(mcx, hw), __fadd_rn(mcy, hh));
-      cscore[ob + pos] = mscore;
-      ccls[ob + pos] = (float)mcls;
+  const bool cand = multi_label ? (__ballot_sync(0xffffffffu, mask != 0u) & gmask) != 0u : (score > conf);
+  if (!cand) return;  // whole 4-lane groups leave together
+  const float4 box = xywh2xyxy_rn(decode_box(ar, sub, lane, gmask));
+  if (multi_label) {
+    // rows in (anchor, class) order: my classes come after those of the lanes with a smaller `sub` (pos is already
+    // the exclusive prefix over lanes, which ARE ordered (anchor, sub))
+    int p = pos;
+    for (unsigned m = mask; m; m &= m - 1u) {
+      const int j = __ffs(m) - 1;
+      if (p < cap) {
+        cbox[ob + p] = box;
+        cscore[ob + p] = sigmoidf_acc(__ldg(ar.row + 64 + c0 + j));
+        ccls[ob + p] = (float)(c0 + j);
+      }
+      ++p;
     }
     return;
   }
-  // multi-label: decode again and emit (anchor, class) pairs in (anchor, class) order
-  for (int k = 0; k < 32; ++k) {
-    const int a = a0 + k;
-    if (a >= hp.A) break;
-    const int pk = __shfl_sync(0xffffffffu, pos, k), nk = __shfl_sync(0xffffffffu, mcnt, k);
-    if (nk == 0) continue;
-    float cx, cy, w, h, sc[kNcj];
-    warp_decode<kNcj>(hp, b, a, lane, cx, cy, w, h, sc);
-    const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
-    const float4 bx = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
-    int before = 0;
-#pragma unroll
-    for (int j = 0; j < kNcj; ++j) {
-      const unsigned m = __ballot_sync(0xffffffffu, sc[j] > conf);
-      if (sc[j] > conf) {
-        const int p = pk + before + __popc(m & ((1u << lane) - 1u));
-        if (p < cap) { cbox[ob + p] = bx; cscore[ob + p] = sc[j]; ccls[ob + p] = (float)(j * 32 + lane); }
-      }
-      before += __popc(m);
-    }
+  // single label: class = FIRST index whose score equals the maximum score (the reference takes max over sigmoid
+  // values, where distinct logits can tie after rounding / saturation); only logits near the maximum can tie
+  const float margin = best > 15.f ? INFINITY : 1e-2f;
+  int cls = 0x7fffffff;
+  for (int j = 0; j < q && c0 + j < hp.nc; ++j) {
+    const float v = __ldg(ar.row + 64 + c0 + j);
+    if (v >= best - margin && sigmoidf_acc(v) == score) { cls = c0 + j; break; }
+  }
+  cls = min(cls, __shfl_xor_sync(gmask, cls, 1));
+  cls = min(cls, __shfl_xor_sync(gmask, cls, 2));
+  const int ppos = __shfl_sync(gmask, pos, lane & ~3);
+  if (sub == 0 && ppos < cap) {
+    cbox[ob + ppos] = box;
+    cscore[ob + ppos] = score;
+    ccls[ob + ppos] = (float)cls;
   }
 }
 
@@ -395,7 +405,7 @@ int next_pow2(int x) {
 
 int fill_head(const y11_head_desc* hd, HeadParams* hp) {
   Y11_REQUIRE(hd->nl >= 1 && hd->nl <= 3, "postprocess: nl=%d", hd->nl);
-  Y11_REQUIRE(hd->nc >= 1 && hd->nc <= 32 * kNcj, "postprocess: nc=%d unsupported (max %d)", hd->nc, 32 * kNcj);
+  Y11_REQUIRE(hd->nc >= 1 && hd->nc <= 128, "postprocess: nc=%d unsupported (max 128)", hd->nc);
   int off = 0;
   for (int l = 0; l < 3; ++l) {
     hp->head[l] = l < hd->nl ? hd->head[l] : nullptr;
@@ -407,7 +417,9 @@ int fill_head(const y11_head_desc* hd, HeadParams* hp) {
   }
   hp->off[3] = off;
   hp->nl = hd->nl; hp->B = hd->B; hp->nc = hd->nc; hp->A = off; hp->no = hd->row_stride;
-  Y11_REQUIRE(hd->row_stride >= 64 + hd->nc, "postprocess: row_stride %d < 64+nc", hd->row_stride);
+  hp->cls_per_lane = 4 * ((hd->nc + 15) / 16);
+  Y11_REQUIRE(hd->row_stride >= 64 + 16 * ((hd->nc + 15) / 16) && hd->row_stride % 4 == 0,
+              "postprocess: row_stride %d must be >= 64 + nc rounded up to 16 and a multiple of 4", hd->row_stride);
   return 0;
 }
 
@@ -492,10 +504,13 @@ extern "C" int y11_detect_postprocess(y11_handle, const y11_head_desc* hd, const
   Workspace w;
   carve(&w, workspace, hp.B, cap, nchunks, cap);
   Y11_REQUIRE(workspace && workspace_bytes >= w.total, "postprocess: workspace %zu < required %zu", workspace_bytes, w.total);
+  // conservative logit pre-filter for the multi-label sigmoid test: sigmoid(x) > conf  =>  x > logit(conf) - slack
+  const double cc = std::min(std::max((double)p->conf, 1e-30), 1.0 - 1e-9);
+  const float logit_lo = (float)(log(cc / (1.0 - cc)) - 1e-2);
   dim3 grid((unsigned)nchunks, (unsigned)hp.B);
-  decode_compact_kernel<0><<<grid, 256, 0, s>>>(hp, p->conf, p->multi_label, cap, nchunks, w.chunk_cnt, w.chunk_off, w.cbox, w.cscore, w.ccls);
+  decode_compact_kernel<0><<<grid, 256, 0, s>>>(hp, p->conf, logit_lo, p->multi_label, cap, nchunks, w.chunk_cnt, w.chunk_off, w.cbox, w.cscore, w.ccls);
   scan_chunks_kernel<<<hp.B, 1024, 0, s>>>(w.chunk_cnt, w.chunk_off, nchunks, cap, w.ncand, out_ncand);
-  decode_compact_kernel<1><<<grid, 256, 0, s>>>(hp, p->conf, p->multi_label, cap, nchunks, w.chunk_cnt, w.chunk_off, w.cbox, w.cscore, w.ccls);
+  decode_compact_kernel<1><<<grid, 256, 0, s>>>(hp, p->conf, logit_lo, p->multi_label, cap, nchunks, w.chunk_cnt, w.chunk_off, w.cbox, w.cscore, w.ccls);
   Y11_CHECK_CUDA(cudaGetLastError());
   NmsArgs a;
   a.cbox = w.cbox; a.cscore = w.cscore; a.ccls = w.ccls; a.ncand = w.ncand; a.keys = w.keys; a.kbox = w.kbox; a.karea = w.karea;
