@@ -274,3 +274,22 @@ def test_every_conv_of_the_plan_matches_torch(engines, oracle_models, scale, B, 
         assert torch.all(err <= tol), f"{op.name}: max err {err.max().item():.4g} (tol {tol.flatten()[err.argmax()].item():.4g})"
         checked += 1
     assert checked >= 80
+
+
+def test_cuda_graph_pipeline_equals_eager_predict(engines):
+    """uint8 batch tensors take the CUDA-graph pipeline (one replay per call); results must be bit-identical to the eager
+    list-of-ndarrays path (same kernels, same inputs), call after call, from pinned host and from device memory."""
+    eng = engines("n")[0]
+    g = torch.Generator().manual_seed(21)
+    frames = torch.randint(0, 256, (3, 360, 640, 3), dtype=torch.uint8, generator=g)
+    eager = eng.predict([f.numpy() for f in frames], conf=0.3, iou=0.45, verbose=False)
+    for src in (frames.pin_memory(), frames.cuda(), frames.pin_memory()):
+        graphed = eng.predict(src, conf=0.3, iou=0.45, verbose=False)
+        assert len(graphed) == 3
+        for a, b in zip(eager, graphed):
+            assert a.orig_shape == b.orig_shape == (360, 640)
+            assert torch.equal(a.boxes.data.cpu(), b.boxes.data.cpu())
+    other = torch.randint(0, 256, (3, 360, 640, 3), dtype=torch.uint8, generator=g)
+    r2 = eng.predict(other.pin_memory(), conf=0.3, iou=0.45, verbose=False)
+    e2 = eng.predict([f.numpy() for f in other], conf=0.3, iou=0.45, verbose=False)
+    assert all(torch.equal(a.boxes.data.cpu(), b.boxes.data.cpu()) for a, b in zip(e2, r2))

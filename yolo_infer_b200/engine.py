@@ -198,6 +198,7 @@ class YOLO:
         return self
 
     def _release(self):
+        getattr(self, "_pipes", {}).clear()
         self._nets.clear()
         self._ws.clear()
         if self._engine and self._lib is not None:
@@ -277,6 +278,24 @@ class YOLO:
                                                     ws.numel(), C.c_void_p(s)), "y11_detect_postprocess")
         return det, count, ncand
 
+    # ---- CUDA-graph pipeline for fixed-shape uint8 batches (throughput and batch-1 latency modes) ----------------
+    def pipeline(self, B: int, h0: int, w0: int, imgsz=640, rect: bool = True, conf: float = 0.25, iou: float = 0.7,
+                 max_det: int = 300, agnostic: bool = False, multi_label: bool = False, frames: Optional[torch.Tensor] = None,
+                 graph: bool = True) -> "GraphedPipeline":
+        """letterbox -> forward -> decode/NMS for B frames of h0 x w0, captured once as a CUDA graph (one replay per call).
+        `frames`: optional device uint8 [B,h0,w0,3] tensor to bind as the graph's input (zero-copy); otherwise the pipeline
+        owns a static input buffer that `run(src)` fills with one async copy (H2D from pinned memory or D2D)."""
+        self._ensure_device()
+        key = (B, h0, w0, imgsz if isinstance(imgsz, int) else tuple(imgsz), rect, conf, iou, max_det, agnostic, multi_label,
+               frames.data_ptr() if frames is not None else None, graph)
+        p = self._pipes.get(key) if hasattr(self, "_pipes") else None
+        if p is None:
+            if not hasattr(self, "_pipes"):
+                self._pipes = {}
+            p = GraphedPipeline(self, B, h0, w0, imgsz, rect, conf, iou, max_det, agnostic, multi_label, frames, graph)
+            self._pipes[key] = p
+        return p
+
     # ---- synthetic-weight conditioning (benchmarks without checkpoints) ----------------------------------
     def condition_synthetic_weights(self, hw: Tuple[int, int] = (640, 640), batch: int = 2, seed: int = 0, iters: int = 3,
                                     act_rms: float = 1.0, box_std: float = 3.0, cls_std: float = 1.1,
@@ -347,6 +366,7 @@ class YOLO:
                 if cp.prefix in bias_shift:
                     sd[f"{cp.prefix}.bias"] = sd[f"{cp.prefix}.bias"] + bias_shift[cp.prefix]
         self.model = DetectionNet(self.scale, self.nc, sd, self.names)
+        getattr(self, "_pipes", {}).clear()
         self._nets.clear()
         with torch.cuda.device(self.device):
             self._packed = pack_weights(self.scale, self.nc, sd, self.device)
@@ -387,6 +407,30 @@ class YOLO:
         self._ensure_device(args["device"])
         imgsz = args["imgsz"]
         new_shape = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        if isinstance(source, torch.Tensor) and source.dtype == torch.uint8:
+            # fixed-shape uint8 batch [B,H,W,3] BGR (pinned host or device): whole path replayed as ONE CUDA graph
+            if source.ndim != 4 or source.shape[-1] != 3:
+                raise ValueError("uint8 tensor source must be [B,H,W,3] BGR")
+            with self._lock, torch.cuda.device(self.device), torch.inference_mode():
+                B, h0, w0, _ = source.shape
+                pipe = self.pipeline(B, h0, w0, imgsz, bool(args["rect"]), float(args["conf"]), float(args["iou"]),
+                                     int(args["max_det"]), bool(args["agnostic_nms"]), bool(args["multi_label"]))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                det, count, _ = pipe.run(source)
+                e1.record()
+                counts = count.cpu().tolist()
+                det = det.clone()
+                ms = e0.elapsed_time(e1) / B
+                speed = {"preprocess": 0.0, "inference": ms, "postprocess": 0.0}  # one graph: stages are not separable
+                self.last_speed = speed
+                results = []
+                for i in range(B):
+                    d = det[i, : counts[i]]
+                    if args["classes"] is not None:
+                        d = d[torch.isin(d[:, 5].long(), torch.as_tensor(list(args["classes"]), device=d.device))]
+                    results.append(Results(None, f"image{i}.jpg", self.names, d, (h0, w0), dict(speed)))
+            return results
         with self._lock, torch.cuda.device(self.device), torch.inference_mode():
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
@@ -471,3 +515,62 @@ class YOLO:
     def info(self, *a, **k):
         n = T.count_parameters(self.scale, self.nc)
         return {"scale": self.scale, "parameters": n}
+
+
+class GraphedPipeline:
+    """One fixed-shape instance of the whole hot path, replayed as a single CUDA graph.
+
+    All device buffers (input frames, letterbox descriptors, activations, post-processing workspace, results) are static,
+    so a call is: one async copy of the frames (skipped when the caller binds its own device tensor) + one graph launch.
+    The launches inside are exactly the ones `YOLO.predict` issues; CUDA graphs only remove the per-launch CPU cost
+    (96 launches for YOLO11n/s), which dominates at batch 1.
+    """
+
+    def __init__(self, eng: YOLO, B: int, h0: int, w0: int, imgsz, rect: bool, conf: float, iou: float, max_det: int,
+                 agnostic: bool, multi_label: bool, frames: Optional[torch.Tensor], graph: bool):
+        self.eng, self.B, self.h0, self.w0 = eng, B, h0, w0
+        self.conf, self.iou, self.max_det, self.agnostic, self.multi_label = conf, iou, max_det, agnostic, multi_label
+        dev = eng.device
+        new_shape = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        geom = letterbox_geometry(h0, w0, new_shape, bool(rect))
+        self.H, self.W = geom[4], geom[5]
+        with torch.cuda.device(dev):
+            self.net = eng.compiled(B, self.H, self.W)
+            self.owns_input = frames is None
+            self.frames = frames if frames is not None else torch.zeros((B, h0, w0, 3), dtype=torch.uint8, device=dev)
+            assert self.frames.shape == (B, h0, w0, 3) and self.frames.dtype == torch.uint8 and self.frames.is_cuda
+            arr = (cabi.Image * B)()
+            for i in range(B):
+                f = self.frames[i]
+                arr[i] = cabi.Image(f.data_ptr(), h0, w0, f.stride(0), geom[1], geom[0], geom[2], geom[3])
+            self.desc = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+            gain, px, py = scale_geometry((self.H, self.W), (h0, w0))
+            self.scale_rows = torch.tensor([[gain, float(px), float(py), float(w0), float(h0)]] * B, dtype=torch.float32, device=dev)
+            self.graph = None
+            self._enqueue()                      # warm-up: allocates workspaces, sets function attributes
+            torch.cuda.synchronize(dev)
+            if graph:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue()
+                self.graph = g
+        self.launches = 1 + self.net.n_launches + 4
+
+    def _enqueue(self):
+        eng = self.eng
+        s = torch.cuda.current_stream(eng.device).cuda_stream
+        cabi.check(eng._lib.y11_letterbox(eng._engine, self.desc.data_ptr(), self.B, self.H, self.W, self.net.input.data_ptr(),
+                                          C.c_void_p(s)), "y11_letterbox")
+        eng.forward(self.net)
+        self.det, self.count, self.ncand = eng.postprocess(self.net, self.scale_rows, self.conf, self.iou, self.max_det,
+                                                           self.agnostic, self.multi_label)
+
+    def run(self, src: Optional[torch.Tensor] = None):
+        """Enqueue one pass on the current stream; returns the static (det [B,max_det,6], count [B], ncand [B]) tensors."""
+        if src is not None:
+            self.frames.copy_(src, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+        return self.det, self.count, self.ncand
