@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(128) attn_kernel(y11_attn_desc d) {
   constexpr int KP = KD + 8, VP = HD + 8;  // padded rows (bf16 elements): 80 B / 144 B pitches
   __shared__ __align__(16) __nv_bfloat16 s_k[kT * KP];
   __shared__ __align__(16) __nv_bfloat16 s_v[kT * VP];
+  pdl_wait();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int head = blockIdx.y, b = blockIdx.z;
   const int q0 = blockIdx.x * kQ + warp * 16;
@@ -156,7 +158,6 @@ int attention_launch(const y11_attn_desc* d, cudaStream_t s) {
   Y11_REQUIRE(d->qkv.c_total % 8 == 0 && d->qkv.c_off % 8 == 0 && d->out.c_total % 8 == 0 && d->out.c_off % 8 == 0,
               "attention: views must be 16-byte aligned");
   dim3 grid((unsigned)((d->N + kQ - 1) / kQ), (unsigned)d->heads, (unsigned)d->B);
-  attn_kernel<32, 64><<<grid, 128, 0, s>>>(*d);
-  Y11_CHECK_CUDA(cudaGetLastError());
+  Y11_CHECK_CUDA(y11_launch_pdl(attn_kernel<32, 64>, grid, dim3(128), 0, s, *d));
   return 0;
 }

@@ -155,6 +155,14 @@ __device__ __forceinline__ uint32_t make_idesc_bf16_m128(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------
+// Every kernel of the plan is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may be scheduled
+// (and run their prologue: barrier init, TMEM alloc, tensor-map prefetch, weight staging) while the previous kernel of the
+// stream drains.  pdl_wait() blocks until that previous kernel has completed and its writes are visible; it must precede
+// the first access to anything the predecessor wrote.  pdl_trigger() lets the NEXT kernel start being scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- misc -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;

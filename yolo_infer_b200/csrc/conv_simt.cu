@@ -49,116 +49,154 @@ int conv_simt_launch(const y11_conv_desc* d, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// stem: 3 -> COUT, 3x3 stride 2 pad 1, +bias, SiLU (CUDA cores: K = 27 is too thin for an MMA tile).
-// Register blocked: one thread owns P output pixels x all COUT channels, so every broadcast weight load from shared
-// memory feeds 4*P FMAs (v1, 1 pixel per thread, was LDS-issue bound: 0.70 ms for YOLO11s batch 64).  A CTA covers
-// TX*P consecutive pixels of one output row; thread tx owns pixels tx, tx+TX, ... (adjacent lanes -> adjacent pixels).
-// The three input rows are staged with 16-byte loads (v2 staged 2 bytes at a time and was 3x slower than v1).
+// stem: 3 -> COUT, 3x3 stride 2 pad 1, +bias, SiLU.  K = 27 (padded to 32) is far too thin for a 128-row tcgen05 tile
+// and the layer is HBM bound (reads the bf16 image once, writes COUT channels per pixel), so it runs on the warp-level
+// tensor-core path: per CTA, three input rows are staged with 16-byte loads, each thread builds the im2col row of one
+// output pixel in shared memory ([pixel][32] bf16, 80-byte pitch = conflict-free fragment loads), every warp does
+// 32 pixels x COUT with mma.sync.m16n8k16 (weights held in registers as B fragments), and the bf16 result goes back
+// through shared memory so that each lane stores 16 contiguous bytes.
+// (v1: CUDA cores, 1 pixel/thread, LDS-issue bound, 0.70 ms for YOLO11s batch 64; v3: register-blocked, 0.91 ms.)
 // ------------------------------------------------------------------------------------------------
-template <int COUT, int P>
-__global__ void __launch_bounds__(128) stem_kernel(y11_stem_desc d, int TX, int tiles_w) {
-  extern __shared__ float s_dyn[];
-  float* s_w = s_dyn;                  // [27][COUT]
-  float* s_b = s_w + 27 * COUT;        // [COUT]
-  float* s_in = s_b + COUT;            // [3][(2*TX*P+1)*3]
-  const int span = TX * P;
-  const int row_f = (2 * span + 1) * 3;
+__device__ __forceinline__ void mma_bf16_16816_s(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int tiles_w) {
+  constexpr int AP = 40;         // im2col / weight row pitch in bf16 (32 + 8 pad)
+  constexpr int OP = COUT + 8;   // output staging pitch in bf16
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int row_e = (2 * PXB + 1) * 3;               // bf16 elements per staged input row
+  const int row_p = (row_e + 7) & ~7;
+  __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(s_raw);          // [3][row_p]
+  __nv_bfloat16* s_a = s_in + 3 * row_p;                                 // [PXB][AP]
+  __nv_bfloat16* s_w = s_a + PXB * AP;                                   // [COUT][AP]
+  __nv_bfloat16* s_o = s_w + COUT * AP;                                  // [PXB][OP]
+  float* s_b = reinterpret_cast<float*>(s_o + PXB * OP);                 // [COUT]
   const int tile = blockIdx.x % tiles_w;
   const int oh = (blockIdx.x / tiles_w) % d.Hout;
   const int n = blockIdx.x / (tiles_w * d.Hout);
-  const int ow0 = tile * span;
-  const int nt = blockDim.x;
+  const int ow0 = tile * PXB;
+  const int nt = blockDim.x, tid = threadIdx.x;
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  // weights [COUT][27] -> [COUT][AP] (k >= 27 zero), bias
   const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(d.w);
-  for (int i = threadIdx.x; i < 27 * COUT; i += nt) s_w[(i % 27) * COUT + i / 27] = __bfloat162float(w[i]);  // w is [COUT][27]
-  for (int i = threadIdx.x; i < COUT; i += nt) s_b[i] = d.bias[i];
-  for (int i = threadIdx.x; i < 3 * row_f; i += nt) s_in[i] = 0.f;
+  for (int i = tid; i < COUT * AP; i += nt) {
+    const int co = i / AP, k = i % AP;
+    s_w[i] = k < 27 ? w[co * 27 + k] : zero;
+  }
+  for (int i = tid; i < COUT; i += nt) s_b[i] = d.bias[i];
+  for (int i = tid; i < 3 * row_p; i += nt) s_in[i] = zero;
+  pdl_wait();   // weights/bias above are constants; the image below is the previous kernel's output
+  pdl_trigger();
   __syncthreads();
+  // stage the three input rows (16-byte global loads; rows are 16-byte aligned because Win % 8 == 0)
   const int iw0 = 2 * ow0 - 1;
-  const int e_lo = max(iw0, 0) * 3, e_hi = min(iw0 + 2 * span + 1, d.Win) * 3;  // bf16 elements of the input row we need
-  const int v_lo = e_lo / 8, v_hi = (e_hi + 7) / 8;                             // 16-byte chunks (rows are 16-byte aligned)
+  const int e_lo = max(iw0, 0) * 3, e_hi = min(iw0 + 2 * PXB + 1, d.Win) * 3;
+  const int v_lo = e_lo / 8, v_hi = (e_hi + 7) / 8;
   for (int r = 0; r < 3; ++r) {
     const int ih = 2 * oh + r - 1;
     if (ih < 0 || ih >= d.Hin) continue;
     const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(d.in) + ((size_t)n * d.Hin + ih) * d.Win * 3);
-    float* dst = s_in + r * row_f - iw0 * 3;
-    for (int v = v_lo + threadIdx.x; v < v_hi; v += nt) {
+    __nv_bfloat16* dst = s_in + r * row_p - iw0 * 3;
+    for (int v = v_lo + tid; v < v_hi; v += nt) {
       const uint4 u = __ldg(rp + v);
-      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int e = v * 8 + 2 * t;
-        if (e >= e_lo && e < e_hi) dst[e] = bf16_lo(uu[t]);
-        if (e + 1 >= e_lo && e + 1 < e_hi) dst[e + 1] = bf16_hi(uu[t]);
+      for (int t = 0; t < 8; ++t) {
+        const int e = v * 8 + t;
+        if (e >= e_lo && e < e_hi) dst[e] = h[t];
       }
     }
   }
   __syncthreads();
-  const int tx = threadIdx.x;
-  if (tx >= TX) return;
-  float acc[P][COUT];
+  // im2col: thread p builds A[p][0..31], k = kh*9 + kw*3 + c  <-  in[kh][(2p+kw)*3 + c] = in[kh][6p + (k - 9kh)]
+  if (tid < PXB) {
+    __nv_bfloat16* ar = s_a + tid * AP;
 #pragma unroll
-  for (int q = 0; q < P; ++q)
+    for (int kh = 0; kh < 3; ++kh) {
+      const __nv_bfloat16* src = s_in + kh * row_p + 6 * tid;
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[q][c] = s_b[c];
+      for (int j = 0; j < 9; ++j) ar[kh * 9 + j] = src[j];
+    }
 #pragma unroll
-  for (int kh = 0; kh < 3; ++kh) {
+    for (int k = 27; k < 32; ++k) ar[k] = zero;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  if (warp * 32 >= PXB) return;
+  // B fragments (weights) in registers: B[k][n] = W[n][k]
+  uint32_t bw[COUT / 8][2][2];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) {  // j = kw*3 + c
-      float x[P];
+  for (int nb = 0; nb < COUT / 8; ++nb)
 #pragma unroll
-      for (int q = 0; q < P; ++q) x[q] = s_in[kh * row_f + (tx + q * TX) * 6 + j];
-      const float4* wr = reinterpret_cast<const float4*>(s_w + (kh * 9 + j) * COUT);
+    for (int ks = 0; ks < 2; ++ks) {
+      const __nv_bfloat16* wp = s_w + (nb * 8 + g) * AP + ks * 16 + 2 * t;
+      bw[nb][ks][0] = *reinterpret_cast<const uint32_t*>(wp);
+      bw[nb][ks][1] = *reinterpret_cast<const uint32_t*>(wp + 8);
+    }
 #pragma unroll
-      for (int c4 = 0; c4 < COUT / 4; ++c4) {
-        const float4 ww = wr[c4];
+  for (int mt = 0; mt < 2; ++mt) {
+    const int p0 = warp * 32 + mt * 16;
+    uint32_t af[2][4];
 #pragma unroll
-        for (int q = 0; q < P; ++q) {
-          acc[q][4 * c4 + 0] = fmaf(x[q], ww.x, acc[q][4 * c4 + 0]);
-          acc[q][4 * c4 + 1] = fmaf(x[q], ww.y, acc[q][4 * c4 + 1]);
-          acc[q][4 * c4 + 2] = fmaf(x[q], ww.z, acc[q][4 * c4 + 2]);
-          acc[q][4 * c4 + 3] = fmaf(x[q], ww.w, acc[q][4 * c4 + 3]);
-        }
-      }
+    for (int ks = 0; ks < 2; ++ks) {
+      const __nv_bfloat16* ap = s_a + (p0 + g) * AP + ks * 16 + 2 * t;
+      af[ks][0] = *reinterpret_cast<const uint32_t*>(ap);
+      af[ks][1] = *reinterpret_cast<const uint32_t*>(ap + 8 * AP);
+      af[ks][2] = *reinterpret_cast<const uint32_t*>(ap + 8);
+      af[ks][3] = *reinterpret_cast<const uint32_t*>(ap + 8 * AP + 8);
+    }
+#pragma unroll
+    for (int nb = 0; nb < COUT / 8; ++nb) {
+      float c[4];
+      const float b0 = s_b[nb * 8 + 2 * t], b1 = s_b[nb * 8 + 2 * t + 1];
+      c[0] = b0; c[1] = b1; c[2] = b0; c[3] = b1;
+      mma_bf16_16816_s(c, af[0], bw[nb][0][0], bw[nb][0][1]);
+      mma_bf16_16816_s(c, af[1], bw[nb][1][0], bw[nb][1][1]);
+      *reinterpret_cast<uint32_t*>(s_o + (p0 + g) * OP + nb * 8 + 2 * t) = pack_bf16x2(silu(c[0]), silu(c[1]));
+      *reinterpret_cast<uint32_t*>(s_o + (p0 + g + 8) * OP + nb * 8 + 2 * t) = pack_bf16x2(silu(c[2]), silu(c[3]));
     }
   }
-#pragma unroll
-  for (int q = 0; q < P; ++q) {
-    const int ow = ow0 + tx + q * TX;
-    if (ow >= d.Wout) continue;
-    const size_t pix = ((size_t)n * d.Hout + oh) * d.Wout + ow;
-    uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(d.out.ptr) + pix * d.out.c_total + d.out.c_off);
-#pragma unroll
-    for (int c = 0; c < COUT; c += 8) {
-      op[c / 8] = make_uint4(pack_bf16x2(silu(acc[q][c]), silu(acc[q][c + 1])), pack_bf16x2(silu(acc[q][c + 2]), silu(acc[q][c + 3])),
-                             pack_bf16x2(silu(acc[q][c + 4]), silu(acc[q][c + 5])), pack_bf16x2(silu(acc[q][c + 6]), silu(acc[q][c + 7])));
-    }
+  __syncwarp();
+  // coalesced write-out of this warp's 32 pixels: 16 bytes per lane, consecutive lanes -> consecutive bytes of a pixel row
+  constexpr int VPP = COUT / 8;  // 16-byte vectors per pixel
+  const size_t pix0 = ((size_t)n * d.Hout + oh) * d.Wout + ow0 + warp * 32;
+  __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(d.out.ptr) + d.out.c_off;
+  for (int i = lane; i < 32 * VPP; i += 32) {
+    const int px = i / VPP, v = i % VPP;
+    if (ow0 + warp * 32 + px < d.Wout)
+      *reinterpret_cast<uint4*>(ob + (pix0 + px) * d.out.c_total + v * 8) = *reinterpret_cast<const uint4*>(s_o + (warp * 32 + px) * OP + v * 8);
   }
 }
 
-template <int COUT, int P>
+template <int COUT>
 static int stem_launch_t(const y11_stem_desc* d, cudaStream_t s) {
   Y11_REQUIRE(d->Win % 8 == 0, "stem: input width must be a multiple of 8 (got %d)", d->Win);
-  const int nblk = y11_ceil_div(d->Wout, P * 128);
-  const int TX = y11_ceil_div(d->Wout, P * nblk);
-  const int threads = (TX + 31) / 32 * 32;
-  const size_t smem = (size_t)(27 * COUT + COUT + 3 * (2 * TX * P + 1) * 3) * sizeof(float);
+  int PXB = 128;
+  for (int c : {160, 128, 96, 64, 32})
+    if (d->Wout % c == 0) { PXB = c; break; }
+  const int tiles_w = y11_ceil_div(d->Wout, PXB);
+  const int row_p = (((2 * PXB + 1) * 3) + 7) & ~7;
+  const size_t smem = (size_t)(3 * row_p + PXB * 40 + COUT * 40 + PXB * (COUT + 8)) * 2 + COUT * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    Y11_CHECK_CUDA(cudaFuncSetAttribute(stem_kernel<COUT, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    Y11_CHECK_CUDA(cudaFuncSetAttribute(stem_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
   }
-  Y11_REQUIRE(smem <= 64 * 1024, "stem: row too wide for shared memory");
-  stem_kernel<COUT, P><<<(unsigned)(nblk * d->Hout * d->B), threads, smem, s>>>(*d, TX, nblk);
-  Y11_CHECK_CUDA(cudaGetLastError());
+  Y11_CHECK_CUDA(y11_launch_pdl(stem_kernel<COUT>, dim3((unsigned)(tiles_w * d->Hout * d->B)), dim3(PXB), smem, s, *d, PXB, tiles_w));
   return 0;
 }
 
 int stem_launch(const y11_stem_desc* d, cudaStream_t s) {
   switch (d->out.c) {
-    case 16: return stem_launch_t<16, 4>(d, s);
-    case 32: return stem_launch_t<32, 4>(d, s);
-    case 64: return stem_launch_t<64, 2>(d, s);
-    case 96: return stem_launch_t<96, 1>(d, s);
+    case 16: return stem_launch_t<16>(d, s);
+    case 32: return stem_launch_t<32>(d, s);
+    case 64: return stem_launch_t<64>(d, s);
+    case 96: return stem_launch_t<96>(d, s);
     default: y11_set_error("stem: unsupported cout %d", d->out.c); return -1;
   }
 }
@@ -167,6 +205,8 @@ int stem_launch(const y11_stem_desc* d, cudaStream_t s) {
 // depthwise 3x3 stride 1 pad 1: one thread = one pixel x 8 channels (16-byte vectors)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dwconv_kernel(y11_dwconv_desc d) {
+  pdl_wait();
+  pdl_trigger();
   const int groups = d.in.c / 8;
   const size_t total = (size_t)d.B * d.H * d.W * groups;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -224,8 +264,7 @@ int dwconv_launch(const y11_dwconv_desc* d, cudaStream_t s) {
                   d->out.c_total % 8 == 0,
               "dwconv: views must be 16-byte aligned (c=%d)", d->in.c);
   const size_t total = (size_t)d->B * d->H * d->W * (d->in.c / 8);
-  dwconv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(*d);
-  Y11_CHECK_CUDA(cudaGetLastError());
+  Y11_CHECK_CUDA(y11_launch_pdl(dwconv_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, *d));
   return 0;
 }
 
@@ -244,6 +283,8 @@ __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
 }
 
 __global__ void __launch_bounds__(256) sppf_kernel(y11_sppf_desc d) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ uint4 s_plane[];  // [2][H*W]
   const int hw = d.H * d.W;
   uint4* cur = s_plane;
@@ -289,8 +330,7 @@ int sppf_launch(const y11_sppf_desc* d, cudaStream_t s) {
     Y11_CHECK_CUDA(cudaFuncSetAttribute(sppf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  sppf_kernel<<<(unsigned)(d->B * (d->c / 8)), 256, smem, s>>>(*d);
-  Y11_CHECK_CUDA(cudaGetLastError());
+  Y11_CHECK_CUDA(y11_launch_pdl(sppf_kernel, dim3((unsigned)(d->B * (d->c / 8))), dim3(256), smem, s, *d));
   return 0;
 }
 
@@ -298,6 +338,8 @@ int sppf_launch(const y11_sppf_desc* d, cudaStream_t s) {
 // nearest 2x upsample into a channel slice of the concat buffer (16-byte vectors)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) upsample_kernel(y11_upsample_desc d) {
+  pdl_wait();
+  pdl_trigger();
   const int groups = d.in.c / 8;
   const int Ho = 2 * d.H, Wo = 2 * d.W;
   const size_t total = (size_t)d.B * Ho * Wo * groups;
@@ -316,7 +358,6 @@ int upsample_launch(const y11_upsample_desc* d, cudaStream_t s) {
   Y11_REQUIRE(d->in.c % 8 == 0 && d->in.c_off % 8 == 0 && d->in.c_total % 8 == 0 && d->out.c_off % 8 == 0 &&
                   d->out.c_total % 8 == 0, "upsample: alignment");
   const size_t total = (size_t)d->B * 4 * d->H * d->W * (d->in.c / 8);
-  upsample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(*d);
-  Y11_CHECK_CUDA(cudaGetLastError());
+  Y11_CHECK_CUDA(y11_launch_pdl(upsample_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, *d));
   return 0;
 }

@@ -105,6 +105,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t acc_stride = p.tmem_cols >> 1;  // column offset of accumulator stage 1
+  // everything above overlapped the tail of the previous kernel (PDL); from here on we touch its output
+  pdl_wait();
+  pdl_trigger();
 
   const int k_iters = p.taps * p.chunks_per_tap;
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
@@ -406,7 +409,6 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
 }
 
 int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t s) {
-  conv_tc_kernel<<<L->grid, kThreads, L->smem_bytes, s>>>(L->maps, L->p);
-  Y11_CHECK_CUDA(cudaGetLastError());
+  Y11_CHECK_CUDA(y11_launch_pdl(conv_tc_kernel, dim3(L->grid), dim3(kThreads), L->smem_bytes, s, L->maps, L->p));
   return 0;
 }

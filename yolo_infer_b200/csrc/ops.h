@@ -1,6 +1,24 @@
 // Internal (non-ABI) declarations shared by the .cu translation units of liby11_b200.
 #pragma once
+#include <utility>
+
 #include "common.cuh"
+
+// Launch with programmatic stream serialization (PDL): see pdl_wait()/pdl_trigger() in common.cuh.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t y11_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- tcgen05 implicit-GEMM conv (conv_tc.cu) ---------------------------------------------------
 struct ConvTcMaps {
