@@ -117,10 +117,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       // ------------------------------------------------------------------ TMA producer
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int nt = t % p.n_tiles; t /= p.n_tiles;
-        const int w0 = (t % p.tiles_w) * p.Tw; t /= p.tiles_w;
-        const int h0 = (t % p.tiles_h) * p.Th; t /= p.tiles_h;
+        uint32_t t = tile, q;
+        q = fast_div(t, p.mg_ntiles); const int nt = t - q * p.n_tiles; t = q;
+        q = fast_div(t, p.mg_tw); const int w0 = (t - q * p.tiles_w) * p.Tw; t = q;
+        q = fast_div(t, p.mg_th); const int h0 = (t - q * p.tiles_h) * p.Th; t = q;
         const int n0 = t * p.Tn;
         for (int tap = 0; tap < p.taps; ++tap) {
           int mi = 0, cw, ch;
@@ -174,25 +174,29 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     }
   } else {
     // -------------------------------------------------------------------- epilogue (warps 2..9)
+    // All 8 warps work on the same chunk of CW = 16*halves output channels: warp quadrant q owns TMEM lanes / tile rows
+    // [32q, 32q+32), `half` picks the 16-column slice inside the chunk.  One staging buffer pair, one named barrier and
+    // one TMA store per chunk (v2 used two independent 4-warp groups with 16-column chunks: twice the barriers/stores).
     const int ew = warp - 2;
-    const int grp = ew >> 2;  // two groups of 4 warps; group g takes 16-column chunks g, g+2, ...
-    const int q = warp & 3;   // TMEM lane quadrant this warp may access
-    const int r = q * 32 + lane;
+    const int half = ew >> 2;  // 0/1: which 16 columns of a 32-column chunk
+    const int quad = warp & 3; // TMEM lane quadrant this warp may access (hardware: warp id % 4)
+    const int r = quad * 32 + lane;
     const int tw = r % p.Tw, th = (r / p.Tw) % p.Th, tn = r / (p.Tw * p.Th);
-    const bool leader = (ew & 3) == 0 && lane == 0;
+    const bool leader = ew == 0 && lane == 0;
     const uint32_t esz = p.out_f32 ? 4u : 2u;
-    const uint32_t pitch = 16u * esz;                      // staging row pitch: 32 B (bf16) / 64 B (fp32)
-    const uint32_t swz = (r / (128u / pitch)) & (pitch / 16u - 1u);  // TMA SWIZZLE_32B / _64B pattern for row r
+    const int halves = p.cw / 16;                          // 1 (16-column chunks) or 2 (32-column chunks)
+    const uint32_t pitch = (uint32_t)p.cw * esz;           // staging row pitch: 32 / 64 / 128 B
+    const uint32_t swz = (r / (128u / pitch)) & (pitch / 16u - 1u);  // TMA SWIZZLE_{32,64,128}B pattern for row r
     const uint32_t stg_bytes = 128u * pitch;
-    const uint32_t stg0 = staging_base + grp * 2 * stg_bytes;
     const uint32_t row_addr = r * pitch;
-    const int n_chunks = p.BN / 16;
+    const int n_chunks = (p.BN + p.cw - 1) / p.cw;
+    const bool active = half < halves;
     int ti = 0, ci = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-      int t = tile;
-      const int nt = t % p.n_tiles; t /= p.n_tiles;
-      const int w0 = (t % p.tiles_w) * p.Tw; t /= p.tiles_w;
-      const int h0 = (t % p.tiles_h) * p.Th; t /= p.tiles_h;
+      uint32_t t = tile, qq;
+      qq = fast_div(t, p.mg_ntiles); const int nt = t - qq * p.n_tiles; t = qq;
+      qq = fast_div(t, p.mg_tw); const int w0 = (t - qq * p.tiles_w) * p.Tw; t = qq;
+      qq = fast_div(t, p.mg_th); const int h0 = (t - qq * p.tiles_h) * p.Th; t = qq;
       const int n0 = t * p.Tn;
       const int ow = w0 + tw, oh = h0 + th, on = n0 + tn;
       const bool valid = (r < p.Tw * p.Th * p.Tn) && ow < p.Wout && oh < p.Hout && on < p.B;
@@ -200,53 +204,57 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       const int as = ti & 1;
       mbar_wait(accf_bar + 8 * as, (ti >> 1) & 1, p.err_flag, 103);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + as * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
-      for (int c = grp; c < n_chunks; c += 2, ++ci) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c * 16, v);
-        tmem_ld_wait();
-        const int n = nt * p.BN + c * 16;
-        float f[16];
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+      const uint32_t taddr = tmem_base + as * acc_stride + (static_cast<uint32_t>(quad * 32) << 16);
+      for (int c = 0; c < n_chunks; ++c, ++ci) {
+        const int col = c * p.cw + half * 16;          // column inside the tile's accumulator
+        const uint32_t dst = staging_base + (ci & 1) * stg_bytes + row_addr;
+        if (active && col < p.BN) {
+          uint32_t v[16];
+          tmem_ld16(taddr + col, v);
+          tmem_ld_wait();
+          const int n = nt * p.BN + col;
+          float f[16];
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 bb = __ldg(b4 + i);
-          f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x;
-          f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
-          f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
-          f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
-        }
-        if (p.act == Y11_ACT_SILU) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = silu(f[i]);
-        }
-        if (p.res && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ct + p.res_co + n);
-          const uint4 r0 = rp[0], r1 = rp[1];
-          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            f[2 * i] += bf16_lo(rr[i]);
-            f[2 * i + 1] += bf16_hi(rr[i]);
+          for (int i = 0; i < 4; ++i) {
+            const float4 bb = __ldg(b4 + i);
+            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x;
+            f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
+            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
+            f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
           }
-        }
-        const uint32_t dst = stg0 + (ci & 1) * stg_bytes + row_addr;
-        if (p.out_f32) {
+          if (p.act == Y11_ACT_SILU) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            st_shared_v4(dst + ((i ^ swz) << 4), __float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]),
-                         __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3]));
-        } else {
-          st_shared_v4(dst + ((0u ^ swz) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                       pack_bf16x2(f[6], f[7]));
-          st_shared_v4(dst + ((1u ^ swz) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                       pack_bf16x2(f[14], f[15]));
+            for (int i = 0; i < 16; ++i) f[i] = silu(f[i]);
+          }
+          if (p.res && valid) {
+            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ct + p.res_co + n);
+            const uint4 r0 = rp[0], r1 = rp[1];
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              f[2 * i] += bf16_lo(rr[i]);
+              f[2 * i + 1] += bf16_hi(rr[i]);
+            }
+          }
+          if (p.out_f32) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              st_shared_v4(dst + (((4u * half + i) ^ swz) << 4), __float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]),
+                           __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3]));
+          } else {
+            st_shared_v4(dst + (((2u * half + 0u) ^ swz) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                         pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            st_shared_v4(dst + (((2u * half + 1u) ^ swz) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                         pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+          }
+          fence_async_smem();            // my generic-proxy smem writes -> visible to the TMA (async proxy)
         }
-        fence_async_smem();              // my generic-proxy smem writes -> visible to the TMA (async proxy)
-        if (leader) bulk_wait_read0();   // the previous store of this group has finished READING its (other) buffer
-        named_bar_sync(1 + grp, 128);    // all 128 rows of this chunk are staged; other buffer is free for the next chunk
+        if (leader) bulk_wait_read0();   // the previous store has finished READING its (other) staging buffer
+        named_bar_sync(1, kEpiWarps * 32);  // all rows/columns of this chunk staged; other buffer free for the next chunk
         if (leader) {
-          tma_store_4d(&maps.out, stg0 + (ci & 1) * stg_bytes, n, w0, h0, n0);
+          // columns beyond cout (only when cout % cw != 0, single N tile) are clipped by the tensor map
+          tma_store_4d(&maps.out, staging_base + (ci & 1) * stg_bytes, nt * p.BN + c * p.cw, w0, h0, n0);
           bulk_commit();
         }
       }
@@ -336,13 +344,17 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
   p.tx_bytes = (uint32_t)(p.Tw * p.Th * p.Tn) * swz_bytes + (uint32_t)bn * swz_bytes;
   const int k_iters = p.taps * p.chunks_per_tap;
   const uint32_t stage = p.a_slot + p.b_slot;
-  const uint32_t staging = 4u * 128u * (d->out_f32 ? 64u : 32u);
+  // epilogue chunk width: 32 output channels per TMA store when the tile allows it (bf16), else 16
+  int cw = (bn % 32 == 0) ? 32 : 16;
+  if (p.n_tiles > 1) Y11_REQUIRE(bn % cw == 0, "conv_tc: BN=%d not a multiple of the chunk width", bn);
+  p.cw = cw;
+  const uint32_t staging = 2u * 128u * (uint32_t)cw * (d->out_f32 ? 4u : 2u);
   // persistent CTAs per SM: TMEM (512 columns) and shared memory are split between them
   // (measured on B200, YOLO11s batch 64: conv time 5.25 / 3.78 / 3.65 / 3.88 ms for 1 / 2 / 3 / 4 CTAs per SM - several
   //  independent TMA->MMA->epilogue chains per SM hide the per-tile latencies better than one deep pipeline)
   int cps = 3;
   if (const char* e = getenv("Y11_CTAS_PER_SM")) cps = std::max(1, std::min(4, atoi(e)));
-  int cols = 32;
+  int cols = 64;  // >= 2 accumulator stages of max(BN, 32) columns (a partial last chunk may read up to 16 spare columns)
   while (cols < 2 * bn) cols *= 2;
   while (cps > 1 && cps * cols > 512) --cps;
   const uint32_t budget = (cps == 1 ? kSmemBudget : (220u * 1024u) / cps - 2048u);
@@ -355,6 +367,12 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
   p.res = d->res.ptr; p.res_ct = d->res.c_total; p.res_co = d->res.c_off;
   p.bias = d->bias; p.act = d->act;
   p.err_flag = eng->dev_error_flag;
+  {
+    const long long tt = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+    Y11_REQUIRE(tt < (1ll << 21), "conv_tc: %lld tiles exceed the fast-division range", tt);
+    auto magic = [](uint32_t dv) { return ((1ull << 42) + dv - 1) / dv; };
+    p.mg_ntiles = magic(p.n_tiles); p.mg_tw = magic(p.tiles_w); p.mg_th = magic(p.tiles_h);
+  }
 
   // activation tensor maps
   const size_t ct = d->in.c_total;
@@ -390,9 +408,11 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
     char* obase = static_cast<char*>(d->out.ptr) + (size_t)d->out.c_off * esz;
     const cuuint64_t gdim[4] = {(cuuint64_t)cout, (cuuint64_t)d->Wout, (cuuint64_t)d->Hout, (cuuint64_t)d->B};
     const cuuint64_t gstr[3] = {oct * esz, oct * esz * d->Wout, oct * esz * d->Wout * d->Hout};
-    const cuuint32_t obox[4] = {16u, (cuuint32_t)p.Tw, (cuuint32_t)p.Th, (cuuint32_t)p.Tn};
+    const cuuint32_t obox[4] = {(cuuint32_t)p.cw, (cuuint32_t)p.Tw, (cuuint32_t)p.Th, (cuuint32_t)p.Tn};
+    const uint32_t opitch = (uint32_t)p.cw * (uint32_t)esz;
+    const CUtensorMapSwizzle oswz = opitch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : opitch == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     if (int e = encode_map(eng, &L->maps.out, d->out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : bf, 4, obase, gdim, gstr, obox,
-                           d->out_f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B))
+                           oswz))
       return e;
   }
   const unsigned total_tiles = (unsigned)(p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles);

@@ -32,6 +32,7 @@ struct ConvTcParams {
   int32_t tiles_w, tiles_h, tiles_n;  // spatial tile grid
   int32_t n_tiles;                    // Cout tiles of BN columns
   int32_t BN, Cc, chunks_per_tap, taps, ksize, stride, stages, tmem_cols;
+  int32_t cw;  // epilogue chunk width in output channels (16 or 32) = inner box of the output tensor map
   uint32_t a_slot, b_slot, tx_bytes, sbo, layout_type;
   int32_t B, Hout, Wout, cout, cin;
   void* out;
@@ -41,6 +42,7 @@ struct ConvTcParams {
   const float* bias;
   int32_t act;
   int* err_flag;
+  uint64_t mg_ntiles, mg_tw, mg_th;  // fast_div magics for n_tiles, tiles_w, tiles_h
 };
 
 struct ConvTcLaunch {
