@@ -292,7 +292,8 @@ class YOLO:
         if p is None:
             if not hasattr(self, "_pipes"):
                 self._pipes = {}
-            p = GraphedPipeline(self, B, h0, w0, imgsz, rect, conf, iou, max_det, agnostic, multi_label, frames, graph)
+            with torch.inference_mode(False):  # static buffers must stay writable from any mode
+                p = GraphedPipeline(self, B, h0, w0, imgsz, rect, conf, iou, max_det, agnostic, multi_label, frames, graph)
             self._pipes[key] = p
         return p
 
