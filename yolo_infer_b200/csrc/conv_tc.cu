@@ -325,6 +325,14 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
   int bn = 16;
   for (int c = 16; c <= std::min(cout, 128); c += 16)
     if (cout % c == 0) bn = c;
+  // Long-K, wide layers are bound by L2->smem operand traffic at 128x128 tiles (64 FLOP/B): a 128x256 tile re-reads the
+  // activation tile half as often (85 FLOP/B).  It needs all 512 TMEM columns (2 accumulator stages), i.e. 1 CTA per SM.
+  {
+    const char* e = getenv("Y11_BN256");
+    const int mode = e ? atoi(e) : 1;
+    const long long k_total = (long long)cin * d->k * d->k;
+    if (mode && cout % 256 == 0 && cin % 64 == 0 && k_total >= 1024) bn = 256;
+  }
   p.BN = bn;
   p.n_tiles = cout / bn;
   p.Cc = (cin % 64 == 0) ? 64 : (cin % 32 == 0) ? 32 : 16;
