@@ -246,7 +246,7 @@ def run_ours(args):
     # ---- e2e through the public API from pinned host frames (H2D + D2H inside the timed region) ----
     def step_e2e(i: int):
         res = eng.predict(host_batches[i % NROT], conf=CONF, iou=IOU, max_det=MAX_DET, imgsz=S, verbose=False)
-        return [r.boxes.data.cpu() for r in res]
+        return [r.cpu().boxes.data for r in res]   # Results.cpu(): host rows of every image
 
     for i in range(min(args.warmup, 3)):
         step_e2e(i)
@@ -330,7 +330,7 @@ def run_ours(args):
                                     f"{sum(b.numel() * b.element_size() for b in net.buffers) / 1e9:.2f} GB of activations per step (> 126 MB L2)"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * S * 3, "d2h_bytes_per_step": d2h,
-                    "api": "YOLO.predict(pinned uint8 [B,H,W,3] host tensor) -> List[Results] -> .cpu()", "steps": e2e_steps},
+                    "api": "YOLO.predict(pinned uint8 [B,H,W,3] host tensor) -> List[Results] -> Results.cpu()", "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps,
             "cuda_graph": use_graph,
             "latency_b1": latency,

@@ -289,6 +289,12 @@ def test_cuda_graph_pipeline_equals_eager_predict(engines):
         for a, b in zip(eager, graphed):
             assert a.orig_shape == b.orig_shape == (360, 640)
             assert torch.equal(a.boxes.data.cpu(), b.boxes.data.cpu())
+            # host mirror fetched with the batch's single D2H == the device rows; .cpu()/.numpy()/indexing use it
+            assert b.boxes.data.is_cuda and not b.cpu().boxes.data.is_cuda
+            assert torch.equal(b.cpu().boxes.data, b.boxes.data.cpu())
+            assert np.array_equal(b.boxes.numpy().data, b.boxes.data.cpu().numpy())
+            if len(b.boxes):
+                assert torch.equal(b.boxes[0].cpu().data, b.boxes.data[:1].cpu())
     other = torch.randint(0, 256, (3, 360, 640, 3), dtype=torch.uint8, generator=g)
     r2 = eng.predict(other.pin_memory(), conf=0.3, iou=0.45, verbose=False)
     e2 = eng.predict([f.numpy() for f in other], conf=0.3, iou=0.45, verbose=False)

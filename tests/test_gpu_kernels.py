@@ -119,6 +119,12 @@ CONV_CASES = [
     (8, 20, 20, 192, 384, 1, 1, True, False),    # cin 192 = 3 chunks, 3 N tiles, (4,4,8) tiling
     (1, 80, 80, 64, 80, 1, 1, False, False),     # cls logits shape: N=80
     (2, 8, 8, 512, 512, 1, 1, True, False),      # 4 N tiles x 8 K chunks
+    # halo mode (3x3 s1, cin in {16,32,64}, maps >= 32x32): cp.async halo tile + un-swizzled shifted descriptors
+    (2, 32, 32, 16, 16, 3, 1, True, False),      # exact 8x16 tiles
+    (1, 48, 40, 32, 16, 3, 1, True, True),       # residual
+    (2, 40, 36, 16, 32, 3, 1, True, False),      # ragged in both directions (clipped stores, zero-filled halo)
+    (1, 32, 64, 64, 32, 3, 1, False, False),     # cin 64 (four K steps per tap), no act
+    (3, 80, 80, 32, 64, 3, 1, True, True),       # many tiles per CTA: ring wrap-around, accumulator double buffering
 ]
 
 
@@ -134,6 +140,9 @@ def test_conv_tcgen05_channel_slices_and_f32_out(ctx):
     close_bf16(got, want)
     got, want = conv_case(ctx, 2, 16, 24, 64, 80, 1, 1, False, out_f32=True, out_off=64)
     assert torch.allclose(got, want, rtol=2e-3, atol=2e-3)
+    # halo mode reading a channel slice of a wider buffer (C3k2's y buffer) and writing into another slice
+    got, want = conv_case(ctx, 2, 32, 40, 32, 16, 3, 1, True, in_off=32, in_extra=16, out_off=16, out_extra=32)
+    close_bf16(got, want)
 
 
 def test_conv_simt_debug_agrees(ctx):
@@ -142,31 +151,32 @@ def test_conv_simt_debug_agrees(ctx):
 
 
 # ------------------------------------------------------------------------------------------- CUDA-core ops
-def test_stem(ctx):
+@pytest.mark.parametrize("H,W", [(64, 96), (32, 608), (96, 640)])   # Wout 48 (ragged tile), 304 (ragged), 320 (two full tiles)
+def test_stem(ctx, H, W):
     for cout in (16, 32, 64, 96):
         g = torch.Generator().manual_seed(cout)
-        x = torch.rand(2, 3, 64, 96, generator=g).to(ctx.dev).to(torch.bfloat16).float()
+        x = torch.rand(2, 3, H, W, generator=g).to(ctx.dev).to(torch.bfloat16).float()
         w = (torch.randn(cout, 3, 3, 3, generator=g) / 27 ** 0.5).to(ctx.dev).to(torch.bfloat16).float()
         b = torch.randn(cout, generator=g).to(ctx.dev)
         want = torch.nn.functional.silu(torch.nn.functional.conv2d(x, w, b, stride=2, padding=1))
         xin = x.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
-        out = torch.zeros((2, 32, 48, cout), dtype=torch.bfloat16, device=ctx.dev)
+        out = torch.zeros((2, H // 2, W // 2, cout), dtype=torch.bfloat16, device=ctx.dev)
         wp = w.permute(0, 2, 3, 1).reshape(cout, 27).to(torch.bfloat16).contiguous()
-        d = cabi.StemDesc(xin.data_ptr(), cabi.View(out.data_ptr(), cout, 0, cout), wp.data_ptr(), b.data_ptr(), 2, 64, 96, 32, 48)
+        d = cabi.StemDesc(xin.data_ptr(), cabi.View(out.data_ptr(), cout, 0, cout), wp.data_ptr(), b.data_ptr(), 2, H, W, H // 2, W // 2)
         p = ctx.plan()
         cabi.check(ctx.lib.y11_plan_add_stem(p, C.byref(d)))
         ctx.run(p)
         close_bf16(out.float().permute(0, 3, 1, 2), want)
 
 
-@pytest.mark.parametrize("act,res", [(True, False), (False, True)])
-def test_dwconv(ctx, act, res):
+@pytest.mark.parametrize("act,res,H,W", [(True, False, 20, 28), (False, True, 20, 28), (True, True, 14, 20), (True, False, 1, 8)])
+def test_dwconv(ctx, act, res, H, W):
     g = torch.Generator().manual_seed(1)
     c = 64
-    x = torch.randn(2, c, 20, 28, generator=g).to(ctx.dev).to(torch.bfloat16).float()
+    x = torch.randn(2, c, H, W, generator=g).to(ctx.dev).to(torch.bfloat16).float()
     w = (torch.randn(c, 1, 3, 3, generator=g) / 3).to(ctx.dev).to(torch.bfloat16).float()
     b = torch.randn(c, generator=g).to(ctx.dev)
-    r = torch.randn(2, c, 20, 28, generator=g).to(ctx.dev).to(torch.bfloat16).float()
+    r = torch.randn(2, c, H, W, generator=g).to(ctx.dev).to(torch.bfloat16).float()
     want = torch.nn.functional.conv2d(x, w, b, padding=1, groups=c)
     if act:
         want = torch.nn.functional.silu(want)
@@ -174,10 +184,10 @@ def test_dwconv(ctx, act, res):
         want = want + r
     xin = nhwc(x, c + 32, 16)
     rb = nhwc(r)
-    out = torch.zeros((2, 20, 28, c), dtype=torch.bfloat16, device=ctx.dev)
+    out = torch.zeros((2, H, W, c), dtype=torch.bfloat16, device=ctx.dev)
     wp = w.view(c, 9).t().to(torch.bfloat16).contiguous()
     d = cabi.DwConvDesc(cabi.View(xin.data_ptr(), c + 32, 16, c), cabi.View(out.data_ptr(), c, 0, c),
-                        cabi.View(rb.data_ptr(), c, 0, c) if res else cabi.NULL_VIEW, wp.data_ptr(), b.data_ptr(), 2, 20, 28, int(act))
+                        cabi.View(rb.data_ptr(), c, 0, c) if res else cabi.NULL_VIEW, wp.data_ptr(), b.data_ptr(), 2, H, W, int(act))
     p = ctx.plan()
     cabi.check(ctx.lib.y11_plan_add_dwconv(p, C.byref(d)))
     ctx.run(p)

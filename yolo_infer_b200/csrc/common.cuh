@@ -161,6 +161,21 @@ __device__ __forceinline__ uint64_t make_umma_desc(uint32_t saddr, uint32_t sbo_
   return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (static_cast<uint64_t>(sbo_bytes >> 4) << 32) |
          (1ull << 46) | (static_cast<uint64_t>(layout_type) << 61);
 }
+// Un-swizzled ("interleaved") K-major descriptor: core matrix = 8 rows x 16 bytes, stored as 128 contiguous bytes;
+// LBO = byte distance between core matrices adjacent in K, SBO = between core matrices adjacent in M/N (8-row groups).
+// The start address only needs 16-byte alignment, which is what lets a conv tap be a plain address offset into a halo tile.
+__device__ __forceinline__ uint64_t make_umma_desc_interleaved(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
+         (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// 16-byte async copy global -> shared (L2 only), zero-filled when src_bytes == 0; completion is reported to an mbarrier by
+// cp_async_mbar_arrive (one pending arrival of the barrier's expected count per calling thread, no increment).
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128.
 __device__ __forceinline__ uint32_t make_idesc_bf16_m128(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
@@ -175,6 +190,16 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- misc -----------------------------------------------------------------------------------
+// One lane of a fully converged warp (warp-uniform branch): lets the compiler keep tcgen05/TMA operands in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));

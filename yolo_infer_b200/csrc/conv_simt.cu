@@ -2,6 +2,9 @@
 //   stem conv (cin=3, K=27), depthwise 3x3 (Detect cls tower, PSA positional encoding), SPPF max-pools,
 //   nearest 2x upsample into a concat slice; plus a naive direct conv used ONLY as a bring-up cross-check of
 //   the tcgen05 kernel (Y11_IMPL_SIMT_DEBUG).  Reference ops replaced: SURVEY.md section 8a rows a7, a9, a11.
+#include <algorithm>
+#include <cstdlib>
+
 #include "ops.h"
 
 using namespace y11;
@@ -49,13 +52,14 @@ int conv_simt_launch(const y11_conv_desc* d, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// stem: 3 -> COUT, 3x3 stride 2 pad 1, +bias, SiLU.  K = 27 (padded to 32) is far too thin for a 128-row tcgen05 tile
-// and the layer is HBM bound (reads the bf16 image once, writes COUT channels per pixel), so it runs on the warp-level
-// tensor-core path: per CTA, three input rows are staged with 16-byte loads, each thread builds the im2col row of one
-// output pixel in shared memory ([pixel][32] bf16, 80-byte pitch = conflict-free fragment loads), every warp does
-// 32 pixels x COUT with mma.sync.m16n8k16 (weights held in registers as B fragments), and the bf16 result goes back
-// through shared memory so that each lane stores 16 contiguous bytes.
-// (v1: CUDA cores, 1 pixel/thread, LDS-issue bound, 0.70 ms for YOLO11s batch 64; v3: register-blocked, 0.91 ms.)
+// stem: 3 -> COUT, 3x3 stride 2 pad 1, +bias, SiLU.  K = 27 is far too thin for a 128-row tcgen05 tile and the layer is
+// HBM bound (reads the bf16 image once, writes COUT channels per pixel), so it runs on the warp-level tensor-core path.
+// v4: one CTA = ROWS output rows x PXB pixels.  The 2*ROWS+1 input rows of the tile are staged ONCE with 16-byte copies
+// (global -> shared, verbatim); there is no im2col pass: K is ordered k = kh*10 + j with j = 0 a zero-weight dummy and
+// j = 1..9 the (kw, c) taps, so that the A-fragment of output pixel p is the 10 consecutive bf16 starting at the EVEN
+// element 6p-4 of input row kh - every mma.sync A register is one aligned 32-bit shared load.  Weights sit in registers as
+// B fragments; each warp owns 32 pixels of a row, stages its bf16 result in a private shared buffer and stores 16 bytes
+// per lane.  (v1: CUDA cores, 0.70 ms for YOLO11s batch 64; v3: one row per CTA + im2col pass through smem, 0.38 ms.)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_bf16_16816_s(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -65,129 +69,152 @@ __device__ __forceinline__ void mma_bf16_16816_s(float (&c)[4], const uint32_t (
 }
 
 template <int COUT>
-__global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int tiles_w) {
-  constexpr int AP = 40;         // im2col / weight row pitch in bf16 (32 + 8 pad)
-  constexpr int OP = COUT + 8;   // output staging pitch in bf16
+__global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int tiles_w, int ROWS) {
+  constexpr int OP = COUT + 8;   // output staging pitch in bf16 (conflict-free 16-byte reads)
+  constexpr int WP = 40;         // weight staging pitch
   extern __shared__ __align__(16) unsigned char s_raw[];
-  const int row_e = (2 * PXB + 1) * 3;               // bf16 elements per staged input row
-  const int row_p = (row_e + 7) & ~7;
-  __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(s_raw);          // [3][row_p]
-  __nv_bfloat16* s_a = s_in + 3 * row_p;                                 // [PXB][AP]
-  __nv_bfloat16* s_w = s_a + PXB * AP;                                   // [COUT][AP]
-  __nv_bfloat16* s_o = s_w + COUT * AP;                                  // [PXB][OP]
-  float* s_b = reinterpret_cast<float*>(s_o + PXB * OP);                 // [COUT]
+  const int row_p = 6 * PXB + 16;                    // bf16 per staged input row: [8 left pad | 6*PXB | 8 slack]
+  const int n_rows = 2 * ROWS + 1;
+  __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(s_raw);          // [n_rows][row_p]
+  __nv_bfloat16* s_o = s_in + n_rows * row_p;                            // [PXB][OP] (also weight staging at start)
+  const int row_blocks = d.Hout / ROWS;
   const int tile = blockIdx.x % tiles_w;
-  const int oh = (blockIdx.x / tiles_w) % d.Hout;
-  const int n = blockIdx.x / (tiles_w * d.Hout);
+  const int oh0 = ((blockIdx.x / tiles_w) % row_blocks) * ROWS;
+  const int n = blockIdx.x / (tiles_w * row_blocks);
   const int ow0 = tile * PXB;
   const int nt = blockDim.x, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
-  // weights [COUT][27] -> [COUT][AP] (k >= 27 zero), bias
-  const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(d.w);
-  for (int i = tid; i < COUT * AP; i += nt) {
-    const int co = i / AP, k = i % AP;
-    s_w[i] = k < 27 ? w[co * 27 + k] : zero;
+  // weights [COUT][27] -> s_w[COUT][32] in the k = kh*10 + j order (j = 0 and k >= 30: zero) -> B fragments in registers
+  {
+    __nv_bfloat16* s_w = s_o;
+    const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(d.w);
+    for (int i = tid; i < COUT * 32; i += nt) {
+      const int co = i >> 5, k = i & 31, kh = k / 10, j = k - kh * 10;
+      s_w[co * WP + k] = (kh < 3 && j >= 1) ? w[co * 27 + kh * 9 + j - 1] : zero;
+    }
   }
-  for (int i = tid; i < COUT; i += nt) s_b[i] = d.bias[i];
-  for (int i = tid; i < 3 * row_p; i += nt) s_in[i] = zero;
+  __syncthreads();
+  uint32_t bw[COUT / 8][2][2];
+  float bias[COUT / 8][2];
+#pragma unroll
+  for (int nb = 0; nb < COUT / 8; ++nb) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const __nv_bfloat16* wp = s_o + (nb * 8 + g) * WP + ks * 16 + 2 * t;
+      bw[nb][ks][0] = *reinterpret_cast<const uint32_t*>(wp);
+      bw[nb][ks][1] = *reinterpret_cast<const uint32_t*>(wp + 8);
+    }
+    bias[nb][0] = __ldg(d.bias + nb * 8 + 2 * t);
+    bias[nb][1] = __ldg(d.bias + nb * 8 + 2 * t + 1);
+  }
   pdl_wait();   // weights/bias above are constants; the image below is the previous kernel's output
   pdl_trigger();
-  __syncthreads();
-  // stage the three input rows (16-byte global loads; rows are 16-byte aligned because Win % 8 == 0)
-  const int iw0 = 2 * ow0 - 1;
-  const int e_lo = max(iw0, 0) * 3, e_hi = min(iw0 + 2 * PXB + 1, d.Win) * 3;
-  const int v_lo = e_lo / 8, v_hi = (e_hi + 7) / 8;
-  for (int r = 0; r < 3; ++r) {
-    const int ih = 2 * oh + r - 1;
-    if (ih < 0 || ih >= d.Hin) continue;
-    const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(d.in) + ((size_t)n * d.Hin + ih) * d.Win * 3);
-    __nv_bfloat16* dst = s_in + r * row_p - iw0 * 3;
-    for (int v = v_lo + tid; v < v_hi; v += nt) {
-      const uint4 u = __ldg(rp + v);
-      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u);
+  __syncthreads();  // s_w (aliasing s_o) fully consumed
+  // stage input rows 2*oh0-1 .. 2*oh0+2*ROWS-1: smem element 8 + e  <-  row element (6*ow0 + e), e in [-8, 6*PXB)
+  {
+    const int vec_per_row = (6 * PXB) / 8 + 1;       // one leading vector (elements -8..-1) + the segment itself
+    const int total = n_rows * vec_per_row;
+    const int row_e = 3 * d.Win;                     // bf16 per image row (multiple of 8)
+    const __nv_bfloat16* img = static_cast<const __nv_bfloat16*>(d.in) + (size_t)n * d.Hin * row_e;
+    // unconditional loads from clamped addresses, four in flight per thread, zeroed afterwards (see dwconv_kernel)
+    for (int i0 = tid; i0 < total; i0 += 4 * nt) {
+      uint4 u[4];
+      bool ok[4];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int e = v * 8 + t;
-        if (e >= e_lo && e < e_hi) dst[e] = h[t];
+      for (int q = 0; q < 4; ++q) {
+        const int i = min(i0 + q * nt, total - 1);
+        const int r = i / vec_per_row, v = i - r * vec_per_row;
+        const int ih = 2 * oh0 - 1 + r;
+        const int e0 = 6 * ow0 - 8 + 8 * v;          // first row element of this vector (a multiple of 8)
+        ok[q] = ih >= 0 && ih < d.Hin && e0 >= 0 && e0 < row_e;  // a vector is entirely inside or outside the row
+        u[q] = ldg_nc_v4(img + (size_t)min(max(ih, 0), d.Hin - 1) * row_e + min(max(e0, 0), row_e - 8));
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q * nt;
+        if (i < total) {
+          const int r = i / vec_per_row, v = i - r * vec_per_row;
+          *reinterpret_cast<uint4*>(s_in + r * row_p + 8 * v) = ok[q] ? u[q] : make_uint4(0, 0, 0, 0);
+        }
       }
     }
   }
   __syncthreads();
-  // im2col: thread p builds A[p][0..31], k = kh*9 + kw*3 + c  <-  in[kh][(2p+kw)*3 + c] = in[kh][6p + (k - 9kh)]
-  if (tid < PXB) {
-    __nv_bfloat16* ar = s_a + tid * AP;
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const __nv_bfloat16* src = s_in + kh * row_p + 6 * tid;
-#pragma unroll
-      for (int j = 0; j < 9; ++j) ar[kh * 9 + j] = src[j];
-    }
-#pragma unroll
-    for (int k = 27; k < 32; ++k) ar[k] = zero;
-  }
-  __syncthreads();
-  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   if (warp * 32 >= PXB) return;
-  // B fragments (weights) in registers: B[k][n] = W[n][k]
-  uint32_t bw[COUT / 8][2][2];
+  // per-lane offsets (bf16 elements, relative to pixel p's window start = smem element 4 + 6p of row kh=0) of the four
+  // k-pairs this lane feeds into the two K=16 steps; k >= 30 has zero weights and re-reads k = 28 (finite data)
+  int koff[2][2];
 #pragma unroll
-  for (int nb = 0; nb < COUT / 8; ++nb)
+  for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const __nv_bfloat16* wp = s_w + (nb * 8 + g) * AP + ks * 16 + 2 * t;
-      bw[nb][ks][0] = *reinterpret_cast<const uint32_t*>(wp);
-      bw[nb][ks][1] = *reinterpret_cast<const uint32_t*>(wp + 8);
+    for (int hh = 0; hh < 2; ++hh) {
+      int k = ks * 16 + hh * 8 + 2 * t;
+      if (k >= 30) k = 28;
+      const int kh = k / 10;
+      koff[ks][hh] = kh * row_p + (k - kh * 10) + 4;
     }
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    const int p0 = warp * 32 + mt * 16;
-    uint32_t af[2][4];
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const __nv_bfloat16* ap = s_a + (p0 + g) * AP + ks * 16 + 2 * t;
-      af[ks][0] = *reinterpret_cast<const uint32_t*>(ap);
-      af[ks][1] = *reinterpret_cast<const uint32_t*>(ap + 8 * AP);
-      af[ks][2] = *reinterpret_cast<const uint32_t*>(ap + 8);
-      af[ks][3] = *reinterpret_cast<const uint32_t*>(ap + 8 * AP + 8);
-    }
-#pragma unroll
-    for (int nb = 0; nb < COUT / 8; ++nb) {
-      float c[4];
-      const float b0 = s_b[nb * 8 + 2 * t], b1 = s_b[nb * 8 + 2 * t + 1];
-      c[0] = b0; c[1] = b1; c[2] = b0; c[3] = b1;
-      mma_bf16_16816_s(c, af[0], bw[nb][0][0], bw[nb][0][1]);
-      mma_bf16_16816_s(c, af[1], bw[nb][1][0], bw[nb][1][1]);
-      *reinterpret_cast<uint32_t*>(s_o + (p0 + g) * OP + nb * 8 + 2 * t) = pack_bf16x2(silu(c[0]), silu(c[1]));
-      *reinterpret_cast<uint32_t*>(s_o + (p0 + g + 8) * OP + nb * 8 + 2 * t) = pack_bf16x2(silu(c[2]), silu(c[3]));
-    }
-  }
-  __syncwarp();
-  // coalesced write-out of this warp's 32 pixels: 16 bytes per lane, consecutive lanes -> consecutive bytes of a pixel row
   constexpr int VPP = COUT / 8;  // 16-byte vectors per pixel
-  const size_t pix0 = ((size_t)n * d.Hout + oh) * d.Wout + ow0 + warp * 32;
+  __nv_bfloat16* so = s_o + warp * 32 * OP;
   __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(d.out.ptr) + d.out.c_off;
-  for (int i = lane; i < 32 * VPP; i += 32) {
-    const int px = i / VPP, v = i % VPP;
-    if (ow0 + warp * 32 + px < d.Wout)
-      *reinterpret_cast<uint4*>(ob + (pix0 + px) * d.out.c_total + v * 8) = *reinterpret_cast<const uint4*>(s_o + (warp * 32 + px) * OP + v * 8);
+  for (int r = 0; r < ROWS; ++r) {
+    const __nv_bfloat16* base = s_in + 2 * r * row_p;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int p0 = warp * 32 + mt * 16 + g;
+      uint32_t af[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        af[ks][0] = *reinterpret_cast<const uint32_t*>(base + 6 * p0 + koff[ks][0]);
+        af[ks][1] = *reinterpret_cast<const uint32_t*>(base + 6 * (p0 + 8) + koff[ks][0]);
+        af[ks][2] = *reinterpret_cast<const uint32_t*>(base + 6 * p0 + koff[ks][1]);
+        af[ks][3] = *reinterpret_cast<const uint32_t*>(base + 6 * (p0 + 8) + koff[ks][1]);
+      }
+#pragma unroll
+      for (int nb = 0; nb < COUT / 8; ++nb) {
+        float c[4] = {bias[nb][0], bias[nb][1], bias[nb][0], bias[nb][1]};
+        mma_bf16_16816_s(c, af[0], bw[nb][0][0], bw[nb][0][1]);
+        mma_bf16_16816_s(c, af[1], bw[nb][1][0], bw[nb][1][1]);
+        *reinterpret_cast<uint32_t*>(so + (mt * 16 + g) * OP + nb * 8 + 2 * t) = pack_bf16x2(silu(c[0]), silu(c[1]));
+        *reinterpret_cast<uint32_t*>(so + (mt * 16 + g + 8) * OP + nb * 8 + 2 * t) = pack_bf16x2(silu(c[2]), silu(c[3]));
+      }
+    }
+    __syncwarp();
+    // coalesced write-out of this warp's 32 pixels: 16 bytes per lane, consecutive lanes -> consecutive bytes of a pixel row
+    const size_t pix0 = ((size_t)n * d.Hout + oh0 + r) * d.Wout + ow0 + warp * 32;
+#pragma unroll
+    for (int i = lane; i < 32 * VPP; i += 32) {
+      const int px = i / VPP, v = i % VPP;
+      if (ow0 + warp * 32 + px < d.Wout)
+        *reinterpret_cast<uint4*>(ob + (pix0 + px) * d.out.c_total + v * 8) = *reinterpret_cast<const uint4*>(so + px * OP + v * 8);
+    }
+    __syncwarp();
   }
 }
 
 template <int COUT>
 static int stem_launch_t(const y11_stem_desc* d, cudaStream_t s) {
-  Y11_REQUIRE(d->Win % 8 == 0, "stem: input width must be a multiple of 8 (got %d)", d->Win);
-  int PXB = 128;
-  for (int c : {160, 128, 96, 64, 32})
-    if (d->Wout % c == 0) { PXB = c; break; }
+  Y11_REQUIRE(d->Win % 8 == 0 && d->Hin % 2 == 0, "stem: input must be even-sized with width a multiple of 8 (got %dx%d)", d->Hin, d->Win);
+  Y11_REQUIRE(d->Wout * 2 == d->Win && d->Hout * 2 == d->Hin, "stem: output must be half the input size");
+  int PXB = 32, best_waste = 1 << 30;
+  for (int c : {160, 128, 96, 64, 32}) {  // fewest wasted pixels in the last tile, then the widest tile
+    const int waste = y11_ceil_div(d->Wout, c) * c - d->Wout;
+    if (waste < best_waste) { best_waste = waste; PXB = c; }
+  }
+  int ROWS = 1, max_rows = 8;
+  if (const char* e = getenv("Y11_STEM_ROWS")) max_rows = std::max(1, atoi(e));
+  for (int r : {8, 4, 2})
+    if (r <= max_rows && d->Hout % r == 0) { ROWS = r; break; }
   const int tiles_w = y11_ceil_div(d->Wout, PXB);
-  const int row_p = (((2 * PXB + 1) * 3) + 7) & ~7;
-  const size_t smem = (size_t)(3 * row_p + PXB * 40 + COUT * 40 + PXB * (COUT + 8)) * 2 + COUT * 4;
+  const int row_p = 6 * PXB + 16;
+  const size_t smem = (size_t)((2 * ROWS + 1) * row_p + std::max(PXB * (COUT + 8), COUT * 40)) * 2;
   static bool attr_set = false;
   if (!attr_set) {
     Y11_CHECK_CUDA(cudaFuncSetAttribute(stem_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
   }
-  Y11_CHECK_CUDA(y11_launch_pdl(stem_kernel<COUT>, dim3((unsigned)(tiles_w * d->Hout * d->B)), dim3(PXB), smem, s, *d, PXB, tiles_w));
+  Y11_CHECK_CUDA(y11_launch_pdl(stem_kernel<COUT>, dim3((unsigned)(tiles_w * (d->Hout / ROWS) * d->B)), dim3(PXB), smem, s, *d, PXB,
+                                tiles_w, ROWS));
   return 0;
 }
 
@@ -202,69 +229,101 @@ int stem_launch(const y11_stem_desc* d, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// depthwise 3x3 stride 1 pad 1: one thread = one pixel x 8 channels (16-byte vectors)
+// depthwise 3x3 stride 1 pad 1.  v2: one thread = 4 channels x one column x a vertical strip of R output rows.
+// The 9x4 weights live in registers as fp32; every input row of the strip is loaded once (3 x 8-byte loads: x-1, x, x+1)
+// and feeds up to three output rows, so the load-store unit sees 3(R+2)/R + 1 accesses per output instead of the
+// 9 inputs + 9 weights + 1 store of v1 (one thread per pixel x 8 channels, 1.4 TB/s: L1-wavefront bound).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dwconv_kernel(y11_dwconv_desc d) {
-  pdl_wait();
-  pdl_trigger();
-  const int groups = d.in.c / 8;
-  const size_t total = (size_t)d.B * d.H * d.W * groups;
+template <int R>
+__global__ void __launch_bounds__(256) dwconv_kernel(y11_dwconv_desc d, int strips) {
+  const int groups = d.in.c / 4;
+  const size_t total = (size_t)d.B * strips * d.W * groups;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int g = idx % groups;
-  const size_t pix = idx / groups;
-  const int x = pix % d.W, y = (pix / d.W) % d.H;
-  const __nv_bfloat16* in = static_cast<const __nv_bfloat16*>(d.in.ptr) + d.in.c_off + g * 8;
-  const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(d.w) + g * 8;
-  float acc[8];
+  size_t rest = idx / groups;
+  const int x = rest % d.W; rest /= d.W;
+  const int y0 = (int)(rest % strips) * R;
+  const size_t n = rest / strips;
+  // constants first (they do not depend on the previous kernel): weights [9][c] tap-major, bias
+  float w[9][4], acc[R][4];
   {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(d.bias + g * 8));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(d.bias + g * 8) + 1);
-    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
-    acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(d.w) + g * 4;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(wp + (size_t)tap * d.in.c));
+      w[tap][0] = bf16_lo(u.x); w[tap][1] = bf16_hi(u.x); w[tap][2] = bf16_lo(u.y); w[tap][3] = bf16_hi(u.y);
+    }
+    const float4 b = __ldg(reinterpret_cast<const float4*>(d.bias + g * 4));
+#pragma unroll
+    for (int r = 0; r < R; ++r) { acc[r][0] = b.x; acc[r][1] = b.y; acc[r][2] = b.z; acc[r][3] = b.w; }
+  }
+  pdl_wait();
+  pdl_trigger();
+  const __nv_bfloat16* in = static_cast<const __nv_bfloat16*>(d.in.ptr) + d.in.c_off + g * 4;
+  const size_t img = n * d.H;
+  // All 3(R+2) loads are issued unconditionally from CLAMPED addresses and zeroed afterwards: guarded loads would be
+  // serialised row by row (the compiler cannot hoist a load above the branch that protects it), which made v1 and the
+  // first strip version latency bound at 1.4 TB/s.
+  const int xl = x > 0 ? -1 : 0, xr = x + 1 < d.W ? 1 : 0;
+  uint2 v[R + 2][3];
+#pragma unroll
+  for (int r = 0; r < R + 2; ++r) {
+    const int iy = min(max(y0 + r - 1, 0), d.H - 1);
+    const __nv_bfloat16* rp = in + ((img + iy) * d.W + x) * d.in.c_total;
+    v[r][0] = *reinterpret_cast<const uint2*>(rp + xl * d.in.c_total);
+    v[r][1] = *reinterpret_cast<const uint2*>(rp);
+    v[r][2] = *reinterpret_cast<const uint2*>(rp + xr * d.in.c_total);
   }
 #pragma unroll
-  for (int kh = 0; kh < 3; ++kh) {
-    const int iy = y + kh - 1;
-    if (iy < 0 || iy >= d.H) continue;
+  for (int r = 0; r < R + 2; ++r) {
+    const int iy = y0 + r - 1;
+    const bool row_ok = iy >= 0 && iy < d.H;
 #pragma unroll
     for (int kw = 0; kw < 3; ++kw) {
-      const int ix = x + kw - 1;
-      if (ix < 0 || ix >= d.W) continue;
-      const size_t ipix = pix + (size_t)(kh - 1) * d.W + (kw - 1);
-      const uint4 v = *reinterpret_cast<const uint4*>(in + ipix * d.in.c_total);
-      const uint4 ww = __ldg(reinterpret_cast<const uint4*>(w + (size_t)(kh * 3 + kw) * d.in.c));
-      const uint32_t vv[4] = {v.x, v.y, v.z, v.w}, wv[4] = {ww.x, ww.y, ww.z, ww.w};
+      const bool ok = row_ok && (kw == 1 || (kw == 0 ? xl != 0 : xr != 0));
+      const uint32_t vx = ok ? v[r][kw].x : 0u, vy = ok ? v[r][kw].y : 0u;
+      const float f0 = bf16_lo(vx), f1 = bf16_hi(vx), f2 = bf16_lo(vy), f3 = bf16_hi(vy);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc[2 * i] = fmaf(bf16_lo(vv[i]), bf16_lo(wv[i]), acc[2 * i]);
-        acc[2 * i + 1] = fmaf(bf16_hi(vv[i]), bf16_hi(wv[i]), acc[2 * i + 1]);
+      for (int kh = 0; kh < 3; ++kh) {
+        const int orow = r - kh;  // input row y0+r-1 is tap kh of output row y0+r-kh
+        if (orow >= 0 && orow < R) {
+          acc[orow][0] = fmaf(f0, w[kh * 3 + kw][0], acc[orow][0]);
+          acc[orow][1] = fmaf(f1, w[kh * 3 + kw][1], acc[orow][1]);
+          acc[orow][2] = fmaf(f2, w[kh * 3 + kw][2], acc[orow][2]);
+          acc[orow][3] = fmaf(f3, w[kh * 3 + kw][3], acc[orow][3]);
+        }
       }
     }
   }
-  if (d.act == Y11_ACT_SILU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = silu(acc[i]);
-  }
-  if (d.res.ptr) {
-    const uint4 r = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(d.res.ptr) + pix * d.res.c_total + d.res.c_off + g * 8);
-    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+  for (int r = 0; r < R; ++r) {
+    const int y = y0 + r;
+    if (y >= d.H) break;
+    const size_t pix = (img + y) * d.W + x;
+    float o[4] = {acc[r][0], acc[r][1], acc[r][2], acc[r][3]};
+    if (d.act == Y11_ACT_SILU) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      acc[2 * i] += bf16_lo(rr[i]);
-      acc[2 * i + 1] += bf16_hi(rr[i]);
+      for (int i = 0; i < 4; ++i) o[i] = silu(o[i]);
     }
+    if (d.res.ptr) {
+      const uint2 rr = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(d.res.ptr) + pix * d.res.c_total + d.res.c_off + g * 4);
+      o[0] += bf16_lo(rr.x); o[1] += bf16_hi(rr.x); o[2] += bf16_lo(rr.y); o[3] += bf16_hi(rr.y);
+    }
+    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(d.out.ptr) + pix * d.out.c_total + d.out.c_off + g * 4) =
+        make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
   }
-  *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(d.out.ptr) + pix * d.out.c_total + d.out.c_off + g * 8) =
-      make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
 }
 
 int dwconv_launch(const y11_dwconv_desc* d, cudaStream_t s) {
   Y11_REQUIRE(d->in.c % 8 == 0 && d->in.c_off % 8 == 0 && d->in.c_total % 8 == 0 && d->out.c_off % 8 == 0 &&
                   d->out.c_total % 8 == 0,
               "dwconv: views must be 16-byte aligned (c=%d)", d->in.c);
-  const size_t total = (size_t)d->B * d->H * d->W * (d->in.c / 8);
-  Y11_CHECK_CUDA(y11_launch_pdl(dwconv_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, *d));
+  Y11_REQUIRE(!d->res.ptr || (d->res.c_off % 4 == 0 && d->res.c_total % 4 == 0), "dwconv: residual view alignment");
+  constexpr int R = 4;
+  const int strips = y11_ceil_div(d->H, R);
+  const size_t total = (size_t)d->B * strips * d->W * (d->in.c / 4);
+  Y11_CHECK_CUDA(y11_launch_pdl(dwconv_kernel<R>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, *d, strips));
   return 0;
 }
 

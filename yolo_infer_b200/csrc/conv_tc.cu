@@ -68,18 +68,22 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   const uint32_t empty_bar = smem_base + 8 * kMaxStages;  // kMaxStages x 8 B
   const uint32_t accf_bar = smem_base + 16 * kMaxStages;  // 2 x 8 B  accumulator full  (MMA -> epilogue)
   const uint32_t acce_bar = accf_bar + 16;                // 2 x 8 B  accumulator empty (epilogue -> MMA)
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_raw + 16 * kMaxStages + 32);
-  const uint32_t stage_bytes = p.a_slot + p.b_slot;
-  const uint32_t staging_base = tiles_base + p.stages * stage_bytes;  // 2 groups x 2 buffers x stg_bytes
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_raw + 16 * kMaxStages + 48);
+  // TMA mode : stages x [A tap box | B tap tile];  halo mode: [resident B, all taps] then stages x [A halo tile]
+  const uint32_t stage_bytes = p.halo ? p.a_slot : p.a_slot + p.b_slot;
+  const uint32_t ring_base = tiles_base + p.b_res_bytes;
+  const uint32_t staging_base = ring_base + p.stages * stage_bytes;  // 2 buffers x stg_bytes
+  const uint32_t bres_bar = acce_bar + 16;               // halo mode: resident weights landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(full_bar + 8 * s, p.halo ? 32 : 1);   // halo mode: every producer lane reports its own cp.async copies
       mbar_init(empty_bar + 8 * s, 1);
     }
+    mbar_init(bres_bar, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(accf_bar + 8 * a, 1);
       mbar_init(acce_bar + 8 * a, kEpiWarps);
@@ -112,64 +116,124 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   const int k_iters = p.taps * p.chunks_per_tap;
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ TMA producer
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        uint32_t t = tile, q;
-        q = fast_div(t, p.mg_ntiles); const int nt = t - q * p.n_tiles; t = q;
-        q = fast_div(t, p.mg_tw); const int w0 = (t - q * p.tiles_w) * p.Tw; t = q;
-        q = fast_div(t, p.mg_th); const int h0 = (t - q * p.tiles_h) * p.Th; t = q;
-        const int n0 = t * p.Tn;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          int mi = 0, cw, ch;
-          if (p.ksize == 1) {
-            cw = w0; ch = h0;
-          } else if (p.stride == 1) {
-            cw = w0 + tap % 3 - 1; ch = h0 + tap / 3 - 1;
-          } else {
-            const int kh = tap / 3, kw = tap % 3;
-            mi = ((kh == 1) ? 0 : 2) + ((kw == 1) ? 0 : 1);  // input row 2*oy+kh-1 has parity (kh != 1)
-            cw = w0 - (kw == 0); ch = h0 - (kh == 0);
+  if (warp == 0 && p.halo) {
+    // ------------------------------------------------------------------ halo producer (whole warp, cp.async)
+    if (lane == 0) {  // weights of all taps: loaded once, stay resident
+      mbar_expect_tx(bres_bar, (uint32_t)(p.taps * p.BN) * (uint32_t)(p.Cc * 2));
+      for (int tap = 0; tap < p.taps; ++tap) tma_load_2d(tiles_base + tap * p.b_slot, &maps.b, bres_bar, tap * p.cin, 0);
+    }
+    constexpr int HWp = 10, HP = 180;  // halo mode fixes Tw = 8, Th = 16: constant divisors, 180 halo positions
+    const int ncg = p.cin >> 3;
+    const __nv_bfloat16* in = static_cast<const __nv_bfloat16*>(p.in);
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      uint32_t t = tile, q;
+      q = fast_div(t, p.mg_tw); const int w0 = (t - q * p.tiles_w) * p.Tw; t = q;
+      q = fast_div(t, p.mg_th); const int h0 = (t - q * p.tiles_h) * p.Th; t = q;
+      const __nv_bfloat16* img = in + (size_t)t * p.Hin * p.Win * p.in_ct;
+      mbar_wait(empty_bar + 8 * stage, phase ^ 1, p.err_flag, 101);
+      const uint32_t dst = ring_base + stage * stage_bytes;
+      // lanes walk the halo positions; each position copies its cin/8 16-byte channel groups into their planes
+      for (int pos = lane; pos < HP; pos += 32) {
+        const int y = pos / HWp, x = pos - y * HWp;
+        const int ih = h0 + y - 1, iw = w0 + x - 1;
+        const bool ok = ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win;  // outside the image: zero fill == conv padding
+        const __nv_bfloat16* src = img + ((size_t)(ok ? ih : 0) * p.Win + (ok ? iw : 0)) * p.in_ct;
+        const uint32_t d0 = dst + pos * 16, nbytes = ok ? 16u : 0u;
+#pragma unroll 4
+        for (int cg = 0; cg < ncg; ++cg) cp_async_16(d0 + cg * (HP * 16), src + cg * 8, nbytes);
+      }
+      cp_async_mbar_arrive(full_bar + 8 * stage);
+      if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (converged warp, one elected lane issues)
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      uint32_t t = tile, q;
+      q = fast_div(t, p.mg_ntiles); const int nt = t - q * p.n_tiles; t = q;
+      q = fast_div(t, p.mg_tw); const int w0 = (t - q * p.tiles_w) * p.Tw; t = q;
+      q = fast_div(t, p.mg_th); const int h0 = (t - q * p.tiles_h) * p.Th; t = q;
+      const int n0 = t * p.Tn;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        int mi = 0, cw, ch;
+        if (p.ksize == 1) {
+          cw = w0; ch = h0;
+        } else if (p.stride == 1) {
+          cw = w0 + tap % 3 - 1; ch = h0 + tap / 3 - 1;
+        } else {
+          const int kh = tap / 3, kw = tap % 3;
+          mi = ((kh == 1) ? 0 : 2) + ((kw == 1) ? 0 : 1);  // input row 2*oy+kh-1 has parity (kh != 1)
+          cw = w0 - (kw == 0); ch = h0 - (kh == 0);
+        }
+        for (int c = 0; c < p.chunks_per_tap; ++c) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1, p.err_flag, 101);
+          if (elect_one()) {
+            const uint32_t fb = full_bar + 8 * stage;
+            const uint32_t a_dst = ring_base + stage * stage_bytes;
+            mbar_expect_tx(fb, p.tx_bytes);
+            tma_load_4d(a_dst, &maps.a[mi], fb, c * p.Cc, cw, ch, n0);
+            tma_load_2d(a_dst + p.a_slot, &maps.b, fb, tap * p.cin + c * p.Cc, nt * p.BN);
           }
-          for (int c = 0; c < p.chunks_per_tap; ++c, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1;
-            mbar_wait(empty_bar + 8 * s, ph ^ 1, p.err_flag, 101);
-            mbar_expect_tx(full_bar + 8 * s, p.tx_bytes);
-            const uint32_t a_dst = tiles_base + s * stage_bytes;
-            tma_load_4d(a_dst, &maps.a[mi], full_bar + 8 * s, c * p.Cc, cw, ch, n0);
-            tma_load_2d(a_dst + p.a_slot, &maps.b, full_bar + 8 * s, tap * p.cin + c * p.Cc, nt * p.BN);
-          }
+          __syncwarp();
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer
-      const uint32_t idesc = make_idesc_bf16_m128(p.BN);
-      const int kk_n = p.Cc / 16;
-      int it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-        const int as = ti & 1;
-        const uint32_t aph = (ti >> 1) & 1;
-        mbar_wait(acce_bar + 8 * as, aph ^ 1, p.err_flag, 104);  // epilogue has drained this accumulator stage
+    // ------------------------------------------------------------------ MMA issuer
+    // The whole warp walks the loop converged and ONE elected lane issues tcgen05.mma / tcgen05.commit.  (The first
+    // version ran the loop inside `if (lane == 0)`: in a divergent region the compiler cannot prove operands warp-uniform
+    // and wrapped every UTCHMMA in an ELECT/R2UR/BRA.U.ANY sequence - ~50 instructions and ~500 cycles per MMA, which
+    // made the issue thread the bottleneck of every short-K layer: ncu source view, profiles/r01c_summary.md.)
+    const uint32_t idesc = make_idesc_bf16_m128(p.BN);
+    const int kk_n = p.Cc / 16;
+    uint32_t stage = 0, phase = 0;  // ring position, advanced incrementally (no div/mod per stage)
+    int ti = 0;
+    if (p.halo) mbar_wait(bres_bar, 0, p.err_flag, 105);
+    const uint64_t bd_res = make_umma_desc(tiles_base, p.sbo, p.layout_type);
+    const uint32_t b_step = p.b_slot >> 4, k_step = (2u * p.a_lbo) >> 4;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int as = ti & 1;
+      mbar_wait(acce_bar + 8 * as, ((ti >> 1) & 1) ^ 1, p.err_flag, 104);  // epilogue has drained this accumulator stage
+      const uint32_t tmem_acc = tmem_base + as * acc_stride;
+      if (p.halo) {
+        mbar_wait(full_bar + 8 * stage, phase, p.err_flag, 102);
+        fence_async_smem();  // cp.async wrote through the generic proxy; the MMA reads through the async proxy
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + as * acc_stride;
-        for (int k = 0; k < k_iters; ++k, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(full_bar + 8 * s, ph, p.err_flag, 102);
-          tc_fence_after();
-          const uint32_t a_src = tiles_base + s * stage_bytes;
-          const uint64_t ad = make_umma_desc(a_src, p.sbo, p.layout_type);
-          const uint64_t bd = make_umma_desc(a_src + p.a_slot, p.sbo, p.layout_type);
-          for (int kk = 0; kk < kk_n; ++kk)  // +32 B (= 16 bf16 of K) inside the swizzle row per UMMA
-            umma_bf16(tmem_acc, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0);
-          umma_commit(empty_bar + 8 * s);  // frees the smem slot once these MMAs retire
+        if (elect_one()) {
+          const uint64_t ad0 = make_umma_desc_interleaved(ring_base + stage * stage_bytes, p.a_lbo, p.a_sbo);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            // tap (kh, kw) = the halo tile shifted by kh rows of (Tw+2) pixels and kw pixels: a 16-byte-unit address offset
+            const uint64_t ad = ad0 + (uint32_t)((tap / 3) * 10 + tap % 3);
+            const uint64_t bd = bd_res + (uint32_t)tap * b_step;
+            umma_bf16(tmem_acc, ad, bd, idesc, tap != 0);
+            for (int kk = 1; kk < kk_n; ++kk)  // next 16 channels = two 8-channel planes further / +32 B in the weight row
+              umma_bf16(tmem_acc, ad + kk * k_step, bd + 2 * kk, idesc, 1);
+          }
+          umma_commit(empty_bar + 8 * stage);
+          umma_commit(accf_bar + 8 * as);
         }
-        umma_commit(accf_bar + 8 * as);  // accumulator complete
+        __syncwarp();
+        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+      } else {
+        for (int k = 0; k < k_iters; ++k) {
+          mbar_wait(full_bar + 8 * stage, phase, p.err_flag, 102);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_src = ring_base + stage * stage_bytes;
+            const uint64_t ad = make_umma_desc(a_src, p.sbo, p.layout_type);
+            const uint64_t bd = make_umma_desc(a_src + p.a_slot, p.sbo, p.layout_type);
+            umma_bf16(tmem_acc, ad, bd, idesc, k != 0);
+            for (int kk = 1; kk < kk_n; ++kk)  // +32 B (= 16 bf16 of K) inside the swizzle row per UMMA
+              umma_bf16(tmem_acc, ad + 2 * kk, bd + 2 * kk, idesc, 1);
+            umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs retire
+            if (k == k_iters - 1) umma_commit(accf_bar + 8 * as);  // accumulator complete
+          }
+          __syncwarp();
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else {
@@ -317,7 +381,19 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
 
   std::memset(L, 0, sizeof(*L));
   ConvTcParams& p = L->p;
-  pick_tile(d->Wout, d->Hout, d->B, &p.Tw, &p.Th, &p.Tn);
+  // Halo mode for 3x3 stride-1 layers with few input channels on large maps.  The tap-by-tap TMA path moves one
+  // 2*cin-byte row per pixel per tap, and the TMA unit retires only ~1 such row per 3 cycles per SM regardless of its
+  // length (measured: 16->16, 32->16 and 16->32 channel 3x3 layers at 160x160 all take the same 0.13-0.18 ms); copying the
+  // halo once needs 1.4 rows of 16 bytes x cin/8 per pixel instead of 9 rows, through the LSU (cp.async), not the TMA unit.
+  {
+    const char* e = getenv("Y11_HALO");
+    const int mode = e ? atoi(e) : 1;
+    const size_t wbytes = (size_t)9 * cin * cout * 2;
+    p.halo = mode && d->k == 3 && d->stride == 1 && (cin == 16 || cin == 32 || cin == 64) && cout <= 128 &&
+             wbytes <= 40 * 1024 && d->Hout >= 32 && d->Wout >= 32;
+  }
+  if (p.halo) { p.Tw = 8; p.Th = 16; p.Tn = 1; }
+  else pick_tile(d->Wout, d->Hout, d->B, &p.Tw, &p.Th, &p.Tn);
   p.tiles_w = y11_ceil_div(d->Wout, p.Tw);
   p.tiles_h = y11_ceil_div(d->Hout, p.Th);
   p.tiles_n = y11_ceil_div(d->B, p.Tn);
@@ -333,6 +409,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
     const long long k_total = (long long)cin * d->k * d->k;
     if (mode && cout % 256 == 0 && cin % 64 == 0 && k_total >= 1024) bn = 256;
   }
+  if (p.halo) bn = cout;
   p.BN = bn;
   p.n_tiles = cout / bn;
   p.Cc = (cin % 64 == 0) ? 64 : (cin % 32 == 0) ? 32 : 16;
@@ -349,9 +426,19 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
   p.a_slot = 128u * swz_bytes;
   p.b_slot = ((uint32_t)bn * swz_bytes + 1023u) & ~1023u;
+  if (p.halo) {
+    const uint32_t hp = (uint32_t)(p.Tw + 2) * (p.Th + 2);
+    p.a_slot = (hp * (uint32_t)cin * 2u + 1023u) & ~1023u;
+    p.a_lbo = hp * 16u;
+    p.a_sbo = (uint32_t)(p.Tw + 2) * 16u;
+    if (const char* e = getenv("Y11_HALO_SWAP")) if (atoi(e)) std::swap(p.a_lbo, p.a_sbo);
+    p.b_res_bytes = 9u * p.b_slot;
+    p.in = static_cast<const __nv_bfloat16*>(d->in.ptr) + d->in.c_off;
+    p.in_ct = d->in.c_total; p.Hin = d->Hin; p.Win = d->Win;
+  }
   p.tx_bytes = (uint32_t)(p.Tw * p.Th * p.Tn) * swz_bytes + (uint32_t)bn * swz_bytes;
   const int k_iters = p.taps * p.chunks_per_tap;
-  const uint32_t stage = p.a_slot + p.b_slot;
+  const uint32_t stage = p.halo ? p.a_slot : p.a_slot + p.b_slot;
   // epilogue chunk width: 32 output channels per TMA store when the tile allows it (bf16), else 16
   int cw = (bn % 32 == 0) ? 32 : 16;
   if (p.n_tiles > 1) Y11_REQUIRE(bn % cw == 0, "conv_tc: BN=%d not a multiple of the chunk width", bn);
@@ -365,9 +452,15 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
   int cols = 64;  // >= 2 accumulator stages of max(BN, 32) columns (a partial last chunk may read up to 16 spare columns)
   while (cols < 2 * bn) cols *= 2;
   while (cps > 1 && cps * cols > 512) --cps;
-  const uint32_t budget = (cps == 1 ? kSmemBudget : (220u * 1024u) / cps - 2048u);
-  int stages = (int)((budget - kHeaderBytes - 1024u - staging) / stage);
-  stages = std::max(2, std::min(stages, kMaxStages));
+  auto budget_of = [](int c) { return c == 1 ? kSmemBudget : (220u * 1024u) / c - 2048u; };
+  const uint32_t fixed = kHeaderBytes + 1024u + staging + p.b_res_bytes;
+  if (p.halo) {  // resident weights + at least two halo tiles must fit
+    while (cps > 1 && budget_of(cps) < fixed + 2 * stage) --cps;
+    Y11_REQUIRE(budget_of(cps) >= fixed + 2 * stage, "conv_tc: halo tile does not fit in shared memory");
+  }
+  const uint32_t budget = budget_of(cps);
+  int stages = budget > fixed ? (int)((budget - fixed) / stage) : 0;
+  stages = std::max(2, std::min(stages, p.halo ? 6 : kMaxStages));
   p.stages = stages;
   p.tmem_cols = cols;
   p.B = d->B; p.Hout = d->Hout; p.Wout = d->Wout; p.cout = cout;
@@ -425,7 +518,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
   }
   const unsigned total_tiles = (unsigned)(p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles);
   L->grid = std::min(total_tiles, (unsigned)(eng->num_sms * cps));
-  L->smem_bytes = kHeaderBytes + 1024u + (unsigned)stages * stage + staging;
+  L->smem_bytes = kHeaderBytes + 1024u + p.b_res_bytes + (unsigned)stages * stage + staging;
   L->flops = 2.0 * d->B * d->Hout * d->Wout * (double)cout * cin * p.taps;
   (void)k_iters;
   static bool attr_set = false;

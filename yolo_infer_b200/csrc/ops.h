@@ -43,6 +43,13 @@ struct ConvTcParams {
   int32_t act;
   int* err_flag;
   uint64_t mg_ntiles, mg_tw, mg_th;  // fast_div magics for n_tiles, tiles_w, tiles_h
+  // halo mode (small-channel 3x3 stride-1 layers): the (Th+2)x(Tw+2) input halo of a tile is copied ONCE by cp.async into
+  // the un-swizzled core-matrix layout [cin/8][Th+2][Tw+2][8 ch]; the nine taps are nine descriptor start offsets into it
+  int32_t halo;
+  const void* in;       // input view base (channel offset applied)
+  int32_t in_ct, Hin, Win;
+  uint32_t b_res_bytes; // resident weight region (all taps), loaded once per CTA
+  uint32_t a_lbo, a_sbo;
 };
 
 struct ConvTcLaunch {

@@ -233,6 +233,21 @@ class YOLO:
             self._ws[key] = t
         return t
 
+    def _fetch_results(self, det: torch.Tensor, count: torch.Tensor):
+        """ONE device->host transfer of the whole batch's results (det fp32 [B,max_det,6] + count int32 [B]) into a pinned
+        staging buffer; also the sync point of the call.  Returns (device copy of det, host copy of det, counts list): the
+        Results objects keep the device rows (reference semantics) plus a host mirror, so `.cpu()` costs nothing more."""
+        key = ("pinned_out", tuple(det.shape))
+        pin = self._ws.get(key)
+        if pin is None:
+            pin = (torch.empty(det.shape, dtype=det.dtype).pin_memory(), torch.empty(count.shape, dtype=count.dtype).pin_memory())
+            self._ws[key] = pin
+        pin[0].copy_(det, non_blocking=True)
+        pin[1].copy_(count, non_blocking=True)
+        det_dev = det.clone()
+        torch.cuda.current_stream(self.device).synchronize()
+        return det_dev, pin[0].clone(), pin[1].tolist()
+
     # ---- stages (each is one or a few kernel launches through the C ABI) -----------------------------
     def preprocess_images(self, net: CompiledNet, frames: Sequence[torch.Tensor], geoms) -> None:
         """frames: device uint8 HWC BGR tensors; writes net.input (bf16 NHWC RGB /255)."""
@@ -420,17 +435,18 @@ class YOLO:
                 e0.record()
                 det, count, _ = pipe.run(source)
                 e1.record()
-                counts = count.cpu().tolist()
-                det = det.clone()
+                det, det_h, counts = self._fetch_results(det, count)
                 ms = e0.elapsed_time(e1) / B
                 speed = {"preprocess": 0.0, "inference": ms, "postprocess": 0.0}  # one graph: stages are not separable
                 self.last_speed = speed
                 results = []
+                classes = torch.as_tensor(list(args["classes"])) if args["classes"] is not None else None
                 for i in range(B):
-                    d = det[i, : counts[i]]
-                    if args["classes"] is not None:
-                        d = d[torch.isin(d[:, 5].long(), torch.as_tensor(list(args["classes"]), device=d.device))]
-                    results.append(Results(None, f"image{i}.jpg", self.names, d, (h0, w0), dict(speed)))
+                    d, dh = det[i, : counts[i]], det_h[i, : counts[i]]
+                    if classes is not None:
+                        keep = torch.isin(dh[:, 5].long(), classes)
+                        d, dh = d[keep.to(d.device)], dh[keep]
+                    results.append(Results(None, f"image{i}.jpg", self.names, d, (h0, w0), speed, dh))
             return results
         with self._lock, torch.cuda.device(self.device), torch.inference_mode():
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -479,19 +495,18 @@ class YOLO:
             det, count, ncand = self.postprocess(net, scale_rows, float(args["conf"]), float(args["iou"]), int(args["max_det"]),
                                                  bool(args["agnostic_nms"]), bool(args["multi_label"]), int(args["max_nms"]))
             ev[3].record()
-            counts = count.cpu().tolist()  # one small D2H; also the sync point of the call
+            det, det_h, counts = self._fetch_results(det, count)  # one D2H; also the sync point of the call
             speed = {"preprocess": ev[0].elapsed_time(ev[1]) / B, "inference": ev[1].elapsed_time(ev[2]) / B,
                      "postprocess": ev[2].elapsed_time(ev[3]) / B}
             self.last_speed = speed
-            det = det.clone()
             results = []
-            classes = args["classes"]
+            classes = torch.as_tensor(list(args["classes"])) if args["classes"] is not None else None
             for i in range(B):
-                d = det[i, : counts[i]]
+                d, dh = det[i, : counts[i]], det_h[i, : counts[i]]
                 if classes is not None:
-                    keep = torch.isin(d[:, 5].long(), torch.as_tensor(list(classes), device=d.device))
-                    d = d[keep]
-                results.append(Results(orig_imgs[i], paths[i], self.names, d, orig_shapes[i], dict(speed)))
+                    keep = torch.isin(dh[:, 5].long(), classes)
+                    d, dh = d[keep.to(d.device)], dh[keep]
+                results.append(Results(orig_imgs[i], paths[i], self.names, d, orig_shapes[i], dict(speed), dh))
         if args["verbose"]:
             logger.info("%d image(s) %dx%d: %.2f ms pre, %.2f ms inference, %.2f ms post per image", B, H, W,
                         speed["preprocess"], speed["inference"], speed["postprocess"])

@@ -16,7 +16,7 @@ import torch
 
 
 class Boxes:
-    def __init__(self, data: torch.Tensor, orig_shape: Tuple[int, int]):
+    def __init__(self, data: torch.Tensor, orig_shape: Tuple[int, int], host: Optional[torch.Tensor] = None):
         if data.ndim == 1:
             data = data[None, :]
         assert data.shape[-1] == 6, f"expected [n,6] boxes, got {tuple(data.shape)}"
@@ -24,6 +24,11 @@ class Boxes:
         self.orig_shape = tuple(orig_shape)
         self.is_track = False
         self.id = None
+        # Optional host mirror of `data`: the engine fetches the whole batch's results with ONE device->host copy per
+        # predict call, so `.cpu()` / `.numpy()` on each Results need no further transfer or stream sync.
+        if host is not None and host.ndim == 1:
+            host = host[None, :]
+        self._host = host
 
     # ---- the accessors the reference reads ------------------------------------------------------
     @property
@@ -72,18 +77,18 @@ class Boxes:
         return int(self.data.shape[0])
 
     def __getitem__(self, idx) -> "Boxes":
-        return Boxes(self.data[idx], self.orig_shape)
+        return Boxes(self.data[idx], self.orig_shape, self._host[idx] if self._host is not None else None)
 
     def __iter__(self) -> Iterator["Boxes"]:
         for i in range(len(self)):
             yield self[i]
 
     def cpu(self) -> "Boxes":
-        return Boxes(self.data.cpu(), self.orig_shape)
+        return Boxes(self._host if self._host is not None else self.data.cpu(), self.orig_shape)
 
     def numpy(self) -> "Boxes":
         b = Boxes.__new__(Boxes)
-        b.data, b.orig_shape, b.is_track, b.id = self.data.cpu().numpy(), self.orig_shape, False, None
+        b.data, b.orig_shape, b.is_track, b.id, b._host = self.cpu().data.numpy(), self.orig_shape, False, None, None
         return b
 
     def cuda(self) -> "Boxes":
@@ -98,12 +103,13 @@ class Boxes:
 
 class Results:
     def __init__(self, orig_img: Optional[np.ndarray], path: str, names: Dict[int, str], boxes: torch.Tensor,
-                 orig_shape: Tuple[int, int], speed: Optional[Dict[str, float]] = None):
+                 orig_shape: Tuple[int, int], speed: Optional[Dict[str, float]] = None,
+                 host_boxes: Optional[torch.Tensor] = None):
         self.orig_img = orig_img
         self.orig_shape = tuple(orig_shape)
         self.path = path
         self.names = names
-        self.boxes = Boxes(boxes, self.orig_shape)
+        self.boxes = Boxes(boxes, self.orig_shape, host_boxes)
         self.masks = None
         self.probs = None
         self.keypoints = None
@@ -114,14 +120,13 @@ class Results:
         return len(self.boxes)
 
     def cpu(self) -> "Results":
-        r = Results(self.orig_img, self.path, self.names, self.boxes.data.cpu(), self.orig_shape, self.speed)
-        return r
+        return Results(self.orig_img, self.path, self.names, self.boxes.cpu().data, self.orig_shape, self.speed)
 
     def to(self, *a, **k) -> "Results":
         return Results(self.orig_img, self.path, self.names, self.boxes.data.to(*a, **k), self.orig_shape, self.speed)
 
     def summary(self):
-        d = self.boxes.data.cpu().tolist()
+        d = self.boxes.cpu().data.tolist()
         return [{"name": self.names[int(r[5])], "class": int(r[5]), "confidence": r[4],
                  "box": {"x1": r[0], "y1": r[1], "x2": r[2], "y2": r[3]}} for r in d]
 
