@@ -17,7 +17,7 @@ SOURCES = ["api.cu", "preprocess.cu", "conv_tc.cu", "conv_simt.cu", "attention.c
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("Y11_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

@@ -56,10 +56,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast
 // __expf/__fdividef, of which 4 FMUL + FSETP were denormal-range fix-ups), so this is the hot scalar of the network.
 // Absolute error <= 2.5e-4*|x| for x < 0 (cancellation in 1+tanh), i.e. below one bf16 ulp of the activations it feeds.
 __device__ __forceinline__ float silu(float x) {
+#ifdef Y11_SILU_EX2
+  // x * sigmoid(x) = x / (1 + 2^(-x*log2 e)): two full-rate MUFU ops (EX2, RCP) + FMUL/FADD/FMUL
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+  return x * r;
+#else
   const float h = 0.5f * x;
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
+#endif
 }
 // magic-number division for the persistent tile loops (exact for n, d < 2^21): q = (n * ceil(2^42/d)) >> 42
 __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint64_t magic) { return (uint32_t)(((uint64_t)n * magic) >> 42); }
@@ -79,14 +87,18 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait WITH a suspend-time hint: the warp is parked by the hardware until the phase completes (or the hint, in ns,
+// elapses) instead of spinning.  Without the hint the wait returns almost immediately and the polling loops of the ten
+// warps of each CTA ate most of the SM's issue slots (ncu: 34 M of 71 M executed instructions of a 1x1 layer were
+// try_wait/branch/clock spin instructions, schedulers ~85 % busy, real work starved - profiles/r01c_summary.md).
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(1000000u)
       : "memory");
   return ok != 0;
 }

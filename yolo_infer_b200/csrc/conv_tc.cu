@@ -25,17 +25,34 @@
 // Warp roles (320 threads): warp0 = TMA producer (1 lane), warp1 = MMA issuer (1 lane), warps2-9 = epilogue;
 // warp2 also owns TMEM alloc/dealloc.
 #include <algorithm>
+#include <climits>
 #include <cstdlib>
 #include <cstring>
 
 #include "ops.h"
+
+#ifdef Y11_TRACE
+// debug timeline: CTA 0 records (event, clock) pairs per role into a global buffer (set with y11_debug_set_trace)
+static long long* g_trace_buf = nullptr;
+extern "C" void y11_debug_set_trace(void* dev_ptr) { g_trace_buf = static_cast<long long*>(dev_ptr); }
+#define TRACE(role, ev)                                                            \
+  do {                                                                             \
+    if (p.trace && blockIdx.x == 0 && trc < 2000) {                                 \
+      p.trace[(role) * 4096 + 2 * trc] = (ev);                                     \
+      p.trace[(role) * 4096 + 2 * trc + 1] = clock64();                            \
+      ++trc;                                                                       \
+    }                                                                              \
+  } while (0)
+#else
+#define TRACE(role, ev) do {} while (0)
+#endif
 
 namespace {
 
 constexpr int kThreads = 320;
 constexpr int kEpiWarps = 8;
 constexpr int kMaxStages = 32;           // small-channel layers have 5-9 KB stages: bytes in flight, not stage count, hide latency
-constexpr uint32_t kHeaderBytes = 1024;  // mbarriers + tmem pointer
+constexpr uint32_t kHeaderBytes = 3072;  // mbarriers + tmem pointer (1 KB) + LSU-mode position table (2 KB)
 constexpr uint32_t kSmemBudget = 200 * 1024;
 
 __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
@@ -46,6 +63,8 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read2() { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -58,7 +77,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcParams p) {
   using namespace y11;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -86,7 +105,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     mbar_init(bres_bar, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(accf_bar + 8 * a, 1);
-      mbar_init(acce_bar + 8 * a, kEpiWarps);
+      mbar_init(acce_bar + 8 * a, p.epi_warp ? kEpiWarps / 2 : kEpiWarps);
     }
     mbar_fence_init();
   }
@@ -94,6 +113,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     prefetch_tmap(&maps.a[0]);
     prefetch_tmap(&maps.b);
     prefetch_tmap(&maps.out);
+    prefetch_tmap(&maps.outq);
     if (p.stride == 2) {
       prefetch_tmap(&maps.a[1]);
       prefetch_tmap(&maps.a[2]);
@@ -103,6 +123,17 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   if (warp == 2) {
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), p.tmem_cols);
     tmem_relinquish();
+  }
+  // LSU mode: per-position table {element offset of the pixel relative to the tile origin, packed (x, y, n)}; positions are
+  // the tile's pixels (1x1) or its (Tw+2)x(Th+2) halo (3x3), in the order they are laid out in shared memory
+  uint2* pos_tab = reinterpret_cast<uint2*>(smem_raw + 1024);
+  if (p.halo) {
+    const int HWp = p.Tw + 2 * p.pad, HHp = p.Th + 2 * p.pad;
+    for (int pos = threadIdx.x; pos < p.n_pos; pos += kThreads) {
+      const int x = pos % HWp, y = (pos / HWp) % HHp, n = pos / (HWp * HHp);
+      const int off = ((n * p.Hin + (y - p.pad)) * p.Win + (x - p.pad)) * p.in_ct;
+      pos_tab[pos] = make_uint2((uint32_t)off, (uint32_t)(x | (y << 8) | (n << 16)));
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -115,35 +146,57 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
 
   const int k_iters = p.taps * p.chunks_per_tap;
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+#ifdef Y11_TRACE
+  int trc = 0;
+#endif
 
   if (warp == 0 && p.halo) {
-    // ------------------------------------------------------------------ halo producer (whole warp, cp.async)
+    // ------------------------------------------------------------------ LSU producer (whole warp, cp.async)
     if (lane == 0) {  // weights of all taps: loaded once, stay resident
-      mbar_expect_tx(bres_bar, (uint32_t)(p.taps * p.BN) * (uint32_t)(p.Cc * 2));
-      for (int tap = 0; tap < p.taps; ++tap) tma_load_2d(tiles_base + tap * p.b_slot, &maps.b, bres_bar, tap * p.cin, 0);
+      const int nb = p.taps * p.chunks_per_tap;
+      mbar_expect_tx(bres_bar, (uint32_t)(nb * p.BN) * (uint32_t)(p.Cc * 2));
+      for (int i = 0; i < nb; ++i) tma_load_2d(tiles_base + i * p.b_slot, &maps.b, bres_bar, i * p.Cc, 0);
     }
-    constexpr int HWp = 10, HP = 180;  // halo mode fixes Tw = 8, Th = 16: constant divisors, 180 halo positions
     const int ncg = p.cin >> 3;
+    const uint32_t plane = p.a_lbo;  // bytes per 8-channel plane
     const __nv_bfloat16* in = static_cast<const __nv_bfloat16*>(p.in);
+    // Lane l owns positions l, l+32, ... (<= 6 per tile): their source offsets relative to the tile origin and their
+    // packed (x, y, n) are per-lane constants in registers.  Consecutive lanes write consecutive 16-byte slots of a plane
+    // (conflict-free shared-memory writes - a lane-per-channel-group mapping that coalesces the global side instead
+    // measured 35 % slower) and each lane copies the cin/8 channel groups of its pixel with immediate offsets.
+    constexpr int kMaxPos = 6;
+    int soff[kMaxPos];
+    uint32_t meta[kMaxPos];
+#pragma unroll
+    for (int i = 0; i < kMaxPos; ++i) {
+      const int pos = lane + 32 * i;
+      const uint2 e = pos < p.n_pos ? pos_tab[pos] : make_uint2(0u, 0xffffffffu);
+      soff[i] = (int)e.x;
+      meta[i] = e.y;
+    }
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       uint32_t t = tile, q;
       q = fast_div(t, p.mg_tw); const int w0 = (t - q * p.tiles_w) * p.Tw; t = q;
       q = fast_div(t, p.mg_th); const int h0 = (t - q * p.tiles_h) * p.Th; t = q;
-      const __nv_bfloat16* img = in + (size_t)t * p.Hin * p.Win * p.in_ct;
+      const int n0 = t * p.Tn;
+      const __nv_bfloat16* org = in + ((size_t)n0 * p.Hin * p.Win + (size_t)h0 * p.Win + w0) * p.in_ct;
       mbar_wait(empty_bar + 8 * stage, phase ^ 1, p.err_flag, 101);
-      const uint32_t dst = ring_base + stage * stage_bytes;
-      // lanes walk the halo positions; each position copies its cin/8 16-byte channel groups into their planes
-      for (int pos = lane; pos < HP; pos += 32) {
-        const int y = pos / HWp, x = pos - y * HWp;
-        const int ih = h0 + y - 1, iw = w0 + x - 1;
-        const bool ok = ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win;  // outside the image: zero fill == conv padding
-        const __nv_bfloat16* src = img + ((size_t)(ok ? ih : 0) * p.Win + (ok ? iw : 0)) * p.in_ct;
-        const uint32_t d0 = dst + pos * 16, nbytes = ok ? 16u : 0u;
+      if (lane == 0) TRACE(0, 1);
+      const uint32_t dst = ring_base + stage * stage_bytes + (uint32_t)lane * 16u;
+#pragma unroll
+      for (int i = 0; i < kMaxPos; ++i) {
+        if (meta[i] == 0xffffffffu) continue;  // beyond the tile's positions
+        const int iw = w0 + (int)(meta[i] & 0xff) - p.pad, ih = h0 + (int)((meta[i] >> 8) & 0xff) - p.pad;
+        const int in_ = n0 + (int)(meta[i] >> 16);
+        const bool ok = ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win && in_ < p.B;  // outside: zero fill == conv padding
+        const __nv_bfloat16* src = org + (ok ? soff[i] : 0);
+        const uint32_t d = dst + (uint32_t)i * 512u, nbytes = ok ? 16u : 0u;
 #pragma unroll 4
-        for (int cg = 0; cg < ncg; ++cg) cp_async_16(d0 + cg * (HP * 16), src + cg * 8, nbytes);
+        for (int cg = 0; cg < ncg; ++cg) cp_async_16(d + cg * plane, src + cg * 8, nbytes);
       }
       cp_async_mbar_arrive(full_bar + 8 * stage);
+      if (lane == 0) TRACE(0, 2);
       if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 0) {
@@ -168,6 +221,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
         }
         for (int c = 0; c < p.chunks_per_tap; ++c) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1, p.err_flag, 101);
+          if (lane == 0) TRACE(0, 1);
           if (elect_one()) {
             const uint32_t fb = full_bar + 8 * stage;
             const uint32_t a_dst = ring_base + stage * stage_bytes;
@@ -176,6 +230,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
             tma_load_2d(a_dst + p.a_slot, &maps.b, fb, tap * p.cin + c * p.Cc, nt * p.BN);
           }
           __syncwarp();
+          if (lane == 0) TRACE(0, 2);
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -196,30 +251,46 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int as = ti & 1;
       mbar_wait(acce_bar + 8 * as, ((ti >> 1) & 1) ^ 1, p.err_flag, 104);  // epilogue has drained this accumulator stage
+      if (lane == 0) TRACE(1, 1);
       const uint32_t tmem_acc = tmem_base + as * acc_stride;
       if (p.halo) {
         mbar_wait(full_bar + 8 * stage, phase, p.err_flag, 102);
+        if (lane == 0) TRACE(1, 2);
         fence_async_smem();  // cp.async wrote through the generic proxy; the MMA reads through the async proxy
         tc_fence_after();
         if (elect_one()) {
           const uint64_t ad0 = make_umma_desc_interleaved(ring_base + stage * stage_bytes, p.a_lbo, p.a_sbo);
+          if (p.pad) {
+            // 3x3: nine taps, fully unrolled with compile-time offsets (cin <= 64, so one weight chunk per tap).  The issue
+            // thread runs ~10 cycles per dependent instruction: every instruction saved per MMA is worth it.
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            // tap (kh, kw) = the halo tile shifted by kh rows of (Tw+2) pixels and kw pixels: a 16-byte-unit address offset
-            const uint64_t ad = ad0 + (uint32_t)((tap / 3) * 10 + tap % 3);
-            const uint64_t bd = bd_res + (uint32_t)tap * b_step;
-            umma_bf16(tmem_acc, ad, bd, idesc, tap != 0);
-            for (int kk = 1; kk < kk_n; ++kk)  // next 16 channels = two 8-channel planes further / +32 B in the weight row
-              umma_bf16(tmem_acc, ad + kk * k_step, bd + 2 * kk, idesc, 1);
+            for (int tap = 0; tap < 9; ++tap) {
+              // tap (kh, kw) = the halo tile shifted by kh rows of (Tw+2) = 10 pixels and kw pixels, in 16-byte units
+              const uint64_t ad = ad0 + (uint32_t)((tap / 3) * 10 + tap % 3);
+              const uint64_t bd = bd_res + (uint32_t)tap * b_step;
+              umma_bf16(tmem_acc, ad, bd, idesc, tap != 0);
+              for (int kk = 1; kk < kk_n; ++kk)  // next 16 channels = two 8-channel planes further / +32 B in the weight row
+                umma_bf16(tmem_acc, ad + kk * k_step, bd + 2 * kk, idesc, 1);
+            }
+          } else {
+            // 1x1: K = cin in weight chunks of Cc channels
+            for (int c = 0; c < p.chunks_per_tap; ++c) {
+              const uint64_t ad = ad0 + (uint32_t)(c * kk_n) * k_step;
+              const uint64_t bd = bd_res + (uint32_t)c * b_step;
+              umma_bf16(tmem_acc, ad, bd, idesc, c != 0);
+              for (int kk = 1; kk < kk_n; ++kk) umma_bf16(tmem_acc, ad + kk * k_step, bd + 2 * kk, idesc, 1);
+            }
           }
           umma_commit(empty_bar + 8 * stage);
           umma_commit(accf_bar + 8 * as);
         }
         __syncwarp();
+        if (lane == 0) TRACE(1, 3);
         if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
       } else {
         for (int k = 0; k < k_iters; ++k) {
           mbar_wait(full_bar + 8 * stage, phase, p.err_flag, 102);
+          if (lane == 0) TRACE(1, 2);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_src = ring_base + stage * stage_bytes;
@@ -232,10 +303,121 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
             if (k == k_iters - 1) umma_commit(accf_bar + 8 * as);  // accumulator complete
           }
           __syncwarp();
+          if (lane == 0) TRACE(1, 3);
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
+  } else if (p.epi_warp) {
+    // -------------------------------------------------------------------- epilogue, warp-independent (warps 2..9)
+    // Two groups of four warps take ALTERNATE tiles (group g owns accumulator stage g); inside a group every warp drains
+    // its own TMEM lane quadrant = 32 tile rows = a (qw x qh x qn) sub-box of the tile, stages it in a private swizzled
+    // buffer and issues its own TMA store.  No CTA-wide barrier, no shared leader: the timeline of the CTA-wide version
+    // (tools/trace_conv.py) showed ~3500 cycles per 128x32 tile spent in one serial chain - wait accumulator -> tcgen05.ld
+    // -> math -> st.shared -> leader waits for the previous store -> named barrier (7 warps idle) -> leader issues the
+    // store -> release - with the MMA warp and the TMA producer both waiting on it.  Here eight such chains run
+    // independently and the accumulator stage is handed back as soon as its last tcgen05.ld has completed.
+    const int ew = warp - 2;
+    const int grp = ew >> 2;
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access (hardware: warp id % 4)
+    const uint32_t esz = p.out_f32 ? 4u : 2u;
+    const uint32_t pitch = (uint32_t)p.cw * esz;           // staging row pitch: 32 / 64 / 128 B
+    const uint32_t swz = ((uint32_t)lane / (128u / pitch)) & (pitch / 16u - 1u);  // TMA SWIZZLE_{32,64,128}B phase of row `lane`
+    const uint32_t wbuf_bytes = 32u * pitch;
+    const uint32_t my_stage = staging_base + (uint32_t)ew * (uint32_t)p.nstg * wbuf_bytes;
+    const int n_chunks = (p.BN + p.cw - 1) / p.cw;
+    const int halves = p.cw / 16;
+    // position of this warp's 32 rows inside the tile, and of this lane's row (for the residual read)
+    const int r0 = quad * 32, r = r0 + lane;
+    const int qw0 = r0 % p.Tw, qh0 = (r0 / p.Tw) % p.Th, qn0 = r0 / (p.Tw * p.Th);
+    const int tw = r % p.Tw, th = (r / p.Tw) % p.Th, tn = r / (p.Tw * p.Th);
+    uint32_t sb = 0;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      if ((ti & 1) != grp) continue;
+      uint32_t t = tile, qq;
+      qq = fast_div(t, p.mg_ntiles); const int nt = t - qq * p.n_tiles; t = qq;
+      qq = fast_div(t, p.mg_tw); const int w0 = (t - qq * p.tiles_w) * p.Tw; t = qq;
+      qq = fast_div(t, p.mg_th); const int h0 = (t - qq * p.tiles_h) * p.Th; t = qq;
+      const int n0 = t * p.Tn;
+      const int ow = w0 + tw, oh = h0 + th, on = n0 + tn;
+      const bool valid = ow < p.Wout && oh < p.Hout && on < p.B;
+      const size_t pix = (static_cast<size_t>(on) * p.Hout + oh) * p.Wout + ow;
+      const __nv_bfloat16* res_row = static_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ct + p.res_co + nt * p.BN;
+      mbar_wait(accf_bar + 8 * grp, (ti >> 1) & 1, p.err_flag, 103);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + grp * acc_stride + (static_cast<uint32_t>(quad * 32) << 16);
+      for (int c = 0; c < n_chunks; ++c) {
+        const uint32_t buf = my_stage + sb * wbuf_bytes;
+        if (lane == 0) {  // the last store that used this buffer (two chunks ago / the previous one) has finished reading it
+          if (p.nstg >= 2) bulk_wait_read1();
+          else bulk_wait_read0();
+        }
+        __syncwarp();
+        for (int hh = 0; hh < halves; ++hh) {
+          const int col = c * p.cw + hh * 16;  // column inside the tile's accumulator
+          if (col >= p.BN) break;
+          uint4 rv0 = make_uint4(0, 0, 0, 0), rv1 = rv0;
+          if (p.res && valid) {  // issued before the TMEM load: independent of it
+            rv0 = *reinterpret_cast<const uint4*>(res_row + col);
+            rv1 = *reinterpret_cast<const uint4*>(res_row + col + 8);
+          }
+          uint32_t v[16];
+          tmem_ld16(taddr + col, v);
+          tmem_ld_wait();
+          if (c == n_chunks - 1 && col + 16 >= p.BN) {
+            // last TMEM read of this accumulator stage: hand it back to the MMA warp before doing the math
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acce_bar + 8 * grp);
+          }
+          const int n = nt * p.BN + col;
+          float f[16];
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 bb = __ldg(b4 + i);
+            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x;
+            f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
+            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
+            f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
+          }
+          if (p.act == Y11_ACT_SILU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = silu(f[i]);
+          }
+          if (p.res) {
+            const uint32_t rr[8] = {rv0.x, rv0.y, rv0.z, rv0.w, rv1.x, rv1.y, rv1.z, rv1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              f[2 * i] += bf16_lo(rr[i]);
+              f[2 * i + 1] += bf16_hi(rr[i]);
+            }
+          }
+          const uint32_t dst = buf + (uint32_t)lane * pitch;
+          if (p.out_f32) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              st_shared_v4(dst + (((4u * hh + i) ^ swz) << 4), __float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]),
+                           __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3]));
+          } else {
+            st_shared_v4(dst + (((2u * hh + 0u) ^ swz) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                         pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            st_shared_v4(dst + (((2u * hh + 1u) ^ swz) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                         pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+          }
+        }
+        fence_async_smem();  // my generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          // columns beyond cout (only when cout % cw != 0, single N tile) and pixels beyond the image are clipped by the map
+          tma_store_4d(&maps.outq, buf, nt * p.BN + c * p.cw, w0 + qw0, h0 + qh0, n0 + qn0);
+          bulk_commit();
+        }
+        if (p.nstg >= 2) sb ^= 1u;
+      }
+    }
+    if (lane == 0) bulk_wait_all();
   } else {
     // -------------------------------------------------------------------- epilogue (warps 2..9)
     // All 8 warps work on the same chunk of CW = 16*halves output channels: warp quadrant q owns TMEM lanes / tile rows
@@ -255,7 +437,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     const uint32_t row_addr = r * pitch;
     const int n_chunks = (p.BN + p.cw - 1) / p.cw;
     const bool active = half < halves;
-    int ti = 0, ci = 0;
+    int ti = 0;
+    uint32_t sb = 0;  // staging ring position
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       uint32_t t = tile, qq;
       qq = fast_div(t, p.mg_ntiles); const int nt = t - qq * p.n_tiles; t = qq;
@@ -266,16 +449,24 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       const bool valid = (r < p.Tw * p.Th * p.Tn) && ow < p.Wout && oh < p.Hout && on < p.B;
       const size_t pix = (static_cast<size_t>(on) * p.Hout + oh) * p.Wout + ow;
       const int as = ti & 1;
+      if (lane == 0 && (ew == 0 || ew == 3)) TRACE(2 + (ew == 3), 0);
       mbar_wait(accf_bar + 8 * as, (ti >> 1) & 1, p.err_flag, 103);
+      if (lane == 0 && (ew == 0 || ew == 3)) TRACE(2 + (ew == 3), 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * acc_stride + (static_cast<uint32_t>(quad * 32) << 16);
-      for (int c = 0; c < n_chunks; ++c, ++ci) {
+      for (int c = 0; c < n_chunks; ++c) {
         const int col = c * p.cw + half * 16;          // column inside the tile's accumulator
-        const uint32_t dst = staging_base + (ci & 1) * stg_bytes + row_addr;
+        const uint32_t dst = staging_base + sb * stg_bytes + row_addr;
         if (active && col < p.BN) {
+          uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+          if (p.res && valid) {  // issued before the TMEM load: independent of it, and a DRAM/L2 round trip long
+            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ct + p.res_co + nt * p.BN + col);
+            r0 = rp[0]; r1 = rp[1];
+          }
           uint32_t v[16];
           tmem_ld16(taddr + col, v);
           tmem_ld_wait();
+          if (lane == 0 && (ew == 0 || ew == 3)) TRACE(2 + (ew == 3), 2);
           const int n = nt * p.BN + col;
           float f[16];
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
@@ -291,9 +482,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = silu(f[i]);
           }
-          if (p.res && valid) {
-            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ct + p.res_co + n);
-            const uint4 r0 = rp[0], r1 = rp[1];
+          if (p.res) {
             const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -312,15 +501,18 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
             st_shared_v4(dst + (((2u * half + 1u) ^ swz) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
                          pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
           }
-          fence_async_smem();            // my generic-proxy smem writes -> visible to the TMA (async proxy)
+          fence_async_smem();  // my generic-proxy smem writes -> visible to the TMA (async proxy)
+          if (lane == 0 && (ew == 0 || ew == 3)) TRACE(2 + (ew == 3), 3);
         }
         if (leader) bulk_wait_read0();   // the previous store has finished READING its (other) staging buffer
         named_bar_sync(1, kEpiWarps * 32);  // all rows/columns of this chunk staged; other buffer free for the next chunk
         if (leader) {
           // columns beyond cout (only when cout % cw != 0, single N tile) are clipped by the tensor map
-          tma_store_4d(&maps.out, staging_base + (ci & 1) * stg_bytes, nt * p.BN + c * p.cw, w0, h0, n0);
+          tma_store_4d(&maps.out, staging_base + sb * stg_bytes, nt * p.BN + c * p.cw, w0, h0, n0);
           bulk_commit();
+          TRACE(2, 6);
         }
+        sb ^= 1u;
       }
       // all tcgen05.ld of this accumulator stage have completed (wait::ld above): hand it back to the MMA warp
       tc_fence_before();
@@ -381,18 +573,24 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
 
   std::memset(L, 0, sizeof(*L));
   ConvTcParams& p = L->p;
-  // Halo mode for 3x3 stride-1 layers with few input channels on large maps.  The tap-by-tap TMA path moves one
-  // 2*cin-byte row per pixel per tap, and the TMA unit retires only ~1 such row per 3 cycles per SM regardless of its
-  // length (measured: 16->16, 32->16 and 16->32 channel 3x3 layers at 160x160 all take the same 0.13-0.18 ms); copying the
-  // halo once needs 1.4 rows of 16 bytes x cin/8 per pixel instead of 9 rows, through the LSU (cp.async), not the TMA unit.
+  // LSU-producer mode.  The TMA unit sustains only ~0.1 box rows (<= 128 B each) per cycle per SM when the rows miss to
+  // DRAM (measured with tools/trace_conv.py: 1x1 layers with 32-, 64- and 128-byte pixel rows all take time proportional
+  // to their ROW count, 1 or 3 CTAs per SM alike), i.e. 3-13 B/clk/SM, and a 3x3 layer issues nine such rows per pixel.
+  // Layers whose whole K extent fits in shared memory therefore fetch the activation tile with cp.async (coalesced
+  // 16-byte copies, weights resident for the CTA's lifetime):
+  //   1x1         : the 128 tile pixels, any tile shape;
+  //   3x3 stride 1: the (Tw+2)x(Th+2) halo ONCE (1.4 instead of 9 rows per pixel); the nine taps are nine descriptor
+  //                 start offsets into the un-swizzled core-matrix layout, which needs Tw = 8.
   {
     const char* e = getenv("Y11_HALO");
-    const int mode = e ? atoi(e) : 1;
-    const size_t wbytes = (size_t)9 * cin * cout * 2;
-    p.halo = mode && d->k == 3 && d->stride == 1 && (cin == 16 || cin == 32 || cin == 64) && cout <= 128 &&
-             wbytes <= 40 * 1024 && d->Hout >= 32 && d->Wout >= 32;
+    const int mode = e ? atoi(e) : 3;  // bit 0: 3x3 halo tiles, bit 1: 1x1
+    const size_t wbytes = (size_t)d->k * d->k * cin * cout * 2;
+    const bool k3 = d->k == 3 && d->stride == 1 && cin <= 64 && d->Hout >= 32 && d->Wout >= 32 && (mode & 1);
+    const bool k1 = d->k == 1 && cin <= 48 && (mode & 2);  // wider 1x1 inputs have >= 128-byte TMA rows: TMA path
+    p.halo = (k1 || k3) && cout <= 128 && wbytes <= 40 * 1024;
+    p.pad = k3 ? 1 : 0;
   }
-  if (p.halo) { p.Tw = 8; p.Th = 16; p.Tn = 1; }
+  if (p.halo && p.pad) { p.Tw = 8; p.Th = 16; p.Tn = 1; }
   else pick_tile(d->Wout, d->Hout, d->B, &p.Tw, &p.Th, &p.Tn);
   p.tiles_w = y11_ceil_div(d->Wout, p.Tw);
   p.tiles_h = y11_ceil_div(d->Hout, p.Th);
@@ -427,23 +625,60 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
   p.a_slot = 128u * swz_bytes;
   p.b_slot = ((uint32_t)bn * swz_bytes + 1023u) & ~1023u;
   if (p.halo) {
-    const uint32_t hp = (uint32_t)(p.Tw + 2) * (p.Th + 2);
-    p.a_slot = (hp * (uint32_t)cin * 2u + 1023u) & ~1023u;
-    p.a_lbo = hp * 16u;
-    p.a_sbo = (uint32_t)(p.Tw + 2) * 16u;
+    p.n_pos = (p.Tw + 2 * p.pad) * (p.Th + 2 * p.pad) * p.Tn;
+    const uint32_t plane = (uint32_t)(p.pad ? p.n_pos : 128) * 16u;  // one 8-channel plane: 16 B per position
+    p.a_slot = (plane * (uint32_t)(cin / 8) + 1023u) & ~1023u;
+    p.a_lbo = plane;
+    p.a_sbo = p.pad ? (uint32_t)(p.Tw + 2) * 16u : 128u;  // next 8 GEMM rows: next halo row (Tw = 8) / next 8 pixels
     if (const char* e = getenv("Y11_HALO_SWAP")) if (atoi(e)) std::swap(p.a_lbo, p.a_sbo);
-    p.b_res_bytes = 9u * p.b_slot;
+    p.b_res_bytes = (uint32_t)(p.taps * p.chunks_per_tap) * p.b_slot;
     p.in = static_cast<const __nv_bfloat16*>(d->in.ptr) + d->in.c_off;
     p.in_ct = d->in.c_total; p.Hin = d->Hin; p.Win = d->Win;
+    p.mg_ncg = ((1ull << 42) + (cin / 8) - 1) / (cin / 8);
   }
   p.tx_bytes = (uint32_t)(p.Tw * p.Th * p.Tn) * swz_bytes + (uint32_t)bn * swz_bytes;
   const int k_iters = p.taps * p.chunks_per_tap;
   const uint32_t stage = p.halo ? p.a_slot : p.a_slot + p.b_slot;
-  // epilogue chunk width: 32 output channels per TMA store when the tile allows it (bf16), else 16
+  // Warp-independent epilogue: possible when the tile has exactly 128 rows and every 32-row quarter (one TMEM lane
+  // quadrant) is itself a (qbw x qbh x qbn) box of pixels, so that each warp can TMA-store its own rows.
+  int qbw = 0, qbh = 0, qbn = 0;
+  {
+    const int Tw = p.Tw, Th = p.Th, Tn = p.Tn;
+    bool ok = Tw * Th * Tn == 128;
+    if (ok) {
+      if (Tw >= 32) { ok = Tw % 32 == 0; qbw = 32; qbh = 1; qbn = 1; }
+      else if (32 % Tw != 0) ok = false;
+      else {
+        const int rows_h = 32 / Tw;
+        if (Th >= rows_h) { ok = Th % rows_h == 0; qbw = Tw; qbh = rows_h; qbn = 1; }
+        else { ok = rows_h % Th == 0 && Tn % (rows_h / Th) == 0; qbw = Tw; qbh = Th; qbn = rows_h / Th; }
+      }
+    }
+    const char* e = getenv("Y11_EPI_WARP");
+    p.epi_warp = ok && (e ? atoi(e) : 0);
+  }
+  // epilogue chunk width: 32 output channels per TMA store when the tile allows it, else 16 (fp32 rows: 16 in warp mode)
   int cw = (bn % 32 == 0) ? 32 : 16;
+  if (p.epi_warp && d->out_f32) cw = 16;
   if (p.n_tiles > 1) Y11_REQUIRE(bn % cw == 0, "conv_tc: BN=%d not a multiple of the chunk width", bn);
   p.cw = cw;
-  const uint32_t staging = 2u * 128u * (uint32_t)cw * (d->out_f32 ? 4u : 2u);
+  // staging for the TMA-store epilogue: CTA-wide mode = ring of 2 whole-tile buffers (3 and 4 measured no faster and cost
+  // load stages); warp mode = 2 private 32-row buffers per epilogue warp
+  p.nstg = 2;
+  const uint32_t opitch_b = (uint32_t)cw * (d->out_f32 ? 4u : 2u);
+  // CTA-wide mode: nstg whole-tile (128-row) buffers; warp mode: nstg private 32-row buffers for each of the 8 warps
+  uint32_t staging = (uint32_t)p.nstg * 128u * opitch_b;
+  if (p.epi_warp) {
+    staging = (uint32_t)kEpiWarps * p.nstg * 32u * opitch_b;
+    {
+      // double-buffer the per-warp staging only when that still leaves >= 3 load stages at 3 CTAs per SM
+      const uint32_t avail = (220u * 1024u) / 3 - 2048u, need = kHeaderBytes + 1024u + staging + p.b_res_bytes;
+      if (avail < need || (avail - need) / stage < 3) {
+        p.nstg = 1;
+        staging = (uint32_t)kEpiWarps * 32u * opitch_b;
+      }
+    }
+  }
   // persistent CTAs per SM: TMEM (512 columns) and shared memory are split between them
   // (measured on B200, YOLO11s batch 64: conv time 5.25 / 3.78 / 3.65 / 3.88 ms for 1 / 2 / 3 / 4 CTAs per SM - several
   //  independent TMA->MMA->epilogue chains per SM hide the per-tile latencies better than one deep pipeline)
@@ -468,6 +703,9 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
   p.res = d->res.ptr; p.res_ct = d->res.c_total; p.res_co = d->res.c_off;
   p.bias = d->bias; p.act = d->act;
   p.err_flag = eng->dev_error_flag;
+#ifdef Y11_TRACE
+  p.trace = g_trace_buf;
+#endif
   {
     const long long tt = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
     Y11_REQUIRE(tt < (1ll << 21), "conv_tc: %lld tiles exceed the fast-division range", tt);
@@ -515,6 +753,13 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
     if (int e = encode_map(eng, &L->maps.out, d->out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : bf, 4, obase, gdim, gstr, obox,
                            oswz))
       return e;
+    L->maps.outq = L->maps.out;
+    if (p.epi_warp) {
+      const cuuint32_t qbox[4] = {(cuuint32_t)p.cw, (cuuint32_t)qbw, (cuuint32_t)qbh, (cuuint32_t)qbn};
+      if (int e = encode_map(eng, &L->maps.outq, d->out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : bf, 4, obase, gdim, gstr, qbox,
+                             oswz))
+        return e;
+    }
   }
   const unsigned total_tiles = (unsigned)(p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles);
   L->grid = std::min(total_tiles, (unsigned)(eng->num_sms * cps));

@@ -24,7 +24,8 @@ static inline cudaError_t y11_launch_pdl(void (*kernel)(KArgs...), dim3 grid, di
 struct ConvTcMaps {
   CUtensorMap a[4];  // activation views: [0] for stride 1; [ph*2+pw] parity sub-grids for stride 2
   CUtensorMap b;     // packed weights [cout][k*k*cin]
-  CUtensorMap out;   // output view, 16-channel boxes (TMA store)
+  CUtensorMap out;   // output view, cw-channel x whole-tile boxes (TMA store, CTA-wide epilogue)
+  CUtensorMap outq;  // output view, cw-channel x quarter-tile (32 pixel) boxes (warp-independent epilogue)
 };
 
 struct ConvTcParams {
@@ -32,6 +33,8 @@ struct ConvTcParams {
   int32_t tiles_w, tiles_h, tiles_n;  // spatial tile grid
   int32_t n_tiles;                    // Cout tiles of BN columns
   int32_t BN, Cc, chunks_per_tap, taps, ksize, stride, stages, tmem_cols;
+  int32_t epi_warp;  // warp-independent epilogue: each warp stores its own 32-row sub-box (tile must decompose)
+  int32_t nstg;  // staging buffers per warp of the warp-independent epilogue (1 or 2); the CTA-wide epilogue uses 2
   int32_t cw;  // epilogue chunk width in output channels (16 or 32) = inner box of the output tensor map
   uint32_t a_slot, b_slot, tx_bytes, sbo, layout_type;
   int32_t B, Hout, Wout, cout, cin;
@@ -42,10 +45,13 @@ struct ConvTcParams {
   const float* bias;
   int32_t act;
   int* err_flag;
+  long long* trace;  // debug timeline buffer (Y11_TRACE builds only)
   uint64_t mg_ntiles, mg_tw, mg_th;  // fast_div magics for n_tiles, tiles_w, tiles_h
   // halo mode (small-channel 3x3 stride-1 layers): the (Th+2)x(Tw+2) input halo of a tile is copied ONCE by cp.async into
   // the un-swizzled core-matrix layout [cin/8][Th+2][Tw+2][8 ch]; the nine taps are nine descriptor start offsets into it
-  int32_t halo;
+  int32_t halo;         // LSU-producer mode (1x1: pad 0; 3x3 stride 1: pad 1, Tw = 8)
+  int32_t pad, n_pos;   // positions per tile = (Tw+2pad)*(Th+2pad)*Tn
+  uint64_t mg_ncg;      // fast_div magic for cin/8
   const void* in;       // input view base (channel offset applied)
   int32_t in_ct, Hin, Win;
   uint32_t b_res_bytes; // resident weight region (all taps), loaded once per CTA
