@@ -129,12 +129,19 @@ int y11_plan_add_dwconv(y11_plan p, const y11_dwconv_desc* d);
 int y11_plan_add_sppf(y11_plan p, const y11_sppf_desc* d);
 int y11_plan_add_upsample(y11_plan p, const y11_upsample_desc* d);
 int y11_plan_add_attention(y11_plan p, const y11_attn_desc* d);
+/* Lanes: ops added after y11_plan_set_lane(p, k) run on side lane k (1..7), concurrently with lane 0 (the caller's
+ * stream).  y11_plan_fork(p, k): lane k starts after everything added to lane 0 so far; y11_plan_join(p, k): lane 0
+ * continues only after everything added to lane k so far.  Used for the six independent Detect towers [a12]. */
+int y11_plan_fork(y11_plan p, int lane);
+int y11_plan_set_lane(y11_plan p, int lane);
+int y11_plan_join(y11_plan p, int lane);
 int y11_plan_num_ops(y11_plan p);
 /* kernels launched by one y11_plan_run (for bench.py's gpu_launches). */
 int y11_plan_num_launches(y11_plan p);
-/* Enqueue every op on `s` (capturable in a CUDA graph). */
+/* Enqueue every op: lane 0 on `s`, side lanes on plan-owned streams forked from / joined into `s` (capturable in a
+ * CUDA graph, where the lanes become parallel branches). */
 int y11_plan_run(y11_plan p, y11_stream s);
-/* Run ops [first, last) only. */
+/* Run ops [first, last) only, serially on `s` (lanes ignored; op order is a valid topological order). */
 int y11_plan_run_range(y11_plan p, int first, int last, y11_stream s);
 /* Run with a CUDA-event pair around every op; ms_per_op has y11_plan_num_ops entries. Synchronises. */
 int y11_plan_run_timed(y11_plan p, y11_stream s, float* ms_per_op);

@@ -84,6 +84,9 @@ SIGNATURES = {
     "y11_plan_add_sppf": (C.c_int, [_P, C.POINTER(SppfDesc)]),
     "y11_plan_add_upsample": (C.c_int, [_P, C.POINTER(UpsampleDesc)]),
     "y11_plan_add_attention": (C.c_int, [_P, C.POINTER(AttnDesc)]),
+    "y11_plan_fork": (C.c_int, [_P, C.c_int]),
+    "y11_plan_set_lane": (C.c_int, [_P, C.c_int]),
+    "y11_plan_join": (C.c_int, [_P, C.c_int]),
     "y11_plan_num_ops": (C.c_int, [_P]),
     "y11_plan_num_launches": (C.c_int, [_P]),
     "y11_plan_run": (C.c_int, [_P, _P]),

@@ -71,9 +71,20 @@ struct PlanOp {
   double flops;
 };
 
+// Schedule entry: a kernel launch on a lane, or a fork/join edge between lane 0 (the caller's stream) and a side lane.
+// Lanes let independent branches of the network (the six Detect towers) run concurrently: the towers of the 80x80 level
+// start as soon as the P3 feature map exists and overlap the small, GPU-underfilling layers of the rest of the neck.
+enum SchedKind { S_OP, S_FORK, S_JOIN };
+struct SchedItem { SchedKind kind; int op; int lane; };
+constexpr int kMaxLanes = 8;
+
 struct y11_plan_s {
   y11_engine* eng;
   std::vector<PlanOp*> ops;
+  std::vector<SchedItem> sched;
+  int cur_lane = 0;
+  cudaStream_t lanes[kMaxLanes] = {};     // [0] unused (caller's stream); side lanes are created lazily
+  cudaEvent_t fork_ev[kMaxLanes] = {}, join_ev[kMaxLanes] = {};
   cudaEvent_t* events = nullptr;
   int n_events = 0;
 };
@@ -89,6 +100,11 @@ extern "C" int y11_plan_create(y11_handle h, y11_plan* out) {
 extern "C" void y11_plan_destroy(y11_plan p) {
   if (!p) return;
   for (PlanOp* op : p->ops) delete op;
+  for (int l = 1; l < kMaxLanes; ++l) {
+    if (p->lanes[l]) cudaStreamDestroy(p->lanes[l]);
+    if (p->fork_ev[l]) cudaEventDestroy(p->fork_ev[l]);
+    if (p->join_ev[l]) cudaEventDestroy(p->join_ev[l]);
+  }
   for (int i = 0; i < p->n_events; ++i) cudaEventDestroy(p->events[i]);
   delete[] p->events;
   delete p;
@@ -111,6 +127,7 @@ extern "C" int y11_plan_add_conv(y11_plan p, const y11_conv_desc* d) {
     if (int e = conv_tc_prepare(p->eng, d, &op->tc)) { delete op; return e; }
   }
   p->ops.push_back(op);
+  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane});
   return 0;
 }
 
@@ -121,6 +138,7 @@ extern "C" int y11_plan_add_stem(y11_plan p, const y11_stem_desc* d) {
   op->d.stem = *d;
   op->flops = 2.0 * d->B * d->Hout * d->Wout * (double)d->out.c * 27;
   p->ops.push_back(op);
+  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane});
   return 0;
 }
 
@@ -130,6 +148,7 @@ extern "C" int y11_plan_add_dwconv(y11_plan p, const y11_dwconv_desc* d) {
   op->d.dw = *d;
   op->flops = 2.0 * d->B * d->H * d->W * (double)d->in.c * 9;
   p->ops.push_back(op);
+  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane});
   return 0;
 }
 
@@ -138,6 +157,7 @@ extern "C" int y11_plan_add_sppf(y11_plan p, const y11_sppf_desc* d) {
   PlanOp* op = new_op(OP_SPPF);
   op->d.sppf = *d;
   p->ops.push_back(op);
+  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane});
   return 0;
 }
 
@@ -146,6 +166,7 @@ extern "C" int y11_plan_add_upsample(y11_plan p, const y11_upsample_desc* d) {
   PlanOp* op = new_op(OP_UPSAMPLE);
   op->d.up = *d;
   p->ops.push_back(op);
+  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane});
   return 0;
 }
 
@@ -155,6 +176,7 @@ extern "C" int y11_plan_add_attention(y11_plan p, const y11_attn_desc* d) {
   op->d.attn = *d;
   op->flops = 2.0 * d->B * d->heads * (double)d->N * d->N * (d->kd + d->hd);
   p->ops.push_back(op);
+  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane});
   return 0;
 }
 
@@ -175,6 +197,32 @@ static int run_op(const PlanOp* op, cudaStream_t s) {
   return -1;
 }
 
+extern "C" int y11_plan_fork(y11_plan p, int lane) {
+  Y11_REQUIRE(p && lane >= 1 && lane < kMaxLanes, "plan_fork: lane %d out of range [1, %d)", lane, kMaxLanes);
+  Y11_REQUIRE(p->cur_lane == 0, "plan_fork: forks are issued from lane 0");
+  if (!p->lanes[lane]) {
+    Y11_CHECK_CUDA(cudaStreamCreateWithFlags(&p->lanes[lane], cudaStreamNonBlocking));
+    Y11_CHECK_CUDA(cudaEventCreateWithFlags(&p->fork_ev[lane], cudaEventDisableTiming));
+    Y11_CHECK_CUDA(cudaEventCreateWithFlags(&p->join_ev[lane], cudaEventDisableTiming));
+  }
+  p->sched.push_back({S_FORK, -1, lane});
+  return 0;
+}
+
+extern "C" int y11_plan_set_lane(y11_plan p, int lane) {
+  Y11_REQUIRE(p && lane >= 0 && lane < kMaxLanes && (lane == 0 || p->lanes[lane]), "plan_set_lane: lane %d not forked", lane);
+  p->cur_lane = lane;
+  return 0;
+}
+
+extern "C" int y11_plan_join(y11_plan p, int lane) {
+  Y11_REQUIRE(p && lane >= 1 && lane < kMaxLanes && p->lanes[lane], "plan_join: lane %d not forked", lane);
+  p->sched.push_back({S_JOIN, -1, lane});
+  return 0;
+}
+
+// Serial execution of ops [first, last) on one stream (tests, per-op timing, weight conditioning): lanes are ignored,
+// the op order is a valid topological order.
 extern "C" int y11_plan_run_range(y11_plan p, int first, int last, y11_stream s) {
   Y11_REQUIRE(p && first >= 0 && last <= (int)p->ops.size() && first <= last, "plan_run_range: bad range");
   for (int i = first; i < last; ++i)
@@ -182,7 +230,28 @@ extern "C" int y11_plan_run_range(y11_plan p, int first, int last, y11_stream s)
   return 0;
 }
 
-extern "C" int y11_plan_run(y11_plan p, y11_stream s) { return y11_plan_run_range(p, 0, p ? (int)p->ops.size() : 0, s); }
+// Whole plan with its lanes: side lanes fork from / join into the caller's stream through events, which is also how a
+// stream capture turns them into parallel branches of the CUDA graph.
+extern "C" int y11_plan_run(y11_plan p, y11_stream s_) {
+  Y11_REQUIRE(p, "plan_run: null plan");
+  cudaStream_t s0 = static_cast<cudaStream_t>(s_);
+  for (const SchedItem& it : p->sched) {
+    switch (it.kind) {
+      case S_OP:
+        if (int e = run_op(p->ops[it.op], it.lane == 0 ? s0 : p->lanes[it.lane])) return e;
+        break;
+      case S_FORK:
+        Y11_CHECK_CUDA(cudaEventRecord(p->fork_ev[it.lane], s0));
+        Y11_CHECK_CUDA(cudaStreamWaitEvent(p->lanes[it.lane], p->fork_ev[it.lane], 0));
+        break;
+      case S_JOIN:
+        Y11_CHECK_CUDA(cudaEventRecord(p->join_ev[it.lane], p->lanes[it.lane]));
+        Y11_CHECK_CUDA(cudaStreamWaitEvent(s0, p->join_ev[it.lane], 0));
+        break;
+    }
+  }
+  return 0;
+}
 
 extern "C" int y11_plan_run_timed(y11_plan p, y11_stream s_, float* ms_per_op) {
   Y11_REQUIRE(p && ms_per_op, "plan_run_timed: null argument");

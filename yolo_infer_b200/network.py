@@ -261,26 +261,34 @@ class CompiledNet:
         cabi.check(self.lib.y11_plan_add_upsample(self.plan, C.byref(d)), "plan_add_upsample")
         self.ops.append(OpRecord("upsample", "upsample", 0.0, self.B * x.H * x.W * x.c * 2 * 5))
 
-    def _detect(self, sp: T.LayerSpec, xs: List[V]):
+    def _detect_level(self, sp: T.LayerSpec, l: int, x: V):
+        """One level of the Detect head.  Its box tower and class tower are independent chains: each gets its own lane
+        (parallel branch of the CUDA graph), forked as soon as the level's feature map exists."""
         p = f"model.{sp.index}"
         c2, c3 = T.detect_dims(sp.ch_in, self.nc)
-        for l, x in enumerate(xs):
-            head = self._alloc(x.H, x.W, self.no, torch.float32)
-            self.head.append(head)
-            t1 = self._new(x.H, x.W, c2)
-            t2 = self._new(x.H, x.W, c2)
-            self._conv(f"{p}.cv2.{l}.0", x, t1)
-            self._conv(f"{p}.cv2.{l}.1", t1, t2)
-            self._conv(f"{p}.cv2.{l}.2", t2, V(head, 0, 64), out_f32=True)
-            u1 = self._new(x.H, x.W, x.c)
-            u2 = self._new(x.H, x.W, c3)
-            u3 = self._new(x.H, x.W, c3)
-            u4 = self._new(x.H, x.W, c3)
-            self._dw(f"{p}.cv3.{l}.0.0", x, u1)
-            self._conv(f"{p}.cv3.{l}.0.1", u1, u2)
-            self._dw(f"{p}.cv3.{l}.1.0", u2, u3)
-            self._conv(f"{p}.cv3.{l}.1.1", u3, u4)
-            self._conv(f"{p}.cv3.{l}.2", u4, V(head, 64, pad16(self.nc)), out_f32=True)
+        lane_box, lane_cls = 1 + 2 * l, 2 + 2 * l
+        for lane in (lane_box, lane_cls):
+            cabi.check(self.lib.y11_plan_fork(self.plan, lane), "plan_fork")
+        head = self._alloc(x.H, x.W, self.no, torch.float32)
+        self.head.append(head)
+        cabi.check(self.lib.y11_plan_set_lane(self.plan, lane_box), "plan_set_lane")
+        t1 = self._new(x.H, x.W, c2)
+        t2 = self._new(x.H, x.W, c2)
+        self._conv(f"{p}.cv2.{l}.0", x, t1)
+        self._conv(f"{p}.cv2.{l}.1", t1, t2)
+        self._conv(f"{p}.cv2.{l}.2", t2, V(head, 0, 64), out_f32=True)
+        cabi.check(self.lib.y11_plan_set_lane(self.plan, lane_cls), "plan_set_lane")
+        u1 = self._new(x.H, x.W, x.c)
+        u2 = self._new(x.H, x.W, c3)
+        u3 = self._new(x.H, x.W, c3)
+        u4 = self._new(x.H, x.W, c3)
+        self._dw(f"{p}.cv3.{l}.0.0", x, u1)
+        self._conv(f"{p}.cv3.{l}.0.1", u1, u2)
+        self._dw(f"{p}.cv3.{l}.1.0", u2, u3)
+        self._conv(f"{p}.cv3.{l}.1.1", u3, u4)
+        self._conv(f"{p}.cv3.{l}.2", u4, V(head, 64, pad16(self.nc)), out_f32=True)
+        cabi.check(self.lib.y11_plan_set_lane(self.plan, 0), "plan_set_lane")
+        self.head_lanes += [lane_box, lane_cls]
 
     # ---- graph ----------------------------------------------------------------------------------
     def _build(self):
@@ -306,6 +314,8 @@ class CompiledNet:
                 return cat_buf[ci].sub(off, sp.c2)
             return self._new(h, w, sp.c2)
 
+        detect = next(sp for sp in specs if sp.kind == "Detect")
+        self.head_lanes: List[int] = []
         for sp in specs:
             if sp.kind == "Conv":
                 if sp.index == 0:
@@ -332,9 +342,13 @@ class CompiledNet:
             elif sp.kind == "Concat":
                 o = cat_buf[sp.index]
             elif sp.kind == "Detect":
-                self._detect(sp, [outs[i] for i in sp.frm])
+                assert len(self.head) == len(sp.frm)     # every level was emitted right after its feature map
+                for lane in self.head_lanes:
+                    cabi.check(self.lib.y11_plan_join(self.plan, lane), "plan_join")
                 o = None
             outs[sp.index] = o
+            if sp.index in detect.frm:
+                self._detect_level(detect, detect.frm.index(sp.index), o)
         self.layer_out = outs
         self.n_ops = self.lib.y11_plan_num_ops(self.plan)
         self.n_launches = self.lib.y11_plan_num_launches(self.plan)
