@@ -141,6 +141,8 @@ int y11_plan_num_launches(y11_plan p);
 /* Enqueue every op: lane 0 on `s`, side lanes on plan-owned streams forked from / joined into `s` (capturable in a
  * CUDA graph, where the lanes become parallel branches). */
 int y11_plan_run(y11_plan p, y11_stream s);
+/* Ops [first, last) with their lanes (a fork/join pair must lie inside one range). */
+int y11_plan_run_ops(y11_plan p, int first, int last, y11_stream s);
 /* Run ops [first, last) only, serially on `s` (lanes ignored; op order is a valid topological order). */
 int y11_plan_run_range(y11_plan p, int first, int last, y11_stream s);
 /* Run with a CUDA-event pair around every op; ms_per_op has y11_plan_num_ops entries. Synchronises. */

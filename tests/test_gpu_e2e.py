@@ -299,3 +299,20 @@ def test_cuda_graph_pipeline_equals_eager_predict(engines):
     r2 = eng.predict(other.pin_memory(), conf=0.3, iou=0.45, verbose=False)
     e2 = eng.predict([f.numpy() for f in other], conf=0.3, iou=0.45, verbose=False)
     assert all(torch.equal(a.boxes.data.cpu(), b.boxes.data.cpu()) for a, b in zip(e2, r2))
+
+
+def test_chunked_host_pipeline_equals_eager_predict(engines):
+    """Host-fed batches with B % 4 == 0, B >= 16 cross PCIe in four chunks while layers 0-4 of the previous chunk run
+    (one graph per chunk + one for the rest): results must be bit-identical to the eager path, call after call."""
+    eng = engines("n")[0]
+    g = torch.Generator().manual_seed(33)
+    for rep in range(2):
+        frames = torch.randint(0, 256, (16, 192, 320, 3), dtype=torch.uint8, generator=g)
+        eager = eng.predict([f.numpy() for f in frames], conf=0.3, iou=0.45, verbose=False)
+        pipe = eng.pipeline(16, 192, 320, 640, True, 0.3, 0.45, 300)
+        assert pipe.chunks == 4 and len(pipe.graphs) == 5 and len(pipe.net.prefix_ranges) == 4, (pipe.chunks, len(pipe.graphs))
+        for src in (frames.pin_memory(), frames.cuda()):
+            got = eng.predict(src, conf=0.3, iou=0.45, verbose=False)
+            assert len(got) == 16
+            for a, b in zip(eager, got):
+                assert torch.equal(a.boxes.data.cpu(), b.boxes.data.cpu())

@@ -90,6 +90,7 @@ SIGNATURES = {
     "y11_plan_num_ops": (C.c_int, [_P]),
     "y11_plan_num_launches": (C.c_int, [_P]),
     "y11_plan_run": (C.c_int, [_P, _P]),
+    "y11_plan_run_ops": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "y11_plan_run_range": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "y11_plan_run_timed": (C.c_int, [_P, _P, C.POINTER(C.c_float)]),
     "y11_plan_op_flops": (C.c_double, [_P, C.c_int]),

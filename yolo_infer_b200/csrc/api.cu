@@ -75,7 +75,7 @@ struct PlanOp {
 // Lanes let independent branches of the network (the six Detect towers) run concurrently: the towers of the 80x80 level
 // start as soon as the P3 feature map exists and overlap the small, GPU-underfilling layers of the rest of the neck.
 enum SchedKind { S_OP, S_FORK, S_JOIN };
-struct SchedItem { SchedKind kind; int op; int lane; };
+struct SchedItem { SchedKind kind; int op; int lane; int pos; };  // pos = number of ops added before this item
 constexpr int kMaxLanes = 8;
 
 struct y11_plan_s {
@@ -127,7 +127,7 @@ extern "C" int y11_plan_add_conv(y11_plan p, const y11_conv_desc* d) {
     if (int e = conv_tc_prepare(p->eng, d, &op->tc)) { delete op; return e; }
   }
   p->ops.push_back(op);
-  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane});
+  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane, (int)p->ops.size() - 1});
   return 0;
 }
 
@@ -138,7 +138,7 @@ extern "C" int y11_plan_add_stem(y11_plan p, const y11_stem_desc* d) {
   op->d.stem = *d;
   op->flops = 2.0 * d->B * d->Hout * d->Wout * (double)d->out.c * 27;
   p->ops.push_back(op);
-  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane});
+  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane, (int)p->ops.size() - 1});
   return 0;
 }
 
@@ -148,7 +148,7 @@ extern "C" int y11_plan_add_dwconv(y11_plan p, const y11_dwconv_desc* d) {
   op->d.dw = *d;
   op->flops = 2.0 * d->B * d->H * d->W * (double)d->in.c * 9;
   p->ops.push_back(op);
-  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane});
+  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane, (int)p->ops.size() - 1});
   return 0;
 }
 
@@ -157,7 +157,7 @@ extern "C" int y11_plan_add_sppf(y11_plan p, const y11_sppf_desc* d) {
   PlanOp* op = new_op(OP_SPPF);
   op->d.sppf = *d;
   p->ops.push_back(op);
-  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane});
+  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane, (int)p->ops.size() - 1});
   return 0;
 }
 
@@ -166,7 +166,7 @@ extern "C" int y11_plan_add_upsample(y11_plan p, const y11_upsample_desc* d) {
   PlanOp* op = new_op(OP_UPSAMPLE);
   op->d.up = *d;
   p->ops.push_back(op);
-  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane});
+  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane, (int)p->ops.size() - 1});
   return 0;
 }
 
@@ -176,7 +176,7 @@ extern "C" int y11_plan_add_attention(y11_plan p, const y11_attn_desc* d) {
   op->d.attn = *d;
   op->flops = 2.0 * d->B * d->heads * (double)d->N * d->N * (d->kd + d->hd);
   p->ops.push_back(op);
-  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane});
+  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane, (int)p->ops.size() - 1});
   return 0;
 }
 
@@ -205,7 +205,7 @@ extern "C" int y11_plan_fork(y11_plan p, int lane) {
     Y11_CHECK_CUDA(cudaEventCreateWithFlags(&p->fork_ev[lane], cudaEventDisableTiming));
     Y11_CHECK_CUDA(cudaEventCreateWithFlags(&p->join_ev[lane], cudaEventDisableTiming));
   }
-  p->sched.push_back({S_FORK, -1, lane});
+  p->sched.push_back({S_FORK, -1, lane, (int)p->ops.size()});
   return 0;
 }
 
@@ -217,7 +217,7 @@ extern "C" int y11_plan_set_lane(y11_plan p, int lane) {
 
 extern "C" int y11_plan_join(y11_plan p, int lane) {
   Y11_REQUIRE(p && lane >= 1 && lane < kMaxLanes && p->lanes[lane], "plan_join: lane %d not forked", lane);
-  p->sched.push_back({S_JOIN, -1, lane});
+  p->sched.push_back({S_JOIN, -1, lane, (int)p->ops.size()});
   return 0;
 }
 
@@ -230,27 +230,36 @@ extern "C" int y11_plan_run_range(y11_plan p, int first, int last, y11_stream s)
   return 0;
 }
 
-// Whole plan with its lanes: side lanes fork from / join into the caller's stream through events, which is also how a
-// stream capture turns them into parallel branches of the CUDA graph.
-extern "C" int y11_plan_run(y11_plan p, y11_stream s_) {
-  Y11_REQUIRE(p, "plan_run: null plan");
+// Ops [first, last) with their lanes: side lanes fork from / join into the caller's stream through events, which is also
+// how a stream capture turns them into parallel branches of the CUDA graph.  A fork belongs to the range of the op that
+// follows it, a join to the range of the op that precedes it.
+extern "C" int y11_plan_run_ops(y11_plan p, int first, int last, y11_stream s_) {
+  Y11_REQUIRE(p && first >= 0 && last <= (int)p->ops.size() && first <= last, "plan_run_ops: bad range");
   cudaStream_t s0 = static_cast<cudaStream_t>(s_);
   for (const SchedItem& it : p->sched) {
     switch (it.kind) {
       case S_OP:
+        if (it.pos < first || it.pos >= last) break;
         if (int e = run_op(p->ops[it.op], it.lane == 0 ? s0 : p->lanes[it.lane])) return e;
         break;
       case S_FORK:
+        if (it.pos < first || it.pos >= last) break;
         Y11_CHECK_CUDA(cudaEventRecord(p->fork_ev[it.lane], s0));
         Y11_CHECK_CUDA(cudaStreamWaitEvent(p->lanes[it.lane], p->fork_ev[it.lane], 0));
         break;
       case S_JOIN:
+        if (it.pos <= first || it.pos > last) break;
         Y11_CHECK_CUDA(cudaEventRecord(p->join_ev[it.lane], p->lanes[it.lane]));
         Y11_CHECK_CUDA(cudaStreamWaitEvent(s0, p->join_ev[it.lane], 0));
         break;
     }
   }
   return 0;
+}
+
+extern "C" int y11_plan_run(y11_plan p, y11_stream s) {
+  Y11_REQUIRE(p, "plan_run: null plan");
+  return y11_plan_run_ops(p, 0, (int)p->ops.size(), s);
 }
 
 extern "C" int y11_plan_run_timed(y11_plan p, y11_stream s_, float* ms_per_op) {

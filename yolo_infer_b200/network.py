@@ -106,6 +106,14 @@ class V:
         assert off + c <= self.c
         return V(self.t, self.off + off, c)
 
+    @property
+    def B(self):
+        return self.t.shape[0]
+
+    def bslice(self, b0: int, nb: int) -> "V":
+        """The same channel view over images [b0, b0+nb) (batch is the outermost dimension: a pointer offset)."""
+        return V(self.t[b0:b0 + nb], self.off, self.c)
+
     def cview(self) -> cabi.View:
         return cabi.View(self.t.data_ptr(), self.t.shape[-1], self.off, self.c)
 
@@ -124,9 +132,17 @@ class OpRecord:
 class CompiledNet:
     """One (scale, B, H, W) instance: owns activation buffers, the plan handle and the head tensors."""
 
+    PREFIX_LAYERS = 5   # yaml layers 0-4 (stem .. first stride-8 C3k2): the high-resolution, memory-heavy part
+
     def __init__(self, engine, scale: str, nc: int, packed: Dict[str, PackedConv], B: int, H: int, W: int, device,
-                 conv_impl: int = cabi.IMPL_TCGEN05):
+                 conv_impl: int = cabi.IMPL_TCGEN05, chunks: int = 1):
+        """chunks > 1: layers 0-4 are emitted once per batch chunk (chunk-major), so that a host-fed pipeline can run chunk c
+        while chunk c+1 is still on the PCIe bus (engine.GraphedPipeline); the rest of the network runs on the whole batch."""
         assert H % 32 == 0 and W % 32 == 0, "network input must be a multiple of 32"
+        assert chunks >= 1 and B % chunks == 0, (B, chunks)
+        self.chunks = chunks
+        self._cur_B = B
+        self.prefix_ranges: List[Tuple[int, int]] = []
         self.lib = cabi.load()
         self.engine = engine
         self.scale, self.nc, self.B, self.H, self.W, self.device = scale, nc, B, H, W, device
@@ -152,7 +168,7 @@ class CompiledNet:
 
     # ---- buffers ------------------------------------------------------------------------------
     def _alloc(self, h: int, w: int, c: int, dtype=torch.bfloat16) -> torch.Tensor:
-        t = torch.zeros((self.B, h, w, c), dtype=dtype, device=self.device)
+        t = torch.zeros((self._cur_B, h, w, c), dtype=dtype, device=self.device)
         self.buffers.append(t)
         return t
 
@@ -170,12 +186,13 @@ class CompiledNet:
         d.inp, d.out = x.cview(), out.cview()
         d.res = res.cview() if res is not None else cabi.NULL_VIEW
         d.w, d.bias = pc.w.data_ptr(), pc.b.data_ptr()
-        d.B, d.Hin, d.Win, d.Hout, d.Wout = self.B, x.H, x.W, out.H, out.W
+        assert x.B == out.B
+        d.B, d.Hin, d.Win, d.Hout, d.Wout = x.B, x.H, x.W, out.H, out.W
         d.k, d.stride, d.act, d.out_f32, d.impl = pc.k, pc.s, pc.act, int(out_f32), self.conv_impl
         cabi.check(self.lib.y11_plan_add_conv(self.plan, C.byref(d)), f"plan_add_conv({name})")
-        px = self.B * out.H * out.W
+        px = x.B * out.H * out.W
         self.ops.append(OpRecord("conv", name, 2.0 * px * pc.c2 * pc.c1 * pc.k * pc.k,
-                                 self.B * x.H * x.W * pc.c1 * 2 + pc.w.numel() * 2 + px * pc.c2 * (4 if out_f32 else 2)
+                                 x.B * x.H * x.W * pc.c1 * 2 + pc.w.numel() * 2 + px * pc.c2 * (4 if out_f32 else 2)
                                  + (px * pc.c2 * 2 if res is not None else 0), out, x, res))
 
     def _dw(self, name: str, x: V, out: V, res: Optional[V] = None):
@@ -185,9 +202,9 @@ class CompiledNet:
         d.inp, d.out = x.cview(), out.cview()
         d.res = res.cview() if res is not None else cabi.NULL_VIEW
         d.w, d.bias = pc.w.data_ptr(), pc.b.data_ptr()
-        d.B, d.H, d.W, d.act = self.B, x.H, x.W, pc.act
+        d.B, d.H, d.W, d.act = x.B, x.H, x.W, pc.act
         cabi.check(self.lib.y11_plan_add_dwconv(self.plan, C.byref(d)), f"plan_add_dwconv({name})")
-        px = self.B * x.H * x.W
+        px = x.B * x.H * x.W
         self.ops.append(OpRecord("dwconv", name, 2.0 * px * pc.c1 * 9, px * pc.c1 * 2 * (3 if res is not None else 2), out, x, res))
 
     # ---- modules ------------------------------------------------------------------------------
@@ -316,31 +333,61 @@ class CompiledNet:
 
         detect = next(sp for sp in specs if sp.kind == "Detect")
         self.head_lanes: List[int] = []
-        for sp in specs:
-            if sp.kind == "Conv":
-                if sp.index == 0:
-                    h, w = H // 2, W // 2
-                    o = out_view(sp, h, w)
-                    pc = self.packed["model.0"]
-                    d = cabi.StemDesc(self.input.data_ptr(), o.cview(), pc.w.data_ptr(), pc.b.data_ptr(), self.B, H, W, h, w)
-                    cabi.check(self.lib.y11_plan_add_stem(self.plan, C.byref(d)), "plan_add_stem")
-                    self.ops.append(OpRecord("stem", "model.0", 2.0 * self.B * h * w * sp.c2 * 27,
-                                             self.B * (H * W * 3 * 2 + h * w * sp.c2 * 2), o))
-                else:
-                    x = outs[sp.frm[0]]
-                    h, w = (x.H + 1) // 2, (x.W + 1) // 2
-                    o = out_view(sp, h, w)
-                    self._conv(f"model.{sp.index}", x, o)
-            elif sp.kind in ("C3k2", "SPPF", "C2PSA"):
-                x = outs[sp.frm[0]]
-                o = out_view(sp, x.H, x.W)
+
+        def out_hw(sp: T.LayerSpec, src_hw: Dict[int, Tuple[int, int]]) -> Tuple[int, int]:
+            if sp.index == 0:
+                return H // 2, W // 2
+            ih, iw = src_hw[sp.frm[0]]
+            return ((ih + 1) // 2, (iw + 1) // 2) if sp.kind == "Conv" else (ih, iw)
+
+        def emit(sp: T.LayerSpec, x: Optional[V], o: V, inp: torch.Tensor):
+            """Ops of one backbone/neck layer: x -> o (stem: the letterboxed frames `inp` -> o)."""
+            if sp.kind == "Conv" and sp.index == 0:
+                pc = self.packed["model.0"]
+                nb = inp.shape[0]
+                d = cabi.StemDesc(inp.data_ptr(), o.cview(), pc.w.data_ptr(), pc.b.data_ptr(), nb, H, W, o.H, o.W)
+                cabi.check(self.lib.y11_plan_add_stem(self.plan, C.byref(d)), "plan_add_stem")
+                self.ops.append(OpRecord("stem", "model.0", 2.0 * nb * o.H * o.W * sp.c2 * 27,
+                                         nb * (H * W * 3 * 2 + o.H * o.W * sp.c2 * 2), o))
+            elif sp.kind == "Conv":
+                self._conv(f"model.{sp.index}", x, o)
+            else:
                 {"C3k2": self._c3k2, "SPPF": self._sppf, "C2PSA": self._c2psa}[sp.kind](sp, x, o)
+
+        n_prefix = 0
+        if self.chunks > 1:
+            # Chunk-major prefix: full-batch output buffers first, then for every batch chunk the ops of layers
+            # 0..PREFIX_LAYERS-1 on that chunk's slice (intermediates are chunk-sized and private to the chunk).
+            n_prefix = self.PREFIX_LAYERS
+            assert all(sp.kind in ("Conv", "C3k2") and tuple(sp.frm) == (sp.index - 1,) for sp in specs[1:n_prefix])
+            for sp in specs[:n_prefix]:
+                hw[sp.index] = out_hw(sp, hw)
+                outs[sp.index] = out_view(sp, *hw[sp.index])
+            Bc = self.B // self.chunks
+            for c in range(self.chunks):
+                first = len(self.ops)
+                self._cur_B = Bc
+                x = None
+                for sp in specs[:n_prefix]:
+                    o = outs[sp.index].bslice(c * Bc, Bc)
+                    emit(sp, x, o, self.input[c * Bc:(c + 1) * Bc])
+                    x = o
+                self._cur_B = self.B
+                self.prefix_ranges.append((first, len(self.ops)))
+        for sp in specs[n_prefix:]:
+            if sp.kind in ("Conv", "C3k2", "SPPF", "C2PSA"):
+                x = outs[sp.frm[0]] if sp.index else None
+                hw[sp.index] = out_hw(sp, hw)
+                o = out_view(sp, *hw[sp.index])
+                emit(sp, x, o, self.input)
             elif sp.kind == "Upsample":
                 x = outs[sp.frm[0]]
+                hw[sp.index] = (2 * x.H, 2 * x.W)
                 o = out_view(sp, 2 * x.H, 2 * x.W)
                 self._upsample(x, o)
             elif sp.kind == "Concat":
                 o = cat_buf[sp.index]
+                hw[sp.index] = (o.H, o.W)
             elif sp.kind == "Detect":
                 assert len(self.head) == len(sp.frm)     # every level was emitted right after its feature map
                 for lane in self.head_lanes:
@@ -349,6 +396,7 @@ class CompiledNet:
             outs[sp.index] = o
             if sp.index in detect.frm:
                 self._detect_level(detect, detect.frm.index(sp.index), o)
+        self.rest_first = self.prefix_ranges[-1][1] if self.prefix_ranges else 0
         self.layer_out = outs
         self.n_ops = self.lib.y11_plan_num_ops(self.plan)
         self.n_launches = self.lib.y11_plan_num_launches(self.plan)
@@ -357,6 +405,10 @@ class CompiledNet:
     # ---- execution ------------------------------------------------------------------------------
     def run(self, stream: int) -> None:
         cabi.check(self.lib.y11_plan_run(self.plan, C.c_void_p(stream)), "y11_plan_run")
+
+    def run_ops(self, first: int, last: int, stream: int) -> None:
+        """Ops [first, last) with their lanes (parallel Detect towers)."""
+        cabi.check(self.lib.y11_plan_run_ops(self.plan, first, last, C.c_void_p(stream)), "y11_plan_run_ops")
 
     def run_range(self, first: int, last: int, stream: int) -> None:
         cabi.check(self.lib.y11_plan_run_range(self.plan, first, last, C.c_void_p(stream)), "y11_plan_run_range")
