@@ -29,3 +29,14 @@ def fetch(i):
 print("copy+replay+fetch    %.3f ms" % t(fetch))
 print("predict              %.3f ms" % t(lambda i: eng.predict(host[i % 3], verbose=False)))
 print("predict + r.cpu()    %.3f ms" % t(lambda i: [r.cpu().boxes.data for r in eng.predict(host[i % 3], verbose=False)]))
+
+# ---- postprocess alone (heads as left by the last pass) ----
+net = pipe.net
+import ctypes as C
+from yolo_infer_b200 import _cabi as cabi
+def post(i):
+    with torch.inference_mode():
+        eng.postprocess(net, pipe.scale_rows, 0.25, 0.7, 300)
+print("postprocess only     %.3f ms  (mean candidates %.0f)" % (t(post, 20), float(pipe.ncand.float().mean())))
+lib = eng._lib
+hd = net.head_desc()

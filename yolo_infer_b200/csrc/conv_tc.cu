@@ -586,7 +586,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
     const int mode = e ? atoi(e) : 3;  // bit 0: 3x3 halo tiles, bit 1: 1x1
     const size_t wbytes = (size_t)d->k * d->k * cin * cout * 2;
     const bool k3 = d->k == 3 && d->stride == 1 && cin <= 64 && d->Hout >= 32 && d->Wout >= 32 && (mode & 1);
-    const bool k1 = d->k == 1 && cin <= 48 && (mode & 2);  // wider 1x1 inputs have >= 128-byte TMA rows: TMA path
+    const bool k1 = d->k == 1 && (cin <= 32 || (cin % 32 != 0 && cin <= 112)) && (mode & 2);  // TMA rows would be 32-64 B
     p.halo = (k1 || k3) && cout <= 128 && wbytes <= 40 * 1024;
     p.pad = k3 ? 1 : 0;
   }

@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
   __shared__ int t_idx[kTile];
   __shared__ unsigned long long t_mask[kTile][kTile / 64];
   __shared__ unsigned int t_dead[kTile / 32];
+  __shared__ int t_keep[kTile];
   __shared__ int s_nk;
 
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -365,30 +366,35 @@ __global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
         if (lane == wsel) todo &= ~((2ull << bit) - 1ull);  // bits <= c are settled
         if (lane > wsel && lane < kTile / 64) { /* later words untouched */ }
         if (lane < wsel) todo = 0ull;
-        if (lane == 0) {
-          kbox[nk] = t_box[c];
-          karea[nk] = t_area[c];
-          const int idx = t_idx[c];
-          if (g.out_keep) g.out_keep[(size_t)b * g.max_det + nk] = idx;
-          if (g.out_det) {
-            float4 bx = g.cbox[ob + idx];
-            if (g.scale) {
-              const float* sc = g.scale + (size_t)b * 5;
-              const float gain = sc[0], px = sc[1], py = sc[2], w0 = sc[3], h0 = sc[4];
-              bx.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.x, px), gain), 0.f), w0);
-              bx.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.y, py), gain), 0.f), h0);
-              bx.z = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.z, px), gain), 0.f), w0);
-              bx.w = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.w, py), gain), 0.f), h0);
-            }
-            float* o = g.out_det + ((size_t)b * g.max_det + nk) * 6;
-            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-            o[4] = g.cscore[ob + idx];
-            o[5] = g.ccls[ob + idx];
-          }
-        }
+        if (lane == 0) t_keep[nk - nk0] = c;  // results are written after the sweep, by many threads at once
         ++nk;
       }
       if (lane == 0) s_nk = nk;
+    }
+    __syncthreads();
+    // (d) publish the boxes kept in this tile: one thread per kept box.  (Doing this inside the sweep put three dependent
+    //     global loads and eight global stores on lane 0's critical path for every one of the up to max_det kept boxes.)
+    for (int k = nk0 + tid; k < s_nk; k += kNmsThreads) {
+      const int c = t_keep[k - nk0];
+      kbox[k] = t_box[c];
+      karea[k] = t_area[c];
+      const int idx = t_idx[c];
+      if (g.out_keep) g.out_keep[(size_t)b * g.max_det + k] = idx;
+      if (g.out_det) {
+        float4 bx = g.cbox[ob + idx];
+        if (g.scale) {
+          const float* sc = g.scale + (size_t)b * 5;
+          const float gain = sc[0], px = sc[1], py = sc[2], w0 = sc[3], h0 = sc[4];
+          bx.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.x, px), gain), 0.f), w0);
+          bx.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.y, py), gain), 0.f), h0);
+          bx.z = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.z, px), gain), 0.f), w0);
+          bx.w = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.w, py), gain), 0.f), h0);
+        }
+        float* o = g.out_det + ((size_t)b * g.max_det + k) * 6;
+        o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+        o[4] = g.cscore[ob + idx];
+        o[5] = g.ccls[ob + idx];
+      }
     }
     __syncthreads();
   }
