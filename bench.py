@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--skip-e2e", action="store_true", help="profiling only: skip the e2e and per-op passes")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying CUDA graphs")
     ap.add_argument("--latency-iters", type=int, default=200, help="batch-1 latency samples (0 = skip)")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="steps in flight: consecutive steps alternate between this many streams (own buffers each), so the "
+                         "under-filled tail of one step (NMS: one CTA per image) overlaps the head of the next")
     return ap.parse_args()
 
 
@@ -206,14 +209,30 @@ def run_ours(args):
     # one CUDA graph per resident input batch (letterbox + 91 network launches + 4 post-processing launches each);
     # --no-graph launches the same kernels one by one (what ncu sees with --skip-e2e)
     use_graph = not args.no_graph
-    pipes = [eng.pipeline(B, S, S, S, True, CONF, IOU, MAX_DET, frames=db, graph=use_graph) for db in dev_batches]
+    NS = max(1, min(args.streams, NROT))
+    streams = [stream] + [torch.cuda.Stream(dev) for _ in range(NS - 1)]
+    pipes = []
+    for j, db in enumerate(dev_batches):
+        with torch.cuda.stream(streams[j % NS]):
+            pipes.append(eng.pipeline(B, S, S, S, True, CONF, IOU, MAX_DET, frames=db, graph=use_graph, replica=j % NS))
+    torch.cuda.synchronize(dev)
 
     def step_resident(i: int):
-        det, cnt, ncand = pipes[i % NROT].run()
-        if world > 1:  # the only collective of the path: gather the fixed-shape results (461 KB/rank) so every rank,
-            from yolo_infer_b200.parallel import gather_detections  # hence rank 0, holds the whole global batch
-            gather_detections(det, cnt)
+        j = i % NROT
+        with torch.cuda.stream(streams[j % NS]):
+            det, cnt, ncand = pipes[j].run()
+            if world > 1:  # the only collective of the path: gather the fixed-shape results (461 KB/rank) so every rank,
+                from yolo_infer_b200.parallel import gather_detections  # hence rank 0, holds the whole global batch
+                gather_detections(det, cnt)
         return det, cnt, ncand
+
+    def fork():   # side streams start after everything enqueued on the main stream
+        for st in streams[1:]:
+            st.wait_stream(stream)
+
+    def join():   # the main stream continues after everything enqueued on the side streams
+        for st in streams[1:]:
+            stream.wait_stream(st)
 
     def barrier():
         if world > 1:
@@ -226,8 +245,10 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         e0.record(stream)
+        fork()
         for i in range(args.steps):
             det, cnt, ncand = step_resident(i)
+        join()
         e1.record(stream)
         barrier()
     ms_total = e0.elapsed_time(e1)
@@ -240,7 +261,7 @@ def run_ours(args):
     mean_det = float(cnt.float().mean())
     if args.skip_e2e:
         if rank == 0:
-            print(json.dumps({"profiling_only": True, "value": value, "ms_per_step": ms_step, "launches_per_step": 1 + net.n_launches + 4}))
+            print(json.dumps({"profiling_only": True, "value": value, "ms_per_step": ms_step, "launches_per_step": pipes[0].launches}))
         return
 
     # ---- e2e through the public API from pinned host frames (H2D + D2H inside the timed region) ----
@@ -296,14 +317,28 @@ def run_ours(args):
     per_op = [m / 3 for m in per_op]
     conv_ms = sum(m for m, o in zip(per_op, net.ops) if o.kind == "conv")
     conv_flops = sum(o.flops for o in net.ops if o.kind == "conv")
+    conv_bytes = sum(o.bytes_algo for o in net.ops if o.kind == "conv")
     all_ms = sum(per_op)
     pk = peaks()
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    achieved_gbs = conv_bytes / (conv_ms / 1e3) / 1e9 if conv_ms > 0 else 0.0
     n_conv = sum(1 for o in net.ops if o.kind == "conv")
+    # DRAM bytes of the same 79 launches from the committed ncu capture (profiles/r01_traffic.json), batch 64 @640 only
+    traffic = None
+    tf = ROOT / "profiles" / "r01_traffic.json"
+    if tf.exists() and B == 64 and S == 640:
+        t = json.loads(tf.read_text()).get(args.model)
+        if t and t.get("conv_tc_launches") == n_conv:
+            traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / pk["tflops_sustained"], "traffic": None,
-            "kernel": f"conv_tc_kernel ({n_conv} launches/step, {conv_ms:.3f} ms of {all_ms:.3f} ms network time)",
+            "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
+            "kernel": f"conv_tc_kernel ({n_conv} launches/step, {conv_ms:.3f} ms of {all_ms:.3f} ms network time; achieved = "
+                      f"{conv_flops / 1e9:.1f} GFLOP / that time; traffic = DRAM bytes of the same {n_conv} launches)",
             "peak_source": f"{pk['source']} sustained bf16 (burst {pk['tflops_burst']})",
+            "algorithmic_bytes": conv_bytes,
+            "hbm_side": {"achieved": achieved_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"],
+                         "note": "same launches against the HBM roof (unfused in+weights+out bytes): the small-channel "
+                                 "layers that dominate YOLO11n/s sit below the ~250 FLOP/B ridge"},
             "whole_path_conv_frac": (value / world) * (net.conv_flops / B) / (pk["tflops_sustained"] * 1e12)}
     if args.per_op and rank == 0:
         for l, h in enumerate(net.head):
@@ -318,7 +353,7 @@ def run_ours(args):
             print(f"{m:8.4f} ms  {o.kind:9s} {o.name:28s} {tf:8.1f} TFLOP/s {gb:8.1f} GB/s(algo)", file=sys.stderr)
         print(f"network total {all_ms:.3f} ms; conv {conv_ms:.3f} ms; step {ms_step:.3f} ms", file=sys.stderr)
 
-    launches_per_step = 1 + net.n_launches + 4   # letterbox + plan + (count, scan, write, sort+nms)
+    launches_per_step = pipes[0].launches        # letterbox + plan + (count, scan, write, sort+nms)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
@@ -326,11 +361,13 @@ def run_ours(args):
                                    f"variance-conditioned weights", "global_batch": B * world, "parallelism": f"image-sharded x{world}",
                        "conf": CONF, "iou": IOU, "max_det": MAX_DET, "mean_candidates_per_image": mean_cand,
                        "mean_detections_per_image": mean_det,
+                       "steps_in_flight": NS,
                        "l2_policy": f"{NROT} rotating input batches ({NROT * B * S * S * 3 / 1e6:.0f} MB) + "
                                     f"{sum(b.numel() * b.element_size() for b in net.buffers) / 1e9:.2f} GB of activations per step (> 126 MB L2)"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * S * 3, "d2h_bytes_per_step": d2h,
-                    "api": "YOLO.predict(pinned uint8 [B,H,W,3] host tensor) -> List[Results] -> Results.cpu()", "steps": e2e_steps},
+                    "api": "YOLO.predict(pinned uint8 [B,H,W,3] host tensor) -> List[Results] -> Results.cpu(); H2D in 4 chunks "
+                           "overlapped with layers 0-4 of the previous chunk, one D2H of all results", "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps,
             "cuda_graph": use_graph,
             "latency_b1": latency,

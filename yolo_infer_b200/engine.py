@@ -217,12 +217,15 @@ class YOLO:
         elif not self._engine:
             self.to("cuda")
 
-    def compiled(self, B: int, H: int, W: int, chunks: int = 1) -> CompiledNet:
-        key = (B, H, W) if chunks == 1 else (B, H, W, chunks)
+    def compiled(self, B: int, H: int, W: int, chunks: int = 1, replica: int = 0) -> CompiledNet:
+        """replica > 0: an independent instance (own activation buffers / plan) for a pipeline that runs concurrently
+        with another one on a second stream."""
+        key = (B, H, W) if (chunks == 1 and replica == 0) else (B, H, W, chunks, replica)
         net = self._nets.get(key)
         if net is None:
             with torch.cuda.device(self.device):
                 net = CompiledNet(self._engine, self.scale, self.nc, self._packed, B, H, W, self.device, self.conv_impl, chunks)
+                net.replica = replica
             self._nets[key] = net
         return net
 
@@ -276,8 +279,9 @@ class YOLO:
         """-> (det fp32 [B,max_det,6], count int32 [B], ncand int32 [B]) device tensors."""
         B = net.B
         nbytes = self._lib.y11_postprocess_workspace(B, net.A, self.nc, int(multi_label), max_nms)
-        ws = self._workspace(("post", B, net.A, multi_label), nbytes)
-        okey = ("post_out", B, max_det)
+        rep = getattr(net, "replica", 0)
+        ws = self._workspace(("post", B, net.A, multi_label, rep), nbytes)
+        okey = ("post_out", B, max_det, rep)
         out = self._ws.get(okey)
         if out is None:
             out = (torch.zeros((B, max_det, 6), dtype=torch.float32, device=self.device),
@@ -297,19 +301,19 @@ class YOLO:
     # ---- CUDA-graph pipeline for fixed-shape uint8 batches (throughput and batch-1 latency modes) ----------------
     def pipeline(self, B: int, h0: int, w0: int, imgsz=640, rect: bool = True, conf: float = 0.25, iou: float = 0.7,
                  max_det: int = 300, agnostic: bool = False, multi_label: bool = False, frames: Optional[torch.Tensor] = None,
-                 graph: bool = True) -> "GraphedPipeline":
+                 graph: bool = True, replica: int = 0) -> "GraphedPipeline":
         """letterbox -> forward -> decode/NMS for B frames of h0 x w0, captured once as a CUDA graph (one replay per call).
         `frames`: optional device uint8 [B,h0,w0,3] tensor to bind as the graph's input (zero-copy); otherwise the pipeline
         owns a static input buffer that `run(src)` fills with one async copy (H2D from pinned memory or D2D)."""
         self._ensure_device()
         key = (B, h0, w0, imgsz if isinstance(imgsz, int) else tuple(imgsz), rect, conf, iou, max_det, agnostic, multi_label,
-               frames.data_ptr() if frames is not None else None, graph)
+               frames.data_ptr() if frames is not None else None, graph, replica)
         p = self._pipes.get(key) if hasattr(self, "_pipes") else None
         if p is None:
             if not hasattr(self, "_pipes"):
                 self._pipes = {}
             with torch.inference_mode(False):  # static buffers must stay writable from any mode
-                p = GraphedPipeline(self, B, h0, w0, imgsz, rect, conf, iou, max_det, agnostic, multi_label, frames, graph)
+                p = GraphedPipeline(self, B, h0, w0, imgsz, rect, conf, iou, max_det, agnostic, multi_label, frames, graph, replica)
             self._pipes[key] = p
         return p
 
@@ -549,7 +553,7 @@ class GraphedPipeline:
     """
 
     def __init__(self, eng: YOLO, B: int, h0: int, w0: int, imgsz, rect: bool, conf: float, iou: float, max_det: int,
-                 agnostic: bool, multi_label: bool, frames: Optional[torch.Tensor], graph: bool):
+                 agnostic: bool, multi_label: bool, frames: Optional[torch.Tensor], graph: bool, replica: int = 0):
         self.eng, self.B, self.h0, self.w0 = eng, B, h0, w0
         self.conf, self.iou, self.max_det, self.agnostic, self.multi_label = conf, iou, max_det, agnostic, multi_label
         dev = eng.device
@@ -559,7 +563,7 @@ class GraphedPipeline:
         self.owns_input = frames is None
         self.chunks = 4 if (self.owns_input and graph and B % 4 == 0 and B >= 16) else 1
         with torch.cuda.device(dev):
-            self.net = eng.compiled(B, self.H, self.W, self.chunks)
+            self.net = eng.compiled(B, self.H, self.W, self.chunks, replica)
             self.frames = frames if frames is not None else torch.zeros((B, h0, w0, 3), dtype=torch.uint8, device=dev)
             assert self.frames.shape == (B, h0, w0, 3) and self.frames.dtype == torch.uint8 and self.frames.is_cuda
             arr = (cabi.Image * B)()
