@@ -112,13 +112,18 @@ __global__ void __launch_bounds__(256) decode_dense_kernel(HeadParams hp, float*
 }
 
 // MODE 0: count candidates per 64-anchor chunk.  MODE 1: write candidates at chunk_off + in-chunk prefix (anchor order).
+// MODE 2 (single-label, A < 65536): ONE pass - the CTA reserves its slots with one atomicAdd on the image's counter, so
+// the candidate list is in arbitrary chunk order; each candidate carries its anchor index (canchor) and the sort key breaks
+// score ties by ANCHOR, which reproduces the stable sort of the anchor-ordered list exactly.
 // Only the class logits are read to decide candidacy (sigmoid is monotone: max score = sigmoid(max logit)); the DFL
 // softmaxes (64 expf per anchor) run for candidates only, in MODE 1.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 decode_compact_kernel(HeadParams hp, float conf, float logit_lo, int multi_label, int cap, int nchunks, int* __restrict__ chunk_cnt,
-                      const int* __restrict__ chunk_off, float4* __restrict__ cbox, float* __restrict__ cscore, float* __restrict__ ccls) {
+                      const int* __restrict__ chunk_off, float4* __restrict__ cbox, float* __restrict__ cscore, float* __restrict__ ccls,
+                      int* __restrict__ canchor, int* __restrict__ ncand, int* __restrict__ ncand_raw) {
   __shared__ int s_warp[8];
+  __shared__ int s_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = threadIdx.x & 3;
   const int b = blockIdx.y;
   const int a = blockIdx.x * kChunk + (threadIdx.x >> 2);
@@ -169,7 +174,19 @@ decode_compact_kernel(HeadParams hp, float conf, float logit_lo, int multi_label
     }
     return;
   }
-  int pos = chunk_off[b * nchunks + blockIdx.x] + incl - mycnt;
+  int pos;
+  if (MODE == 2) {
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int i = 0; i < 8; ++i) t += s_warp[i];
+      s_base = t ? atomicAdd(&ncand[b], t) : 0;
+      if (t && ncand_raw) atomicAdd(&ncand_raw[b], t);
+    }
+    __syncthreads();
+    pos = s_base + incl - mycnt;
+  } else {
+    pos = chunk_off[b * nchunks + blockIdx.x] + incl - mycnt;
+  }
   for (int i = 0; i < warp; ++i) pos += s_warp[i];
   const size_t ob = (size_t)b * cap;
   const bool cand = multi_label ? (__ballot_sync(0xffffffffu, mask != 0u) & gmask) != 0u : (score > conf);
@@ -205,6 +222,7 @@ decode_compact_kernel(HeadParams hp, float conf, float logit_lo, int multi_label
     cbox[ob + ppos] = box;
     cscore[ob + ppos] = score;
     ccls[ob + ppos] = (float)cls;
+    if (MODE == 2) canchor[ob + ppos] = a;
   }
 }
 
@@ -248,6 +266,7 @@ struct NmsArgs {
   const float* cscore;   // [B, cap]
   const float* ccls;     // [B, cap]
   const int* ncand;      // [B]
+  const int* canchor;    // [B, cap] anchor index of each candidate (single-pass compaction) or nullptr (list in anchor order)
   unsigned long long* keys;  // [B, keys_stride] scratch (used when n > kSmemKeys)
   float4* kbox;          // [B, max_det] kept boxes (with class offset)
   float* karea;          // [B, max_det]
@@ -284,7 +303,8 @@ __global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
     if (i < n) {
       unsigned u = __float_as_uint(g.cscore[ob + i]);
       u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // monotone map float -> unsigned
-      k = ((unsigned long long)(~u) << 32) | (unsigned)i;
+      // ties: list position when the list is in anchor order, else (anchor, slot) with the slot in the low 16 bits
+      k = ((unsigned long long)(~u) << 32) | (g.canchor ? (((unsigned)g.canchor[ob + i] << 16) | (unsigned)i) : (unsigned)i);
     }
     keys[i] = k;
   }
@@ -314,7 +334,7 @@ __global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
     const int cnt = min(kTile, K - c0);
     if (tid < kTile) {
       if (tid < cnt) {
-        const int idx = (int)(keys[c0 + tid] & 0xffffffffu);
+        const int idx = (int)(keys[c0 + tid] & (g.canchor ? 0xffffu : 0xffffffffu));
         float4 bx = g.cbox[ob + idx];
         const float off = __fmul_rn(g.ccls[ob + idx], g.class_offset);
         bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off); bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
@@ -436,7 +456,7 @@ float thr_round_down(double iou) {
 }
 
 struct Workspace {
-  float4* cbox; float* cscore; float* ccls; int* chunk_cnt; int* chunk_off; int* ncand;
+  float4* cbox; float* cscore; float* ccls; int* canchor; int* chunk_cnt; int* chunk_off; int* ncand;
   unsigned long long* keys; float4* kbox; float* karea;
   int cap, keys_stride, nchunks;
   size_t total;
@@ -456,6 +476,7 @@ void carve(Workspace* w, void* base, int B, int cap, int nchunks, int kept_cap) 
   w->cbox = (float4*)take((size_t)B * cap * 16);
   w->cscore = (float*)take((size_t)B * cap * 4);
   w->ccls = (float*)take((size_t)B * cap * 4);
+  w->canchor = (int*)take((size_t)B * cap * 4);
   w->chunk_cnt = (int*)take((size_t)B * nchunks * 4);
   w->chunk_off = (int*)take((size_t)B * nchunks * 4);
   w->ncand = (int*)take((size_t)B * 4);
@@ -514,12 +535,25 @@ extern "C" int y11_detect_postprocess(y11_handle, const y11_head_desc* hd, const
   const double cc = std::min(std::max((double)p->conf, 1e-30), 1.0 - 1e-9);
   const float logit_lo = (float)(log(cc / (1.0 - cc)) - 1e-2);
   dim3 grid((unsigned)nchunks, (unsigned)hp.B);
-  decode_compact_kernel<0><<<grid, 256, 0, s>>>(hp, p->conf, logit_lo, p->multi_label, cap, nchunks, w.chunk_cnt, w.chunk_off, w.cbox, w.cscore, w.ccls);
-  scan_chunks_kernel<<<hp.B, 1024, 0, s>>>(w.chunk_cnt, w.chunk_off, nchunks, cap, w.ncand, out_ncand);
-  decode_compact_kernel<1><<<grid, 256, 0, s>>>(hp, p->conf, logit_lo, p->multi_label, cap, nchunks, w.chunk_cnt, w.chunk_off, w.cbox, w.cscore, w.ccls);
+  // single-label with A < 65536 (every real configuration): one pass with atomic slot reservation; the candidate count
+  // cannot exceed the capacity (one candidate per anchor at most), so nothing depends on the arrival order
+  const bool one_pass = !p->multi_label && hp.A < 65536 && cap >= hp.A;
+  if (one_pass) {
+    Y11_CHECK_CUDA(cudaMemsetAsync(w.ncand, 0, (size_t)hp.B * sizeof(int), s));
+    if (out_ncand) Y11_CHECK_CUDA(cudaMemsetAsync(out_ncand, 0, (size_t)hp.B * sizeof(int), s));
+    decode_compact_kernel<2><<<grid, 256, 0, s>>>(hp, p->conf, logit_lo, 0, cap, nchunks, w.chunk_cnt, w.chunk_off, w.cbox, w.cscore,
+                                                  w.ccls, w.canchor, w.ncand, out_ncand);
+  } else {
+    decode_compact_kernel<0><<<grid, 256, 0, s>>>(hp, p->conf, logit_lo, p->multi_label, cap, nchunks, w.chunk_cnt, w.chunk_off, w.cbox,
+                                                  w.cscore, w.ccls, nullptr, nullptr, nullptr);
+    scan_chunks_kernel<<<hp.B, 1024, 0, s>>>(w.chunk_cnt, w.chunk_off, nchunks, cap, w.ncand, out_ncand);
+    decode_compact_kernel<1><<<grid, 256, 0, s>>>(hp, p->conf, logit_lo, p->multi_label, cap, nchunks, w.chunk_cnt, w.chunk_off, w.cbox,
+                                                  w.cscore, w.ccls, nullptr, nullptr, nullptr);
+  }
   Y11_CHECK_CUDA(cudaGetLastError());
   NmsArgs a;
   a.cbox = w.cbox; a.cscore = w.cscore; a.ccls = w.ccls; a.ncand = w.ncand; a.keys = w.keys; a.kbox = w.kbox; a.karea = w.karea;
+  a.canchor = one_pass ? w.canchor : nullptr;
   a.cap = cap; a.keys_stride = w.keys_stride;
   a.iou_thr = thr_round_down(p->iou);
   a.class_offset = p->agnostic ? 0.0f : (float)p->max_wh;
@@ -547,6 +581,7 @@ extern "C" int y11_nms_batched(y11_handle, const float* boxes, const float* scor
   wp += align_up((size_t)B * K * 16);
   a.karea = reinterpret_cast<float*>(wp);
   a.cbox = reinterpret_cast<const float4*>(boxes); a.cscore = scores; a.ccls = cls; a.ncand = n;
+  a.canchor = nullptr;
   a.cap = K; a.keys_stride = np2;
   a.iou_thr = thr_round_down(p->iou);
   a.class_offset = p->agnostic ? 0.0f : (float)p->max_wh;

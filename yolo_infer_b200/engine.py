@@ -588,7 +588,8 @@ class GraphedPipeline:
             if self.chunks > 1:
                 self.copy_stream = torch.cuda.Stream(dev)
                 self.copy_events = [torch.cuda.Event() for _ in range(self.chunks)]
-        self.launches = 1 + self.net.n_launches + 4 + (self.chunks - 1)
+        post_launches = 4 if (multi_label or self.net.A >= 65536) else 2   # (count, scan, write | one-pass decode) + sort/NMS
+        self.launches = self.chunks + self.net.n_launches + post_launches   # letterbox per chunk + plan + post-processing
 
     # ---- the enqueue functions: [chunk 0 prefix, ..., chunk K-1 prefix, rest]  (chunks == 1: a single stage) -------------
     def _stages(self):
