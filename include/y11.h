@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define Y11_ABI_VERSION 1
+#define Y11_ABI_VERSION 2
 
 typedef struct y11_engine* y11_handle;
 typedef struct y11_plan_s* y11_plan;
@@ -69,6 +69,8 @@ enum { Y11_IMPL_TCGEN05 = 0, Y11_IMPL_SIMT_DEBUG = 1 };
 
 /* Dense conv k in {1,3}, stride in {1,2}, pad k/2, BN folded  [a7 Conv.forward_fuse]:
  *   out = act(conv(in, w) + bias) (+ res)
+ * k = 2 (stride 1, taps at offsets {-1,0} x {-1,0}, i.e. zero padding on the top/left only, Hout = Hin) is the form a
+ * 3x3 stride-2 conv takes on a space-to-depth input (see y11_stem_desc.s2d): the host repacks the 3x3 weights.
  * w: bf16 [cout][k*k*cin] with K ordered (kh, kw, cin); bias: fp32 [cout].
  * out may be bf16 (default) or fp32 (out_f32 != 0, used for the Detect logits). */
 typedef struct {
@@ -87,6 +89,11 @@ typedef struct {
   const void* w;  /* bf16 [cout][27], K ordered (kh, kw, c) */
   const float* bias;
   int32_t B, Hin, Win, Hout, Wout;
+  /* s2d != 0: write the Hout x Wout x cout result in SPACE-TO-DEPTH form, i.e. as a [Hout/2, Wout/2, 4*cout] tensor whose
+   * channel block (dy*2 + dx) of pixel (y, x) is output pixel (2y+dy, 2x+dx); `out` then describes that tensor
+   * (out.c = 4*cout).  The following 3x3 stride-2 layer becomes a 2x2 stride-1 conv over 4*cout channels, whose
+   * 128-byte-or-longer pixel rows the TMA unit can stream (32-byte rows through four parity maps could not). */
+  int32_t s2d;
 } y11_stem_desc;
 
 /* Depthwise 3x3 stride 1 pad 1  [a7 DWConv, Attention.pe]: out = act(dw(in)+bias) (+ res).

@@ -148,6 +148,56 @@ def test_conv_tcgen05_channel_slices_and_f32_out(ctx):
     close_bf16(got, want)
 
 
+def test_conv_2x2_space_to_depth_form(ctx):
+    """k = 2 (taps {-1,0}^2, top/left zero padding): what a 3x3 stride-2 conv becomes on a space-to-depth input.  Checked
+    (a) as a plain 2x2 conv against torch and (b) end to end: stem-style s2d repacking of a 3x3/2 conv == the 3x3/2 conv."""
+    g = torch.Generator().manual_seed(3)
+    dev = ctx.dev
+    for (B, H, W, cin, cout) in [(2, 16, 24, 64, 32), (1, 40, 40, 128, 64)]:
+        x = torch.randn(B, cin, H, W, generator=g).to(dev).to(torch.bfloat16).float()
+        w = (torch.randn(cout, cin, 2, 2, generator=g) / (cin * 4) ** 0.5).to(dev).to(torch.bfloat16).float()
+        bias = torch.randn(cout, generator=g).to(dev)
+        want = torch.nn.functional.silu(torch.nn.functional.conv2d(torch.nn.functional.pad(x, (1, 0, 1, 0)), w, bias))
+        xin = nhwc(x)
+        out = torch.zeros((B, H, W, cout), dtype=torch.bfloat16, device=dev)
+        wp = w.permute(0, 2, 3, 1).reshape(cout, -1).to(torch.bfloat16).contiguous()
+        d = cabi.ConvDesc()
+        d.inp, d.out = cabi.View(xin.data_ptr(), cin, 0, cin), cabi.View(out.data_ptr(), cout, 0, cout)
+        d.w, d.bias = wp.data_ptr(), bias.data_ptr()
+        d.B, d.Hin, d.Win, d.Hout, d.Wout = B, H, W, H, W
+        d.k, d.stride, d.act, d.out_f32, d.impl = 2, 1, 1, 0, cabi.IMPL_TCGEN05
+        p = ctx.plan()
+        cabi.check(ctx.lib.y11_plan_add_conv(p, C.byref(d)), "add_conv")
+        ctx.run(p)
+        close_bf16(out.float().permute(0, 3, 1, 2), want)
+    # (b) 3x3 stride-2 conv on [2,16,32,48] == 2x2 conv on its space-to-depth form with repacked weights
+    B, c, H, W, cout = 2, 16, 32, 48, 32
+    x = torch.randn(B, c, H, W, generator=g).to(dev).to(torch.bfloat16).float()
+    w3 = (torch.randn(cout, c, 3, 3, generator=g) / (c * 9) ** 0.5).to(dev).to(torch.bfloat16).float()
+    bias = torch.randn(cout, generator=g).to(dev)
+    want = torch.nn.functional.conv2d(x, w3, bias, stride=2, padding=1)
+    xs = x.view(B, c, H // 2, 2, W // 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, H // 2, W // 2, 4 * c).to(torch.bfloat16).contiguous()
+    wp = torch.zeros(cout, 2, 2, 4, c, device=dev)
+    for ty in range(2):
+        for tx in range(2):
+            for dy in range(2):
+                for dx in range(2):
+                    kh, kw = 2 * (ty - 1) + dy + 1, 2 * (tx - 1) + dx + 1
+                    if 0 <= kh <= 2 and 0 <= kw <= 2:
+                        wp[:, ty, tx, dy * 2 + dx, :] = w3[:, :, kh, kw]
+    wp = wp.view(cout, -1).to(torch.bfloat16).contiguous()
+    out = torch.zeros((B, H // 2, W // 2, cout), dtype=torch.bfloat16, device=dev)
+    d = cabi.ConvDesc()
+    d.inp, d.out = cabi.View(xs.data_ptr(), 4 * c, 0, 4 * c), cabi.View(out.data_ptr(), cout, 0, cout)
+    d.w, d.bias = wp.data_ptr(), bias.data_ptr()
+    d.B, d.Hin, d.Win, d.Hout, d.Wout = B, H // 2, W // 2, H // 2, W // 2
+    d.k, d.stride, d.act, d.out_f32, d.impl = 2, 1, 0, 0, cabi.IMPL_TCGEN05
+    p = ctx.plan()
+    cabi.check(ctx.lib.y11_plan_add_conv(p, C.byref(d)), "add_conv")
+    ctx.run(p)
+    close_bf16(out.float().permute(0, 3, 1, 2), want)
+
+
 def test_conv_simt_debug_agrees(ctx):
     got, want = conv_case(ctx, 1, 12, 12, 32, 32, 3, 2, True, res=False, impl=cabi.IMPL_SIMT_DEBUG)
     close_bf16(got, want)
@@ -165,11 +215,19 @@ def test_stem(ctx, H, W):
         xin = x.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
         out = torch.zeros((2, H // 2, W // 2, cout), dtype=torch.bfloat16, device=ctx.dev)
         wp = w.permute(0, 2, 3, 1).reshape(cout, 27).to(torch.bfloat16).contiguous()
-        d = cabi.StemDesc(xin.data_ptr(), cabi.View(out.data_ptr(), cout, 0, cout), wp.data_ptr(), b.data_ptr(), 2, H, W, H // 2, W // 2)
+        d = cabi.StemDesc(xin.data_ptr(), cabi.View(out.data_ptr(), cout, 0, cout), wp.data_ptr(), b.data_ptr(), 2, H, W, H // 2, W // 2, 0)
         p = ctx.plan()
         cabi.check(ctx.lib.y11_plan_add_stem(p, C.byref(d)))
         ctx.run(p)
         close_bf16(out.float().permute(0, 3, 1, 2), want)
+        # space-to-depth output: [H/4, W/4, 4*cout], block dy*2+dx of pixel (y, x) = output pixel (2y+dy, 2x+dx): identical values
+        out2 = torch.zeros((2, H // 4, W // 4, 4 * cout), dtype=torch.bfloat16, device=ctx.dev)
+        d = cabi.StemDesc(xin.data_ptr(), cabi.View(out2.data_ptr(), 4 * cout, 0, 4 * cout), wp.data_ptr(), b.data_ptr(), 2, H, W, H // 2, W // 2, 1)
+        p = ctx.plan()
+        cabi.check(ctx.lib.y11_plan_add_stem(p, C.byref(d)))
+        ctx.run(p)
+        back = out2.view(2, H // 4, W // 4, 2, 2, cout).permute(0, 1, 3, 2, 4, 5).reshape(2, H // 2, W // 2, cout)
+        assert torch.equal(back, out)
 
 
 @pytest.mark.parametrize("act,res,H,W", [(True, False, 20, 28), (False, True, 20, 28), (True, True, 14, 20), (True, False, 1, 8)])

@@ -9,7 +9,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "_lib" / "liby11_b200.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 ACT_NONE, ACT_SILU = 0, 1
 IMPL_TCGEN05, IMPL_SIMT_DEBUG = 0, 1
 
@@ -35,7 +35,8 @@ class ConvDesc(C.Structure):
 
 class StemDesc(C.Structure):
     _fields_ = [("inp", C.c_void_p), ("out", View), ("w", C.c_void_p), ("bias", C.c_void_p),
-                ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32)]
+                ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32),
+                ("s2d", C.c_int32)]
 
 
 class DwConvDesc(C.Structure):

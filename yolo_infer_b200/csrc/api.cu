@@ -136,7 +136,7 @@ extern "C" int y11_plan_add_stem(y11_plan p, const y11_stem_desc* d) {
   Y11_REQUIRE(d->out.c_off % 8 == 0 && d->out.c_total % 8 == 0, "plan_add_stem: output alignment");
   PlanOp* op = new_op(OP_STEM);
   op->d.stem = *d;
-  op->flops = 2.0 * d->B * d->Hout * d->Wout * (double)d->out.c * 27;
+  op->flops = 2.0 * d->B * d->Hout * d->Wout * (double)(d->s2d ? d->out.c / 4 : d->out.c) * 27;
   p->ops.push_back(op);
   p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane, (int)p->ops.size() - 1});
   return 0;

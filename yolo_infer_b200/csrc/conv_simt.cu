@@ -181,12 +181,18 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
     }
     __syncwarp();
     // coalesced write-out of this warp's 32 pixels: 16 bytes per lane, consecutive lanes -> consecutive bytes of a pixel row
-    const size_t pix0 = ((size_t)n * d.Hout + oh0 + r) * d.Wout + ow0 + warp * 32;
+    const int oy = oh0 + r;
+    // plain NHWC: pixel (oy, ox).  space-to-depth: pixel (oy/2, ox/2) of the half-size map, channel block (oy&1)*2 + (ox&1)
+    const size_t row0 = d.s2d ? ((size_t)n * (d.Hout >> 1) + (oy >> 1)) * (d.Wout >> 1) : ((size_t)n * d.Hout + oy) * d.Wout;
+    const int blk_y = d.s2d ? (oy & 1) * 2 * COUT : 0;
 #pragma unroll
     for (int i = lane; i < 32 * VPP; i += 32) {
       const int px = i / VPP, v = i % VPP;
-      if (ow0 + warp * 32 + px < d.Wout)
-        *reinterpret_cast<uint4*>(ob + (pix0 + px) * d.out.c_total + v * 8) = *reinterpret_cast<const uint4*>(so + px * OP + v * 8);
+      const int ox = ow0 + warp * 32 + px;
+      if (ox < d.Wout) {
+        const size_t off = d.s2d ? (row0 + (ox >> 1)) * d.out.c_total + blk_y + (ox & 1) * COUT : (row0 + ox) * d.out.c_total;
+        *reinterpret_cast<uint4*>(ob + off + v * 8) = *reinterpret_cast<const uint4*>(so + px * OP + v * 8);
+      }
     }
     __syncwarp();
   }
@@ -196,6 +202,8 @@ template <int COUT>
 static int stem_launch_t(const y11_stem_desc* d, cudaStream_t s) {
   Y11_REQUIRE(d->Win % 8 == 0 && d->Hin % 2 == 0, "stem: input must be even-sized with width a multiple of 8 (got %dx%d)", d->Hin, d->Win);
   Y11_REQUIRE(d->Wout * 2 == d->Win && d->Hout * 2 == d->Hin, "stem: output must be half the input size");
+  Y11_REQUIRE(!d->s2d || (d->Hout % 2 == 0 && d->Wout % 2 == 0 && d->out.c == 4 * COUT),
+              "stem: space-to-depth output needs even Hout/Wout and a 4*cout-channel view");
   int PXB = 32, best_waste = 1 << 30;
   for (int c : {160, 128, 96, 64, 32}) {  // fewest wasted pixels in the last tile, then the widest tile
     const int waste = y11_ceil_div(d->Wout, c) * c - d->Wout;
@@ -219,7 +227,7 @@ static int stem_launch_t(const y11_stem_desc* d, cudaStream_t s) {
 }
 
 int stem_launch(const y11_stem_desc* d, cudaStream_t s) {
-  switch (d->out.c) {
+  switch (d->s2d ? d->out.c / 4 : d->out.c) {
     case 16: return stem_launch_t<16>(d, s);
     case 32: return stem_launch_t<32>(d, s);
     case 64: return stem_launch_t<64>(d, s);

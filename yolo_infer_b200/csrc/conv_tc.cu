@@ -28,6 +28,7 @@
 #include <climits>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "ops.h"
 
@@ -212,6 +213,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
         int mi = 0, cw, ch;
         if (p.ksize == 1) {
           cw = w0; ch = h0;
+        } else if (p.ksize == 2) {  // taps at {-1, 0} x {-1, 0}: a 3x3 stride-2 conv on a space-to-depth input
+          cw = w0 + tap % 2 - 1; ch = h0 + tap / 2 - 1;
         } else if (p.stride == 1) {
           cw = w0 + tap % 3 - 1; ch = h0 + tap / 3 - 1;
         } else {
@@ -288,6 +291,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
         if (lane == 0) TRACE(1, 3);
         if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
       } else {
+        uint32_t started = 0u;  // kmask mode: the first MMA actually issued for this tile overwrites the accumulator
         for (int k = 0; k < k_iters; ++k) {
           mbar_wait(full_bar + 8 * stage, phase, p.err_flag, 102);
           if (lane == 0) TRACE(1, 2);
@@ -296,9 +300,20 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
             const uint32_t a_src = ring_base + stage * stage_bytes;
             const uint64_t ad = make_umma_desc(a_src, p.sbo, p.layout_type);
             const uint64_t bd = make_umma_desc(a_src + p.a_slot, p.sbo, p.layout_type);
-            umma_bf16(tmem_acc, ad, bd, idesc, k != 0);
-            for (int kk = 1; kk < kk_n; ++kk)  // +32 B (= 16 bf16 of K) inside the swizzle row per UMMA
-              umma_bf16(tmem_acc, ad + 2 * kk, bd + 2 * kk, idesc, 1);
+            if (p.kmask_on) {
+              // structurally sparse K (the 2x2 space-to-depth form of a 3x3 stride-2 conv has 7 of 16 all-zero
+              // 16-channel blocks): issue only the K steps whose weights are not all zero
+              for (int kk = 0; kk < kk_n; ++kk) {
+                if ((p.kmask >> (k * kk_n + kk)) & 1ull) {
+                  umma_bf16(tmem_acc, ad + 2 * kk, bd + 2 * kk, idesc, started);
+                  started = 1u;
+                }
+              }
+            } else {
+              umma_bf16(tmem_acc, ad, bd, idesc, k != 0);
+              for (int kk = 1; kk < kk_n; ++kk)  // +32 B (= 16 bf16 of K) inside the swizzle row per UMMA
+                umma_bf16(tmem_acc, ad + 2 * kk, bd + 2 * kk, idesc, 1);
+            }
             umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs retire
             if (k == k_iters - 1) umma_commit(accf_bar + 8 * as);  // accumulator complete
           }
@@ -560,7 +575,7 @@ static void pick_tile(int W, int H, int B, int* tw, int* th, int* tn) {
 
 int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
   Y11_REQUIRE(eng && eng->encode_tiled, "conv_tc: engine has no cuTensorMapEncodeTiled entry point");
-  Y11_REQUIRE((d->k == 1 && d->stride == 1) || (d->k == 3 && (d->stride == 1 || d->stride == 2)),
+  Y11_REQUIRE((d->k == 1 && d->stride == 1) || (d->k == 2 && d->stride == 1) || (d->k == 3 && (d->stride == 1 || d->stride == 2)),
               "conv_tc: unsupported k=%d stride=%d", d->k, d->stride);
   const int cin = d->in.c, cout = d->out.c;
   Y11_REQUIRE(cin % 16 == 0 && cout % 16 == 0, "conv_tc: cin=%d cout=%d must be multiples of 16", cin, cout);
@@ -759,6 +774,23 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
       if (int e = encode_map(eng, &L->maps.outq, d->out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : bf, 4, obase, gdim, gstr, qbox,
                              oswz))
         return e;
+    }
+  }
+  if (d->k == 2 && !p.halo) {
+    // zero-block scan of the weights (one-off, at plan-build time): K step (k_iter, kk) = 16 consecutive K elements
+    const int k_total = p.taps * cin, steps = k_total / 16;
+    if (steps <= 64) {
+      std::vector<__nv_bfloat16> hw((size_t)cout * k_total);
+      Y11_CHECK_CUDA(cudaMemcpy(hw.data(), d->w, hw.size() * sizeof(__nv_bfloat16), cudaMemcpyDeviceToHost));
+      unsigned long long mask = 0ull;
+      for (int st = 0; st < steps; ++st) {
+        bool nz = false;
+        for (int co = 0; co < cout && !nz; ++co)
+          for (int e = 0; e < 16; ++e)
+            if (__bfloat162float(hw[(size_t)co * k_total + st * 16 + e]) != 0.0f) { nz = true; break; }
+        if (nz) mask |= 1ull << st;
+      }
+      if (mask != 0ull && mask != (steps == 64 ? ~0ull : ((1ull << steps) - 1ull))) { p.kmask = mask; p.kmask_on = 1; }
     }
   }
   const unsigned total_tiles = (unsigned)(p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles);

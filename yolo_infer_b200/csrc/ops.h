@@ -44,6 +44,8 @@ struct ConvTcParams {
   int32_t res_ct, res_co;
   const float* bias;
   int32_t act;
+  uint64_t kmask;       // bit (k_iter * Cc/16 + kk): that 16-element K step has non-zero weights (TMA path, k == 2)
+  int32_t kmask_on;
   int* err_flag;
   long long* trace;  // debug timeline buffer (Y11_TRACE builds only)
   uint64_t mg_ntiles, mg_tw, mg_th;  // fast_div magics for n_tiles, tiles_w, tiles_h

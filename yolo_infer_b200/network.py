@@ -21,6 +21,7 @@ from . import _cabi as cabi
 from . import topology as T
 
 BN_EPS = 1e-3
+S2D_STEM = True   # stem output in space-to-depth form, model.1 as a 2x2 stride-1 conv (see pack_weights)
 
 
 def pad16(c: int) -> int:
@@ -37,6 +38,7 @@ class PackedConv:
     s: int
     act: int
     depthwise: bool = False
+    alg_k: int = 0           # algorithmic K per output (e.g. 9*cin of the 3x3 conv a repacked 2x2 space-to-depth conv stands for)
 
 
 def fold(sd: Dict[str, torch.Tensor], cp: T.ConvParam) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -76,6 +78,21 @@ def pack_weights(scale: str, nc: int, sd: Dict[str, torch.Tensor], device) -> Di
         elif cp.c1 == 3:  # stem
             wp = w.permute(0, 2, 3, 1).reshape(cp.c2, 27).contiguous()
             packed[cp.prefix] = PackedConv(wp.to(device, torch.bfloat16), b.to(device).contiguous(), 3, cp.c2, 3, 2, act)
+        elif cp.prefix == "model.1" and S2D_STEM:
+            # The stem writes its output in space-to-depth form ([H/2, W/2, 4*c] blocks (dy*2+dx)), on which this 3x3
+            # stride-2 conv is a 2x2 stride-1 conv with taps at block offsets {-1, 0}^2: input row 2*(oy+by)+dy = 2*oy+kh-1
+            # => kh = 2*by + dy + 1 (by in {-1, 0}); combinations outside 0..2 get zero weights.
+            assert cp.k == 3 and cp.s == 2 and cp.c1 % 16 == 0 and cp.c2 % 16 == 0
+            wp = torch.zeros(cp.c2, 2, 2, 4, cp.c1)                       # [cout][tap_y][tap_x][dy*2+dx][c]
+            for ty in range(2):
+                for tx in range(2):
+                    for dy in range(2):
+                        for dx in range(2):
+                            kh, kw = 2 * (ty - 1) + dy + 1, 2 * (tx - 1) + dx + 1
+                            if 0 <= kh <= 2 and 0 <= kw <= 2:
+                                wp[:, ty, tx, dy * 2 + dx, :] = w[:, :, kh, kw]
+            packed[cp.prefix] = PackedConv(wp.view(cp.c2, -1).to(device, torch.bfloat16).contiguous(), b.to(device).contiguous(),
+                                           4 * cp.c1, cp.c2, 2, 1, act, alg_k=9 * cp.c1)
         else:
             c1p, c2p = pad16(cp.c1), pad16(cp.c2)
             wp = torch.zeros(c2p, cp.k, cp.k, c1p)
@@ -191,7 +208,7 @@ class CompiledNet:
         d.k, d.stride, d.act, d.out_f32, d.impl = pc.k, pc.s, pc.act, int(out_f32), self.conv_impl
         cabi.check(self.lib.y11_plan_add_conv(self.plan, C.byref(d)), f"plan_add_conv({name})")
         px = x.B * out.H * out.W
-        self.ops.append(OpRecord("conv", name, 2.0 * px * pc.c2 * pc.c1 * pc.k * pc.k,
+        self.ops.append(OpRecord("conv", name, 2.0 * px * pc.c2 * (pc.alg_k or pc.c1 * pc.k * pc.k),
                                  x.B * x.H * x.W * pc.c1 * 2 + pc.w.numel() * 2 + px * pc.c2 * (4 if out_f32 else 2)
                                  + (px * pc.c2 * 2 if res is not None else 0), out, x, res))
 
@@ -334,21 +351,32 @@ class CompiledNet:
         detect = next(sp for sp in specs if sp.kind == "Detect")
         self.head_lanes: List[int] = []
 
+        s2d = S2D_STEM and self.packed["model.1"].k == 2 and 0 not in concat_of
+
         def out_hw(sp: T.LayerSpec, src_hw: Dict[int, Tuple[int, int]]) -> Tuple[int, int]:
+            """LOGICAL output size of a layer (the stem's space-to-depth buffer is stored at half of it)."""
             if sp.index == 0:
                 return H // 2, W // 2
             ih, iw = src_hw[sp.frm[0]]
             return ((ih + 1) // 2, (iw + 1) // 2) if sp.kind == "Conv" else (ih, iw)
+
+        plain_out_view = out_view
+
+        def out_view(sp: T.LayerSpec, h: int, w: int) -> V:  # noqa: F811
+            if sp.index == 0 and s2d:
+                return self._new(h // 2, w // 2, 4 * sp.c2)
+            return plain_out_view(sp, h, w)
 
         def emit(sp: T.LayerSpec, x: Optional[V], o: V, inp: torch.Tensor):
             """Ops of one backbone/neck layer: x -> o (stem: the letterboxed frames `inp` -> o)."""
             if sp.kind == "Conv" and sp.index == 0:
                 pc = self.packed["model.0"]
                 nb = inp.shape[0]
-                d = cabi.StemDesc(inp.data_ptr(), o.cview(), pc.w.data_ptr(), pc.b.data_ptr(), nb, H, W, o.H, o.W)
+                s2d = int(o.c == 4 * sp.c2)          # o is then the [H/4, W/4, 4*c2] space-to-depth tensor
+                d = cabi.StemDesc(inp.data_ptr(), o.cview(), pc.w.data_ptr(), pc.b.data_ptr(), nb, H, W, H // 2, W // 2, s2d)
                 cabi.check(self.lib.y11_plan_add_stem(self.plan, C.byref(d)), "plan_add_stem")
-                self.ops.append(OpRecord("stem", "model.0", 2.0 * nb * o.H * o.W * sp.c2 * 27,
-                                         nb * (H * W * 3 * 2 + o.H * o.W * sp.c2 * 2), o))
+                self.ops.append(OpRecord("stem", "model.0", 2.0 * nb * (H // 2) * (W // 2) * sp.c2 * 27,
+                                         nb * (H * W * 3 * 2 + (H // 2) * (W // 2) * sp.c2 * 2), o))
             elif sp.kind == "Conv":
                 self._conv(f"model.{sp.index}", x, o)
             else:
