@@ -230,10 +230,14 @@ def test_stem(ctx, H, W):
         assert torch.equal(back, out)
 
 
-@pytest.mark.parametrize("act,res,H,W", [(True, False, 20, 28), (False, True, 20, 28), (True, True, 14, 20), (True, False, 1, 8)])
-def test_dwconv(ctx, act, res, H, W):
+@pytest.mark.parametrize("act,res,H,W,c", [(True, False, 20, 28, 64), (False, True, 20, 28, 64), (True, True, 14, 20, 64),
+                                           (True, False, 1, 8, 64),
+                                           # TMA-ring kernel (W >= 32, H >= 16; ragged tiles in the last two): 2/4/8-row groups, 80 channels
+                                           # (surplus threads), two 128-channel chunks, residual, many tiles per CTA
+                                           (True, False, 16, 32, 64), (False, True, 32, 48, 128), (True, True, 24, 64, 80),
+                                           (True, False, 16, 32, 256), (True, False, 8 * 20, 16 * 12, 32), (True, True, 40, 40, 128), (False, False, 20, 36, 64)])
+def test_dwconv(ctx, act, res, H, W, c):
     g = torch.Generator().manual_seed(1)
-    c = 64
     x = torch.randn(2, c, H, W, generator=g).to(ctx.dev).to(torch.bfloat16).float()
     w = (torch.randn(c, 1, 3, 3, generator=g) / 3).to(ctx.dev).to(torch.bfloat16).float()
     b = torch.randn(c, generator=g).to(ctx.dev)

@@ -60,6 +60,8 @@ enum OpKind { OP_CONV_TC, OP_CONV_SIMT, OP_STEM, OP_DWCONV, OP_SPPF, OP_UPSAMPLE
 struct PlanOp {
   OpKind kind;
   ConvTcLaunch tc;  // OP_CONV_TC
+  DwTmaLaunch dwt;  // OP_DWCONV on large maps
+  bool use_dwt;
   union {
     y11_conv_desc conv;
     y11_stem_desc stem;
@@ -147,6 +149,10 @@ extern "C" int y11_plan_add_dwconv(y11_plan p, const y11_dwconv_desc* d) {
   PlanOp* op = new_op(OP_DWCONV);
   op->d.dw = *d;
   op->flops = 2.0 * d->B * d->H * d->W * (double)d->in.c * 9;
+  op->use_dwt = dwconv_tma_eligible(d);
+  if (op->use_dwt) {
+    if (int e = dwconv_tma_prepare(p->eng, d, &op->dwt)) { delete op; return e; }
+  }
   p->ops.push_back(op);
   p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane, (int)p->ops.size() - 1});
   return 0;
@@ -189,7 +195,7 @@ static int run_op(const PlanOp* op, cudaStream_t s) {
     case OP_CONV_TC: return conv_tc_launch(&op->tc, s);
     case OP_CONV_SIMT: return conv_simt_launch(&op->d.conv, s);
     case OP_STEM: return stem_launch(&op->d.stem, s);
-    case OP_DWCONV: return dwconv_launch(&op->d.dw, s);
+    case OP_DWCONV: return op->use_dwt ? dwconv_tma_launch(&op->dwt, s) : dwconv_launch(&op->d.dw, s);
     case OP_SPPF: return sppf_launch(&op->d.sppf, s);
     case OP_UPSAMPLE: return upsample_launch(&op->d.up, s);
     case OP_ATTN: return attention_launch(&op->d.attn, s);

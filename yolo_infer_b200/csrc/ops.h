@@ -78,5 +78,28 @@ int dwconv_launch(const y11_dwconv_desc* d, cudaStream_t s);
 int sppf_launch(const y11_sppf_desc* d, cudaStream_t s);
 int upsample_launch(const y11_upsample_desc* d, cudaStream_t s);
 
+// ---- TMA-ring depthwise conv for large maps (dwconv_tma.cu) ---------------------------------------
+struct DwTmaParams {
+  int32_t C, CC, chunks, cg4, nsub;   // channels, channels per chunk (<= 128), chunks, CC/4, row groups per column
+  int32_t B, H, W, tiles_w, tiles_h;
+  uint32_t stage_tx, stage_bytes;
+  const void* w;
+  const float* bias;
+  int32_t act;
+  void* out;
+  int32_t out_ct, out_co;
+  const void* res;
+  int32_t res_ct, res_co;
+  int* err_flag;
+};
+struct DwTmaLaunch {
+  CUtensorMap tmap;
+  DwTmaParams p;
+  unsigned grid, smem_bytes;
+};
+bool dwconv_tma_eligible(const y11_dwconv_desc* d);
+int dwconv_tma_prepare(y11_engine* eng, const y11_dwconv_desc* d, DwTmaLaunch* out);
+int dwconv_tma_launch(const DwTmaLaunch* l, cudaStream_t s);
+
 // ---- attention.cu --------------------------------------------------------------------------------
 int attention_launch(const y11_attn_desc* d, cudaStream_t s);
