@@ -319,3 +319,35 @@ def test_chunked_host_pipeline_equals_eager_predict(engines):
             assert len(got) == 16
             for a, b in zip(eager, got):
                 assert torch.equal(a.boxes.data.cpu(), b.boxes.data.cpu())
+
+
+def test_val_on_a_synthetic_dataset(engines, tmp_path):
+    """`YOLO11Model.val(data)` (reference core/model.py:180-195, read back at core/validator.py:339-359): a dataset whose
+    labels are the engine's own confident detections must score a high mAP50; shuffled class labels must not."""
+    import cv2
+    eng = engines("n")[0]
+    rng = np.random.default_rng(5)
+    root = tmp_path / "ds"
+    (root / "images" / "val").mkdir(parents=True)
+    (root / "labels" / "val").mkdir(parents=True)
+    n_lab = 0
+    for i in range(6):
+        img = rng.integers(0, 256, (360, 640, 3), dtype=np.uint8)
+        path = root / "images" / "val" / f"{i}.png"
+        cv2.imwrite(str(path), img)                                  # png: lossless, the engine sees the same pixels
+        # labels = everything the val-mode pipeline itself detects above conf 0.4 (same NMS settings as val uses)
+        det = eng.predict(cv2.imread(str(path)), conf=0.4, iou=0.6, multi_label=True, verbose=False)[0].cpu().boxes.data.numpy()
+        rows = []
+        for x1, y1, x2, y2, _, c in det:
+            rows.append(f"{int(c)} {(x1 + x2) / 2 / 640:.6f} {(y1 + y2) / 2 / 360:.6f} {(x2 - x1) / 640:.6f} {(y2 - y1) / 360:.6f}")
+        n_lab += len(rows)
+        (root / "labels" / "val" / f"{i}.txt").write_text("\n".join(rows) + "\n")
+    assert n_lab >= 6, "calibrated synthetic weights should give confident detections"
+    (root / "data.yaml").write_text(f"path: {root}\nval: images/val\nnames:\n" + "".join(f"  {k}: c{k}\n" for k in range(80)))
+    model = YOLO11Model(size="n", device="cuda:0", verbose=False)
+    model.model = eng                                                  # same weights as the labels were made with
+    m = model.val(data=str(root / "data.yaml"), batch=4)
+    assert m.n_images == 6 and m.n_labels == n_lab
+    assert m.box.map50 > 0.9 and m.box.mr > 0.9 and 0.0 <= m.box.map <= 1.0 and 0.0 <= m.box.map75 <= 1.0
+    assert set(m.speed) >= {"preprocess", "inference", "postprocess"} and m.speed["inference"] > 0
+    assert "metrics/mAP50-95(B)" in m.results_dict

@@ -398,6 +398,39 @@ def test_golden_nms_fixture(ctx):
     assert keep[0, :cnt[0]].tolist() == g["keep"].tolist()
 
 
+def test_multi_label_more_candidates_than_max_nms(ctx):
+    """val regime (conf 0.001, multi-label) where almost every (anchor, class) pair passes: 168 000 candidates per image, far
+    more than max_nms and than the 131 072-entry list the first version kept (in anchor order, silently dropping the rest).
+    The max_nms best BY SCORE must survive (stable on ties), exactly as the oracle's restatement of ultralytics does."""
+    B, nc = 2, 80
+    g = torch.Generator().manual_seed(11)
+    dims = [(40, 40), (20, 20), (10, 10)]
+    feats = [(torch.randn(B, h, w, 64 + nc, generator=g) * 2).to(ctx.dev) for (h, w) in dims]
+    for f in feats:
+        f[..., 64:] -= 3.0
+    hd = head_desc(feats, nc, B)
+    A = sum(h * w for h, w in dims)
+    y = torch.zeros((B, 84, A), device=ctx.dev)
+    cabi.check(ctx.lib.y11_decode_dense(ctx.h, C.byref(hd), y.data_ptr(), ctx.stream()))
+    conf, iou, max_det, max_nms = 0.001, 0.6, 100, 4000
+    det = torch.zeros((B, max_det, 6), device=ctx.dev)
+    cnt = torch.zeros((B,), dtype=torch.int32, device=ctx.dev)
+    ncand = torch.zeros((B,), dtype=torch.int32, device=ctx.dev)
+    ws = torch.empty(ctx.lib.y11_postprocess_workspace(B, A, nc, 1, max_nms), dtype=torch.uint8, device=ctx.dev)
+    p = cabi.NmsParams(conf, iou, max_det, max_nms, 7680, 0, 1)
+    cabi.check(ctx.lib.y11_detect_postprocess(ctx.h, C.byref(hd), C.byref(p), None, det.data_ptr(), cnt.data_ptr(),
+                                              ncand.data_ptr(), ws.data_ptr(), ws.numel(), ctx.stream()))
+    torch.cuda.synchronize()
+    assert int(ncand.min()) > 131072
+    want = P.non_max_suppression(y.cpu(), conf, iou, multi_label=True, max_det=max_det, max_nms=max_nms)
+    for b in range(B):
+        n = int(cnt[b])
+        assert n == want[b].shape[0] == max_det
+        got = det[b, :n].cpu()
+        assert torch.equal(got[:, 4:], want[b][:, 4:])
+        assert (got[:, :4] - want[b][:, :4]).abs().max() <= 1e-3
+
+
 @pytest.mark.parametrize("multi_label", [False, True])
 def test_fused_postprocess_matches_oracle_nms(ctx, multi_label):
     """decode -> compaction -> sort -> NMS -> scale_boxes, vs oracle non_max_suppression on the GPU's own dense decode

@@ -462,11 +462,16 @@ struct Workspace {
   size_t total;
 };
 
+// Candidate capacity per image.  Multi-label (val mode, conf 0.001): room for EVERY (anchor, class) pair up to 4 M, so
+// that "keep the max_nms best by score" (ultralytics non_max_suppression) is exact - the list is sorted by score before
+// it is cut.  (The first version capped the list at 128 K entries in anchor order, which silently dropped the
+// high-resolution levels' successors whenever nearly every pair passed the threshold.)
 int candidate_cap(int A, int nc, int multi_label) {
   if (!multi_label) return A;
   const long long full = (long long)A * nc;
-  return (int)(full < (1ll << 17) ? full : (1ll << 17));
+  return (int)(full < (1ll << 22) ? full : (1ll << 22));
 }
+int kept_cap_of(int cap) { return cap < (1 << 15) ? cap : (1 << 15); }
 
 void carve(Workspace* w, void* base, int B, int cap, int nchunks, int kept_cap) {
   size_t o = 0;
@@ -515,7 +520,7 @@ extern "C" size_t y11_postprocess_workspace(int B, int A, int nc, int multi_labe
   (void)max_nms;
   Workspace w;
   const int cap = candidate_cap(A, nc, multi_label);
-  carve(&w, nullptr, B, cap, y11_ceil_div(A, kChunk), cap);
+  carve(&w, nullptr, B, cap, y11_ceil_div(A, kChunk), kept_cap_of(cap));
   return w.total;
 }
 
@@ -526,10 +531,10 @@ extern "C" int y11_detect_postprocess(y11_handle, const y11_head_desc* hd, const
   if (int e = fill_head(hd, &hp)) return e;
   Y11_REQUIRE(p->max_det >= 1, "postprocess: max_det=%d", p->max_det);
   const int cap = candidate_cap(hp.A, hp.nc, p->multi_label);
-  Y11_REQUIRE(p->max_det <= cap, "postprocess: max_det=%d exceeds candidate capacity %d", p->max_det, cap);
+  Y11_REQUIRE(p->max_det <= kept_cap_of(cap), "postprocess: max_det=%d exceeds capacity %d", p->max_det, kept_cap_of(cap));
   const int nchunks = y11_ceil_div(hp.A, kChunk);
   Workspace w;
-  carve(&w, workspace, hp.B, cap, nchunks, cap);
+  carve(&w, workspace, hp.B, cap, nchunks, kept_cap_of(cap));
   Y11_REQUIRE(workspace && workspace_bytes >= w.total, "postprocess: workspace %zu < required %zu", workspace_bytes, w.total);
   // conservative logit pre-filter for the multi-label sigmoid test: sigmoid(x) > conf  =>  x > logit(conf) - slack
   const double cc = std::min(std::max((double)p->conf, 1e-30), 1.0 - 1e-9);

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
+import os
 import math
 import threading
 from pathlib import Path
@@ -520,9 +521,15 @@ class YOLO:
     __call__ = predict
 
     # ---- out-of-scope surface: fail loudly, never silently fall back -----------------------------------
-    def val(self, *a, **k):
-        raise NotImplementedError("val: forward + multi-label NMS are available via predict(multi_label=True, conf=0.001, "
-                                  "iou=0.6); dataset loading and mAP maths are a 'next' row (SURVEY.md section 8f)")
+    def val(self, data=None, **kwargs):
+        """Detection validation (ultralytics `YOLO.val` as the reference uses it, `core/model.py:180-195`): runs `predict`
+        with multi-label NMS at conf 0.001 / iou 0.6 over the dataset and scores it on the host.  Returns an object with
+        `.box.{map, map50, map75, mp, mr}` and `.speed` (`core/validator.py:339-359`)."""
+        if data is None:
+            raise ValueError("val: `data` (dataset yaml or image directory with YOLO labels) is required - no dataset is bundled")
+        from .val import validate
+        self._ensure_device(kwargs.pop("device", None))
+        return validate(self, data, **kwargs)
 
     def train(self, *a, **k):
         raise NotImplementedError("training is out of scope for the B200 inference path (SURVEY.md section 2 #8)")
@@ -562,6 +569,9 @@ class GraphedPipeline:
         self.H, self.W = geom[4], geom[5]
         self.owns_input = frames is None
         self.chunks = 4 if (self.owns_input and graph and B % 4 == 0 and B >= 16) else 1
+        if os.environ.get("Y11_CHUNKS"):   # experiment knob: chunk-major prefix also for device-resident frames
+            k = int(os.environ["Y11_CHUNKS"])
+            self.chunks = k if (k >= 1 and B % k == 0 and graph) else self.chunks
         with torch.cuda.device(dev):
             self.net = eng.compiled(B, self.H, self.W, self.chunks, replica)
             self.frames = frames if frames is not None else torch.zeros((B, h0, w0, 3), dtype=torch.uint8, device=dev)
