@@ -57,7 +57,10 @@ def oracle_head(fused, x):
     return y, torch.cat([f.view(B, f.shape[1], -1) for f in feats], 2)
 
 
-@pytest.mark.parametrize("scale,B,H,W", [("n", 2, 640, 640), ("n", 1, 448, 640), ("s", 2, 640, 640), ("n", 3, 384, 640)])
+# BASELINE.json configs as parity cases: n @640 / @448x640 (config 0, 1), s @640 (config 2), m @1280 (config 3, A = 33600),
+# x @640 batch 1 (config 4)
+@pytest.mark.parametrize("scale,B,H,W", [("n", 2, 640, 640), ("n", 1, 448, 640), ("s", 2, 640, 640), ("n", 3, 384, 640),
+                                         ("m", 1, 1280, 1280), ("x", 1, 640, 640)])
 def test_raw_head_outputs_within_bf16_tolerance(engines, scale, B, H, W):
     eng, fused, emul = engines(scale)
     g = torch.Generator().manual_seed(B * H + W)
