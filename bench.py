@@ -190,8 +190,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         # NCCL prints its version banner on STDOUT when NCCL_DEBUG is VERSION/INFO; stdout carries exactly one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-            os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
+        # (the level may also come from /etc/nccl.conf, so the redirection is unconditional)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     B, S = args.batch, args.imgsz
@@ -220,13 +220,18 @@ def run_ours(args):
             pipes.append(eng.pipeline(B, S, S, S, True, CONF, IOU, MAX_DET, frames=db, graph=use_graph, replica=j % NS))
     torch.cuda.synchronize(dev)
 
+    gathered = None
+    if world > 1:
+        from yolo_infer_b200.parallel import gather_flat
+        n_flat = B * MAX_DET * 6 + B
+        gathered = [torch.empty((world * n_flat,), dtype=torch.float32, device=dev) for _ in range(NS)]
+
     def step_resident(i: int):
         j = i % NROT
         with torch.cuda.stream(streams[j % NS]):
             det, cnt, ncand = pipes[j].run()
-            if world > 1:  # the only collective of the path: gather the fixed-shape results (461 KB/rank) so every rank,
-                from yolo_infer_b200.parallel import gather_detections  # hence rank 0, holds the whole global batch
-                gather_detections(det, cnt)
+            if world > 1:  # the only collective of the path: ONE all-gather of the fixed-shape results (461 KB/rank) per step,
+                gather_flat(eng.result_flat(pipes[j].net, MAX_DET), gathered[j % NS])   # so that rank 0 holds the global batch
         return det, cnt, ncand
 
     def fork():   # side streams start after everything enqueued on the main stream

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from yolo_infer_b200.parallel import gather_detections, pad_shard, shard_range, unpad_gathered
+from yolo_infer_b200.parallel import gather_detections, gather_flat, pad_shard, shard_range, split_flat, unpad_gathered
 
 
 def test_shard_range_partitions_exactly():
@@ -34,6 +34,12 @@ def _worker(rank, world, port, n_items, max_det, q):
     gd, gc = gather_detections(det, cnt)
     gd, gc = unpad_gathered(gd, gc, n_items, world)
     ok = torch.equal(gd, det_all) and torch.equal(gc, cnt_all)
+    # single-collective form used by bench.py: det and count share one flat fp32 buffer (count bit-cast)
+    flat = torch.cat((det.reshape(-1), cnt.view(torch.float32)))
+    out = torch.empty(world * flat.numel())
+    fd, fc = split_flat(gather_flat(flat, out), b_max, max_det)
+    fd, fc = unpad_gathered(fd, fc, n_items, world)
+    ok = ok and torch.equal(fd, det_all) and torch.equal(fc, cnt_all)
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, bool(ok)))

@@ -285,11 +285,13 @@ class YOLO:
         okey = ("post_out", B, max_det, rep)
         out = self._ws.get(okey)
         if out is None:
-            out = (torch.zeros((B, max_det, 6), dtype=torch.float32, device=self.device),
-                   torch.zeros((B,), dtype=torch.int32, device=self.device),
-                   torch.zeros((B,), dtype=torch.int32, device=self.device))
+            # det and count live in ONE flat buffer ([B*max_det*6] fp32 followed by [B] int32) so that a multi-GPU caller
+            # can gather a step's results with a single collective (parallel.gather_flat)
+            flat = torch.zeros((B * max_det * 6 + B,), dtype=torch.float32, device=self.device)
+            out = (flat[: B * max_det * 6].view(B, max_det, 6), flat[B * max_det * 6:].view(torch.int32),
+                   torch.zeros((B,), dtype=torch.int32, device=self.device), flat)
             self._ws[okey] = out
-        det, count, ncand = out
+        det, count, ncand, _flat = out
         hd = net.head_desc()
         p = cabi.NmsParams(conf, iou, max_det, max_nms, 7680, int(agnostic), int(multi_label))
         s = torch.cuda.current_stream(self.device).cuda_stream
@@ -300,6 +302,10 @@ class YOLO:
         return det, count, ncand
 
     # ---- CUDA-graph pipeline for fixed-shape uint8 batches (throughput and batch-1 latency modes) ----------------
+    def result_flat(self, net: CompiledNet, max_det: int) -> torch.Tensor:
+        """The flat [B*max_det*6 fp32 | B int32] buffer behind the (det, count) tensors `postprocess` returns for `net`."""
+        return self._ws[("post_out", net.B, max_det, getattr(net, "replica", 0))][3]
+
     def pipeline(self, B: int, h0: int, w0: int, imgsz=640, rect: bool = True, conf: float = 0.25, iou: float = 0.7,
                  max_det: int = 300, agnostic: bool = False, multi_label: bool = False, frames: Optional[torch.Tensor] = None,
                  graph: bool = True, replica: int = 0) -> "GraphedPipeline":

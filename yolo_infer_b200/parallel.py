@@ -36,6 +36,27 @@ def gather_detections(det: torch.Tensor, count: torch.Tensor, group=None) -> Tup
     return torch.cat(dets, 0), torch.cat(counts, 0)
 
 
+def gather_flat(flat: torch.Tensor, out: Optional[torch.Tensor] = None, group=None) -> torch.Tensor:
+    """ONE collective per step: every rank contributes its flat result buffer ([b*max_det*6] fp32 det followed by [b] int32
+    count bit-cast into the same fp32 tensor, see `engine.YOLO.postprocess`) and receives [world, len(flat)] in rank order.
+    `out` is a persistent [world * len(flat)] buffer (no allocation, no concatenation on the hot path)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return flat.view(1, -1)
+    world = dist.get_world_size(group)
+    if out is None:
+        out = torch.empty((world * flat.numel(),), dtype=flat.dtype, device=flat.device)
+    dist.all_gather_into_tensor(out, flat, group=group)
+    return out.view(world, -1)
+
+
+def split_flat(gathered: torch.Tensor, b: int, max_det: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[world, b*max_det*6 + b] -> (det [world*b, max_det, 6] fp32, count [world*b] int32) in global image order."""
+    world = gathered.shape[0]
+    det = gathered[:, : b * max_det * 6].reshape(world * b, max_det, 6)
+    count = gathered[:, b * max_det * 6:].contiguous().view(torch.int32).reshape(world * b)
+    return det, count
+
+
 def pad_shard(det: torch.Tensor, count: torch.Tensor, b_max: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """Pad a ragged last shard to b_max images so all_gather sees equal shapes (count 0 for padding)."""
     b = det.shape[0]
