@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define Y11_ABI_VERSION 2
+#define Y11_ABI_VERSION 3
 
 typedef struct y11_engine* y11_handle;
 typedef struct y11_plan_s* y11_plan;
@@ -66,9 +66,17 @@ typedef struct {
 
 enum { Y11_ACT_NONE = 0, Y11_ACT_SILU = 1 };
 enum { Y11_IMPL_TCGEN05 = 0, Y11_IMPL_SIMT_DEBUG = 1 };
+/* How y11_conv_desc.res enters the conv:
+ *   Y11_RES_POST      : out = act(conv + bias) + res            (Bottleneck / PSABlock shortcut; res has the output's size)
+ *   Y11_RES_PRE_UP2   : out = act(conv + bias + up2(res))       res is [B, Hout/2, Wout/2] and is read with nearest-neighbour
+ *                       2x upsampling.  This is how `Concat([Upsample(2)(p), skip]) -> 1x1 conv` [a11] runs without ever
+ *                       materialising the upsampled tensor: a 1x1 conv commutes with nearest upsampling, so the host splits
+ *                       the weights by input channel, runs W_up . p (+bias, no activation) at LOW resolution and hands the
+ *                       result to the conv over `skip` as this pre-activation term. */
+enum { Y11_RES_POST = 0, Y11_RES_PRE_UP2 = 1 };
 
 /* Dense conv k in {1,3}, stride in {1,2}, pad k/2, BN folded  [a7 Conv.forward_fuse]:
- *   out = act(conv(in, w) + bias) (+ res)
+ *   out = act(conv(in, w) + bias) (+ res)          (res_mode selects where the residual enters, see above)
  * k = 2 (stride 1, taps at offsets {-1,0} x {-1,0}, i.e. zero padding on the top/left only, Hout = Hin) is the form a
  * 3x3 stride-2 conv takes on a space-to-depth input (see y11_stem_desc.s2d): the host repacks the 3x3 weights.
  * w: bf16 [cout][k*k*cin] with K ordered (kh, kw, cin); bias: fp32 [cout].
@@ -80,6 +88,7 @@ typedef struct {
   int32_t B, Hin, Win, Hout, Wout;
   int32_t k, stride, act, out_f32;
   int32_t impl; /* Y11_IMPL_TCGEN05 (product) | Y11_IMPL_SIMT_DEBUG (bring-up cross-check only) */
+  int32_t res_mode; /* Y11_RES_POST | Y11_RES_PRE_UP2 (ignored when res.ptr == NULL) */
 } y11_conv_desc;
 
 /* Stem conv: 3 -> cout, 3x3 stride 2, input is the dense 3-channel bf16 NHWC letterbox output. */

@@ -41,7 +41,7 @@ def nhwc(x_nchw: torch.Tensor, c_total=None, c_off=0, dtype=torch.bfloat16):
 
 
 def conv_case(ctx: Ctx, B, H, W, cin, cout, k, stride, act, res=False, out_f32=False, in_off=0, in_extra=0, out_off=0,
-              out_extra=0, impl=cabi.IMPL_TCGEN05, seed=0):
+              out_extra=0, impl=cabi.IMPL_TCGEN05, seed=0, res_mode=cabi.RES_POST):
     """Runs one conv op; returns (got NCHW fp32, want NCHW fp32 computed by torch fp32 on the same bf16 inputs)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     dev = ctx.dev
@@ -49,11 +49,15 @@ def conv_case(ctx: Ctx, B, H, W, cin, cout, k, stride, act, res=False, out_f32=F
     w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev).to(torch.bfloat16).float()
     bias = torch.randn(cout, generator=g).to(dev)
     Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
-    r = torch.randn(B, cout, Ho, Wo, generator=g).to(dev).to(torch.bfloat16).float() if res else None
+    pre = res and res_mode == cabi.RES_PRE_UP2     # residual = half-resolution map, nearest-upsampled, added BEFORE the activation
+    rh, rw = (Ho // 2, Wo // 2) if pre else (Ho, Wo)
+    r = torch.randn(B, cout, rh, rw, generator=g).to(dev).to(torch.bfloat16).float() if res else None
     want = torch.nn.functional.conv2d(x, w, bias, stride=stride, padding=k // 2)
+    if pre:
+        want = want + torch.nn.functional.interpolate(r, scale_factor=2, mode="nearest")
     if act:
         want = torch.nn.functional.silu(want)
-    if res:
+    if res and not pre:
         want = want + r
     xin = nhwc(x, cin + in_off + in_extra, in_off)
     out_dtype = torch.float32 if out_f32 else torch.bfloat16
@@ -68,6 +72,7 @@ def conv_case(ctx: Ctx, B, H, W, cin, cout, k, stride, act, res=False, out_f32=F
     d.w, d.bias = wp.data_ptr(), bias.data_ptr()
     d.B, d.Hin, d.Win, d.Hout, d.Wout = B, H, W, Ho, Wo
     d.k, d.stride, d.act, d.out_f32, d.impl = k, stride, int(act), int(out_f32), impl
+    d.res_mode = res_mode
     p = ctx.plan()
     cabi.check(ctx.lib.y11_plan_add_conv(p, C.byref(d)), "add_conv")
     ctx.run(p)

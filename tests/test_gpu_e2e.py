@@ -101,6 +101,24 @@ def test_tcgen05_and_simt_debug_paths_agree(engines, oracle_models):
     assert rel_l2(outs[0], outs[1]) <= 1e-2, rel_l2(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("scale,B,H,W", [("n", 2, 320, 320), ("s", 1, 224, 320)])
+def test_folded_upsample_concat_equals_copy_ops(engines, scale, B, H, W):
+    """Upsample -> Concat -> C3k2.cv1 run as `W_up . p` at low resolution + a pre-activation term (no upsampled / concatenated
+    tensor) gives the same head as the plan that materialises both (one extra bf16 rounding of the low-resolution term)."""
+    eng = engines(scale)[0]
+    x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(5)).to("cuda:0")
+    outs = []
+    for fold in (True, False):
+        net = eng.compiled(B, H, W, fold_upsample=fold)
+        assert bool(net.folds) == fold
+        assert any(o.kind == "upsample" for o in net.ops) != fold
+        eng.preprocess_tensor(net, x, 1.0)
+        eng.forward(net)
+        torch.cuda.synchronize()
+        outs.append(net.raw_head().cpu())
+    assert rel_l2(outs[0], outs[1]) <= 1e-2, rel_l2(outs[0], outs[1])
+
+
 def match_detections(got: torch.Tensor, want: torch.Tensor, conf: float, margin: float = 0.03):
     """Every detection of one side whose score clears the threshold by `margin` must exist on the other side
     (same class, IoU >= 0.8, |score delta| <= margin).  Returns (fraction matched both ways, median over matches of the max coordinate delta in px)."""
@@ -271,9 +289,11 @@ def test_every_conv_of_the_plan_matches_torch(engines, oracle_models, scale, B, 
                 want = torch.nn.functional.conv2d(torch.nn.functional.pad(xin, (1, 0, 1, 0)), w, pc.b)
             else:
                 want = torch.nn.functional.conv2d(xin, w, pc.b, stride=pc.s, padding=pc.k // 2)
+        if res is not None and op.res_mode == cabi.RES_PRE_UP2:   # folded Upsample+Concat: up2(W_up . p + b) enters before SiLU
+            want = want + torch.nn.functional.interpolate(res, scale_factor=2, mode="nearest")
         if pc.act:
             want = torch.nn.functional.silu(want)
-        if res is not None:
+        if res is not None and op.res_mode != cabi.RES_PRE_UP2:
             want = want + res
         err = (got - want).abs()
         tol = 1e-2 * want.abs() + 2e-2

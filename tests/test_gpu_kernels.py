@@ -148,6 +148,23 @@ def test_conv_tcgen05_channel_slices_and_f32_out(ctx):
     close_bf16(got, want)
 
 
+@pytest.mark.parametrize("case", [
+    (2, 40, 40, 128, 128, 1, True),     # TMA producer, 40x40 (model.13.cv1#skip of YOLO11n-like sizes)
+    (1, 80, 80, 64, 64, 1, True),       # 80x80
+    (3, 28, 40, 32, 64, 1, True),       # cp.async producer (cin 32), rect map
+    (2, 16, 24, 256, 256, 1, False),    # 2 N tiles, no activation
+    (1, 32, 32, 32, 32, 3, True),       # 3x3 halo mode with the pre-activation term
+], ids=lambda c: "x".join(map(str, c)))
+def test_conv_pre_activation_upsampled_term(ctx, case):
+    """Y11_RES_PRE_UP2: out = act(conv(x) + b + up2(r)), r at half resolution - the folded Upsample+Concat form - on the
+    tcgen05 kernel, and the CUDA-core cross-check kernel agrees."""
+    B, H, W, cin, cout, k, act = case
+    got, want = conv_case(ctx, B, H, W, cin, cout, k, 1, act, res=True, res_mode=cabi.RES_PRE_UP2)
+    close_bf16(got, want)
+    got2, want2 = conv_case(ctx, B, H, W, cin, cout, k, 1, act, res=True, res_mode=cabi.RES_PRE_UP2, impl=cabi.IMPL_SIMT_DEBUG)
+    close_bf16(got2, want2)
+
+
 def test_conv_2x2_space_to_depth_form(ctx):
     """k = 2 (taps {-1,0}^2, top/left zero padding): what a 3x3 stride-2 conv becomes on a space-to-depth input.  Checked
     (a) as a plain 2x2 conv against torch and (b) end to end: stem-style s2d repacking of a 3x3/2 conv == the 3x3/2 conv."""

@@ -79,6 +79,24 @@ def test_pack_weights_layout(oracle_models):
     assert torch.allclose(pc.w.float().view(-1, 3, 3, 3).permute(0, 3, 1, 2), w, rtol=1e-2, atol=1e-3)
 
 
+def test_upsample_concat_fold_split(oracle_models):
+    """Upsample -> Concat -> C3k2.cv1 folding: the two neck chains are found for every scale, and the split weights
+    reproduce cv1 on the concatenated input: W . cat(up2(p), skip) + b == up2(W_up . p + b) + W_skip . skip."""
+    from yolo_infer_b200.network import upsample_folds
+    for scale in "nsmlx":
+        assert upsample_folds(scale) == {13: (10, 6, 11, 12), 16: (13, 4, 14, 15)}
+    _, sd = oracle_models("n")
+    packed = pack_weights("n", 80, sd, torch.device("cpu"))
+    full, up, skip = packed["model.13.cv1"], packed["model.13.cv1#up"], packed["model.13.cv1#skip"]
+    assert up.c1 + skip.c1 == full.c1 and up.c2 == skip.c2 == full.c2 and up.act == 0 and skip.act == full.act
+    assert torch.equal(torch.cat((up.w, skip.w), 1), full.w) and torch.equal(up.b, full.b) and torch.all(skip.b == 0)
+    g = torch.Generator().manual_seed(0)
+    p, s_ = torch.randn(1, up.c1, 4, 6, generator=g), torch.randn(1, skip.c1, 8, 12, generator=g)
+    up2 = lambda t: torch.nn.functional.interpolate(t, scale_factor=2, mode="nearest")  # noqa: E731
+    conv = lambda x, pc: torch.nn.functional.conv2d(x, pc.w.float().view(pc.c2, pc.c1, 1, 1), pc.b)  # noqa: E731
+    assert torch.allclose(conv(torch.cat((up2(p), s_), 1), full), up2(conv(p, up)) + conv(s_, skip), atol=1e-5)
+
+
 def test_qkv_permutation_groups_heads():
     perm = qkv_permutation(128, 2, 32, 64)
     assert sorted(perm.tolist()) == list(range(256))

@@ -9,9 +9,10 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "_lib" / "liby11_b200.so"
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 ACT_NONE, ACT_SILU = 0, 1
 IMPL_TCGEN05, IMPL_SIMT_DEBUG = 0, 1
+RES_POST, RES_PRE_UP2 = 0, 1
 
 
 class Y11Error(RuntimeError):
@@ -30,7 +31,7 @@ class View(C.Structure):
 class ConvDesc(C.Structure):
     _fields_ = [("inp", View), ("out", View), ("res", View), ("w", C.c_void_p), ("bias", C.c_void_p),
                 ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32),
-                ("k", C.c_int32), ("stride", C.c_int32), ("act", C.c_int32), ("out_f32", C.c_int32), ("impl", C.c_int32)]
+                ("k", C.c_int32), ("stride", C.c_int32), ("act", C.c_int32), ("out_f32", C.c_int32), ("impl", C.c_int32), ("res_mode", C.c_int32)]
 
 
 class StemDesc(C.Structure):

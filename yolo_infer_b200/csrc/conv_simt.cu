@@ -36,8 +36,13 @@ __global__ void conv_simt_kernel(y11_conv_desc d) {
     }
   }
   acc += d.bias[co];
+  const bool pre = d.res.ptr && d.res_mode == Y11_RES_PRE_UP2;
+  if (pre) {
+    const size_t rpix = ((size_t)n * (d.Hout >> 1) + (oh >> 1)) * (d.Wout >> 1) + (ow >> 1);
+    acc += __bfloat162float(static_cast<const __nv_bfloat16*>(d.res.ptr)[rpix * d.res.c_total + d.res.c_off + co]);
+  }
   if (d.act == Y11_ACT_SILU) acc = silu(acc);
-  if (d.res.ptr) acc += __bfloat162float(static_cast<const __nv_bfloat16*>(d.res.ptr)[pix * d.res.c_total + d.res.c_off + co]);
+  if (d.res.ptr && !pre) acc += __bfloat162float(static_cast<const __nv_bfloat16*>(d.res.ptr)[pix * d.res.c_total + d.res.c_off + co]);
   if (d.out_f32)
     static_cast<float*>(d.out.ptr)[pix * d.out.c_total + d.out.c_off + co] = acc;
   else

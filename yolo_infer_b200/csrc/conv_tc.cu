@@ -358,7 +358,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       const int ow = w0 + tw, oh = h0 + th, on = n0 + tn;
       const bool valid = ow < p.Wout && oh < p.Hout && on < p.B;
       const size_t pix = (static_cast<size_t>(on) * p.Hout + oh) * p.Wout + ow;
-      const __nv_bfloat16* res_row = static_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ct + p.res_co + nt * p.BN;
+      // residual row: the output pixel itself, or (pre-activation, nearest-upsampled term) pixel (oh/2, ow/2) of a half-size map
+      const size_t rpix = p.res_pre ? (static_cast<size_t>(on) * (p.Hout >> 1) + (oh >> 1)) * (p.Wout >> 1) + (ow >> 1) : pix;
+      const __nv_bfloat16* res_row = static_cast<const __nv_bfloat16*>(p.res) + rpix * p.res_ct + p.res_co + nt * p.BN;
       mbar_wait(accf_bar + 8 * grp, (ti >> 1) & 1, p.err_flag, 103);
       tc_fence_after();
       const uint32_t taddr = tmem_base + grp * acc_stride + (static_cast<uint32_t>(quad * 32) << 16);
@@ -397,16 +399,25 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
             f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
             f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
           }
-          if (p.act == Y11_ACT_SILU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = silu(f[i]);
-          }
-          if (p.res) {
+          {
             const uint32_t rr[8] = {rv0.x, rv0.y, rv0.z, rv0.w, rv1.x, rv1.y, rv1.z, rv1.w};
+            if (p.res_pre) {  // up2(W_up . p) of a folded Upsample+Concat: part of the pre-activation sum
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              f[2 * i] += bf16_lo(rr[i]);
-              f[2 * i + 1] += bf16_hi(rr[i]);
+              for (int i = 0; i < 8; ++i) {
+                f[2 * i] += bf16_lo(rr[i]);
+                f[2 * i + 1] += bf16_hi(rr[i]);
+              }
+            }
+            if (p.act == Y11_ACT_SILU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = silu(f[i]);
+            }
+            if (p.res && !p.res_pre) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                f[2 * i] += bf16_lo(rr[i]);
+                f[2 * i + 1] += bf16_hi(rr[i]);
+              }
             }
           }
           const uint32_t dst = buf + (uint32_t)lane * pitch;
@@ -463,6 +474,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       const int ow = w0 + tw, oh = h0 + th, on = n0 + tn;
       const bool valid = (r < p.Tw * p.Th * p.Tn) && ow < p.Wout && oh < p.Hout && on < p.B;
       const size_t pix = (static_cast<size_t>(on) * p.Hout + oh) * p.Wout + ow;
+      // residual pixel: the output pixel itself, or (pre-activation, nearest-upsampled term) pixel (oh/2, ow/2) of a half-size map
+      const size_t rpix = p.res_pre ? (static_cast<size_t>(on) * (p.Hout >> 1) + (oh >> 1)) * (p.Wout >> 1) + (ow >> 1) : pix;
       const int as = ti & 1;
       if (lane == 0 && (ew == 0 || ew == 3)) TRACE(2 + (ew == 3), 0);
       mbar_wait(accf_bar + 8 * as, (ti >> 1) & 1, p.err_flag, 103);
@@ -475,7 +488,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
         if (active && col < p.BN) {
           uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
           if (p.res && valid) {  // issued before the TMEM load: independent of it, and a DRAM/L2 round trip long
-            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ct + p.res_co + nt * p.BN + col);
+            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res) + rpix * p.res_ct + p.res_co + nt * p.BN + col);
             r0 = rp[0]; r1 = rp[1];
           }
           uint32_t v[16];
@@ -493,16 +506,25 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
             f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
             f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
           }
-          if (p.act == Y11_ACT_SILU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = silu(f[i]);
-          }
-          if (p.res) {
+          {
             const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            if (p.res_pre) {  // up2(W_up . p) of a folded Upsample+Concat: part of the pre-activation sum
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              f[2 * i] += bf16_lo(rr[i]);
-              f[2 * i + 1] += bf16_hi(rr[i]);
+              for (int i = 0; i < 8; ++i) {
+                f[2 * i] += bf16_lo(rr[i]);
+                f[2 * i + 1] += bf16_hi(rr[i]);
+              }
+            }
+            if (p.act == Y11_ACT_SILU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = silu(f[i]);
+            }
+            if (p.res && !p.res_pre) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                f[2 * i] += bf16_lo(rr[i]);
+                f[2 * i + 1] += bf16_hi(rr[i]);
+              }
             }
           }
           if (p.out_f32) {
@@ -716,6 +738,8 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
   p.B = d->B; p.Hout = d->Hout; p.Wout = d->Wout; p.cout = cout;
   p.out = d->out.ptr; p.out_ct = d->out.c_total; p.out_co = d->out.c_off; p.out_f32 = d->out_f32;
   p.res = d->res.ptr; p.res_ct = d->res.c_total; p.res_co = d->res.c_off;
+  p.res_pre = (d->res.ptr && d->res_mode == Y11_RES_PRE_UP2) ? 1 : 0;
+  if (p.res_pre) Y11_REQUIRE(d->Hout % 2 == 0 && d->Wout % 2 == 0, "conv_tc: RES_PRE_UP2 needs an even output size");
   p.bias = d->bias; p.act = d->act;
   p.err_flag = eng->dev_error_flag;
 #ifdef Y11_TRACE

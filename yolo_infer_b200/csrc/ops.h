@@ -42,6 +42,7 @@ struct ConvTcParams {
   int32_t out_ct, out_co, out_f32;
   const void* res;
   int32_t res_ct, res_co;
+  int32_t res_pre;  // 1: residual is a half-resolution map added BEFORE the activation (Y11_RES_PRE_UP2)
   const float* bias;
   int32_t act;
   uint64_t kmask;       // bit (k_iter * Cc/16 + kk): that 16-element K step has non-zero weights (TMA path, k == 2)

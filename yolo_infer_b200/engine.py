@@ -218,14 +218,18 @@ class YOLO:
         elif not self._engine:
             self.to("cuda")
 
-    def compiled(self, B: int, H: int, W: int, chunks: int = 1, replica: int = 0) -> CompiledNet:
+    def compiled(self, B: int, H: int, W: int, chunks: int = 1, replica: int = 0, fold_upsample: Optional[bool] = None) -> CompiledNet:
         """replica > 0: an independent instance (own activation buffers / plan) for a pipeline that runs concurrently
-        with another one on a second stream."""
+        with another one on a second stream.  fold_upsample=False: keep Upsample/Concat as copy ops (one op per reference
+        conv, which is what the weight conditioning walks)."""
         key = (B, H, W) if (chunks == 1 and replica == 0) else (B, H, W, chunks, replica)
+        if fold_upsample is not None:
+            key = key + ("fold", fold_upsample)
         net = self._nets.get(key)
         if net is None:
             with torch.cuda.device(self.device):
-                net = CompiledNet(self._engine, self.scale, self.nc, self._packed, B, H, W, self.device, self.conv_impl, chunks)
+                net = CompiledNet(self._engine, self.scale, self.nc, self._packed, B, H, W, self.device, self.conv_impl, chunks,
+                                  fold_upsample)
                 net.replica = replica
             self._nets[key] = net
         return net
@@ -340,7 +344,7 @@ class YOLO:
         self._ensure_device()
         H, W = hw
         with torch.cuda.device(self.device), torch.inference_mode():
-            net = self.compiled(batch, H, W)
+            net = self.compiled(batch, H, W, fold_upsample=False)
             g = torch.Generator().manual_seed(seed)
             frames = torch.randint(0, 256, (batch, H, W, 3), generator=g, dtype=torch.uint8).to(self.device)
             geoms = [letterbox_geometry(H, W, (H, W), False)] * batch

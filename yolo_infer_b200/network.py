@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -22,6 +23,32 @@ from . import topology as T
 
 BN_EPS = 1e-3
 S2D_STEM = True   # stem output in space-to-depth form, model.1 as a 2x2 stride-1 conv (see pack_weights)
+# Upsample -> Concat -> C3k2.cv1 (yaml layers 11-13 and 14-16) without the upsampled / concatenated tensors: a 1x1 conv
+# commutes with nearest upsampling, so cv1's weights are split by input channel, W_up . p (+bias) runs at LOW resolution and
+# enters the conv over the skip tensor as a pre-activation term (Y11_RES_PRE_UP2).  Y11_FOLD_UP=0 restores the copy ops.
+FOLD_UPSAMPLE = os.environ.get("Y11_FOLD_UP", "1") != "0"
+
+
+def upsample_folds(scale: str) -> Dict[int, Tuple[int, int, int, int]]:
+    """C3k2 layer index -> (low-res source layer, skip layer, upsample layer, concat layer) for every
+    `Upsample(2) -> Concat([up, skip]) -> C3k2` chain whose intermediate tensors have no other consumer."""
+    specs = T.layer_specs(scale)
+    users: Dict[int, List[int]] = {}
+    for sp in specs:
+        for f in sp.frm:
+            users.setdefault(f, []).append(sp.index)
+    folds = {}
+    for sp in specs:
+        if sp.kind != "C3k2" or len(sp.frm) != 1:
+            continue
+        cat = specs[sp.frm[0]]
+        if cat.kind != "Concat" or len(cat.frm) != 2 or users.get(cat.index) != [sp.index]:
+            continue
+        up = specs[cat.frm[0]]
+        if up.kind != "Upsample" or users.get(up.index) != [cat.index]:
+            continue
+        folds[sp.index] = (up.frm[0], cat.frm[1], up.index, cat.index)
+    return folds
 
 
 def pad16(c: int) -> int:
@@ -101,6 +128,16 @@ def pack_weights(scale: str, nc: int, sd: Dict[str, torch.Tensor], device) -> Di
             bp[: cp.c2] = b
             packed[cp.prefix] = PackedConv(wp.view(c2p, -1).to(device, torch.bfloat16).contiguous(), bp.to(device), c1p, c2p,
                                            cp.k, cp.s, act)
+    specs = T.layer_specs(scale)
+    for idx, (low, skip, _up, _cat) in upsample_folds(scale).items():
+        # cv1 over Concat([up2(p), skip]) = up2(W[:, :c_up] . p + b)  +  W[:, c_up:] . skip      (then SiLU)
+        full = packed[f"model.{idx}.cv1"]
+        c_up, c_skip = specs[low].c2, specs[skip].c2
+        if full.k != 1 or c_up % 16 or c_skip % 16 or full.c1 != c_up + c_skip:
+            continue
+        packed[f"model.{idx}.cv1#up"] = PackedConv(full.w[:, :c_up].contiguous(), full.b.clone(), c_up, full.c2, 1, 1, cabi.ACT_NONE)
+        packed[f"model.{idx}.cv1#skip"] = PackedConv(full.w[:, c_up:].contiguous(), torch.zeros_like(full.b), c_skip, full.c2, 1, 1,
+                                                     full.act)
     return packed
 
 
@@ -144,6 +181,7 @@ class OpRecord:
     out: object = None  # where the op writes (used by weight conditioning and the per-layer parity test)
     inp: object = None
     res: object = None
+    res_mode: int = 0
 
 
 class CompiledNet:
@@ -152,12 +190,14 @@ class CompiledNet:
     PREFIX_LAYERS = 5   # yaml layers 0-4 (stem .. first stride-8 C3k2): the high-resolution, memory-heavy part
 
     def __init__(self, engine, scale: str, nc: int, packed: Dict[str, PackedConv], B: int, H: int, W: int, device,
-                 conv_impl: int = cabi.IMPL_TCGEN05, chunks: int = 1):
+                 conv_impl: int = cabi.IMPL_TCGEN05, chunks: int = 1, fold_upsample: Optional[bool] = None):
         """chunks > 1: layers 0-4 are emitted once per batch chunk (chunk-major), so that a host-fed pipeline can run chunk c
         while chunk c+1 is still on the PCIe bus (engine.GraphedPipeline); the rest of the network runs on the whole batch."""
         assert H % 32 == 0 and W % 32 == 0, "network input must be a multiple of 32"
         assert chunks >= 1 and B % chunks == 0, (B, chunks)
         self.chunks = chunks
+        self.folds = upsample_folds(scale) if (FOLD_UPSAMPLE if fold_upsample is None else fold_upsample) else {}
+        self.folds = {k: v for k, v in self.folds.items() if f"model.{k}.cv1#up" in packed}
         self._cur_B = B
         self.prefix_ranges: List[Tuple[int, int]] = []
         self.lib = cabi.load()
@@ -194,7 +234,7 @@ class CompiledNet:
         return V(self._alloc(h, w, cp), 0, cp)
 
     # ---- op emitters --------------------------------------------------------------------------
-    def _conv(self, name: str, x: V, out: V, res: Optional[V] = None, out_f32: bool = False):
+    def _conv(self, name: str, x: V, out: V, res: Optional[V] = None, out_f32: bool = False, res_mode: int = cabi.RES_POST):
         pc = self.packed[name]
         assert not pc.depthwise
         assert x.c == pc.c1, (name, x.c, pc.c1)
@@ -206,11 +246,13 @@ class CompiledNet:
         assert x.B == out.B
         d.B, d.Hin, d.Win, d.Hout, d.Wout = x.B, x.H, x.W, out.H, out.W
         d.k, d.stride, d.act, d.out_f32, d.impl = pc.k, pc.s, pc.act, int(out_f32), self.conv_impl
+        d.res_mode = res_mode
         cabi.check(self.lib.y11_plan_add_conv(self.plan, C.byref(d)), f"plan_add_conv({name})")
         px = x.B * out.H * out.W
+        res_bytes = 0 if res is None else res.B * res.H * res.W * pc.c2 * 2
         self.ops.append(OpRecord("conv", name, 2.0 * px * pc.c2 * (pc.alg_k or pc.c1 * pc.k * pc.k),
                                  x.B * x.H * x.W * pc.c1 * 2 + pc.w.numel() * 2 + px * pc.c2 * (4 if out_f32 else 2)
-                                 + (px * pc.c2 * 2 if res is not None else 0), out, x, res))
+                                 + res_bytes, out, x, res, res_mode))
 
     def _dw(self, name: str, x: V, out: V, res: Optional[V] = None):
         pc = self.packed[name]
@@ -241,11 +283,18 @@ class CompiledNet:
         self._conv(f"{p}.cv2", x, z.sub(c_, c_))
         self._conv(f"{p}.cv3", z, out)
 
-    def _c3k2(self, sp: T.LayerSpec, x: V, out: V):
+    def _c3k2(self, sp: T.LayerSpec, x: V, out: V, low: Optional[V] = None):
+        """low != None: x is only the skip half of a folded Upsample+Concat input and `low` the low-resolution half."""
         p = f"model.{sp.index}"
         c = int(sp.c2 * sp.e)
         y = self._new(x.H, x.W, (2 + sp.n) * c)
-        self._conv(f"{p}.cv1", x, y.sub(0, 2 * c))
+        if low is not None:
+            pre = self._new(low.H, low.W, 2 * c)                   # W_up . low + b at low resolution (bf16, no activation)
+            self._conv(f"{p}.cv1#up", low, pre)
+            self.ops[-1].flops *= 4.0     # ALGORITHMIC FLOPs: the reference runs these MACs on the 4x larger upsampled map
+            self._conv(f"{p}.cv1#skip", x, y.sub(0, 2 * c), res=pre, res_mode=cabi.RES_PRE_UP2)
+        else:
+            self._conv(f"{p}.cv1", x, y.sub(0, 2 * c))
         for j in range(sp.n):
             src, dst = y.sub((1 + j) * c, c), y.sub((2 + j) * c, c)
             if sp.c3k:
@@ -330,8 +379,10 @@ class CompiledNet:
         H, W = self.H, self.W
         # where each layer's output lives: concat consumers own the storage, producers write into slices
         concat_of: Dict[int, Tuple[int, int]] = {}   # producer layer -> (concat layer, channel offset)
+        folded_cats = {v[3] for v in self.folds.values()}
+        folded_ups = {v[2] for v in self.folds.values()}
         for sp in specs:
-            if sp.kind == "Concat":
+            if sp.kind == "Concat" and sp.index not in folded_cats:
                 off = 0
                 for src in sp.frm:
                     concat_of[src] = (sp.index, off)
@@ -403,11 +454,20 @@ class CompiledNet:
                 self._cur_B = self.B
                 self.prefix_ranges.append((first, len(self.ops)))
         for sp in specs[n_prefix:]:
-            if sp.kind in ("Conv", "C3k2", "SPPF", "C2PSA"):
+            if sp.index in self.folds:
+                low_i, skip_i, _, cat_i = self.folds[sp.index]
+                hw[sp.index] = hw[cat_i]
+                o = out_view(sp, *hw[sp.index])
+                self._c3k2(sp, outs[skip_i], o, low=outs[low_i])
+            elif sp.kind in ("Conv", "C3k2", "SPPF", "C2PSA"):
                 x = outs[sp.frm[0]] if sp.index else None
                 hw[sp.index] = out_hw(sp, hw)
                 o = out_view(sp, *hw[sp.index])
                 emit(sp, x, o, self.input)
+            elif sp.index in folded_ups or sp.index in folded_cats:
+                src = outs[sp.frm[0]] if sp.index in folded_ups else None
+                hw[sp.index] = (2 * src.H, 2 * src.W) if src is not None else hw[sp.frm[0]]
+                o = None                                         # never materialised
             elif sp.kind == "Upsample":
                 x = outs[sp.frm[0]]
                 hw[sp.index] = (2 * x.H, 2 * x.W)
