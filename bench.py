@@ -354,11 +354,12 @@ def run_ours(args):
             print(f"head level {l}: cls mean {cls_l.mean():.3f} std {cls_l.std():.3f} max {cls_l.max():.3f} "
                   f"p99.9 {cls_l.flatten()[::7].kthvalue(int(cls_l.numel() / 7 * 0.999)).values:.3f}; box std {box_l.std():.3f}",
                   file=sys.stderr)
-        rows = sorted(zip(per_op, net.ops), key=lambda r: -r[0])
-        for m, o in rows[:40]:
+        rows = sorted(zip(per_op, net.ops, net.variants()), key=lambda r: -r[0])
+        for m, o, v in rows[:60]:
             tf = o.flops / (m / 1e3) / 1e12 if m > 0 else 0
             gb = o.bytes_algo / (m / 1e3) / 1e9 if m > 0 else 0
-            print(f"{m:8.4f} ms  {o.kind:9s} {o.name:28s} {tf:8.1f} TFLOP/s {gb:8.1f} GB/s(algo)", file=sys.stderr)
+            var = f"  [{'lsu' if v[0] else 'tma'} {'epiW' if v[1] else 'epiC'} {v[2]}cta/SM BN{v[3]}]" if v[2] > 0 else ""
+            print(f"{m:8.4f} ms  {o.kind:9s} {o.name:28s} {tf:8.1f} TFLOP/s {gb:8.1f} GB/s(algo){var}", file=sys.stderr)
         print(f"network total {all_ms:.3f} ms; conv {conv_ms:.3f} ms; step {ms_step:.3f} ms", file=sys.stderr)
 
     launches_per_step = pipes[0].launches        # letterbox + plan + (count, scan, write, sort+nms)

@@ -140,6 +140,10 @@ typedef struct {
 int y11_plan_create(y11_handle h, y11_plan* out);
 void y11_plan_destroy(y11_plan p);
 int y11_plan_add_conv(y11_plan p, const y11_conv_desc* d);
+/* Same, with an explicit launch variant of the tcgen05 kernel instead of the built-in per-layer heuristic (-1 = heuristic):
+ * lsu: activation tiles fetched by cp.async (1) or TMA (0) where both are possible; epi_warp: warp-independent epilogue;
+ * ctas_per_sm: persistent CTAs per SM; bn_max: largest N tile.  All variants produce bit-identical results. */
+int y11_plan_add_conv_tuned(y11_plan p, const y11_conv_desc* d, int lsu, int epi_warp, int ctas_per_sm, int bn_max);
 int y11_plan_add_stem(y11_plan p, const y11_stem_desc* d);
 int y11_plan_add_dwconv(y11_plan p, const y11_dwconv_desc* d);
 int y11_plan_add_sppf(y11_plan p, const y11_sppf_desc* d);
@@ -163,6 +167,11 @@ int y11_plan_run_ops(y11_plan p, int first, int last, y11_stream s);
 int y11_plan_run_range(y11_plan p, int first, int last, y11_stream s);
 /* Run with a CUDA-event pair around every op; ms_per_op has y11_plan_num_ops entries. Synchronises. */
 int y11_plan_run_timed(y11_plan p, y11_stream s, float* ms_per_op);
+/* Time every tcgen05 conv of the plan in each feasible launch variant on its real buffers (`reps` launches each) and keep
+ * the fastest.  One-off, at plan-build time; synchronises `s`; overwrites activation buffers (not weights). */
+int y11_plan_autotune(y11_plan p, y11_stream s, int reps);
+/* Launch variant of op i: out4 = {lsu, epi_warp, ctas_per_sm, bn}; all -1 for ops that are not tcgen05 convs. */
+int y11_plan_op_variant(y11_plan p, int i, int32_t* out4);
 /* FLOPs (2*MAC) of op i as launched; 0 for non-conv ops. */
 double y11_plan_op_flops(y11_plan p, int i);
 

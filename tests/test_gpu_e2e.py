@@ -119,6 +119,25 @@ def test_folded_upsample_concat_equals_copy_ops(engines, scale, B, H, W):
     assert rel_l2(outs[0], outs[1]) <= 1e-2, rel_l2(outs[0], outs[1])
 
 
+def test_autotuned_plan_is_bit_identical_to_heuristic_plan(engines, monkeypatch):
+    """The plan autotuner only changes launch variants: the head of an autotuned plan equals the heuristic plan bit for bit."""
+    from yolo_infer_b200 import network as N
+    eng = engines("n")[0]
+    x = torch.rand(2, 3, 320, 320, generator=torch.Generator().manual_seed(9)).to("cuda:0")
+    outs, variants = [], []
+    for tuned in (True, False):
+        monkeypatch.setattr(N, "AUTOTUNE", tuned)
+        with torch.cuda.device(eng.device):
+            net = N.CompiledNet(eng._engine, eng.scale, eng.nc, eng._packed, 2, 320, 320, eng.device)
+        eng.preprocess_tensor(net, x, 1.0)
+        eng.forward(net)
+        torch.cuda.synchronize()
+        outs.append(net.raw_head().cpu())
+        variants.append(net.variants())
+    assert torch.equal(outs[0], outs[1])
+    assert all(v[2] in (1, 2, 3, 4) for v, o in zip(variants[0], net.ops) if o.kind == "conv")
+
+
 def match_detections(got: torch.Tensor, want: torch.Tensor, conf: float, margin: float = 0.03):
     """Every detection of one side whose score clears the threshold by `margin` must exist on the other side
     (same class, IoU >= 0.8, |score delta| <= margin).  Returns (fraction matched both ways, median over matches of the max coordinate delta in px)."""

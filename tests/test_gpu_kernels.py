@@ -165,6 +165,34 @@ def test_conv_pre_activation_upsampled_term(ctx, case):
     close_bf16(got2, want2)
 
 
+VARIANT_SHAPES = [
+    # B, H, W, cin, cout, k, s, act, res
+    (2, 32, 32, 32, 64, 1, 1, True, False),      # LSU-eligible 1x1
+    (2, 40, 36, 32, 32, 3, 1, True, True),       # LSU-eligible 3x3 (halo), ragged, residual
+    (4, 20, 20, 128, 128, 1, 1, True, True),     # TMA 1x1, (4,4,8) tiles
+    (2, 16, 16, 64, 128, 3, 1, True, False),     # TMA 3x3
+    (2, 32, 32, 64, 128, 3, 2, True, False),     # stride 2
+]
+
+
+@pytest.mark.parametrize("shape", VARIANT_SHAPES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_launch_variants_are_bit_identical(ctx, shape):
+    """Every launch variant the plan autotuner may pick (producer TMA | cp.async, epilogue CTA-wide | warp-independent,
+    2 | 3 CTAs per SM, narrower N tiles) matches torch and is BIT-identical to the default variant."""
+    B, H, W, cin, cout, k, s_, act, res = shape
+    base, want = conv_case(ctx, B, H, W, cin, cout, k, s_, act, res)
+    close_bf16(base, want)
+    n = 0
+    for lsu in (0, 1):
+        for ew in (0, 1):
+            for cps in (2, 3):
+                for bn in (-1, 64, 32):
+                    got, _ = conv_case(ctx, B, H, W, cin, cout, k, s_, act, res, tune=(lsu, ew, cps, bn))
+                    assert torch.equal(got, base), (lsu, ew, cps, bn, (got - base).abs().max().item())
+                    n += 1
+    assert n == 24
+
+
 def test_conv_2x2_space_to_depth_form(ctx):
     """k = 2 (taps {-1,0}^2, top/left zero padding): what a 3x3 stride-2 conv becomes on a space-to-depth input.  Checked
     (a) as a plain 2x2 conv against torch and (b) end to end: stem-style s2d repacking of a 3x3/2 conv == the 3x3/2 conv."""

@@ -81,6 +81,9 @@ SIGNATURES = {
     "y11_plan_create": (C.c_int, [_P, C.POINTER(_P)]),
     "y11_plan_destroy": (None, [_P]),
     "y11_plan_add_conv": (C.c_int, [_P, C.POINTER(ConvDesc)]),
+    "y11_plan_add_conv_tuned": (C.c_int, [_P, C.POINTER(ConvDesc), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "y11_plan_autotune": (C.c_int, [_P, _P, C.c_int]),
+    "y11_plan_op_variant": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int32)]),
     "y11_plan_add_stem": (C.c_int, [_P, C.POINTER(StemDesc)]),
     "y11_plan_add_dwconv": (C.c_int, [_P, C.POINTER(DwConvDesc)]),
     "y11_plan_add_sppf": (C.c_int, [_P, C.POINTER(SppfDesc)]),

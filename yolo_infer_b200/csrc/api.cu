@@ -1,6 +1,7 @@
 // C ABI plumbing of liby11_b200: engine lifecycle, error string, and the op-list "plan" executor that replays
 // the fused YOLO11 network (built once per (model, B, H, W) by the Python host from the reference topology,
 // see yolo_infer_b200/network.py) as a fixed sequence of kernel launches on the caller's stream.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -131,6 +132,85 @@ extern "C" int y11_plan_add_conv(y11_plan p, const y11_conv_desc* d) {
   p->ops.push_back(op);
   p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane, (int)p->ops.size() - 1});
   return 0;
+}
+
+extern "C" int y11_plan_add_conv_tuned(y11_plan p, const y11_conv_desc* d, int lsu, int epi_warp, int ctas_per_sm, int bn_max) {
+  Y11_REQUIRE(p && d, "plan_add_conv_tuned: null argument");
+  Y11_REQUIRE(d->in.ptr && d->out.ptr && d->w && d->bias, "plan_add_conv_tuned: null tensor");
+  Y11_REQUIRE(d->impl == Y11_IMPL_TCGEN05, "plan_add_conv_tuned: tcgen05 convs only");
+  PlanOp* op = new_op(OP_CONV_TC);
+  op->d.conv = *d;
+  op->flops = 2.0 * d->B * d->Hout * d->Wout * (double)d->out.c * d->in.c * d->k * d->k;
+  const ConvTcTune t{lsu, epi_warp, ctas_per_sm, bn_max};
+  if (int e = conv_tc_prepare(p->eng, d, &op->tc, &t)) { delete op; return e; }
+  p->ops.push_back(op);
+  p->sched.push_back({S_OP, (int)p->ops.size() - 1, p->cur_lane, (int)p->ops.size() - 1});
+  return 0;
+}
+
+extern "C" int y11_plan_op_variant(y11_plan p, int i, int32_t* out4) {
+  Y11_REQUIRE(p && out4 && i >= 0 && i < (int)p->ops.size(), "plan_op_variant: bad argument");
+  const PlanOp* op = p->ops[i];
+  if (op->kind != OP_CONV_TC) { out4[0] = out4[1] = out4[2] = out4[3] = -1; return 0; }
+  out4[0] = op->tc.variant.lsu; out4[1] = op->tc.variant.epi_warp; out4[2] = op->tc.variant.cps; out4[3] = op->tc.variant.bn_max;
+  return 0;
+}
+
+// Plan autotuner: every tcgen05 conv is timed on its real buffers in each feasible launch variant (producer: TMA | cp.async,
+// epilogue: CTA-wide | warp-independent, 2 | 3 persistent CTAs per SM, narrower N tiles for layers with few M tiles) and the
+// fastest is kept.  All variants compute bit-identical results (same per-element K order, same epilogue arithmetic), so
+// the choice affects time only.  Runs `reps` back-to-back launches per variant after one warm-up; synchronises.
+extern "C" int y11_plan_autotune(y11_plan p, y11_stream s_, int reps) {
+  Y11_REQUIRE(p, "plan_autotune: null plan");
+  cudaStream_t s = static_cast<cudaStream_t>(s_);
+  reps = std::max(1, std::min(reps, 50));
+  cudaEvent_t e0, e1;
+  Y11_CHECK_CUDA(cudaEventCreate(&e0));
+  Y11_CHECK_CUDA(cudaEventCreate(&e1));
+  int rc = 0;
+  for (PlanOp* op : p->ops) {
+    if (op->kind != OP_CONV_TC) continue;
+    const y11_conv_desc* d = &op->d.conv;
+    const ConvTcLaunch base = op->tc;
+    std::vector<ConvTcTune> cands;
+    const int bn0 = base.variant.bn_max;
+    const long long tiles0 = (long long)base.p.tiles_w * base.p.tiles_h * base.p.tiles_n * base.p.n_tiles;
+    for (int lsu = base.lsu_eligible ? 1 : 0; lsu >= 0; --lsu)
+      for (int ew = 0; ew <= 1; ++ew)
+        for (int cps = 3; cps >= 2; --cps) {
+          cands.push_back(ConvTcTune{lsu, ew, cps, -1});
+          // few tiles (less than two waves of persistent CTAs): narrower N tiles spread the layer over more SMs
+          if (!(lsu && base.lsu_eligible) && bn0 >= 64 && bn0 <= 128 && tiles0 < 2ll * p->eng->num_sms * 3)
+            cands.push_back(ConvTcTune{lsu, ew, cps, bn0 / 2});
+        }
+    float best = 1e30f;
+    ConvTcLaunch best_l = base;
+    std::vector<ConvTcTune> seen;
+    for (const ConvTcTune& c : cands) {
+      ConvTcLaunch L;
+      if (conv_tc_prepare(p->eng, d, &L, &c)) continue;  // variant not feasible for this layer
+      bool dup = false;
+      for (const ConvTcTune& v : seen)
+        dup |= v.lsu == L.variant.lsu && v.epi_warp == L.variant.epi_warp && v.cps == L.variant.cps && v.bn_max == L.variant.bn_max;
+      if (dup) continue;
+      seen.push_back(L.variant);
+      if ((rc = conv_tc_launch(&L, s))) break;
+      Y11_CHECK_CUDA(cudaEventRecord(e0, s));
+      for (int r = 0; r < reps && !rc; ++r) rc = conv_tc_launch(&L, s);
+      if (rc) break;
+      Y11_CHECK_CUDA(cudaEventRecord(e1, s));
+      Y11_CHECK_CUDA(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      Y11_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (ms < best) { best = ms; best_l = L; }
+    }
+    if (rc) break;
+    op->tc = best_l;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  y11_set_error("");  // infeasible candidates leave their message behind
+  return rc;
 }
 
 extern "C" int y11_plan_add_stem(y11_plan p, const y11_stem_desc* d) {

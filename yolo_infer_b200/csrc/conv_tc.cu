@@ -595,7 +595,8 @@ static void pick_tile(int W, int H, int B, int* tw, int* th, int* tn) {
   }
 }
 
-int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
+int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, const ConvTcTune* tune_in) {
+  const ConvTcTune tune = tune_in ? *tune_in : conv_tc_default_tune();
   Y11_REQUIRE(eng && eng->encode_tiled, "conv_tc: engine has no cuTensorMapEncodeTiled entry point");
   Y11_REQUIRE((d->k == 1 && d->stride == 1) || (d->k == 2 && d->stride == 1) || (d->k == 3 && (d->stride == 1 || d->stride == 2)),
               "conv_tc: unsupported k=%d stride=%d", d->k, d->stride);
@@ -620,12 +621,15 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
   //                 start offsets into the un-swizzled core-matrix layout, which needs Tw = 8.
   {
     const char* e = getenv("Y11_HALO");
-    const int mode = e ? atoi(e) : 3;  // bit 0: 3x3 halo tiles, bit 1: 1x1
+    const int mode = tune.lsu >= 0 ? (tune.lsu ? 3 : 0) : (e ? atoi(e) : 3);  // bit 0: 3x3 halo tiles, bit 1: 1x1
     const size_t wbytes = (size_t)d->k * d->k * cin * cout * 2;
-    const bool k3 = d->k == 3 && d->stride == 1 && cin <= 64 && d->Hout >= 32 && d->Wout >= 32 && (mode & 1);
-    const bool k1 = d->k == 1 && (cin <= 32 || (cin % 32 != 0 && cin <= 112)) && (mode & 2);  // TMA rows would be 32-64 B
-    p.halo = (k1 || k3) && cout <= 128 && wbytes <= 40 * 1024;
-    p.pad = k3 ? 1 : 0;
+    const bool k3e = d->k == 3 && d->stride == 1 && cin <= 64 && d->Hout >= 32 && d->Wout >= 32;
+    const bool k1e = d->k == 1 && (cin <= 32 || (cin % 32 != 0 && cin <= 112));  // TMA rows would be 32-64 B
+    const bool fits = cout <= 128 && wbytes <= 40 * 1024;
+    const bool k3 = k3e && (mode & 1), k1 = k1e && (mode & 2);
+    L->lsu_eligible = (k3e || k1e) && fits;
+    p.halo = (k1 || k3) && fits;
+    p.pad = (p.halo && k3) ? 1 : 0;
   }
   if (p.halo && p.pad) { p.Tw = 8; p.Th = 16; p.Tn = 1; }
   else pick_tile(d->Wout, d->Hout, d->B, &p.Tw, &p.Th, &p.Tn);
@@ -634,7 +638,8 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
   p.tiles_n = y11_ceil_div(d->B, p.Tn);
   // N tile: largest multiple of 16 that divides cout and is <= 128
   int bn = 16;
-  for (int c = 16; c <= std::min(cout, 128); c += 16)
+  const int bn_cap = tune.bn_max > 0 ? tune.bn_max : 256;
+  for (int c = 16; c <= std::min(cout, std::min(128, bn_cap)); c += 16)
     if (cout % c == 0) bn = c;
   // Long-K, wide layers are bound by L2->smem operand traffic at 128x128 tiles (64 FLOP/B): a 128x256 tile re-reads the
   // activation tile half as often (85 FLOP/B).  It needs all 512 TMEM columns (2 accumulator stages), i.e. 1 CTA per SM.
@@ -642,7 +647,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
     const char* e = getenv("Y11_BN256");
     const int mode = e ? atoi(e) : 1;
     const long long k_total = (long long)cin * d->k * d->k;
-    if (mode && cout % 256 == 0 && cin % 64 == 0 && k_total >= 1024) bn = 256;
+    if (mode && bn_cap >= 256 && cout % 256 == 0 && cin % 64 == 0 && k_total >= 1024) bn = 256;
   }
   if (p.halo) bn = cout;
   p.BN = bn;
@@ -692,7 +697,8 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
       }
     }
     const char* e = getenv("Y11_EPI_WARP");
-    p.epi_warp = ok && (e ? atoi(e) : 0);
+    L->epi_warp_possible = ok;
+    p.epi_warp = ok && (tune.epi_warp >= 0 ? tune.epi_warp : (e ? atoi(e) : 0));
   }
   // epilogue chunk width: 32 output channels per TMA store when the tile allows it, else 16 (fp32 rows: 16 in warp mode)
   int cw = (bn % 32 == 0) ? 32 : 16;
@@ -721,6 +727,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
   //  independent TMA->MMA->epilogue chains per SM hide the per-tile latencies better than one deep pipeline)
   int cps = 3;
   if (const char* e = getenv("Y11_CTAS_PER_SM")) cps = std::max(1, std::min(4, atoi(e)));
+  if (tune.cps > 0) cps = std::max(1, std::min(4, tune.cps));
   int cols = 64;  // >= 2 accumulator stages of max(BN, 32) columns (a partial last chunk may read up to 16 spare columns)
   while (cols < 2 * bn) cols *= 2;
   while (cps > 1 && cps * cols > 512) --cps;
@@ -819,6 +826,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L) {
   }
   const unsigned total_tiles = (unsigned)(p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles);
   L->grid = std::min(total_tiles, (unsigned)(eng->num_sms * cps));
+  L->variant = ConvTcTune{p.halo, p.epi_warp, cps, bn};
   L->smem_bytes = kHeaderBytes + 1024u + p.b_res_bytes + (unsigned)stages * stage + staging;
   L->flops = 2.0 * d->B * d->Hout * d->Wout * (double)cout * cin * p.taps;
   (void)k_iters;

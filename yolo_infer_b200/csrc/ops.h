@@ -61,15 +61,27 @@ struct ConvTcParams {
   uint32_t a_lbo, a_sbo;
 };
 
+// Per-layer launch variant.  -1 = the built-in heuristic (which an environment knob may override globally); the plan
+// autotuner (y11_plan_autotune) times the feasible combinations of a layer on its real buffers and keeps the fastest.
+struct ConvTcTune {
+  int32_t lsu;       // 0: TMA producer even where the cp.async (LSU) producer is eligible; 1/-1: LSU where eligible
+  int32_t epi_warp;  // warp-independent epilogue (0/1)
+  int32_t cps;       // persistent CTAs per SM (1..4)
+  int32_t bn_max;    // largest N tile to consider (16..256)
+};
+static inline ConvTcTune conv_tc_default_tune() { return ConvTcTune{-1, -1, -1, -1}; }
+
 struct ConvTcLaunch {
   ConvTcMaps maps;
   ConvTcParams p;
   unsigned grid;
   unsigned smem_bytes;
   double flops;
+  ConvTcTune variant;  // what was actually used (resolved values)
+  int32_t lsu_eligible, epi_warp_possible;
 };
 
-int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* out);
+int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* out, const ConvTcTune* tune = nullptr);
 int conv_tc_launch(const ConvTcLaunch* l, cudaStream_t s);
 
 // ---- CUDA-core kernels (conv_simt.cu) ------------------------------------------------------------

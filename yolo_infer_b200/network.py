@@ -27,6 +27,10 @@ S2D_STEM = True   # stem output in space-to-depth form, model.1 as a 2x2 stride-
 # commutes with nearest upsampling, so cv1's weights are split by input channel, W_up . p (+bias) runs at LOW resolution and
 # enters the conv over the skip tensor as a pre-activation term (Y11_RES_PRE_UP2).  Y11_FOLD_UP=0 restores the copy ops.
 FOLD_UPSAMPLE = os.environ.get("Y11_FOLD_UP", "1") != "0"
+# Plan autotuner: time every tcgen05 conv in each feasible launch variant at plan-build time and keep the fastest
+# (y11_plan_autotune; variants are bit-identical in their results).  Y11_AUTOTUNE=0 keeps the built-in heuristics.
+AUTOTUNE = os.environ.get("Y11_AUTOTUNE", "1") != "0"
+AUTOTUNE_REPS = int(os.environ.get("Y11_AUTOTUNE_REPS", "4"))
 
 
 def upsample_folds(scale: str) -> Dict[int, Tuple[int, int, int, int]]:
@@ -214,6 +218,11 @@ class CompiledNet:
         self.head: List[torch.Tensor] = []
         self._build()
         self.A = sum(h.shape[1] * h.shape[2] for h in self.head)
+        if AUTOTUNE and conv_impl == cabi.IMPL_TCGEN05:
+            s = torch.cuda.current_stream(device).cuda_stream
+            cabi.check(self.lib.y11_plan_autotune(self.plan, C.c_void_p(s), AUTOTUNE_REPS), "y11_plan_autotune")
+            for t in self.buffers:      # the timing runs left garbage (in-place residual ops accumulate): start from zeros again
+                t.zero_()
 
     def __del__(self):
         try:
@@ -505,6 +514,15 @@ class CompiledNet:
         ms = (C.c_float * self.n_ops)()
         cabi.check(self.lib.y11_plan_run_timed(self.plan, C.c_void_p(stream), ms), "y11_plan_run_timed")
         return list(ms)
+
+    def variants(self) -> List[Tuple[int, int, int, int]]:
+        """Per op: (lsu, epi_warp, ctas_per_sm, bn) of the tcgen05 launch variant in use; (-1,)*4 for other kernels."""
+        out = []
+        v = (C.c_int32 * 4)()
+        for i in range(self.n_ops):
+            cabi.check(self.lib.y11_plan_op_variant(self.plan, i, v), "y11_plan_op_variant")
+            out.append(tuple(v))
+        return out
 
     def head_desc(self) -> cabi.HeadDesc:
         hd = cabi.HeadDesc()
