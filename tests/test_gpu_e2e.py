@@ -363,6 +363,24 @@ def test_chunked_host_pipeline_equals_eager_predict(engines):
                 assert torch.equal(a.boxes.data.cpu(), b.boxes.data.cpu())
 
 
+def test_split_host_batch_equals_eager_predict(engines, monkeypatch):
+    """Optional mode (Y11_SPLIT_HOST=1): host-fed batches of >= 32 frames as two half-batch pipelines on two streams (second
+    half on the PCIe bus while the first half computes): same rows, same order as the eager path, call after call."""
+    from yolo_infer_b200 import engine as E
+    monkeypatch.setattr(E, "SPLIT_HOST_BATCH", True)
+    eng = engines("n")[0]
+    g = torch.Generator().manual_seed(44)
+    for rep in range(3):
+        frames = torch.randint(0, 256, (32, 160, 256, 3), dtype=torch.uint8, generator=g)
+        eager = eng.predict([f.numpy() for f in frames], conf=0.3, iou=0.45, verbose=False)
+        got = eng.predict(frames.pin_memory(), conf=0.3, iou=0.45, verbose=False)
+        assert len(got) == 32
+        for a, b in zip(eager, got):
+            assert torch.equal(a.boxes.data.cpu(), b.boxes.data.cpu())
+            assert torch.equal(b.cpu().boxes.data, b.boxes.data.cpu())
+    assert any(k[0] == 16 and k[-1] == 1 for k in eng._pipes), "the half-batch replica pipeline was not used"
+
+
 def test_val_on_a_synthetic_dataset(engines, tmp_path):
     """`YOLO11Model.val(data)` (reference core/model.py:180-195, read back at core/validator.py:339-359): a dataset whose
     labels are the engine's own confident detections must score a high mAP50; shuffled class labels must not."""

@@ -25,6 +25,10 @@ from .results import Results
 
 logger = logging.getLogger(__name__)
 
+# Y11_SPLIT_HOST=1: host-fed uint8 batches of >= 32 frames run as two half-batch pipelines on two streams (see
+# YOLO.predict).  Off by default: measured on B200 it does not pay (YOLO11n 18.1 k vs 18.3 k img/s, YOLO11s 13.6 k vs 14.1 k) -
+# the low-resolution layers are latency bound, so two half batches cost almost as much as two whole ones.
+SPLIT_HOST_BATCH = os.environ.get("Y11_SPLIT_HOST", "0") != "0"
 PREDICT_DEFAULTS = dict(conf=0.25, iou=0.7, max_det=300, imgsz=640, rect=True, agnostic_nms=False, classes=None,
                         half=False, verbose=True, save=False, show=False, stream=False, batch=1, device=None,
                         multi_label=False, max_nms=30000)
@@ -241,10 +245,40 @@ class YOLO:
             self._ws[key] = t
         return t
 
-    def _fetch_results(self, det: torch.Tensor, count: torch.Tensor):
+    def _side_stream(self) -> torch.cuda.Stream:
+        if getattr(self, "_side", None) is None or self._side.device != self.device:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
+
+    def shared_copy_stream(self) -> torch.cuda.Stream:
+        """One upload stream per engine: host->device copies of concurrently running pipelines stay in submission order."""
+        if getattr(self, "_copy", None) is None or self._copy.device != self.device:
+            self._copy = torch.cuda.Stream(self.device)
+        return self._copy
+
+    def _fetch_results(self, det, count):
         """ONE device->host transfer of the whole batch's results (det fp32 [B,max_det,6] + count int32 [B]) into a pinned
         staging buffer; also the sync point of the call.  Returns (device copy of det, host copy of det, counts list): the
-        Results objects keep the device rows (reference semantics) plus a host mirror, so `.cpu()` costs nothing more."""
+        Results objects keep the device rows (reference semantics) plus a host mirror, so `.cpu()` costs nothing more.
+        det / count may be lists (the half-batch pipelines of a host-fed call): their rows are concatenated in order."""
+        if isinstance(det, (list, tuple)):
+            n = [d.shape[0] for d in det]
+            shape = (sum(n),) + tuple(det[0].shape[1:])
+            key = ("pinned_out_parts", shape, len(det))
+            pin = self._ws.get(key)
+            if pin is None:
+                with torch.inference_mode(False):
+                    pin = (torch.empty(shape, dtype=det[0].dtype).pin_memory(), torch.empty((shape[0],), dtype=count[0].dtype).pin_memory())
+                self._ws[key] = pin
+            det_dev = torch.empty(shape, dtype=det[0].dtype, device=self.device)
+            o = 0
+            for d, c, k in zip(det, count, n):
+                pin[0][o:o + k].copy_(d, non_blocking=True)
+                pin[1][o:o + k].copy_(c, non_blocking=True)
+                det_dev[o:o + k].copy_(d, non_blocking=True)
+                o += k
+            torch.cuda.current_stream(self.device).synchronize()
+            return det_dev, pin[0].clone(), pin[1].tolist()
         key = ("pinned_out", tuple(det.shape))
         pin = self._ws.get(key)
         if pin is None:
@@ -445,13 +479,30 @@ class YOLO:
                 raise ValueError("uint8 tensor source must be [B,H,W,3] BGR")
             with self._lock, torch.cuda.device(self.device), torch.inference_mode():
                 B, h0, w0, _ = source.shape
-                pipe = self.pipeline(B, h0, w0, imgsz, bool(args["rect"]), float(args["conf"]), float(args["iou"]),
-                                     int(args["max_det"]), bool(args["agnostic_nms"]), bool(args["multi_label"]))
+                pargs = (imgsz, bool(args["rect"]), float(args["conf"]), float(args["iou"]), int(args["max_det"]),
+                         bool(args["agnostic_nms"]), bool(args["multi_label"]))
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                det, count, _ = pipe.run(source)
-                e1.record()
-                det, det_h, counts = self._fetch_results(det, count)
+                if (not source.is_cuda) and B >= 32 and B % 8 == 0 and SPLIT_HOST_BATCH:
+                    # Host-fed batch: two half-batch pipelines on two streams.  The frames cross PCIe in order (one shared
+                    # copy stream), so the first half's network, decode and NMS run while the second half is still on the bus;
+                    # each half is itself chunked (H2D chunk c+1 under layers 0-4 of chunk c).
+                    Bh = B // 2
+                    cur = torch.cuda.current_stream(self.device)
+                    side = self._side_stream()
+                    pipes = [self.pipeline(Bh, h0, w0, *pargs, replica=r) for r in (0, 1)]
+                    side.wait_stream(cur)
+                    det0, count0, _ = pipes[0].run(source[:Bh])
+                    with torch.cuda.stream(side):   # its uploads queue behind the first half's on the shared copy stream
+                        det1, count1, _ = pipes[1].run(source[Bh:])
+                    cur.wait_stream(side)
+                    e1.record()
+                    det, det_h, counts = self._fetch_results([det0, det1], [count0, count1])
+                else:
+                    pipe = self.pipeline(B, h0, w0, *pargs)
+                    det, count, _ = pipe.run(source)
+                    e1.record()
+                    det, det_h, counts = self._fetch_results(det, count)
                 ms = e0.elapsed_time(e1) / B
                 speed = {"preprocess": 0.0, "inference": ms, "postprocess": 0.0}  # one graph: stages are not separable
                 self.last_speed = speed
@@ -606,7 +657,7 @@ class GraphedPipeline:
                         fn()
                     self.graphs.append(g)
             if self.chunks > 1:
-                self.copy_stream = torch.cuda.Stream(dev)
+                self.copy_stream = eng.shared_copy_stream()
                 self.copy_events = [torch.cuda.Event() for _ in range(self.chunks)]
         post_launches = 4 if (multi_label or self.net.A >= 65536) else 2   # (count, scan, write | one-pass decode) + sort/NMS
         self.launches = self.chunks + self.net.n_launches + post_launches   # letterbox per chunk + plan + post-processing
