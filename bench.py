@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--skip-e2e", action="store_true", help="profiling only: skip the e2e and per-op passes")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying CUDA graphs")
     ap.add_argument("--latency-iters", type=int, default=200, help="batch-1 latency samples (0 = skip)")
+    ap.add_argument("--dump-ops", default=None, help="write the plan's op list (kind, name, algorithmic flops/bytes, launch variant) "
+                                                     "to this JSON file (joined with ncu launch lists by tools/ncu_join.py)")
+    ap.add_argument("--no-gather", action="store_true", help="experiment only (N > 1): skip the per-step result gather")
     ap.add_argument("--streams", type=int, default=2,
                     help="steps in flight: consecutive steps alternate between this many streams (own buffers each), so the "
                          "under-filled tail of one step (NMS: one CTA per image) overlaps the head of the next")
@@ -189,6 +192,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        try:   # bind this rank to the CPU cores / NUMA node next to its GPU: pinned staging buffers are then allocated locally
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        except Exception:
+            pass
         # NCCL prints its version banner on STDOUT when NCCL_DEBUG is VERSION/INFO; stdout carries exactly one JSON line
         # (the level may also come from /etc/nccl.conf, so the redirection is unconditional)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -200,6 +209,9 @@ def run_ours(args):
         eng.condition_synthetic_weights((S, S), batch=2, seed=0)
     net = eng.compiled(B, S, S)
     stream = torch.cuda.current_stream(dev)
+    if args.dump_ops and rank == 0:
+        Path(args.dump_ops).write_text(json.dumps([{"kind": o.kind, "name": o.name, "flops": o.flops, "bytes_algo": o.bytes_algo,
+                                                    "variant": list(v)} for o, v in zip(net.ops, net.variants())]))
 
     # inputs: NROT distinct device-resident uint8 batches (> L2) rotated between steps
     NROT = 4
@@ -220,26 +232,45 @@ def run_ours(args):
             pipes.append(eng.pipeline(B, S, S, S, True, CONF, IOU, MAX_DET, frames=db, graph=use_graph, replica=j % NS))
     torch.cuda.synchronize(dev)
 
-    gathered = None
-    if world > 1:
+    gathered = comm = None
+    do_gather = world > 1 and not args.no_gather
+    if do_gather:
         from yolo_infer_b200.parallel import gather_flat
         n_flat = B * MAX_DET * 6 + B
         gathered = [torch.empty((world * n_flat,), dtype=torch.float32, device=dev) for _ in range(NS)]
+        # The only collective of the path - ONE all-gather of the fixed-shape results (461 KB/rank) per step, so that every rank
+        # (rank 0 in particular) holds the global batch - runs on its own stream: the compute streams never wait for the
+        # other ranks to arrive (a gather issued on the compute stream put every step in lockstep with the slowest rank:
+        # 86.7 % weak-scaling efficiency at 8 GPUs), only for the gather that last READ the result buffer they overwrite.
+        comm = torch.cuda.Stream(dev)
+        ready = [torch.cuda.Event() for _ in range(NS)]
+        drained = [torch.cuda.Event() for _ in range(NS)]
+        for ev in drained:
+            ev.record(stream)
 
     def step_resident(i: int):
         j = i % NROT
-        with torch.cuda.stream(streams[j % NS]):
+        r = j % NS
+        st = streams[r]
+        with torch.cuda.stream(st):
+            if do_gather:
+                st.wait_event(drained[r])     # the previous gather of this replica's result buffer has read it
             det, cnt, ncand = pipes[j].run()
-            if world > 1:  # the only collective of the path: ONE all-gather of the fixed-shape results (461 KB/rank) per step,
-                gather_flat(eng.result_flat(pipes[j].net, MAX_DET), gathered[j % NS])   # so that rank 0 holds the global batch
+            if do_gather:
+                ready[r].record(st)
+        if do_gather:
+            comm.wait_event(ready[r])
+            with torch.cuda.stream(comm):
+                gather_flat(eng.result_flat(pipes[j].net, MAX_DET), gathered[r])
+                drained[r].record(comm)
         return det, cnt, ncand
 
     def fork():   # side streams start after everything enqueued on the main stream
-        for st in streams[1:]:
+        for st in streams[1:] + ([comm] if comm is not None else []):
             st.wait_stream(stream)
 
-    def join():   # the main stream continues after everything enqueued on the side streams
-        for st in streams[1:]:
+    def join():   # the main stream continues after everything enqueued on the side streams (and after the last gather)
+        for st in streams[1:] + ([comm] if comm is not None else []):
             stream.wait_stream(st)
 
     def barrier():
@@ -333,11 +364,11 @@ def run_ours(args):
     n_conv = sum(1 for o in net.ops if o.kind == "conv")
     # DRAM bytes of the same 79 launches from the committed ncu capture (profiles/r01_traffic.json), batch 64 @640 only
     traffic = None
-    tf = ROOT / "profiles" / "r01_traffic.json"
-    if tf.exists() and B == 64 and S == 640:
-        t = json.loads(tf.read_text()).get(args.model)
-        if t and t.get("conv_tc_launches") == n_conv:
-            traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
+    for tf in sorted((ROOT / "profiles").glob("r*_traffic.json"), reverse=True):   # newest capture whose launch count matches
+        if B == 64 and S == 640 and traffic is None:
+            t = json.loads(tf.read_text()).get(args.model)
+            if t and t.get("conv_tc_launches") == n_conv:
+                traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
             "kernel": f"conv_tc_kernel ({n_conv} launches/step, {conv_ms:.3f} ms of {all_ms:.3f} ms network time; achieved = "

@@ -138,6 +138,24 @@ def test_autotuned_plan_is_bit_identical_to_heuristic_plan(engines, monkeypatch)
     assert all(v[2] in (1, 2, 3, 4) for v, o in zip(variants[0], net.ops) if o.kind == "conv")
 
 
+def test_tune_cache_round_trip(engines, monkeypatch, tmp_path):
+    """Y11_TUNE_CACHE: the variants an autotune run picked are stored and re-applied verbatim by the next build."""
+    import json
+    from yolo_infer_b200 import network as N
+    eng = engines("n")[0]
+    cache = tmp_path / "tune.json"
+    monkeypatch.setattr(N, "AUTOTUNE", True)
+    monkeypatch.setattr(N, "TUNE_CACHE", str(cache))
+    nets = []
+    for _ in range(2):
+        with torch.cuda.device(eng.device):
+            nets.append(N.CompiledNet(eng._engine, eng.scale, eng.nc, eng._packed, 1, 256, 320, eng.device))
+    stored = json.loads(cache.read_text())
+    assert list(stored) == [nets[0]._tune_key]
+    assert nets[0]._cached_variants is None and nets[1]._cached_variants is not None
+    assert nets[0].variants() == nets[1].variants() == [tuple(v) for v in stored[nets[0]._tune_key]]
+
+
 def match_detections(got: torch.Tensor, want: torch.Tensor, conf: float, margin: float = 0.03):
     """Every detection of one side whose score clears the threshold by `margin` must exist on the other side
     (same class, IoU >= 0.8, |score delta| <= margin).  Returns (fraction matched both ways, median over matches of the max coordinate delta in px)."""

@@ -514,3 +514,14 @@ def test_fused_postprocess_matches_oracle_nms(ctx, multi_label):
         got = det[b, :n].cpu()
         assert torch.equal(got[:, 4:], w[:, 4:])                        # same candidates, same order, same scores/classes
         assert (got[:, :4] - w[:, :4]).abs().max() <= 0.5 if n else True  # stated tolerance 0.5 px (observed ~1e-4)
+
+
+def test_conv_dynamic_tile_scheduler_matches_static(ctx, monkeypatch):
+    """Y11_DYN_TILES=1 (global atomic tile counter, re-armed by the last CTA of every launch) gives the same bits as the
+    static tile walk, launch after launch of the same op."""
+    shapes = [(3, 80, 80, 32, 64, 3, 1, True, True), (8, 20, 20, 192, 384, 1, 1, True, False), (2, 32, 32, 64, 128, 3, 2, True, False)]
+    base = [conv_case(ctx, *sh)[0] for sh in shapes]
+    monkeypatch.setenv("Y11_DYN_TILES", "1")
+    for sh, want in zip(shapes, base):
+        for repeats in (1, 4):  # repeated launches of the same op exercise the counter re-arm (the output is idempotent)
+            assert torch.equal(conv_case(ctx, *sh, repeats=repeats)[0], want)

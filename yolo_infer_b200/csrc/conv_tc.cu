@@ -55,6 +55,13 @@ constexpr int kEpiWarps = 8;
 constexpr int kMaxStages = 32;           // small-channel layers have 5-9 KB stages: bytes in flight, not stage count, hide latency
 constexpr uint32_t kHeaderBytes = 3072;  // mbarriers + tmem pointer (1 KB) + LSU-mode position table (2 KB)
 constexpr uint32_t kSmemBudget = 200 * 1024;
+// Tile queue: the producer warp owns the CTA's tile sequence and publishes it to the MMA warp and the epilogue warps through
+// a small shared-memory ring guarded by mbarriers.  Default: the static walk blockIdx.x, +gridDim.x, ...  With
+// Y11_DYN_TILES=1 every tile after the first comes from a global atomic counter (a CTA that becomes resident late - kernels of
+// another stream, NCCL CTAs, the drain of a non-persistent predecessor - then simply takes fewer tiles); measured neutral
+// on B200 (see api.cu), so it is off by default.
+constexpr int kTileQ = 8;
+constexpr uint32_t kTqFullOff = 640, kTqEmptyOff = 704, kTqTileOff = 768;  // inside the first KB of the header
 
 __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
@@ -73,6 +80,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ int ld_shared_s32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_s32(uint32_t addr, int v) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -104,6 +119,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       mbar_init(empty_bar + 8 * s, 1);
     }
     mbar_init(bres_bar, 1);
+    for (int q = 0; q < kTileQ; ++q) {
+      mbar_init(smem_base + kTqFullOff + 8 * q, 1);
+      mbar_init(smem_base + kTqEmptyOff + 8 * q, 1 + kEpiWarps);  // consumers: the MMA warp + every epilogue warp
+    }
     for (int a = 0; a < 2; ++a) {
       mbar_init(accf_bar + 8 * a, 1);
       mbar_init(acce_bar + 8 * a, p.epi_warp ? kEpiWarps / 2 : kEpiWarps);
@@ -150,6 +169,32 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
 #ifdef Y11_TRACE
   int trc = 0;
 #endif
+  const uint32_t tq_full = smem_base + kTqFullOff, tq_empty = smem_base + kTqEmptyOff, tq_tile = smem_base + kTqTileOff;
+  // producer side: hand tile `t` (or -1 = no more tiles) to the consumers; qi = running queue index
+  auto tq_publish = [&](uint32_t qi, int t) {
+    const uint32_t slot = qi & (kTileQ - 1), ph = (qi / kTileQ) & 1u;
+    mbar_wait(tq_empty + 8 * slot, ph ^ 1u, p.err_flag, 106);
+    if (lane == 0) {
+      st_shared_s32(tq_tile + 4 * slot, t);
+      mbar_arrive(tq_full + 8 * slot);  // release: the tile index above is visible to whoever observes this phase
+    }
+    __syncwarp();
+  };
+  // consumer side (whole warp): next tile of this CTA, -1 when there is none
+  auto tq_take = [&](uint32_t qi) -> int {
+    const uint32_t slot = qi & (kTileQ - 1), ph = (qi / kTileQ) & 1u;
+    mbar_wait(tq_full + 8 * slot, ph, p.err_flag, 107);
+    const int t = ld_shared_s32(tq_tile + 4 * slot);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tq_empty + 8 * slot);
+    return t;
+  };
+  // producer: index of the tile after the current one (lane 0 asks the global counter; issued early, consumed late)
+  auto tq_next = [&](int cur) -> int {
+    int nx = 0;
+    if (lane == 0) nx = p.tile_counter ? atomicAdd(p.tile_counter, 1) + (int)gridDim.x : cur + (int)gridDim.x;
+    return nx;
+  };
 
   if (warp == 0 && p.halo) {
     // ------------------------------------------------------------------ LSU producer (whole warp, cp.async)
@@ -175,8 +220,11 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       soff[i] = (int)e.x;
       meta[i] = e.y;
     }
-    uint32_t stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    uint32_t stage = 0, phase = 0, qi = 0;
+    for (int tile = blockIdx.x; ; ++qi) {
+      tq_publish(qi, tile);
+      if (tile < 0) break;
+      const int nx_raw = tq_next(tile);
       uint32_t t = tile, q;
       q = fast_div(t, p.mg_tw); const int w0 = (t - q * p.tiles_w) * p.Tw; t = q;
       q = fast_div(t, p.mg_th); const int h0 = (t - q * p.tiles_h) * p.Th; t = q;
@@ -199,11 +247,16 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       cp_async_mbar_arrive(full_bar + 8 * stage);
       if (lane == 0) TRACE(0, 2);
       if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+      const int nx = __shfl_sync(0xffffffffu, nx_raw, 0);
+      tile = nx < total_tiles ? nx : -1;
     }
   } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (converged warp, one elected lane issues)
-    uint32_t stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    uint32_t stage = 0, phase = 0, qi = 0;
+    for (int tile = blockIdx.x; ; ++qi) {
+      tq_publish(qi, tile);
+      if (tile < 0) break;
+      const int nx_raw = tq_next(tile);
       uint32_t t = tile, q;
       q = fast_div(t, p.mg_ntiles); const int nt = t - q * p.n_tiles; t = q;
       q = fast_div(t, p.mg_tw); const int w0 = (t - q * p.tiles_w) * p.Tw; t = q;
@@ -237,6 +290,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
       }
+      const int nx = __shfl_sync(0xffffffffu, nx_raw, 0);
+      tile = nx < total_tiles ? nx : -1;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -251,7 +306,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     if (p.halo) mbar_wait(bres_bar, 0, p.err_flag, 105);
     const uint64_t bd_res = make_umma_desc(tiles_base, p.sbo, p.layout_type);
     const uint32_t b_step = p.b_slot >> 4, k_step = (2u * p.a_lbo) >> 4;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    for (;; ++ti) {
+      if (tq_take((uint32_t)ti) < 0) break;
       const int as = ti & 1;
       mbar_wait(acce_bar + 8 * as, ((ti >> 1) & 1) ^ 1, p.err_flag, 104);  // epilogue has drained this accumulator stage
       if (lane == 0) TRACE(1, 1);
@@ -348,7 +404,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     const int tw = r % p.Tw, th = (r / p.Tw) % p.Th, tn = r / (p.Tw * p.Th);
     uint32_t sb = 0;
     int ti = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    for (;; ++ti) {
+      const int tile = tq_take((uint32_t)ti);
+      if (tile < 0) break;
       if ((ti & 1) != grp) continue;
       uint32_t t = tile, qq;
       qq = fast_div(t, p.mg_ntiles); const int nt = t - qq * p.n_tiles; t = qq;
@@ -465,7 +523,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     const bool active = half < halves;
     int ti = 0;
     uint32_t sb = 0;  // staging ring position
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    for (;; ++ti) {
+      const int tile = tq_take((uint32_t)ti);
+      if (tile < 0) break;
       uint32_t t = tile, qq;
       qq = fast_div(t, p.mg_ntiles); const int nt = t - qq * p.n_tiles; t = qq;
       qq = fast_div(t, p.mg_tw); const int w0 = (t - qq * p.tiles_w) * p.Tw; t = qq;
@@ -559,6 +619,15 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     if (leader) bulk_wait_all();
   }
 
+  if (threadIdx.x == 0 && p.tile_counter) {
+    // thread 0 is the producer lane that made this CTA's last request; the last CTA to get here re-arms the counters for the
+    // next launch of this op (visible to it through the kernel boundary / griddepcontrol.wait)
+    if (atomicAdd(p.tile_counter + 1, 1) == (int)gridDim.x - 1) {
+      p.tile_counter[0] = 0;
+      p.tile_counter[1] = 0;
+      __threadfence();
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);

@@ -48,6 +48,7 @@ struct ConvTcParams {
   uint64_t kmask;       // bit (k_iter * Cc/16 + kk): that 16-element K step has non-zero weights (TMA path, k == 2)
   int32_t kmask_on;
   int* err_flag;
+  int* tile_counter;  // [0] next tile request, [1] CTAs done (dynamic tile scheduler); nullptr = static `tile += gridDim.x` walk
   long long* trace;  // debug timeline buffer (Y11_TRACE builds only)
   uint64_t mg_ntiles, mg_tw, mg_th;  // fast_div magics for n_tiles, tiles_w, tiles_h
   // halo mode (small-channel 3x3 stride-1 layers): the (Th+2)x(Tw+2) input halo of a tile is copied ONCE by cp.async into

@@ -31,6 +31,28 @@ FOLD_UPSAMPLE = os.environ.get("Y11_FOLD_UP", "1") != "0"
 # (y11_plan_autotune; variants are bit-identical in their results).  Y11_AUTOTUNE=0 keeps the built-in heuristics.
 AUTOTUNE = os.environ.get("Y11_AUTOTUNE", "1") != "0"
 AUTOTUNE_REPS = int(os.environ.get("Y11_AUTOTUNE_REPS", "4"))
+# Y11_TUNE_CACHE=<file.json>: tuned variants are stored per (scale, nc, B, H, W, chunks, fold) and re-applied on the next
+# build instead of re-timing (a service restarts with the same plans; ncu sees the tuned plan without the tuning launches).
+TUNE_CACHE = os.environ.get("Y11_TUNE_CACHE")
+
+
+def _tune_cache_load() -> Dict[str, list]:
+    import json
+    try:
+        with open(TUNE_CACHE) as f:
+            return json.load(f)
+    except (OSError, ValueError, TypeError):
+        return {}
+
+
+def _tune_cache_store(key: str, variants: list) -> None:
+    import json
+    data = _tune_cache_load()
+    data[key] = variants
+    tmp = f"{TUNE_CACHE}.{os.getpid()}.tmp"
+    with open(tmp, "w") as f:
+        json.dump(data, f)
+    os.replace(tmp, TUNE_CACHE)
 
 
 def upsample_folds(scale: str) -> Dict[int, Tuple[int, int, int, int]]:
@@ -216,13 +238,18 @@ class CompiledNet:
         self.input = self._alloc(H, W, 3)                      # bf16 NHWC, written by the letterbox kernel
         self.no = 64 + pad16(nc)
         self.head: List[torch.Tensor] = []
+        tune = AUTOTUNE and conv_impl == cabi.IMPL_TCGEN05
+        self._tune_key = f"{scale}/nc{nc}/B{B}/{H}x{W}/chunks{chunks}/fold{int(bool(self.folds))}"
+        self._cached_variants = _tune_cache_load().get(self._tune_key) if (tune and TUNE_CACHE) else None
         self._build()
         self.A = sum(h.shape[1] * h.shape[2] for h in self.head)
-        if AUTOTUNE and conv_impl == cabi.IMPL_TCGEN05:
+        if tune and self._cached_variants is None:
             s = torch.cuda.current_stream(device).cuda_stream
             cabi.check(self.lib.y11_plan_autotune(self.plan, C.c_void_p(s), AUTOTUNE_REPS), "y11_plan_autotune")
             for t in self.buffers:      # the timing runs left garbage (in-place residual ops accumulate): start from zeros again
                 t.zero_()
+            if TUNE_CACHE:
+                _tune_cache_store(self._tune_key, [list(v) for v in self.variants()])
 
     def __del__(self):
         try:
@@ -256,7 +283,13 @@ class CompiledNet:
         d.B, d.Hin, d.Win, d.Hout, d.Wout = x.B, x.H, x.W, out.H, out.W
         d.k, d.stride, d.act, d.out_f32, d.impl = pc.k, pc.s, pc.act, int(out_f32), self.conv_impl
         d.res_mode = res_mode
-        cabi.check(self.lib.y11_plan_add_conv(self.plan, C.byref(d)), f"plan_add_conv({name})")
+        var = None
+        if self._cached_variants is not None and len(self.ops) < len(self._cached_variants):
+            var = self._cached_variants[len(self.ops)]
+        if var is not None and var[2] > 0 and self.conv_impl == cabi.IMPL_TCGEN05:   # variant chosen by an earlier autotune run
+            cabi.check(self.lib.y11_plan_add_conv_tuned(self.plan, C.byref(d), *[int(v) for v in var]), f"plan_add_conv_tuned({name})")
+        else:
+            cabi.check(self.lib.y11_plan_add_conv(self.plan, C.byref(d)), f"plan_add_conv({name})")
         px = x.B * out.H * out.W
         res_bytes = 0 if res is None else res.B * res.H * res.W * pc.c2 * 2
         self.ops.append(OpRecord("conv", name, 2.0 * px * pc.c2 * (pc.alg_k or pc.c1 * pc.k * pc.k),
