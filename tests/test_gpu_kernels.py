@@ -166,6 +166,8 @@ def test_conv_pre_activation_upsampled_term(ctx, case):
 
 
 VARIANT_SHAPES = [
+    (1, 80, 80, 64, 80, 1, 1, False, False),     # N = 80: a 64-channel fat chunk + a clipped 16-channel one
+    (2, 40, 40, 128, 256, 1, 1, True, True),     # two N tiles of 128 = 2 fat chunks each, residual
     # B, H, W, cin, cout, k, s, act, res
     (2, 32, 32, 32, 64, 1, 1, True, False),      # LSU-eligible 1x1
     (2, 40, 36, 32, 32, 3, 1, True, True),       # LSU-eligible 3x3 (halo), ragged, residual
@@ -184,13 +186,13 @@ def test_conv_launch_variants_are_bit_identical(ctx, shape):
     close_bf16(base, want)
     n = 0
     for lsu in (0, 1):
-        for ew in (0, 1):
+        for ew in (0, 1, 2, 3):     # bit 0: per-warp epilogue, bit 1: fat epilogue (conv_tc_kernel_fat, 64-channel chunks)
             for cps in (2, 3):
                 for bn in (-1, 64, 32):
                     got, _ = conv_case(ctx, B, H, W, cin, cout, k, s_, act, res, tune=(lsu, ew, cps, bn))
                     assert torch.equal(got, base), (lsu, ew, cps, bn, (got - base).abs().max().item())
                     n += 1
-    assert n == 24
+    assert n == 48
 
 
 def test_conv_2x2_space_to_depth_form(ctx):

@@ -194,7 +194,7 @@ extern "C" int y11_plan_autotune(y11_plan p, y11_stream s_, int reps) {
     const int bn0 = base.variant.bn_max;
     const long long tiles0 = (long long)base.p.tiles_w * base.p.tiles_h * base.p.tiles_n * base.p.n_tiles;
     for (int lsu = base.lsu_eligible ? 1 : 0; lsu >= 0; --lsu)
-      for (int ew = 0; ew <= 1; ++ew)
+      for (int ew = 0; ew <= 3; ++ew)  // bit 0: per-warp epilogue, bit 1: fat epilogue
         for (int cps = 3; cps >= 2; --cps) {
           cands.push_back(ConvTcTune{lsu, ew, cps, -1});
           // few tiles (less than two waves of persistent CTAs): narrower N tiles spread the layer over more SMs

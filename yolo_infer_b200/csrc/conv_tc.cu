@@ -93,8 +93,59 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 3)
-conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcParams p) {
+// 16 accumulator columns of one tile row: +bias, (+pre-activation term), SiLU, (+residual), convert, and the swizzled
+// 16-byte stores into the staging row at `dst`; `unit0` = index of the first 16-byte unit of these columns in the row.
+__device__ __forceinline__ void epi16(const ConvTcParams& p, const uint32_t (&v)[16], const uint4 r0, const uint4 r1, int n,
+                                      uint32_t dst, uint32_t unit0, uint32_t swz) {
+  using namespace y11;
+  float f[16];
+  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 bb = __ldg(b4 + i);
+    f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x;
+    f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
+    f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
+    f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
+  }
+  const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  if (p.res_pre) {  // up2(W_up . p) of a folded Upsample+Concat: part of the pre-activation sum
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      f[2 * i] += bf16_lo(rr[i]);
+      f[2 * i + 1] += bf16_hi(rr[i]);
+    }
+  }
+  if (p.act == Y11_ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = silu(f[i]);
+  }
+  if (p.res && !p.res_pre) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      f[2 * i] += bf16_lo(rr[i]);
+      f[2 * i + 1] += bf16_hi(rr[i]);
+    }
+  }
+  if (p.out_f32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      st_shared_v4(dst + (((2u * unit0 + i) ^ swz) << 4), __float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]),
+                   __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3]));
+  } else {
+    st_shared_v4(dst + (((unit0 + 0u) ^ swz) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                 pack_bf16x2(f[6], f[7]));
+    st_shared_v4(dst + (((unit0 + 1u) ^ swz) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                 pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+  }
+}
+
+// kCpw = accumulator columns an epilogue warp drains per step: 16 (3 CTAs/SM, 64 registers) or 32 ("fat" epilogue: two
+// tcgen05.ld in flight, 64-channel store chunks = half the fences / barriers / TMA stores per tile; needs > 64 registers,
+// i.e. 2 CTAs/SM).  The ncu source view of the store-heavy 1x1 layers showed the epilogue chain - tcgen05.wait::ld,
+// fence.proxy.async, the CTA-wide barrier - as the top stall sites with the issue slots half idle.
+template <int kCpw>
+__device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvTcParams& p) {
   using namespace y11;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
@@ -397,7 +448,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     const uint32_t wbuf_bytes = 32u * pitch;
     const uint32_t my_stage = staging_base + (uint32_t)ew * (uint32_t)p.nstg * wbuf_bytes;
     const int n_chunks = (p.BN + p.cw - 1) / p.cw;
-    const int halves = p.cw / 16;
+    const int steps = p.cw / kCpw;  // kCpw-column steps per chunk
     // position of this warp's 32 rows inside the tile, and of this lane's row (for the residual read)
     const int r0 = quad * 32, r = r0 + lane;
     const int qw0 = r0 % p.Tw, qh0 = (r0 / p.Tw) % p.Th, qn0 = r0 / (p.Tw * p.Th);
@@ -429,67 +480,33 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
           else bulk_wait_read0();
         }
         __syncwarp();
-        for (int hh = 0; hh < halves; ++hh) {
-          const int col = c * p.cw + hh * 16;  // column inside the tile's accumulator
+        const uint32_t dst = buf + (uint32_t)lane * pitch;
+        for (int st = 0; st < steps; ++st) {
+          const int col = c * p.cw + st * kCpw;  // column inside the tile's accumulator
           if (col >= p.BN) break;
-          uint4 rv0 = make_uint4(0, 0, 0, 0), rv1 = rv0;
+          const bool two = kCpw == 32 && col + 16 < p.BN;
+          uint4 ra0 = make_uint4(0, 0, 0, 0), ra1 = ra0, rb0 = ra0, rb1 = ra0;
           if (p.res && valid) {  // issued before the TMEM load: independent of it
-            rv0 = *reinterpret_cast<const uint4*>(res_row + col);
-            rv1 = *reinterpret_cast<const uint4*>(res_row + col + 8);
+            ra0 = *reinterpret_cast<const uint4*>(res_row + col);
+            ra1 = *reinterpret_cast<const uint4*>(res_row + col + 8);
+            if (two) {
+              rb0 = *reinterpret_cast<const uint4*>(res_row + col + 16);
+              rb1 = *reinterpret_cast<const uint4*>(res_row + col + 24);
+            }
           }
-          uint32_t v[16];
-          tmem_ld16(taddr + col, v);
+          uint32_t va[16], vb[16];
+          tmem_ld16(taddr + col, va);
+          if (two) tmem_ld16(taddr + col + 16, vb);
           tmem_ld_wait();
-          if (c == n_chunks - 1 && col + 16 >= p.BN) {
+          if (c == n_chunks - 1 && col + kCpw >= p.BN) {
             // last TMEM read of this accumulator stage: hand it back to the MMA warp before doing the math
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acce_bar + 8 * grp);
           }
           const int n = nt * p.BN + col;
-          float f[16];
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 bb = __ldg(b4 + i);
-            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x;
-            f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
-            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
-            f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
-          }
-          {
-            const uint32_t rr[8] = {rv0.x, rv0.y, rv0.z, rv0.w, rv1.x, rv1.y, rv1.z, rv1.w};
-            if (p.res_pre) {  // up2(W_up . p) of a folded Upsample+Concat: part of the pre-activation sum
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                f[2 * i] += bf16_lo(rr[i]);
-                f[2 * i + 1] += bf16_hi(rr[i]);
-              }
-            }
-            if (p.act == Y11_ACT_SILU) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = silu(f[i]);
-            }
-            if (p.res && !p.res_pre) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                f[2 * i] += bf16_lo(rr[i]);
-                f[2 * i + 1] += bf16_hi(rr[i]);
-              }
-            }
-          }
-          const uint32_t dst = buf + (uint32_t)lane * pitch;
-          if (p.out_f32) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              st_shared_v4(dst + (((4u * hh + i) ^ swz) << 4), __float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]),
-                           __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3]));
-          } else {
-            st_shared_v4(dst + (((2u * hh + 0u) ^ swz) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                         pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            st_shared_v4(dst + (((2u * hh + 1u) ^ swz) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
-                         pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
-          }
+          epi16(p, va, ra0, ra1, n, dst, (uint32_t)(st * kCpw) / 8u, swz);
+          if (two) epi16(p, vb, rb0, rb1, n + 16, dst, (uint32_t)(st * kCpw + 16) / 8u, swz);
         }
         fence_async_smem();  // my generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
@@ -504,17 +521,17 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     if (lane == 0) bulk_wait_all();
   } else {
     // -------------------------------------------------------------------- epilogue (warps 2..9)
-    // All 8 warps work on the same chunk of CW = 16*halves output channels: warp quadrant q owns TMEM lanes / tile rows
-    // [32q, 32q+32), `half` picks the 16-column slice inside the chunk.  One staging buffer pair, one named barrier and
+    // All 8 warps work on the same chunk of CW output channels: warp quadrant q owns TMEM lanes / tile rows
+    // [32q, 32q+32), `half` picks the kCpw-column slice inside the chunk.  One staging buffer pair, one named barrier and
     // one TMA store per chunk (v2 used two independent 4-warp groups with 16-column chunks: twice the barriers/stores).
     const int ew = warp - 2;
-    const int half = ew >> 2;  // 0/1: which 16 columns of a 32-column chunk
+    const int half = ew >> 2;  // 0/1: which kCpw columns of a 2*kCpw-column chunk
     const int quad = warp & 3; // TMEM lane quadrant this warp may access (hardware: warp id % 4)
     const int r = quad * 32 + lane;
     const int tw = r % p.Tw, th = (r / p.Tw) % p.Th, tn = r / (p.Tw * p.Th);
     const bool leader = ew == 0 && lane == 0;
     const uint32_t esz = p.out_f32 ? 4u : 2u;
-    const int halves = p.cw / 16;                          // 1 (16-column chunks) or 2 (32-column chunks)
+    const int halves = p.cw / kCpw;                        // 1 or 2 warps per row share a chunk
     const uint32_t pitch = (uint32_t)p.cw * esz;           // staging row pitch: 32 / 64 / 128 B
     const uint32_t swz = (r / (128u / pitch)) & (pitch / 16u - 1u);  // TMA SWIZZLE_{32,64,128}B pattern for row r
     const uint32_t stg_bytes = 128u * pitch;
@@ -536,6 +553,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       const size_t pix = (static_cast<size_t>(on) * p.Hout + oh) * p.Wout + ow;
       // residual pixel: the output pixel itself, or (pre-activation, nearest-upsampled term) pixel (oh/2, ow/2) of a half-size map
       const size_t rpix = p.res_pre ? (static_cast<size_t>(on) * (p.Hout >> 1) + (oh >> 1)) * (p.Wout >> 1) + (ow >> 1) : pix;
+      const __nv_bfloat16* res_row = static_cast<const __nv_bfloat16*>(p.res) + rpix * p.res_ct + p.res_co + nt * p.BN;
       const int as = ti & 1;
       if (lane == 0 && (ew == 0 || ew == 3)) TRACE(2 + (ew == 3), 0);
       mbar_wait(accf_bar + 8 * as, (ti >> 1) & 1, p.err_flag, 103);
@@ -543,61 +561,27 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * acc_stride + (static_cast<uint32_t>(quad * 32) << 16);
       for (int c = 0; c < n_chunks; ++c) {
-        const int col = c * p.cw + half * 16;          // column inside the tile's accumulator
+        const int col = c * p.cw + half * kCpw;          // column inside the tile's accumulator
         const uint32_t dst = staging_base + sb * stg_bytes + row_addr;
         if (active && col < p.BN) {
-          uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+          const bool two = kCpw == 32 && col + 16 < p.BN;
+          uint4 ra0 = make_uint4(0, 0, 0, 0), ra1 = ra0, rb0 = ra0, rb1 = ra0;
           if (p.res && valid) {  // issued before the TMEM load: independent of it, and a DRAM/L2 round trip long
-            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res) + rpix * p.res_ct + p.res_co + nt * p.BN + col);
-            r0 = rp[0]; r1 = rp[1];
+            ra0 = *reinterpret_cast<const uint4*>(res_row + col);
+            ra1 = *reinterpret_cast<const uint4*>(res_row + col + 8);
+            if (two) {
+              rb0 = *reinterpret_cast<const uint4*>(res_row + col + 16);
+              rb1 = *reinterpret_cast<const uint4*>(res_row + col + 24);
+            }
           }
-          uint32_t v[16];
-          tmem_ld16(taddr + col, v);
+          uint32_t va[16], vb[16];
+          tmem_ld16(taddr + col, va);
+          if (two) tmem_ld16(taddr + col + 16, vb);
           tmem_ld_wait();
           if (lane == 0 && (ew == 0 || ew == 3)) TRACE(2 + (ew == 3), 2);
           const int n = nt * p.BN + col;
-          float f[16];
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 bb = __ldg(b4 + i);
-            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x;
-            f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
-            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
-            f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
-          }
-          {
-            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-            if (p.res_pre) {  // up2(W_up . p) of a folded Upsample+Concat: part of the pre-activation sum
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                f[2 * i] += bf16_lo(rr[i]);
-                f[2 * i + 1] += bf16_hi(rr[i]);
-              }
-            }
-            if (p.act == Y11_ACT_SILU) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = silu(f[i]);
-            }
-            if (p.res && !p.res_pre) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                f[2 * i] += bf16_lo(rr[i]);
-                f[2 * i + 1] += bf16_hi(rr[i]);
-              }
-            }
-          }
-          if (p.out_f32) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              st_shared_v4(dst + (((4u * half + i) ^ swz) << 4), __float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]),
-                           __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3]));
-          } else {
-            st_shared_v4(dst + (((2u * half + 0u) ^ swz) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                         pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            st_shared_v4(dst + (((2u * half + 1u) ^ swz) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
-                         pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
-          }
+          epi16(p, va, ra0, ra1, n, dst, (uint32_t)(half * kCpw) / 8u, swz);
+          if (two) epi16(p, vb, rb0, rb1, n + 16, dst, (uint32_t)(half * kCpw + 16) / 8u, swz);
           fence_async_smem();  // my generic-proxy smem writes -> visible to the TMA (async proxy)
           if (lane == 0 && (ew == 0 || ew == 3)) TRACE(2 + (ew == 3), 3);
         }
@@ -631,6 +615,16 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
+conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcParams p) {
+  conv_tc_body<16>(maps, p);
+}
+// "fat" epilogue variant: up to 102 registers per thread, 2 CTAs per SM
+__global__ void __launch_bounds__(kThreads, 2)
+conv_tc_kernel_fat(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcParams p) {
+  conv_tc_body<32>(maps, p);
 }
 
 int encode_map(y11_engine* eng, CUtensorMap* m, CUtensorMapDataType dt, int rank, void* base, const cuuint64_t* gdim,
@@ -767,11 +761,17 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     }
     const char* e = getenv("Y11_EPI_WARP");
     L->epi_warp_possible = ok;
-    p.epi_warp = ok && (tune.epi_warp >= 0 ? tune.epi_warp : (e ? atoi(e) : 0));
+    // tune.epi_warp: bit 0 = warp-independent epilogue, bit 1 = "fat" epilogue (32 columns per warp step, 64-channel chunks)
+    const int mode = tune.epi_warp >= 0 ? tune.epi_warp : (e ? atoi(e) : 0);
+    p.epi_warp = ok && (mode & 1);
+    // fat: bf16 outputs only (64 fp32 channels would be 256-byte staging rows), and the chunk grid must tile BN
+    p.fat = (mode & 2) && !d->out_f32 && bn > 32 && (bn % 64 == 0 || p.n_tiles == 1);
   }
-  // epilogue chunk width: 32 output channels per TMA store when the tile allows it, else 16 (fp32 rows: 16 in warp mode)
+  // epilogue chunk width: 32 output channels per TMA store when the tile allows it, else 16 (fp32 rows: 16 in warp mode);
+  // 64 in fat mode
   int cw = (bn % 32 == 0) ? 32 : 16;
   if (p.epi_warp && d->out_f32) cw = 16;
+  if (p.fat) cw = 64;
   if (p.n_tiles > 1) Y11_REQUIRE(bn % cw == 0, "conv_tc: BN=%d not a multiple of the chunk width", bn);
   p.cw = cw;
   // staging for the TMA-store epilogue: CTA-wide mode = ring of 2 whole-tile buffers (3 and 4 measured no faster and cost
@@ -797,6 +797,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   int cps = 3;
   if (const char* e = getenv("Y11_CTAS_PER_SM")) cps = std::max(1, std::min(4, atoi(e)));
   if (tune.cps > 0) cps = std::max(1, std::min(4, tune.cps));
+  if (p.fat) cps = std::min(cps, 2);  // conv_tc_kernel_fat is compiled for 2 CTAs per SM (up to 102 registers)
   int cols = 64;  // >= 2 accumulator stages of max(BN, 32) columns (a partial last chunk may read up to 16 spare columns)
   while (cols < 2 * bn) cols *= 2;
   while (cps > 1 && cps * cols > 512) --cps;
@@ -895,19 +896,21 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   }
   const unsigned total_tiles = (unsigned)(p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles);
   L->grid = std::min(total_tiles, (unsigned)(eng->num_sms * cps));
-  L->variant = ConvTcTune{p.halo, p.epi_warp, cps, bn};
+  L->variant = ConvTcTune{p.halo, p.epi_warp | (p.fat << 1), cps, bn};
   L->smem_bytes = kHeaderBytes + 1024u + p.b_res_bytes + (unsigned)stages * stage + staging;
   L->flops = 2.0 * d->B * d->Hout * d->Wout * (double)cout * cin * p.taps;
   (void)k_iters;
   static bool attr_set = false;
   if (!attr_set) {
     Y11_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    Y11_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel_fat, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
   return 0;
 }
 
 int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t s) {
-  Y11_CHECK_CUDA(y11_launch_pdl(conv_tc_kernel, dim3(L->grid), dim3(kThreads), L->smem_bytes, s, L->maps, L->p));
+  Y11_CHECK_CUDA(y11_launch_pdl(L->p.fat ? conv_tc_kernel_fat : conv_tc_kernel, dim3(L->grid), dim3(kThreads), L->smem_bytes, s,
+                                L->maps, L->p));
   return 0;
 }

@@ -34,6 +34,7 @@ struct ConvTcParams {
   int32_t n_tiles;                    // Cout tiles of BN columns
   int32_t BN, Cc, chunks_per_tap, taps, ksize, stride, stages, tmem_cols;
   int32_t epi_warp;  // warp-independent epilogue: each warp stores its own 32-row sub-box (tile must decompose)
+  int32_t fat;       // conv_tc_kernel_fat: 32 accumulator columns per epilogue warp step, 64-channel store chunks, 2 CTAs/SM
   int32_t nstg;  // staging buffers per warp of the warp-independent epilogue (1 or 2); the CTA-wide epilogue uses 2
   int32_t cw;  // epilogue chunk width in output channels (16 or 32) = inner box of the output tensor map
   uint32_t a_slot, b_slot, tx_bytes, sbo, layout_type;
@@ -66,7 +67,7 @@ struct ConvTcParams {
 // autotuner (y11_plan_autotune) times the feasible combinations of a layer on its real buffers and keeps the fastest.
 struct ConvTcTune {
   int32_t lsu;       // 0: TMA producer even where the cp.async (LSU) producer is eligible; 1/-1: LSU where eligible
-  int32_t epi_warp;  // warp-independent epilogue (0/1)
+  int32_t epi_warp;  // bit 0: warp-independent epilogue, bit 1: fat epilogue (conv_tc_kernel_fat)
   int32_t cps;       // persistent CTAs per SM (1..4)
   int32_t bn_max;    // largest N tile to consider (16..256)
 };
