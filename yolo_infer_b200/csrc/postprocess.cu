@@ -24,6 +24,7 @@ constexpr int kChunk = 64;         // anchors per CTA in decode/compaction (4 la
 constexpr int kNmsThreads = 1024;  // sort + nms CTA
 constexpr int kTile = 256;         // candidates per NMS tile
 constexpr int kSmemKeys = 16384;   // sort in shared memory up to this many keys (128 KB)
+constexpr int kKeptSmem = 1024;    // kept-box list in shared memory up to this max_det (20 KB)
 
 struct HeadParams {
   const float* head[3];
@@ -112,9 +113,7 @@ __global__ void __launch_bounds__(256) decode_dense_kernel(HeadParams hp, float*
 }
 
 // MODE 0: count candidates per 64-anchor chunk.  MODE 1: write candidates at chunk_off + in-chunk prefix (anchor order).
-// MODE 2 (single-label, A < 65536): ONE pass - the CTA reserves its slots with one atomicAdd on the image's counter, so
-// the candidate list is in arbitrary chunk order; each candidate carries its anchor index (canchor) and the sort key breaks
-// score ties by ANCHOR, which reproduces the stable sort of the anchor-ordered list exactly.
+// (Single-label with A < 65536 uses decode_onepass_kernel below instead of these two passes.)
 // Only the class logits are read to decide candidacy (sigmoid is monotone: max score = sigmoid(max logit)); the DFL
 // softmaxes (64 expf per anchor) run for candidates only, in MODE 1.
 template <int MODE>
@@ -123,7 +122,6 @@ decode_compact_kernel(HeadParams hp, float conf, float logit_lo, int multi_label
                       const int* __restrict__ chunk_off, float4* __restrict__ cbox, float* __restrict__ cscore, float* __restrict__ ccls,
                       int* __restrict__ canchor, int* __restrict__ ncand, int* __restrict__ ncand_raw) {
   __shared__ int s_warp[8];
-  __shared__ int s_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = threadIdx.x & 3;
   const int b = blockIdx.y;
   const int a = blockIdx.x * kChunk + (threadIdx.x >> 2);
@@ -174,19 +172,7 @@ decode_compact_kernel(HeadParams hp, float conf, float logit_lo, int multi_label
     }
     return;
   }
-  int pos;
-  if (MODE == 2) {
-    if (threadIdx.x == 0) {
-      int t = 0;
-      for (int i = 0; i < 8; ++i) t += s_warp[i];
-      s_base = t ? atomicAdd(&ncand[b], t) : 0;
-      if (t && ncand_raw) atomicAdd(&ncand_raw[b], t);
-    }
-    __syncthreads();
-    pos = s_base + incl - mycnt;
-  } else {
-    pos = chunk_off[b * nchunks + blockIdx.x] + incl - mycnt;
-  }
+  int pos = chunk_off[b * nchunks + blockIdx.x] + incl - mycnt;
   for (int i = 0; i < warp; ++i) pos += s_warp[i];
   const size_t ob = (size_t)b * cap;
   const bool cand = multi_label ? (__ballot_sync(0xffffffffu, mask != 0u) & gmask) != 0u : (score > conf);
@@ -222,7 +208,101 @@ decode_compact_kernel(HeadParams hp, float conf, float logit_lo, int multi_label
     cbox[ob + ppos] = box;
     cscore[ob + ppos] = score;
     ccls[ob + ppos] = (float)cls;
-    if (MODE == 2) canchor[ob + ppos] = a;
+  }
+}
+
+// Single-label, A < 65536 (every real configuration): ONE pass.  Candidates are written in arbitrary order - each warp
+// reserves its slots with one atomicAdd on the image's counter - and carry their anchor index (canchor); the sort key breaks
+// score ties by ANCHOR, which reproduces the stable sort of the anchor-ordered list exactly.
+// Two phases per 64-anchor chunk, because candidates are sparse (~20 % of the anchors at conf 0.25) but scattered: with the
+// per-candidate work (accurate sigmoid, four 16-bin softmaxes, class search) done in place, nearly every warp executed it for
+// one or two of its 8 anchors (90 us for 64 x 8400 anchors, instruction bound).  Phase 1 scans the class logits of all 64
+// anchors and lists those whose maximum logit passes a conservative threshold; phase 2 runs the per-candidate work on the
+// DENSE list (4 lanes per entry), so only ceil(n/8) warps execute it.
+__global__ void __launch_bounds__(256)
+decode_onepass_kernel(HeadParams hp, float conf, float logit_lo, int cap, float4* __restrict__ cbox, float* __restrict__ cscore,
+                      float* __restrict__ ccls, int* __restrict__ canchor, int* __restrict__ ncand, int* __restrict__ ncand_raw) {
+  __shared__ int s_list[kChunk];
+  __shared__ float s_best[kChunk];
+  __shared__ int s_n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = threadIdx.x & 3;
+  const int b = blockIdx.y;
+  const int grp = threadIdx.x >> 2;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  {
+    // ---- phase 1: this lane's quarter of the classes of anchor `grp` of the chunk
+    const int a = blockIdx.x * kChunk + grp;
+    const bool in_range = a < hp.A;
+    float best = -INFINITY;
+    if (in_range) {
+      const AnchorRef ar = anchor_ref(hp, b, a);
+      const int q = hp.cls_per_lane, c0 = sub * q;
+      for (int j = 0; j < q; j += 4) {
+        if (c0 + j >= hp.nc) break;
+        const float4 t = __ldg(reinterpret_cast<const float4*>(ar.row + 64 + c0 + j));
+        const float v[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (c0 + j + k < hp.nc) best = fmaxf(best, v[k]);
+      }
+    }
+    best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 1));
+    best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 2));
+    // sigmoid(x) > conf  =>  x > logit(conf) - slack: everything that can be a candidate gets listed
+    const bool pre = in_range && best > logit_lo;
+    const unsigned bal = __ballot_sync(0xffffffffu, pre && sub == 0);
+    if (bal) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_n, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (pre && sub == 0) {
+        const int slot = base + __popc(bal & ((1u << lane) - 1u));
+        s_list[slot] = grp;
+        s_best[slot] = best;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: list entry `grp`, 4 lanes per entry; whole warps beyond the list leave
+  const int n = s_n;
+  if (warp * 8 >= n) return;
+  const bool have = grp < n;
+  const int e = have ? grp : 0;
+  const int a = blockIdx.x * kChunk + s_list[e];
+  const float best = s_best[e];
+  const AnchorRef ar = anchor_ref(hp, b, a);
+  const float score = sigmoidf_acc(best);
+  const bool cand = have && score > conf;
+  const unsigned cb = __ballot_sync(0xffffffffu, cand && sub == 0);
+  int wbase = 0;
+  if (cb) {
+    if (lane == 0) {
+      wbase = atomicAdd(&ncand[b], __popc(cb));
+      if (ncand_raw) atomicAdd(&ncand_raw[b], __popc(cb));
+    }
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+  }
+  if (!cand) return;  // whole 4-lane groups leave together
+  const unsigned gmask = 0xFu << (lane & ~3);
+  const int pos = wbase + __popc(cb & ((1u << (lane & ~3)) - 1u));
+  const float4 box = xywh2xyxy_rn(decode_box(ar, sub, lane, gmask));
+  // class = FIRST index whose score equals the maximum score (see decode_compact_kernel)
+  const int q = hp.cls_per_lane, c0 = sub * q;
+  const float margin = best > 15.f ? INFINITY : 1e-2f;
+  int cls = 0x7fffffff;
+  for (int j = 0; j < q && c0 + j < hp.nc; ++j) {
+    const float v = __ldg(ar.row + 64 + c0 + j);
+    if (v >= best - margin && sigmoidf_acc(v) == score) { cls = c0 + j; break; }
+  }
+  cls = min(cls, __shfl_xor_sync(gmask, cls, 1));
+  cls = min(cls, __shfl_xor_sync(gmask, cls, 2));
+  if (sub == 0 && pos < cap) {
+    const size_t ob = (size_t)b * cap;
+    cbox[ob + pos] = box;
+    cscore[ob + pos] = score;
+    ccls[ob + pos] = (float)cls;
+    canchor[ob + pos] = a;
   }
 }
 
@@ -302,6 +382,10 @@ __global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
   __shared__ unsigned int t_dead[kTile / 32];
   __shared__ int t_keep[kTile];
   __shared__ int s_nk;
+  // kept boxes (with class offset) and their areas: every later tile tests its candidates against them, 4 threads per
+  // candidate walking the list serially - from shared memory when max_det allows (it is 300), else from the global scratch
+  __shared__ float4 s_kbox[kKeptSmem];
+  __shared__ float s_karea[kKeptSmem];
 
   const int b = blockIdx.x, tid = threadIdx.x;
   const size_t ob = (size_t)b * g.cap;
@@ -337,8 +421,8 @@ __global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
   }
   // 3. greedy NMS over score order, 256 candidates per tile
   const int K = min(n, g.max_nms);
-  float4* kbox = g.kbox + (size_t)b * g.max_det;
-  float* karea = g.karea + (size_t)b * g.max_det;
+  float4* kbox = g.max_det <= kKeptSmem ? s_kbox : g.kbox + (size_t)b * g.max_det;
+  float* karea = g.max_det <= kKeptSmem ? s_karea : g.karea + (size_t)b * g.max_det;
   if (tid == 0) s_nk = 0;
   __syncthreads();
   for (int c0 = 0; c0 < K; c0 += kTile) {
@@ -559,8 +643,7 @@ extern "C" int y11_detect_postprocess(y11_handle, const y11_head_desc* hd, const
   if (one_pass) {
     Y11_CHECK_CUDA(cudaMemsetAsync(w.ncand, 0, (size_t)hp.B * sizeof(int), s));
     if (out_ncand) Y11_CHECK_CUDA(cudaMemsetAsync(out_ncand, 0, (size_t)hp.B * sizeof(int), s));
-    decode_compact_kernel<2><<<grid, 256, 0, s>>>(hp, p->conf, logit_lo, 0, cap, nchunks, w.chunk_cnt, w.chunk_off, w.cbox, w.cscore,
-                                                  w.ccls, w.canchor, w.ncand, out_ncand);
+    decode_onepass_kernel<<<grid, 256, 0, s>>>(hp, p->conf, logit_lo, cap, w.cbox, w.cscore, w.ccls, w.canchor, w.ncand, out_ncand);
   } else {
     decode_compact_kernel<0><<<grid, 256, 0, s>>>(hp, p->conf, logit_lo, p->multi_label, cap, nchunks, w.chunk_cnt, w.chunk_off, w.cbox,
                                                   w.cscore, w.ccls, nullptr, nullptr, nullptr);

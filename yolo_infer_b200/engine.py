@@ -509,10 +509,13 @@ class YOLO:
                 results = []
                 classes = torch.as_tensor(list(args["classes"])) if args["classes"] is not None else None
                 for i in range(B):
+                    if classes is None:   # rows are sliced on first access (Results/Boxes keep a view descriptor)
+                        results.append(Results(None, f"image{i}.jpg", self.names, None, (h0, w0), speed, None,
+                                               (det, det_h, i, counts[i])))
+                        continue
                     d, dh = det[i, : counts[i]], det_h[i, : counts[i]]
-                    if classes is not None:
-                        keep = torch.isin(dh[:, 5].long(), classes)
-                        d, dh = d[keep.to(d.device)], dh[keep]
+                    keep = torch.isin(dh[:, 5].long(), classes)
+                    d, dh = d[keep.to(d.device)], dh[keep]
                     results.append(Results(None, f"image{i}.jpg", self.names, d, (h0, w0), speed, dh))
             return results
         with self._lock, torch.cuda.device(self.device), torch.inference_mode():

@@ -16,11 +16,19 @@ import torch
 
 
 class Boxes:
-    def __init__(self, data: torch.Tensor, orig_shape: Tuple[int, int], host: Optional[torch.Tensor] = None):
-        if data.ndim == 1:
-            data = data[None, :]
-        assert data.shape[-1] == 6, f"expected [n,6] boxes, got {tuple(data.shape)}"
-        self.data = data
+    def __init__(self, data: Optional[torch.Tensor], orig_shape: Tuple[int, int], host: Optional[torch.Tensor] = None,
+                 lazy: Optional[tuple] = None):
+        # lazy = (device batch [B,max_det,6], host batch [B,max_det,6], image index, row count): the engine hands every image
+        # of a batch a view descriptor instead of slicing 2 x B tensors up front (64 images: ~0.3 ms of Python per call);
+        # the rows are materialised on first access of `.data` / `.cpu()`.
+        self._lazy = lazy
+        if data is not None:
+            if data.ndim == 1:
+                data = data[None, :]
+            assert data.shape[-1] == 6, f"expected [n,6] boxes, got {tuple(data.shape)}"
+        else:
+            assert lazy is not None
+        self._data = data
         self.orig_shape = tuple(orig_shape)
         self.is_track = False
         self.id = None
@@ -29,6 +37,23 @@ class Boxes:
         if host is not None and host.ndim == 1:
             host = host[None, :]
         self._host = host
+
+    @property
+    def data(self) -> torch.Tensor:
+        if self._data is None:
+            dev, _, i, n = self._lazy
+            self._data = dev[i, :n]
+        return self._data
+
+    @data.setter
+    def data(self, value) -> None:
+        self._data = value
+
+    def _host_rows(self) -> Optional[torch.Tensor]:
+        if self._host is None and self._lazy is not None and self._lazy[1] is not None:
+            _, host, i, n = self._lazy
+            self._host = host[i, :n]
+        return self._host
 
     # ---- the accessors the reference reads ------------------------------------------------------
     @property
@@ -74,21 +99,25 @@ class Boxes:
         return self.data.shape
 
     def __len__(self) -> int:
-        return int(self.data.shape[0])
+        if self._data is None:
+            return int(self._lazy[3])
+        return int(self._data.shape[0])
 
     def __getitem__(self, idx) -> "Boxes":
-        return Boxes(self.data[idx], self.orig_shape, self._host[idx] if self._host is not None else None)
+        host = self._host_rows()
+        return Boxes(self.data[idx], self.orig_shape, host[idx] if host is not None else None)
 
     def __iter__(self) -> Iterator["Boxes"]:
         for i in range(len(self)):
             yield self[i]
 
     def cpu(self) -> "Boxes":
-        return Boxes(self._host if self._host is not None else self.data.cpu(), self.orig_shape)
+        host = self._host_rows()
+        return Boxes(host if host is not None else self.data.cpu(), self.orig_shape)
 
     def numpy(self) -> "Boxes":
         b = Boxes.__new__(Boxes)
-        b.data, b.orig_shape, b.is_track, b.id, b._host = self.cpu().data.numpy(), self.orig_shape, False, None, None
+        b._lazy, b._data, b.orig_shape, b.is_track, b.id, b._host = None, self.cpu().data.numpy(), self.orig_shape, False, None, None
         return b
 
     def cuda(self) -> "Boxes":
@@ -104,12 +133,12 @@ class Boxes:
 class Results:
     def __init__(self, orig_img: Optional[np.ndarray], path: str, names: Dict[int, str], boxes: torch.Tensor,
                  orig_shape: Tuple[int, int], speed: Optional[Dict[str, float]] = None,
-                 host_boxes: Optional[torch.Tensor] = None):
+                 host_boxes: Optional[torch.Tensor] = None, lazy: Optional[tuple] = None):
         self.orig_img = orig_img
         self.orig_shape = tuple(orig_shape)
         self.path = path
         self.names = names
-        self.boxes = Boxes(boxes, self.orig_shape, host_boxes)
+        self.boxes = Boxes(boxes, self.orig_shape, host_boxes, lazy)
         self.masks = None
         self.probs = None
         self.keypoints = None
