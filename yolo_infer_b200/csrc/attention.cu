@@ -32,8 +32,11 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, ui
 template <int KD, int HD>
 __global__ void __launch_bounds__(128) attn_kernel(y11_attn_desc d) {
   constexpr int KP = KD + 8, VP = HD + 8;  // padded rows (bf16 elements): 80 B / 144 B pitches
-  __shared__ __align__(16) __nv_bfloat16 s_k[kT * KP];
-  __shared__ __align__(16) __nv_bfloat16 s_v[kT * VP];
+  // two K/V tile buffers: tile i+1 streams in (cp.async) while tile i is multiplied.  (v2 loaded each tile with plain
+  // loads + shared stores between two barriers: 53 % of the kernel's stall samples sat on those stores, i.e. on the global
+  // loads feeding them.)
+  __shared__ __align__(16) __nv_bfloat16 s_kb[2][kT * KP];
+  __shared__ __align__(16) __nv_bfloat16 s_vb[2][kT * VP];
   pdl_wait();
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -62,23 +65,32 @@ __global__ void __launch_bounds__(128) attn_kernel(y11_attn_desc d) {
   for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   const float sc = d.scale * 1.4426950408889634f;
-  const uint32_t sv_base = smem_u32(s_v);
-
-  for (int t0 = 0; t0 < d.N; t0 += kT) {
-    __syncthreads();
+  // async copy of the 64-key K and V tiles starting at key t0 into buffer `buf` (keys beyond N: zero-filled)
+  auto load_tile = [&](int buf, int t0) {
+    const uint32_t kdst = smem_u32(s_kb[buf]), vdst = smem_u32(s_vb[buf]);
     for (int i = threadIdx.x; i < kT * (KD / 8); i += 128) {
       const int row = i / (KD / 8), c = i % (KD / 8);
       const int key = t0 + row;
-      const uint4 v = key < d.N ? *(reinterpret_cast<const uint4*>(kb + (size_t)key * ct) + c) : make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(s_k + row * KP + c * 8) = v;
+      cp_async_16(kdst + (uint32_t)(row * KP + c * 8) * 2u, kb + (size_t)min(key, d.N - 1) * ct + c * 8, key < d.N ? 16u : 0u);
     }
     for (int i = threadIdx.x; i < kT * (HD / 8); i += 128) {
       const int row = i / (HD / 8), c = i % (HD / 8);
       const int key = t0 + row;
-      const uint4 v = key < d.N ? *(reinterpret_cast<const uint4*>(vb + (size_t)key * ct) + c) : make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(s_v + row * VP + c * 8) = v;
+      cp_async_16(vdst + (uint32_t)(row * VP + c * 8) * 2u, vb + (size_t)min(key, d.N - 1) * ct + c * 8, key < d.N ? 16u : 0u);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_tile(0, 0);
+
+  for (int t0 = 0, it = 0; t0 < d.N; t0 += kT, ++it) {
+    const int buf = it & 1;
+    const bool more = t0 + kT < d.N;
+    if (more) load_tile(buf ^ 1, t0 + kT);  // the other buffer was released by the barrier that ended the previous iteration
+    if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    const __nv_bfloat16* s_k = s_kb[buf];
+    const uint32_t sv_base = smem_u32(s_vb[buf]);
 
     // S = Q K^T for 16 queries x 64 keys: 8 n-blocks of 8 keys
     float s[kT / 8][4];
@@ -137,6 +149,7 @@ __global__ void __launch_bounds__(128) attn_kernel(y11_attn_desc d) {
         mma_bf16_16816(o[db + 1], pa[kk], r2, r3);
       }
     }
+    __syncthreads();  // everyone is done with this buffer before the next iteration's prefetch overwrites it
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);

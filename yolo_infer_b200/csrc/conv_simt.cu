@@ -122,12 +122,14 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
     const int total = n_rows * vec_per_row;
     const int row_e = 3 * d.Win;                     // bf16 per image row (multiple of 8)
     const __nv_bfloat16* img = static_cast<const __nv_bfloat16*>(d.in) + (size_t)n * d.Hin * row_e;
-    // unconditional loads from clamped addresses, four in flight per thread, zeroed afterwards (see dwconv_kernel)
-    for (int i0 = tid; i0 < total; i0 += 4 * nt) {
-      uint4 u[4];
-      bool ok[4];
+    // unconditional loads from clamped addresses, eight in flight per thread, zeroed afterwards (see dwconv_kernel); with four
+    // the first use of the loaded vectors was the kernel's top stall site (16 % of the samples, ncu source view)
+    constexpr int kFly = 8;
+    for (int i0 = tid; i0 < total; i0 += kFly * nt) {
+      uint4 u[kFly];
+      bool ok[kFly];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < kFly; ++q) {
         const int i = min(i0 + q * nt, total - 1);
         const int r = i / vec_per_row, v = i - r * vec_per_row;
         const int ih = 2 * oh0 - 1 + r;
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
         u[q] = ldg_nc_v4(img + (size_t)min(max(ih, 0), d.Hin - 1) * row_e + min(max(e0, 0), row_e - 8));
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < kFly; ++q) {
         const int i = i0 + q * nt;
         if (i < total) {
           const int r = i / vec_per_row, v = i - r * vec_per_row;

@@ -47,16 +47,19 @@ struct AnchorRef {
 };
 
 __device__ __forceinline__ AnchorRef anchor_ref(const HeadParams& hp, int b, int a) {
-  int l = 0;
-  if (hp.nl > 1 && a >= hp.off[1]) l = 1;
-  if (hp.nl > 2 && a >= hp.off[2]) l = 2;
-  const int i = a - hp.off[l];
-  const int wl = hp.wl[l];
+  // level selection with constant indices only: a runtime index into the by-value parameter arrays makes the compiler copy
+  // them to local memory at kernel entry (8 STL per thread in the ncu source view)
+  const bool l1 = hp.nl > 1 && a >= hp.off[1], l2 = hp.nl > 2 && a >= hp.off[2];
+  const int off = l2 ? hp.off[2] : l1 ? hp.off[1] : hp.off[0];
+  const int wl = l2 ? hp.wl[2] : l1 ? hp.wl[1] : hp.wl[0];
+  const int hl = l2 ? hp.hl[2] : l1 ? hp.hl[1] : hp.hl[0];
+  const float* head = l2 ? hp.head[2] : l1 ? hp.head[1] : hp.head[0];
+  const int i = a - off;
   AnchorRef r;
-  r.row = hp.head[l] + ((size_t)b * hp.hl[l] * wl + i) * hp.no;
+  r.row = head + ((size_t)b * hl * wl + i) * hp.no;
   r.ax = (float)(i % wl) + 0.5f;
   r.ay = (float)(i / wl) + 0.5f;
-  r.stride = hp.stride[l];
+  r.stride = l2 ? hp.stride[2] : l1 ? hp.stride[1] : hp.stride[0];
   return r;
 }
 
@@ -79,6 +82,24 @@ __device__ __forceinline__ float dfl_side(const float* p) {
     num = fmaf(e, (float)i, num);
   }
   return __fdiv_rn(num, den);
+}
+
+// maximum of this lane's `q` class logits [c0, c0+q) (q a multiple of 4, <= 4*kMaxClsVec), all loads issued up front
+constexpr int kMaxClsVec = 8;  // nc <= 128 -> at most 32 classes = 8 float4 per lane
+__device__ __forceinline__ float lane_class_max(const float* cls_row, int q, int c0, int nc) {
+  float4 t[kMaxClsVec];
+#pragma unroll
+  for (int j = 0; j < kMaxClsVec; ++j)
+    t[j] = (4 * j < q && c0 + 4 * j < nc) ? __ldg(reinterpret_cast<const float4*>(cls_row + c0) + j) : make_float4(0, 0, 0, 0);
+  float best = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kMaxClsVec; ++j) {
+    const float v[4] = {t[j].x, t[j].y, t[j].z, t[j].w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (4 * j + k < q && c0 + 4 * j + k < nc) best = fmaxf(best, v[k]);
+  }
+  return best;
 }
 
 // all 4 lanes of the anchor's group call this (gmask = the group's lanes); returns cx,cy,w,h in every lane
@@ -237,15 +258,7 @@ decode_onepass_kernel(HeadParams hp, float conf, float logit_lo, int cap, float4
     float best = -INFINITY;
     if (in_range) {
       const AnchorRef ar = anchor_ref(hp, b, a);
-      const int q = hp.cls_per_lane, c0 = sub * q;
-      for (int j = 0; j < q; j += 4) {
-        if (c0 + j >= hp.nc) break;
-        const float4 t = __ldg(reinterpret_cast<const float4*>(ar.row + 64 + c0 + j));
-        const float v[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (c0 + j + k < hp.nc) best = fmaxf(best, v[k]);
-      }
+      best = lane_class_max(ar.row + 64, hp.cls_per_lane, sub * hp.cls_per_lane, hp.nc);
     }
     best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 1));
     best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 2));
@@ -291,9 +304,22 @@ decode_onepass_kernel(HeadParams hp, float conf, float logit_lo, int cap, float4
   const int q = hp.cls_per_lane, c0 = sub * q;
   const float margin = best > 15.f ? INFINITY : 1e-2f;
   int cls = 0x7fffffff;
-  for (int j = 0; j < q && c0 + j < hp.nc; ++j) {
-    const float v = __ldg(ar.row + 64 + c0 + j);
-    if (v >= best - margin && sigmoidf_acc(v) == score) { cls = c0 + j; break; }
+  {
+    // this lane's quarter of the class logits, all loads issued before the first use (v1 walked them one dependent load
+    // at a time: the hottest loop of the kernel in the ncu source view)
+    float4 t[kMaxClsVec];
+#pragma unroll
+    for (int j = 0; j < kMaxClsVec; ++j)
+      t[j] = (4 * j < q && c0 + 4 * j < hp.nc) ? __ldg(reinterpret_cast<const float4*>(ar.row + 64 + c0) + j) : make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = kMaxClsVec - 1; j >= 0; --j) {   // descending, so that the FIRST matching index wins
+      const float v[4] = {t[j].x, t[j].y, t[j].z, t[j].w};
+#pragma unroll
+      for (int k = 3; k >= 0; --k) {
+        const int c = c0 + 4 * j + k;
+        if (4 * j + k < q && c < hp.nc && v[k] >= best - margin && sigmoidf_acc(v[k]) == score) cls = c;
+      }
+    }
   }
   cls = min(cls, __shfl_xor_sync(gmask, cls, 1));
   cls = min(cls, __shfl_xor_sync(gmask, cls, 2));
@@ -380,6 +406,7 @@ __global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
   __shared__ int t_idx[kTile];
   __shared__ unsigned long long t_mask[kTile][kTile / 64];
   __shared__ unsigned int t_dead[kTile / 32];
+  __shared__ unsigned int t_nz[kTile / 32];  // bit c: candidate c of the tile suppresses at least one later candidate
   __shared__ int t_keep[kTile];
   __shared__ int s_nk;
   // kept boxes (with class offset) and their areas: every later tile tests its candidates against them, 4 threads per
@@ -408,9 +435,9 @@ __global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
   __syncthreads();
   // 2. bitonic sort, ascending keys
   for (int k = 2; k <= np2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
+    for (int j = k >> 1, lj = 31 - __clz(k >> 1); j > 0; j >>= 1, --lj) {
       for (int t = tid; t < (np2 >> 1); t += kNmsThreads) {
-        const int i = 2 * j * (t / j) + (t % j);
+        const int i = ((t >> lj) << (lj + 1)) + (t & (j - 1));  // 2*j*(t/j) + t%j, j = 2^lj (the division was 20 instructions)
         const int l = i + j;
         const unsigned long long x = keys[i], y = keys[l];
         const bool up = (i & k) == 0;
@@ -439,7 +466,7 @@ __global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
         t_area[tid] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
         t_idx[tid] = idx;
       }
-      if (tid < kTile / 32) t_dead[tid] = 0u;
+      if (tid < kTile / 32) { t_dead[tid] = 0u; t_nz[tid] = 0u; }
     }
     __syncthreads();
     {
@@ -457,36 +484,45 @@ __global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
         for (int j = max(j0, c + 1); j < min(j0 + 64, cnt); ++j)
           if (iou_gt(bx, ar, t_box[j], t_area[j], g.iou_thr)) bits |= 1ull << (j - j0);
         t_mask[c][part] = bits;
+        if (bits) atomicOr(&t_nz[c >> 5], 1u << (c & 31));  // rare: most candidates suppress nobody
       }
     }
     __syncthreads();
-    // (c) warp-level sweep: lane w (< 4) owns word w of the `removed` bitset
-    if (tid < 32) {
-      const int lane = tid;
-      unsigned long long removed = ~0ull, todo = 0ull;
-      if (lane < kTile / 64) {
-        const unsigned long long dead = (unsigned long long)t_dead[2 * lane] | ((unsigned long long)t_dead[2 * lane + 1] << 32);
-        const int lo = lane * 64;
+    // (c) suppression sweep over the tile's candidates in score order.  v1 was a warp-level loop (ballot / shuffle / ffs /
+    //     shared-memory load on one dependent chain, ~300 cycles per kept box: 55 % of the kernel's stall samples were the
+    //     other 31 warps waiting for it).  Now ONE thread walks the four 64-bit words in registers; a kept candidate whose
+    //     bit row is empty (it suppresses nobody - the common case) costs a find-first-set and a store, only the others load
+    //     their row.  Rows only contain LATER candidates, so finishing word w before word w+1 is exact.
+    if (tid == 0) {
+      constexpr int kW = kTile / 64;
+      unsigned long long removed[kW], todo[kW], nz[kW];
+#pragma unroll
+      for (int w = 0; w < kW; ++w) {
+        const unsigned long long dead = (unsigned long long)t_dead[2 * w] | ((unsigned long long)t_dead[2 * w + 1] << 32);
+        const int lo = w * 64;
         const unsigned long long valid = cnt >= lo + 64 ? ~0ull : (cnt > lo ? ((1ull << (cnt - lo)) - 1ull) : 0ull);
-        removed = dead | ~valid;
-        todo = valid;
+        removed[w] = dead | ~valid;
+        todo[w] = valid;
+        nz[w] = (unsigned long long)t_nz[2 * w] | ((unsigned long long)t_nz[2 * w + 1] << 32);
       }
       int nk = nk0;
-      while (nk < g.max_det) {
-        const unsigned long long avail = ~removed & todo;
-        const unsigned have = __ballot_sync(0xffffffffu, avail != 0ull);
-        if (!have) break;
-        const int wsel = __ffs(have) - 1;
-        const int bit = __ffsll((long long)__shfl_sync(0xffffffffu, avail, wsel)) - 1;
-        const int c = wsel * 64 + bit;
-        if (lane < kTile / 64) removed |= t_mask[c][lane];
-        if (lane == wsel) todo &= ~((2ull << bit) - 1ull);  // bits <= c are settled
-        if (lane > wsel && lane < kTile / 64) { /* later words untouched */ }
-        if (lane < wsel) todo = 0ull;
-        if (lane == 0) t_keep[nk - nk0] = c;  // results are written after the sweep, by many threads at once
-        ++nk;
+#pragma unroll
+      for (int w = 0; w < kW; ++w) {
+        unsigned long long avail = ~removed[w] & todo[w];
+        while (avail != 0ull && nk < g.max_det) {
+          const int bit = __ffsll((long long)avail) - 1;
+          const int c = w * 64 + bit;
+          t_keep[nk - nk0] = c;
+          ++nk;
+          avail &= avail - 1ull;
+          if ((nz[w] >> bit) & 1ull) {
+            avail &= ~t_mask[c][w];
+#pragma unroll
+            for (int ww = w + 1; ww < kW; ++ww) removed[ww] |= t_mask[c][ww];
+          }
+        }
       }
-      if (lane == 0) s_nk = nk;
+      s_nk = nk;
     }
     __syncthreads();
     // (d) publish the boxes kept in this tile: one thread per kept box.  (Doing this inside the sweep put three dependent
