@@ -23,7 +23,7 @@ constexpr int kTH = 8, kTW = 16;
 constexpr int kHaloH = kTH + 2, kHaloW = kTW + 2;
 constexpr int kComputeThreads = 512;
 constexpr int kThreadsDw = kComputeThreads + 32;
-constexpr int kStagesDw = 3;
+constexpr int kMaxStagesDw = 6;  // ring depth is per launch: as many halo tiles as fit in ~190 KB, at most 6 (v1: fixed 3)
 
 // One thread's share of a tile: 4 channels x 1 column x RPS output rows starting at tile row r0 (halo rows r0 .. r0+RPS+1).
 template <int RPS>
@@ -82,11 +82,12 @@ __global__ void __launch_bounds__(kThreadsDw, 1)
 dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DwTmaParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
-  const uint32_t full_bar = smem_base, empty_bar = smem_base + 8 * kStagesDw;
+  const uint32_t full_bar = smem_base, empty_bar = smem_base + 8 * kMaxStagesDw;
+  const uint32_t n_stages = (uint32_t)p.stages;
   const uint32_t tiles_base = smem_base + 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStagesDw; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, kComputeThreads / 32);
     }
@@ -117,7 +118,7 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         tma_load_4d(tiles_base + stage * p.stage_bytes, &tmap, full_bar + 8 * stage, ck * p.CC, tw * kTW - 1, th * kTH - 1, t);
       }
       __syncwarp();
-      if (++stage == kStagesDw) { stage = 0; phase ^= 1; }
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
     return;
   }
@@ -157,7 +158,7 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     if (lane == 0) {
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_bar + 8 * stage) : "memory");
     }
-    if (++stage == kStagesDw) { stage = 0; phase ^= 1; }
+    if (++stage == n_stages) { stage = 0; phase ^= 1; }
   }
 }
 
@@ -205,7 +206,10 @@ int dwconv_tma_prepare(y11_engine* eng, const y11_dwconv_desc* d, DwTmaLaunch* L
   Y11_REQUIRE(r == CUDA_SUCCESS, "dwconv_tma: cuTensorMapEncodeTiled failed (%d) for C=%d %dx%d", (int)r, C, d->H, d->W);
   const int total = p.tiles_w * p.tiles_h * p.B * p.chunks;
   L->grid = (unsigned)std::min(total, eng->num_sms);
-  L->smem_bytes = 128u + kStagesDw * p.stage_bytes;
+  // the compute warps' top stall site was the wait for the next halo tile (ncu source view, 3 stages): run the producer as
+  // far ahead as shared memory allows
+  p.stages = (int)std::max(3u, std::min((uint32_t)kMaxStagesDw, (190u * 1024u) / p.stage_bytes));
+  L->smem_bytes = 128u + (unsigned)p.stages * p.stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     Y11_CHECK_CUDA(cudaFuncSetAttribute(dwconv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

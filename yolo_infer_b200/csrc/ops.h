@@ -98,6 +98,7 @@ struct DwTmaParams {
   int32_t C, CC, chunks, cg4, nsub;   // channels, channels per chunk (<= 128), chunks, CC/4, row groups per column
   int32_t B, H, W, tiles_w, tiles_h;
   uint32_t stage_tx, stage_bytes;
+  int32_t stages;  // ring depth (3..6 halo tiles)
   const void* w;
   const float* bias;
   int32_t act;
