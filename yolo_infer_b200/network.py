@@ -30,6 +30,10 @@ FOLD_UPSAMPLE = os.environ.get("Y11_FOLD_UP", "1") != "0"
 # Plan autotuner: time every tcgen05 conv in each feasible launch variant at plan-build time and keep the fastest
 # (y11_plan_autotune; variants are bit-identical in their results).  Y11_AUTOTUNE=0 keeps the built-in heuristics.
 AUTOTUNE = os.environ.get("Y11_AUTOTUNE", "1") != "0"
+# C3k.cv2 on a side lane (see CompiledNet._c3k): "auto" = scales m/l/x only.  Measured (batch 64, two steps in flight): YOLO11m
+# 8.67 -> 8.98 k img/s, but YOLO11n 34.3 -> 33.6 k and YOLO11s 20.9 -> 20.8 k (their three C3k blocks sit on small maps where
+# the extra fork/join edges cost more than the overlapped launch saves).
+C3K_LANES = os.environ.get("Y11_C3K_LANES", "auto")
 AUTOTUNE_REPS = int(os.environ.get("Y11_AUTOTUNE_REPS", "4"))
 # Y11_TUNE_CACHE=<file.json>: tuned variants are stored per (scale, nc, B, H, W, chunks, fold) and re-applied on the next
 # build instead of re-timing (a service restarts with the same plans; ncu sees the tuned plan without the tuning launches).
@@ -314,15 +318,29 @@ class CompiledNet:
         self._conv(f"{p}.cv1", x, hidden)
         self._conv(f"{p}.cv2", hidden, out, res=x)  # shortcut: c1 == c2 everywhere in YOLO11
 
+    C3K_SIDE_LANE = 7   # lanes 1-6 belong to the Detect towers
+
     def _c3k(self, p: str, x: V, out: V):
+        """C3k = cv3(cat(m(cv1(x)), cv2(x))).  cv2 depends only on x, so it runs on a side lane (a parallel branch of the CUDA
+        graph) next to the cv1 -> Bottleneck x2 chain: on the 20x20 / 40x40 maps every launch is latency bound and one of
+        the block's seven is taken off the critical path."""
         c_ = int(out.c * 0.5)
         z = self._new(x.H, x.W, 2 * c_)
+        side = C3K_LANES == "1" or (C3K_LANES == "auto" and self.scale in "mlx")
+        if side:
+            cabi.check(self.lib.y11_plan_fork(self.plan, self.C3K_SIDE_LANE), "plan_fork")
+            cabi.check(self.lib.y11_plan_set_lane(self.plan, self.C3K_SIDE_LANE), "plan_set_lane")
+            self._conv(f"{p}.cv2", x, z.sub(c_, c_))
+            cabi.check(self.lib.y11_plan_set_lane(self.plan, 0), "plan_set_lane")
         t0 = self._new(x.H, x.W, c_)
         self._conv(f"{p}.cv1", x, t0)
         t1 = self._new(x.H, x.W, c_)
         self._bottleneck(f"{p}.m.0", t0, t1, 1.0)
         self._bottleneck(f"{p}.m.1", t1, z.sub(0, c_), 1.0)
-        self._conv(f"{p}.cv2", x, z.sub(c_, c_))
+        if side:
+            cabi.check(self.lib.y11_plan_join(self.plan, self.C3K_SIDE_LANE), "plan_join")
+        else:
+            self._conv(f"{p}.cv2", x, z.sub(c_, c_))
         self._conv(f"{p}.cv3", z, out)
 
     def _c3k2(self, sp: T.LayerSpec, x: V, out: V, low: Optional[V] = None):
