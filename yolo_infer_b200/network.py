@@ -34,6 +34,7 @@ AUTOTUNE = os.environ.get("Y11_AUTOTUNE", "1") != "0"
 # 8.67 -> 8.98 k img/s, but YOLO11n 34.3 -> 33.6 k and YOLO11s 20.9 -> 20.8 k (their three C3k blocks sit on small maps where
 # the extra fork/join edges cost more than the overlapped launch saves).
 C3K_LANES = os.environ.get("Y11_C3K_LANES", "auto")
+C3K_LANES_MAX_SMALL_B = int(os.environ.get("Y11_C3K_LANES_SMALL_B", "8"))   # "auto" also enables the lane for batches <= this (batch 1: n 0.505 -> 0.498 ms, s 0.691 -> 0.680 ms)
 AUTOTUNE_REPS = int(os.environ.get("Y11_AUTOTUNE_REPS", "4"))
 # Y11_TUNE_CACHE=<file.json>: tuned variants are stored per (scale, nc, B, H, W, chunks, fold) and re-applied on the next
 # build instead of re-timing (a service restarts with the same plans; ncu sees the tuned plan without the tuning launches).
@@ -326,7 +327,7 @@ class CompiledNet:
         the block's seven is taken off the critical path."""
         c_ = int(out.c * 0.5)
         z = self._new(x.H, x.W, 2 * c_)
-        side = C3K_LANES == "1" or (C3K_LANES == "auto" and self.scale in "mlx")
+        side = C3K_LANES == "1" or (C3K_LANES == "auto" and (self.scale in "mlx" or self.B <= C3K_LANES_MAX_SMALL_B))
         if side:
             cabi.check(self.lib.y11_plan_fork(self.plan, self.C3K_SIDE_LANE), "plan_fork")
             cabi.check(self.lib.y11_plan_set_lane(self.plan, self.C3K_SIDE_LANE), "plan_set_lane")
