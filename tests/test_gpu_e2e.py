@@ -345,7 +345,7 @@ def test_cuda_graph_pipeline_equals_eager_predict(engines):
     eng = engines("n")[0]
     g = torch.Generator().manual_seed(21)
     frames = torch.randint(0, 256, (3, 360, 640, 3), dtype=torch.uint8, generator=g)
-    eager = eng.predict([f.numpy() for f in frames], conf=0.3, iou=0.45, verbose=False)
+    eager = eng.predict([f.numpy() for f in frames], conf=0.3, iou=0.45, verbose=False, graph=False)
     for src in (frames.pin_memory(), frames.cuda(), frames.pin_memory()):
         graphed = eng.predict(src, conf=0.3, iou=0.45, verbose=False)
         assert len(graphed) == 3
@@ -360,8 +360,44 @@ def test_cuda_graph_pipeline_equals_eager_predict(engines):
                 assert torch.equal(b.boxes[0].cpu().data, b.boxes.data[:1].cpu())
     other = torch.randint(0, 256, (3, 360, 640, 3), dtype=torch.uint8, generator=g)
     r2 = eng.predict(other.pin_memory(), conf=0.3, iou=0.45, verbose=False)
-    e2 = eng.predict([f.numpy() for f in other], conf=0.3, iou=0.45, verbose=False)
+    e2 = eng.predict([f.numpy() for f in other], conf=0.3, iou=0.45, verbose=False, graph=False)
     assert all(torch.equal(a.boxes.data.cpu(), b.boxes.data.cpu()) for a, b in zip(e2, r2))
+
+
+def test_array_and_file_sources_use_the_graph_pipeline(engines, tmp_path):
+    """BGR arrays / image files of one shape (the demo's per-frame `predict(frame, conf=, iou=)` loop, reference
+    demos/detection_demo.py:190-196) run through the CUDA-graph pipeline: same rows as the eager launches, `orig_img`, `path`
+    and `orig_shape` as the reference's Results carry them; mixed shapes fall back to the eager path."""
+    import cv2
+    eng = engines("n")[0]
+    rng = np.random.default_rng(12)
+    frames = [rng.integers(0, 256, (360, 640, 3), dtype=np.uint8) for _ in range(2)]
+    for src in (frames[0], frames):
+        lst = src if isinstance(src, list) else [src]
+        want = eng.predict(src, conf=0.3, iou=0.45, verbose=False, graph=False)
+        n_pipes = len(getattr(eng, "_pipes", {}))
+        got = eng.predict(src, conf=0.3, iou=0.45, verbose=False)
+        assert len(got) == len(want) == len(lst)
+        for a, b, im in zip(want, got, lst):
+            assert torch.equal(a.boxes.data.cpu(), b.boxes.data.cpu())
+            assert b.orig_img is im and b.orig_shape == (360, 640) and b.path == a.path
+        assert len(eng._pipes) >= max(n_pipes, 1)
+    # a video-like loop reuses one pipeline, frame after frame
+    n_pipes = len(eng._pipes)
+    for _ in range(3):
+        f = rng.integers(0, 256, (360, 640, 3), dtype=np.uint8)
+        a = eng.predict(f, conf=0.3, iou=0.45, verbose=False, graph=False)[0]
+        b = eng.predict(f, conf=0.3, iou=0.45, verbose=False)[0]
+        assert torch.equal(a.boxes.data.cpu(), b.boxes.data.cpu())
+    assert len(eng._pipes) == n_pipes
+    # files keep their paths; mixed shapes take the eager path
+    p0, p1 = tmp_path / "a.png", tmp_path / "b.png"
+    cv2.imwrite(str(p0), frames[0])
+    cv2.imwrite(str(p1), frames[1][:200, :320])
+    r = eng.predict(str(p0), conf=0.3, iou=0.45, verbose=False)[0]
+    assert r.path == str(p0) and torch.equal(r.boxes.data.cpu(), eng.predict(frames[0], conf=0.3, iou=0.45, verbose=False, graph=False)[0].boxes.data.cpu())
+    mixed = eng.predict([str(p0), str(p1)], conf=0.3, iou=0.45, verbose=False)
+    assert [m.path for m in mixed] == [str(p0), str(p1)] and mixed[1].orig_shape == (200, 320)
 
 
 def test_chunked_host_pipeline_equals_eager_predict(engines):
@@ -371,7 +407,7 @@ def test_chunked_host_pipeline_equals_eager_predict(engines):
     g = torch.Generator().manual_seed(33)
     for rep in range(2):
         frames = torch.randint(0, 256, (16, 192, 320, 3), dtype=torch.uint8, generator=g)
-        eager = eng.predict([f.numpy() for f in frames], conf=0.3, iou=0.45, verbose=False)
+        eager = eng.predict([f.numpy() for f in frames], conf=0.3, iou=0.45, verbose=False, graph=False)
         pipe = eng.pipeline(16, 192, 320, 640, True, 0.3, 0.45, 300)
         assert pipe.chunks == 4 and len(pipe.graphs) == 5 and len(pipe.net.prefix_ranges) == 4, (pipe.chunks, len(pipe.graphs))
         for src in (frames.pin_memory(), frames.cuda()):
@@ -390,7 +426,7 @@ def test_split_host_batch_equals_eager_predict(engines, monkeypatch):
     g = torch.Generator().manual_seed(44)
     for rep in range(3):
         frames = torch.randint(0, 256, (32, 160, 256, 3), dtype=torch.uint8, generator=g)
-        eager = eng.predict([f.numpy() for f in frames], conf=0.3, iou=0.45, verbose=False)
+        eager = eng.predict([f.numpy() for f in frames], conf=0.3, iou=0.45, verbose=False, graph=False)
         got = eng.predict(frames.pin_memory(), conf=0.3, iou=0.45, verbose=False)
         assert len(got) == 32
         for a, b in zip(eager, got):

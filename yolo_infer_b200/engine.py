@@ -29,9 +29,11 @@ logger = logging.getLogger(__name__)
 # YOLO.predict).  Off by default: measured on B200 it does not pay (YOLO11n 18.1 k vs 18.3 k img/s, YOLO11s 13.6 k vs 14.1 k) -
 # the low-resolution layers are latency bound, so two half batches cost almost as much as two whole ones.
 SPLIT_HOST_BATCH = os.environ.get("Y11_SPLIT_HOST", "0") != "0"
+MAX_CACHED_PIPELINES = 16   # CUDA-graph pipeline instances kept per engine (one per source shape x thresholds)
 PREDICT_DEFAULTS = dict(conf=0.25, iou=0.7, max_det=300, imgsz=640, rect=True, agnostic_nms=False, classes=None,
                         half=False, verbose=True, save=False, show=False, stream=False, batch=1, device=None,
-                        multi_label=False, max_nms=30000)
+                        multi_label=False, max_nms=30000,
+                        graph=True)   # extension: False = launch the kernels one by one (no CUDA-graph pipeline) for file/array sources
 
 
 def letterbox_geometry(h0: int, w0: int, new_shape: Tuple[int, int], auto: bool, stride: int = 32):
@@ -359,6 +361,8 @@ class YOLO:
                 self._pipes = {}
             with torch.inference_mode(False):  # static buffers must stay writable from any mode
                 p = GraphedPipeline(self, B, h0, w0, imgsz, rect, conf, iou, max_det, agnostic, multi_label, frames, graph, replica)
+            if len(self._pipes) >= MAX_CACHED_PIPELINES:   # dicts keep insertion order: drop the oldest instance
+                self._pipes.pop(next(iter(self._pipes)))
             self._pipes[key] = p
         return p
 
@@ -473,11 +477,31 @@ class YOLO:
         self._ensure_device(args["device"])
         imgsz = args["imgsz"]
         new_shape = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
-        if isinstance(source, torch.Tensor) and source.dtype == torch.uint8:
+        orig_imgs = paths = None
+        if args["graph"] and not isinstance(source, torch.Tensor):
+            # files / BGR arrays of ONE shape (a video stream, a demo frame, a folder of equal-sized images): staged into a
+            # pinned uint8 batch and run through the same CUDA-graph pipeline as tensor batches - one replay per call
+            # instead of ~95 eager launches (reference call sites: demos/detection_demo.py:87-93, 190-196, 280-286)
+            preloaded = self._load_sources(source)
+            if len({im.shape for im in preloaded[0]}) == 1:
+                orig_imgs, paths = preloaded
+        else:
+            preloaded = None
+        if orig_imgs is not None or (isinstance(source, torch.Tensor) and source.dtype == torch.uint8):
             # fixed-shape uint8 batch [B,H,W,3] BGR (pinned host or device): whole path replayed as ONE CUDA graph
-            if source.ndim != 4 or source.shape[-1] != 3:
+            if orig_imgs is None and (source.ndim != 4 or source.shape[-1] != 3):
                 raise ValueError("uint8 tensor source must be [B,H,W,3] BGR")
             with self._lock, torch.cuda.device(self.device), torch.inference_mode():
+                if orig_imgs is not None:   # stage the frames in a pinned batch (under the lock: the buffer is per engine)
+                    key = ("pinned_frames", len(orig_imgs)) + tuple(orig_imgs[0].shape)
+                    source = self._ws.get(key)
+                    if source is None:
+                        with torch.inference_mode(False):
+                            source = torch.empty((len(orig_imgs),) + tuple(orig_imgs[0].shape), dtype=torch.uint8).pin_memory()
+                        self._ws[key] = source
+                    stage_np = source.numpy()
+                    for i, im in enumerate(orig_imgs):
+                        stage_np[i] = im
                 B, h0, w0, _ = source.shape
                 pargs = (imgsz, bool(args["rect"]), float(args["conf"]), float(args["iou"]), int(args["max_det"]),
                          bool(args["agnostic_nms"]), bool(args["multi_label"]))
@@ -509,14 +533,18 @@ class YOLO:
                 results = []
                 classes = torch.as_tensor(list(args["classes"])) if args["classes"] is not None else None
                 for i in range(B):
+                    img_i = orig_imgs[i] if orig_imgs is not None else None
+                    path_i = paths[i] if paths is not None else f"image{i}.jpg"
                     if classes is None:   # rows are sliced on first access (Results/Boxes keep a view descriptor)
-                        results.append(Results(None, f"image{i}.jpg", self.names, None, (h0, w0), speed, None,
-                                               (det, det_h, i, counts[i])))
+                        results.append(Results(img_i, path_i, self.names, None, (h0, w0), speed, None, (det, det_h, i, counts[i])))
                         continue
                     d, dh = det[i, : counts[i]], det_h[i, : counts[i]]
                     keep = torch.isin(dh[:, 5].long(), classes)
                     d, dh = d[keep.to(d.device)], dh[keep]
-                    results.append(Results(None, f"image{i}.jpg", self.names, d, (h0, w0), speed, dh))
+                    results.append(Results(img_i, path_i, self.names, d, (h0, w0), speed, dh))
+                if args["verbose"]:
+                    logger.info("%d image(s) %dx%d: %.2f ms per image (letterbox + forward + decode + NMS, one CUDA graph)",
+                                B, h0, w0, ms)
             return results
         with self._lock, torch.cuda.device(self.device), torch.inference_mode():
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -544,7 +572,7 @@ class YOLO:
                     paths = [f"image{i}.jpg" for i in range(len(frames))]
                     orig_imgs = [None] * len(frames)
                 else:
-                    imgs, paths = self._load_sources(source)
+                    imgs, paths = preloaded if preloaded is not None else self._load_sources(source)
                     frames = [torch.from_numpy(im).pin_memory().to(self.device, non_blocking=True) for im in imgs]
                     orig_imgs = list(imgs)
                 orig_shapes = [(int(f.shape[0]), int(f.shape[1])) for f in frames]

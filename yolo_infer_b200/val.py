@@ -270,7 +270,8 @@ def validate(engine, data, imgsz: int = 640, batch: int = 16, conf: float = 0.00
                 raise FileNotFoundError(f"cannot read image {f}")
             imgs.append(im)
         t_read += time.perf_counter() - t0
-        res = engine.predict(imgs, conf=conf, iou=iou, max_det=max_det, imgsz=imgsz, multi_label=True, verbose=False)
+        # graph=False: a dataset has many distinct image sizes; a captured pipeline per size would cost more than it saves
+        res = engine.predict(imgs, conf=conf, iou=iou, max_det=max_det, imgsz=imgsz, multi_label=True, verbose=False, graph=False)
         for f, im, r in zip(chunk, imgs, res):
             preds.append(r.cpu().boxes.data.numpy())
             gts.append(read_labels(f, im.shape[1], im.shape[0]))
