@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define Y11_ABI_VERSION 3
+#define Y11_ABI_VERSION 4
 
 typedef struct y11_engine* y11_handle;
 typedef struct y11_plan_s* y11_plan;
@@ -103,6 +103,12 @@ typedef struct {
    * (out.c = 4*cout).  The following 3x3 stride-2 layer becomes a 2x2 stride-1 conv over 4*cout channels, whose
    * 128-byte-or-longer pixel rows the TMA unit can stream (32-byte rows through four parity maps could not). */
   int32_t s2d;
+  /* u8_src != 0: read the frames directly (`in` is ignored): images = DEVICE array of B y11_image descriptors whose frames
+   * are already at network resolution (h0 == new_h == Hin, w0 == new_w == Win, top == left == 0, src 4-byte aligned, pitch a
+   * multiple of 4).  The conversion (BGR->RGB, x*(1/255), bf16) is bit-identical to y11_letterbox's for such frames, so the
+   * letterbox launch and its bf16 round trip through HBM are skipped.  See y11_plan_set_stem_source. */
+  const y11_image* images;
+  int32_t u8_src;
 } y11_stem_desc;
 
 /* Depthwise 3x3 stride 1 pad 1  [a7 DWConv, Attention.pe]: out = act(dw(in)+bias) (+ res).
@@ -145,6 +151,10 @@ int y11_plan_add_conv(y11_plan p, const y11_conv_desc* d);
  * ctas_per_sm: persistent CTAs per SM; bn_max: largest N tile.  All variants produce bit-identical results. */
 int y11_plan_add_conv_tuned(y11_plan p, const y11_conv_desc* d, int lsu, int epi_warp, int ctas_per_sm, int bn_max);
 int y11_plan_add_stem(y11_plan p, const y11_stem_desc* d);
+/* Re-point the stem op(s) of the plan: images != NULL -> uint8 frames (u8_src mode; chunk-major plans hand each of their
+ * stem ops its slice of the descriptor array), NULL -> the bf16 letterbox output given at y11_plan_add_stem.  Takes effect
+ * for launches (and graph captures) made after the call. */
+int y11_plan_set_stem_source(y11_plan p, const y11_image* images);
 int y11_plan_add_dwconv(y11_plan p, const y11_dwconv_desc* d);
 int y11_plan_add_sppf(y11_plan p, const y11_sppf_desc* d);
 int y11_plan_add_upsample(y11_plan p, const y11_upsample_desc* d);

@@ -400,6 +400,33 @@ def test_array_and_file_sources_use_the_graph_pipeline(engines, tmp_path):
     assert [m.path for m in mixed] == [str(p0), str(p1)] and mixed[1].orig_shape == (200, 320)
 
 
+def test_fused_uint8_stem_pipeline_equals_letterbox_pipeline(engines, monkeypatch):
+    """Frames already at network resolution: the pipeline skips the letterbox launch (the stem reads the uint8 frames) - for
+    device-resident, host-fed and chunked host-fed batches the detections are bit-identical to the eager path, which runs
+    y11_letterbox + the bf16 stem, and the two kinds of pipeline can share one plan without disturbing each other."""
+    from yolo_infer_b200 import engine as E
+    eng = engines("n")[0]
+    g = torch.Generator().manual_seed(77)
+    for B, hw in ((3, 320), (16, 256)):
+        frames = torch.randint(0, 256, (B, hw, hw, 3), dtype=torch.uint8, generator=g)
+        eager = eng.predict([f.numpy() for f in frames], conf=0.3, iou=0.45, imgsz=hw, verbose=False, graph=False)
+        for src in (frames.cuda(), frames.pin_memory()):
+            got = eng.predict(src, conf=0.3, iou=0.45, imgsz=hw, verbose=False)
+            pipe = eng.pipeline(B, hw, hw, hw, True, 0.3, 0.45, 300)
+            assert pipe.fused_stem and pipe.launches == pipe.net.n_launches + 2
+            assert len(got) == B and sum(len(r.boxes) for r in got) > 0
+            for a, b in zip(eager, got):
+                assert torch.equal(a.boxes.data.cpu(), b.boxes.data.cpu())
+        again = eng.predict([f.numpy() for f in frames], conf=0.3, iou=0.45, imgsz=hw, verbose=False, graph=False)   # eager after fused
+        assert all(torch.equal(a.boxes.data.cpu(), b.boxes.data.cpu()) for a, b in zip(eager, again))
+    # padded / resized frames keep the letterbox launch
+    assert not eng.pipeline(2, 360, 640, 640, True, 0.3, 0.45, 300).fused_stem
+    monkeypatch.setattr(E, "FUSE_U8_STEM", False)
+    eng._pipes.clear()
+    assert not eng.pipeline(3, 320, 320, 320, True, 0.3, 0.45, 300).fused_stem
+    eng._pipes.clear()
+
+
 def test_chunked_host_pipeline_equals_eager_predict(engines):
     """Host-fed batches with B % 4 == 0, B >= 16 cross PCIe in four chunks while layers 0-4 of the previous chunk run
     (one graph per chunk + one for the rest): results must be bit-identical to the eager path, call after call."""

@@ -277,6 +277,41 @@ def test_stem(ctx, H, W):
         assert torch.equal(back, out)
 
 
+@pytest.mark.parametrize("H,W", [(64, 96), (32, 608), (96, 640), (128, 72)])
+def test_stem_reading_uint8_frames_equals_letterbox_then_stem(ctx, H, W):
+    """u8_src mode (frames already at network resolution): the stem converts BGR uint8 -> RGB bf16 /255 while staging its
+    input rows; the result is BIT-identical to y11_letterbox followed by the bf16 stem (plain and space-to-depth output,
+    ragged tiles, two images), and switching the source back restores the bf16 path."""
+    g = torch.Generator().manual_seed(H + W)
+    B = 2
+    frames = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).to(ctx.dev)
+    arr = (cabi.Image * B)()
+    for i in range(B):
+        arr[i] = cabi.Image(frames[i].data_ptr(), H, W, frames[i].stride(0), H, W, 0, 0)
+    desc = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(ctx.dev)
+    xin = torch.zeros((B, H, W, 3), dtype=torch.bfloat16, device=ctx.dev)
+    cabi.check(ctx.lib.y11_letterbox(ctx.h, desc.data_ptr(), B, H, W, xin.data_ptr(), ctx.stream()))
+    for cout, s2d in ((16, 1), (32, 0), (64, 1), (96, 0)):
+        w = (torch.randn(cout, 27, generator=g) / 27 ** 0.5).to(ctx.dev).to(torch.bfloat16).contiguous()
+        b = torch.randn(cout, generator=g).to(ctx.dev)
+        shape = (B, H // 4, W // 4, 4 * cout) if s2d else (B, H // 2, W // 2, cout)
+        outs = []
+        p = ctx.plan()
+        out = torch.zeros(shape, dtype=torch.bfloat16, device=ctx.dev)
+        d = cabi.StemDesc(xin.data_ptr(), cabi.View(out.data_ptr(), shape[-1], 0, shape[-1]), w.data_ptr(), b.data_ptr(), B, H, W, H // 2, W // 2, s2d)
+        cabi.check(ctx.lib.y11_plan_add_stem(p, C.byref(d)))
+        for source in (None, desc.data_ptr(), None):
+            cabi.check(ctx.lib.y11_plan_set_stem_source(p, C.c_void_p(source or 0)))
+            out.zero_()
+            cabi.check(ctx.lib.y11_plan_run(p, ctx.stream()))
+            torch.cuda.synchronize()
+            outs.append(out.clone())
+        ctx.lib.y11_plan_destroy(p)
+        assert outs[0].abs().sum() > 0
+        assert torch.equal(outs[0], outs[1]), (cout, s2d, (outs[0].float() - outs[1].float()).abs().max().item())
+        assert torch.equal(outs[0], outs[2])
+
+
 @pytest.mark.parametrize("act,res,H,W,c", [(True, False, 20, 28, 64), (False, True, 20, 28, 64), (True, True, 14, 20, 64),
                                            (True, False, 1, 8, 64),
                                            # TMA-ring kernel (W >= 32, H >= 16; ragged tiles in the last two): 2/4/8-row groups, 80 channels

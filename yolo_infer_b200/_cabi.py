@@ -9,7 +9,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "_lib" / "liby11_b200.so"
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 ACT_NONE, ACT_SILU = 0, 1
 IMPL_TCGEN05, IMPL_SIMT_DEBUG = 0, 1
 RES_POST, RES_PRE_UP2 = 0, 1
@@ -37,7 +37,7 @@ class ConvDesc(C.Structure):
 class StemDesc(C.Structure):
     _fields_ = [("inp", C.c_void_p), ("out", View), ("w", C.c_void_p), ("bias", C.c_void_p),
                 ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32),
-                ("s2d", C.c_int32)]
+                ("s2d", C.c_int32), ("images", C.c_void_p), ("u8_src", C.c_int32)]
 
 
 class DwConvDesc(C.Structure):
@@ -85,6 +85,7 @@ SIGNATURES = {
     "y11_plan_autotune": (C.c_int, [_P, _P, C.c_int]),
     "y11_plan_op_variant": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int32)]),
     "y11_plan_add_stem": (C.c_int, [_P, C.POINTER(StemDesc)]),
+    "y11_plan_set_stem_source": (C.c_int, [_P, _P]),
     "y11_plan_add_dwconv": (C.c_int, [_P, C.POINTER(DwConvDesc)]),
     "y11_plan_add_sppf": (C.c_int, [_P, C.POINTER(SppfDesc)]),
     "y11_plan_add_upsample": (C.c_int, [_P, C.POINTER(UpsampleDesc)]),

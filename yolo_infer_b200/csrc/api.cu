@@ -261,6 +261,18 @@ extern "C" int y11_plan_add_stem(y11_plan p, const y11_stem_desc* d) {
   return 0;
 }
 
+extern "C" int y11_plan_set_stem_source(y11_plan p, const y11_image* images) {
+  Y11_REQUIRE(p, "plan_set_stem_source: null plan");
+  size_t first = 0;
+  for (PlanOp* op : p->ops) {
+    if (op->kind != OP_STEM) continue;
+    op->d.stem.images = images ? images + first : nullptr;
+    op->d.stem.u8_src = images ? 1 : 0;
+    first += (size_t)op->d.stem.B;
+  }
+  return 0;
+}
+
 extern "C" int y11_plan_add_dwconv(y11_plan p, const y11_dwconv_desc* d) {
   Y11_REQUIRE(p && d && d->in.ptr && d->out.ptr && d->w && d->bias, "plan_add_dwconv: null argument");
   PlanOp* op = new_op(OP_DWCONV);

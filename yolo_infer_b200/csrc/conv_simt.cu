@@ -73,14 +73,19 @@ __device__ __forceinline__ void mma_bf16_16816_s(float (&c)[4], const uint32_t (
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int COUT>
+// U8 = true: the input rows are read straight from the uint8 BGR source frames (y11_stem_desc.images) and converted while
+// they are staged - BGR -> RGB, x * (1/255), round to bf16: bit for bit what letterbox_kernel writes for a frame that needs
+// neither resizing nor padding - so that for frames already at network resolution the letterbox launch and its 2.4 MB/image
+// bf16 round trip through HBM disappear.
+template <int COUT, bool U8>
 __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int tiles_w, int ROWS) {
   constexpr int OP = COUT + 8;   // output staging pitch in bf16 (conflict-free 16-byte reads)
   constexpr int WP = 40;         // weight staging pitch
   extern __shared__ __align__(16) unsigned char s_raw[];
   const int row_p = 6 * PXB + 16;                    // bf16 per staged input row: [8 left pad | 6*PXB | 8 slack]
   const int n_rows = 2 * ROWS + 1;
-  __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(s_raw);          // [n_rows][row_p]
+  // (U8: 16 bytes of front slack - the first 4-pixel group of row 0 starts 4 elements before the row)
+  __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(s_raw) + (U8 ? 8 : 0);   // [n_rows][row_p]
   __nv_bfloat16* s_o = s_in + n_rows * row_p;                            // [PXB][OP] (also weight staging at start)
   const int row_blocks = d.Hout / ROWS;
   const int tile = blockIdx.x % tiles_w;
@@ -117,7 +122,52 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
   pdl_trigger();
   __syncthreads();  // s_w (aliasing s_o) fully consumed
   // stage input rows 2*oh0-1 .. 2*oh0+2*ROWS-1: smem element 8 + e  <-  row element (6*ow0 + e), e in [-8, 6*PXB)
-  {
+  if (U8) {
+    // groups of 4 pixels = 12 source bytes (three aligned 32-bit loads) -> 12 bf16 (three 8-byte shared stores); group g of a
+    // row holds row elements [6*ow0 - 12 + 12g, +12) and lands at smem element 12g - 4 of the row (the 4 elements in front of
+    // a row are unused slack of the previous row / the front slack)
+    const y11_image im = d.images[n];
+    const int gpr = PXB / 2 + 1;                     // groups per row
+    const int total = n_rows * gpr;
+    const float r255 = 1.0f / 255.0f;
+    constexpr int kFly = 4;
+    for (int i0 = tid; i0 < total; i0 += kFly * nt) {
+      uint32_t w[kFly][3];
+      bool ok[kFly];
+#pragma unroll
+      for (int q = 0; q < kFly; ++q) {
+        const int i = min(i0 + q * nt, total - 1);
+        const int r = i / gpr, gi = i - r * gpr;
+        const int ih = 2 * oh0 - 1 + r;
+        const int x = 2 * ow0 - 4 + 4 * gi;          // first pixel of the group (a multiple of 4: all in or all out)
+        ok[q] = ih >= 0 && ih < d.Hin && x >= 0 && x < d.Win;
+        const uint32_t* sp = reinterpret_cast<const uint32_t*>(im.src + (size_t)min(max(ih, 0), d.Hin - 1) * im.pitch +
+                                                               (size_t)min(max(x, 0), d.Win - 4) * 3);
+        w[q][0] = __ldg(sp); w[q][1] = __ldg(sp + 1); w[q][2] = __ldg(sp + 2);
+      }
+#pragma unroll
+      for (int q = 0; q < kFly; ++q) {
+        const int i = i0 + q * nt;
+        if (i < total) {
+          const int r = i / gpr, gi = i - r * gpr;
+          uint2 o[3] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
+          if (ok[q]) {
+            // source bytes B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3  ->  elements R0 G0 B0 R1 G1 B1 R2 G2 B2 R3 G3 B3
+            float f[12];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) {
+              const int sb = 3 * (e / 3) + 2 - (e % 3);  // source byte of element e (compile-time after unrolling)
+              f[e] = __fmul_rn((float)((w[q][sb >> 2] >> (8 * (sb & 3))) & 0xffu), r255);
+            }
+#pragma unroll
+            for (int v = 0; v < 3; ++v) o[v] = make_uint2(pack_bf16x2(f[4 * v], f[4 * v + 1]), pack_bf16x2(f[4 * v + 2], f[4 * v + 3]));
+          }
+          uint2* dst = reinterpret_cast<uint2*>(s_in + r * row_p + 12 * gi - 4);
+          dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
+        }
+      }
+    }
+  } else {
     const int vec_per_row = (6 * PXB) / 8 + 1;       // one leading vector (elements -8..-1) + the segment itself
     const int total = n_rows * vec_per_row;
     const int row_e = 3 * d.Win;                     // bf16 per image row (multiple of 8)
@@ -205,7 +255,7 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
   }
 }
 
-template <int COUT>
+template <int COUT, bool U8>
 static int stem_launch_t(const y11_stem_desc* d, cudaStream_t s) {
   Y11_REQUIRE(d->Win % 8 == 0 && d->Hin % 2 == 0, "stem: input must be even-sized with width a multiple of 8 (got %dx%d)", d->Hin, d->Win);
   Y11_REQUIRE(d->Wout * 2 == d->Win && d->Hout * 2 == d->Hin, "stem: output must be half the input size");
@@ -222,25 +272,37 @@ static int stem_launch_t(const y11_stem_desc* d, cudaStream_t s) {
     if (r <= max_rows && d->Hout % r == 0) { ROWS = r; break; }
   const int tiles_w = y11_ceil_div(d->Wout, PXB);
   const int row_p = 6 * PXB + 16;
-  const size_t smem = (size_t)((2 * ROWS + 1) * row_p + std::max(PXB * (COUT + 8), COUT * 40)) * 2;
+  const size_t smem = (size_t)((2 * ROWS + 1) * row_p + std::max(PXB * (COUT + 8), COUT * 40)) * 2 + (U8 ? 16 : 0);
   static bool attr_set = false;
   if (!attr_set) {
-    Y11_CHECK_CUDA(cudaFuncSetAttribute(stem_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    Y11_CHECK_CUDA(cudaFuncSetAttribute(stem_kernel<COUT, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
   }
-  Y11_CHECK_CUDA(y11_launch_pdl(stem_kernel<COUT>, dim3((unsigned)(tiles_w * (d->Hout / ROWS) * d->B)), dim3(PXB), smem, s, *d, PXB,
-                                tiles_w, ROWS));
+  Y11_CHECK_CUDA(y11_launch_pdl(stem_kernel<COUT, U8>, dim3((unsigned)(tiles_w * (d->Hout / ROWS) * d->B)), dim3(PXB), smem, s, *d,
+                                PXB, tiles_w, ROWS));
   return 0;
 }
 
 int stem_launch(const y11_stem_desc* d, cudaStream_t s) {
-  switch (d->s2d ? d->out.c / 4 : d->out.c) {
-    case 16: return stem_launch_t<16>(d, s);
-    case 32: return stem_launch_t<32>(d, s);
-    case 64: return stem_launch_t<64>(d, s);
-    case 96: return stem_launch_t<96>(d, s);
-    default: y11_set_error("stem: unsupported cout %d", d->out.c); return -1;
+  const int cout = d->s2d ? d->out.c / 4 : d->out.c;
+  if (d->u8_src) {
+    Y11_REQUIRE(d->images, "stem: u8_src without image descriptors");
+    switch (cout) {
+      case 16: return stem_launch_t<16, true>(d, s);
+      case 32: return stem_launch_t<32, true>(d, s);
+      case 64: return stem_launch_t<64, true>(d, s);
+      case 96: return stem_launch_t<96, true>(d, s);
+    }
+  } else {
+    switch (cout) {
+      case 16: return stem_launch_t<16, false>(d, s);
+      case 32: return stem_launch_t<32, false>(d, s);
+      case 64: return stem_launch_t<64, false>(d, s);
+      case 96: return stem_launch_t<96, false>(d, s);
+    }
   }
+  y11_set_error("stem: unsupported cout %d", d->out.c);
+  return -1;
 }
 
 // ------------------------------------------------------------------------------------------------

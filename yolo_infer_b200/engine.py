@@ -29,6 +29,8 @@ logger = logging.getLogger(__name__)
 # YOLO.predict).  Off by default: measured on B200 it does not pay (YOLO11n 18.1 k vs 18.3 k img/s, YOLO11s 13.6 k vs 14.1 k) -
 # the low-resolution layers are latency bound, so two half batches cost almost as much as two whole ones.
 SPLIT_HOST_BATCH = os.environ.get("Y11_SPLIT_HOST", "0") != "0"
+# Y11_FUSE_STEM=0: always run the letterbox kernel, even for frames that need neither resizing nor padding
+FUSE_U8_STEM = os.environ.get("Y11_FUSE_STEM", "1") != "0"
 MAX_CACHED_PIPELINES = 16   # CUDA-graph pipeline instances kept per engine (one per source shape x thresholds)
 PREDICT_DEFAULTS = dict(conf=0.25, iou=0.7, max_det=300, imgsz=640, rect=True, agnostic_nms=False, classes=None,
                         half=False, verbose=True, save=False, show=False, stream=False, batch=1, device=None,
@@ -304,11 +306,13 @@ class YOLO:
         dev = self._workspace(("img_desc", len(frames)), host.numel())
         dev[: host.numel()].copy_(host, non_blocking=False)
         s = torch.cuda.current_stream(self.device).cuda_stream
+        net.set_stem_source(None)    # a pipeline sharing this plan may have pointed the stem at its uint8 frames
         cabi.check(self._lib.y11_letterbox(self._engine, dev.data_ptr(), len(frames), net.H, net.W, net.input.data_ptr(),
                                            C.c_void_p(s)), "y11_letterbox")
 
     def preprocess_tensor(self, net: CompiledNet, x: torch.Tensor, divisor: float) -> None:
         s = torch.cuda.current_stream(self.device).cuda_stream
+        net.set_stem_source(None)
         cabi.check(self._lib.y11_nchw_f32_to_nhwc_bf16(self._engine, x.data_ptr(), net.B, net.H, net.W, divisor,
                                                        net.input.data_ptr(), C.c_void_p(s)), "y11_nchw_f32_to_nhwc_bf16")
 
@@ -674,6 +678,12 @@ class GraphedPipeline:
                 arr[i] = cabi.Image(f.data_ptr(), h0, w0, f.stride(0), geom[1], geom[0], geom[2], geom[3])
             self.desc = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
             self.desc_stride = C.sizeof(cabi.Image)
+            # Frames already at network resolution (no resize, no padding): the stem reads the uint8 frames itself - bit for
+            # bit the letterbox kernel's conversion - and the letterbox launch with its bf16 round trip through HBM is skipped.
+            new_w, new_h, top, left = geom[0], geom[1], geom[2], geom[3]
+            self.fused_stem = bool(FUSE_U8_STEM and new_w == w0 and new_h == h0 and top == 0 and left == 0 and self.H == h0
+                                   and self.W == w0 and self.frames.data_ptr() % 4 == 0 and self.frames.stride(1) % 4 == 0
+                                   and self.frames.stride(0) % 4 == 0)
             gain, px, py = scale_geometry((self.H, self.W), (h0, w0))
             self.scale_rows = torch.tensor([[gain, float(px), float(py), float(w0), float(h0)]] * B, dtype=torch.float32, device=dev)
             self.graphs: List[torch.cuda.CUDAGraph] = []
@@ -691,13 +701,18 @@ class GraphedPipeline:
                 self.copy_stream = eng.shared_copy_stream()
                 self.copy_events = [torch.cuda.Event() for _ in range(self.chunks)]
         post_launches = 4 if (multi_label or self.net.A >= 65536) else 2   # (count, scan, write | one-pass decode) + sort/NMS
-        self.launches = self.chunks + self.net.n_launches + post_launches   # letterbox per chunk + plan + post-processing
+        # letterbox per chunk (none when the stem reads the frames) + plan + post-processing
+        self.launches = (0 if self.fused_stem else self.chunks) + self.net.n_launches + post_launches
 
     # ---- the enqueue functions: [chunk 0 prefix, ..., chunk K-1 prefix, rest]  (chunks == 1: a single stage) -------------
     def _stages(self):
         eng, net = self.eng, self.net
 
         def letterbox(b0: int, nb: int):
+            if self.fused_stem:      # (re-)point the plan's stem op(s) at this pipeline's frames; no letterbox launch
+                net.set_stem_source(self.desc.data_ptr())
+                return
+            net.set_stem_source(None)
             s = torch.cuda.current_stream(eng.device).cuda_stream
             cabi.check(eng._lib.y11_letterbox(eng._engine, self.desc.data_ptr() + b0 * self.desc_stride, nb, self.H, self.W,
                                               net.input[b0:b0 + nb].data_ptr(), C.c_void_p(s)), "y11_letterbox")

@@ -562,6 +562,11 @@ class CompiledNet:
     def run_range(self, first: int, last: int, stream: int) -> None:
         cabi.check(self.lib.y11_plan_run_range(self.plan, first, last, C.c_void_p(stream)), "y11_plan_run_range")
 
+    def set_stem_source(self, images_dev_ptr: Optional[int]) -> None:
+        """Point the stem at a device array of `y11_image` descriptors of frames ALREADY at network resolution (the stem then
+        reads the uint8 frames itself and no letterbox launch is needed), or back at `self.input` (None)."""
+        cabi.check(self.lib.y11_plan_set_stem_source(self.plan, C.c_void_p(images_dev_ptr or 0)), "y11_plan_set_stem_source")
+
     def run_timed(self, stream: int) -> List[float]:
         ms = (C.c_float * self.n_ops)()
         cabi.check(self.lib.y11_plan_run_timed(self.plan, C.c_void_p(stream), ms), "y11_plan_run_timed")
