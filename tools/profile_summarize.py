@@ -25,9 +25,9 @@ traffic = {"what": "dram__bytes_read.sum + dram__bytes_write.sum summed over the
                    f"pass), per model; raw rows profiles/{TAG}_conv_dram_M.csv, per-layer join profiles/{TAG}_layers_M.md"}
 for m in "ns":
     rows = ncu_csv(G / f"{TAG}_launches_yolo11{m}_b64.csv")
-    # one pass = from the first letterbox_kernel up to and including the first sort_nms_kernel after it (what precedes is
-    # set-up: torch.zeros fills of the activation buffers, weight packing)
-    first = next(i for i, r in enumerate(rows) if "letterbox" in r["Kernel Name"])
+    # one pass = from the first letterbox_kernel / stem_kernel (frames at network resolution need no letterbox launch) up to and
+    # including the first sort_nms_kernel after it (what precedes is set-up: torch.zeros fills of the buffers, weight packing)
+    first = next(i for i, r in enumerate(rows) if "letterbox" in r["Kernel Name"] or "stem_kernel" in r["Kernel Name"])
     per, n_pass = defaultdict(lambda: [0, 0.0]), 0
     for r in rows[first:]:
         name = r["Kernel Name"].split("(")[0].replace("<unnamed>::", "").replace("void ", "")

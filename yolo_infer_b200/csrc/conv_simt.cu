@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
     const y11_image im = d.images[n];
     const int gpr = PXB / 2 + 1;                     // groups per row
     const int total = n_rows * gpr;
+    const uint32_t gmagic = 0xffffffffu / (uint32_t)gpr + 1u;  // i / gpr == umulhi(i, gmagic) for the few thousand i of a tile
     const float r255 = 1.0f / 255.0f;
     constexpr int kFly = 4;
     for (int i0 = tid; i0 < total; i0 += kFly * nt) {
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
 #pragma unroll
       for (int q = 0; q < kFly; ++q) {
         const int i = min(i0 + q * nt, total - 1);
-        const int r = i / gpr, gi = i - r * gpr;
+        const int r = (int)__umulhi((uint32_t)i, gmagic), gi = i - r * gpr;
         const int ih = 2 * oh0 - 1 + r;
         const int x = 2 * ow0 - 4 + 4 * gi;          // first pixel of the group (a multiple of 4: all in or all out)
         ok[q] = ih >= 0 && ih < d.Hin && x >= 0 && x < d.Win;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
       for (int q = 0; q < kFly; ++q) {
         const int i = i0 + q * nt;
         if (i < total) {
-          const int r = i / gpr, gi = i - r * gpr;
+          const int r = (int)__umulhi((uint32_t)i, gmagic), gi = i - r * gpr;
           uint2 o[3] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
           if (ok[q]) {
             // source bytes B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3  ->  elements R0 G0 B0 R1 G1 B1 R2 G2 B2 R3 G3 B3
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
   } else {
     const int vec_per_row = (6 * PXB) / 8 + 1;       // one leading vector (elements -8..-1) + the segment itself
     const int total = n_rows * vec_per_row;
+    const uint32_t vmagic = 0xffffffffu / (uint32_t)vec_per_row + 1u;
     const int row_e = 3 * d.Win;                     // bf16 per image row (multiple of 8)
     const __nv_bfloat16* img = static_cast<const __nv_bfloat16*>(d.in) + (size_t)n * d.Hin * row_e;
     // unconditional loads from clamped addresses, eight in flight per thread, zeroed afterwards (see dwconv_kernel); with four
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
 #pragma unroll
       for (int q = 0; q < kFly; ++q) {
         const int i = min(i0 + q * nt, total - 1);
-        const int r = i / vec_per_row, v = i - r * vec_per_row;
+        const int r = (int)__umulhi((uint32_t)i, vmagic), v = i - r * vec_per_row;
         const int ih = 2 * oh0 - 1 + r;
         const int e0 = 6 * ow0 - 8 + 8 * v;          // first row element of this vector (a multiple of 8)
         ok[q] = ih >= 0 && ih < d.Hin && e0 >= 0 && e0 < row_e;  // a vector is entirely inside or outside the row
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
       for (int q = 0; q < kFly; ++q) {
         const int i = i0 + q * nt;
         if (i < total) {
-          const int r = i / vec_per_row, v = i - r * vec_per_row;
+          const int r = (int)__umulhi((uint32_t)i, vmagic), v = i - r * vec_per_row;
           *reinterpret_cast<uint4*>(s_in + r * row_p + 8 * v) = ok[q] ? u[q] : make_uint4(0, 0, 0, 0);
         }
       }
