@@ -27,7 +27,16 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "end-to-end images/sec @640 (letterbox+forward+decode+NMS)"
+def _baseline_metric() -> str:
+    """BASELINE.json's metric string when the file is there (the driver compares lines by it); both arms use the same one.
+    `value` is its throughput half (letterbox + forward + decode + NMS, images/s); `latency_b1` its batch-1 latency half."""
+    try:
+        return json.loads((ROOT / "BASELINE.json").read_text())["metric"]
+    except Exception:
+        return "end-to-end images/sec @640 (letterbox+forward+decode+NMS)"
+
+
+METRIC = _baseline_metric()
 UNIT = "images/s"
 CONF, IOU, MAX_DET = 0.25, 0.7, 300   # the reference benchmark's thresholds (ultralytics predict defaults, SURVEY 3.2)
 
