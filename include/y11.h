@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define Y11_ABI_VERSION 4
+#define Y11_ABI_VERSION 5
 
 typedef struct y11_engine* y11_handle;
 typedef struct y11_plan_s* y11_plan;
@@ -38,6 +38,9 @@ const char* y11_last_error(void);
 /* One engine per device.  Replaces the device placement of reference core/model.py:110-112. */
 int y11_create(y11_handle* out, int device);
 void y11_destroy(y11_handle h);
+/* Non-zero after a kernel of this engine gave up on a pipeline wait (bounded mbarrier wait, then __trap): the code names
+ * the wait (101-107, see conv_tc.cu).  Readable even when the trapped kernel has left the CUDA context unusable. */
+int y11_engine_error_code(y11_handle h);
 
 /* ---- (1) letterbox preprocess  [a4: ultralytics LetterBox + BasePredictor.preprocess] -------- */
 typedef struct {
@@ -55,6 +58,11 @@ int y11_letterbox(y11_handle h, const y11_image* images, int B, int H, int W, vo
 int y11_letterbox_u8(y11_handle h, const y11_image* images, int B, int H, int W, uint8_t* out_u8_hwc, y11_stream s);
 /* Tensor sources [a3: LoadTensor]: fp32 NCHW [B,3,H,W] / divisor -> bf16 NHWC (divisor = 255 when max>1, else 1). */
 int y11_nchw_f32_to_nhwc_bf16(y11_handle h, const float* in, int B, int H, int W, float divisor, void* out, y11_stream s);
+/* Same with LoadTensor's divisor rule evaluated ON THE DEVICE (no host sync, capturable in a CUDA graph): a max-reduction of
+ * the whole tensor into *scratch_max (4 bytes of device memory), then the conversion divides by 255 iff max > 1 + eps.
+ * This is the path the reference's own benchmark harness drives (torch.randn batches, benchmarks/speed_benchmark.py:100-102). */
+int y11_nchw_f32_to_nhwc_bf16_auto(y11_handle h, const float* in, int B, int H, int W, uint32_t* scratch_max, void* out,
+                                   y11_stream s);
 
 /* ---- (2) network plan  [a6-a12: DetectionModel._predict_once over fused Conv/C3k2/SPPF/C2PSA/Detect] */
 typedef struct {
@@ -219,6 +227,27 @@ size_t y11_postprocess_workspace(int B, int A, int nc, int multi_label, int max_
 int y11_detect_postprocess(y11_handle h, const y11_head_desc* hd, const y11_nms_params* p, const float* scale,
                            float* out_det, int32_t* out_count, int32_t* out_ncand, void* workspace,
                            size_t workspace_bytes, y11_stream s);
+
+/* Same, for the multi-GPU result gather WITHOUT a collective ("result push"): out_det / out_count may point into
+ * ANOTHER GPU's memory (an NVLink peer mapping: cudaDeviceEnablePeerAccess in one process, CUDA IPC / symmetric memory
+ * across processes) - the NMS kernel's publish loop then writes the kept boxes straight into the gathering rank's buffer.
+ * push->signal (system-scope, normally in the consumer's memory) is incremented ONCE per call, after every result write of
+ * the call is visible system-wide; push->done_counter is a device-local int, zero when the call starts, used to find the
+ * last CTA.  push == NULL: identical to y11_detect_postprocess. */
+typedef struct {
+  int32_t* done_counter;
+  uint32_t* signal;
+} y11_push;
+int y11_detect_postprocess_push(y11_handle h, const y11_head_desc* hd, const y11_nms_params* p, const float* scale,
+                                float* out_det, int32_t* out_count, int32_t* out_ncand, void* workspace,
+                                size_t workspace_bytes, const y11_push* push, y11_stream s);
+/* Consumer side: enqueue a one-warp kernel that parks until signals[i] >= target (wrap-safe) for all i < n (n <= 32). */
+int y11_wait_signals(y11_handle h, const uint32_t* signals, int n, uint32_t target, y11_stream s);
+/* Measurement only: same launches with CUDA events between them; ms_decode_nms[0] = decode + compaction, [1] = sort + NMS.
+ * Synchronises the stream. */
+int y11_detect_postprocess_timed(y11_handle h, const y11_head_desc* hd, const y11_nms_params* p, const float* scale,
+                                 float* out_det, int32_t* out_count, int32_t* out_ncand, void* workspace,
+                                 size_t workspace_bytes, float* ms_decode_nms, y11_stream s);
 
 /* NMS only, batched, on caller-provided candidates (the bit-exact test against torchvision.ops.nms):
  * boxes fp32 [B, K, 4] xyxy (class offset NOT yet applied), scores fp32 [B,K], cls fp32 [B,K],

@@ -448,23 +448,96 @@ def calibrated_init(model: DetectionModel, seed: int = 0, calib_hw: Tuple[int, i
     return model
 
 
-def emulate_bf16_storage(fused: DetectionModel) -> DetectionModel:
-    """Turn a FUSED oracle model into the fp32-accumulate / bf16-storage network the B200 path computes:
-    conv weights rounded to bf16 once; every Conv output, every residual sum (Bottleneck, PSABlock) rounded to bf16,
-    exactly the places where the CUDA path writes an activation tensor to HBM.  The Detect logits stay fp32 (the last
-    1x1 convs of the head write fp32 on the GPU).  Used by tests to separate kernel arithmetic (must agree to <= 1e-2)
-    from the storage-format noise floor that any bf16 implementation has against an fp32 run."""
+def emulate_bf16_storage(fused: DetectionModel, fold_upsample: bool = True) -> DetectionModel:
+    """Turn a FUSED oracle model into the fp32-accumulate / bf16-storage network the B200 path computes, with a rounding to
+    bf16 at EXACTLY the places where the CUDA path writes an activation tensor to HBM (and nowhere else):
+
+      * conv weights rounded to bf16 once; the network input rounded to bf16;
+      * every Conv output, EXCEPT a conv whose epilogue adds a residual before the store (Bottleneck.cv2, Attention.proj,
+        PSABlock.ffn[1]): there the fp32 sum `act(conv) + x` is rounded once, as the fused epilogue does;
+      * Attention: the softmax(QK^T)V product is written as a bf16 tensor (with bf16 probabilities feeding the PV product, fp32
+        row sums - the flash kernel's operand format), the positional dwconv adds it in fp32 and stores one bf16 tensor;
+      * Upsample -> Concat -> C3k2.cv1 (yaml layers 11-13, 14-16; `fold_upsample`): the low-resolution half `W_up . p + b` is
+        stored in bf16 before it enters the skip half's accumulator (network.upsample_folds);
+      * the Detect logits stay fp32 (the last 1x1 convs of the head write fp32 on the GPU).
+
+    Used by tests to separate kernel arithmetic (must agree to <= 1e-2) from the storage-format noise floor that any bf16
+    implementation has against an fp32 run.  What it cannot reproduce: fp32 summation order inside a conv, the MUFU
+    tanh / exp2 approximations (2^-11 relative)."""
+    import types
+
     def rq(t):
         return t.to(torch.bfloat16).float()
 
     for m in fused.modules():
         if isinstance(m, nn.Conv2d) and not (m.out_channels == 1 and m.in_channels == 16):
             m.weight.data = rq(m.weight.data)
+
+    def conv_forward(self, x):
+        y = self.act(self.conv(x))
+        return y if getattr(self, "_keep_fp32", False) else rq(y)
+
+    def bottleneck_forward(self, x):
+        return rq(x + self.cv2(self.cv1(x))) if self.add else self.cv2(self.cv1(x))
+
+    def attention_forward(self, x):
+        B, C, H, W = x.shape
+        N = H * W
+        qkv = self.qkv(x)
+        q, k, v = qkv.view(B, self.num_heads, self.key_dim * 2 + self.head_dim, N).split(
+            [self.key_dim, self.key_dim, self.head_dim], dim=2)
+        s = (q.transpose(-2, -1) @ k) * self.scale
+        p = torch.exp(s - s.amax(-1, keepdim=True))
+        o = rq((v @ rq(p).transpose(-2, -1)) / p.sum(-1).unsqueeze(-2)).view(B, C, H, W)   # bf16 P, fp32 row sums, bf16 store
+        t = rq(o + self.pe(v.reshape(B, C, H, W)))                                         # dwconv epilogue: + residual, one store
+        return self.proj(t)                                                                # fp32: PSABlock adds x, then stores
+
+    def psa_forward(self, x):
+        x = rq(x + self.attn(x)) if self.add else self.attn(x)
+        x = rq(x + self.ffn(x)) if self.add else self.ffn(x)
+        return x
+
     for m in fused.modules():
-        if isinstance(m, (Conv, Bottleneck, PSABlock)):
-            m.register_forward_hook(lambda mod, inp, out: rq(out))
+        if isinstance(m, Conv):
+            m.forward = types.MethodType(conv_forward, m)
+        if isinstance(m, Bottleneck):
+            m.forward = types.MethodType(bottleneck_forward, m)
+            m.cv2._keep_fp32 = bool(m.add)
+        elif isinstance(m, Attention):
+            m.forward = types.MethodType(attention_forward, m)
+            m.pe._keep_fp32 = True
+        elif isinstance(m, PSABlock):
+            m.forward = types.MethodType(psa_forward, m)
+            m.attn.proj._keep_fp32 = bool(m.add)
+            m.ffn[1]._keep_fp32 = bool(m.add)
+    if fold_upsample:
+        for i, m in enumerate(fused.model):
+            f = fused.froms[i]
+            if not (isinstance(m, C3k2) and f == -1 and isinstance(fused.model[i - 1], Concat)):
+                continue
+            cat_from = fused.froms[i - 1]
+            if not (isinstance(cat_from, list) and cat_from[0] == -1 and isinstance(fused.model[i - 2], nn.Upsample)):
+                continue
+
+            def folded_cv1(self, x):
+                # x = cat(up2(p), skip); c_up = channels of p = all input channels minus the skip tensor's
+                w, bias = self.conv.weight, self.conv.bias
+                low = rq(torch.nn.functional.conv2d(x[:, :self._c_up], w[:, :self._c_up], bias))     # == up2(W_up . p + b), stored bf16
+                return rq(self.act(torch.nn.functional.conv2d(x[:, self._c_up:], w[:, self._c_up:]) + low))
+
+            skip_layer = cat_from[1]
+            c_skip = _out_channels(fused.model[skip_layer])
+            m.cv1._c_up = m.cv1.conv.in_channels - c_skip
+            m.cv1.forward = types.MethodType(folded_cv1, m.cv1)
     fused.register_forward_pre_hook(lambda mod, inp: (rq(inp[0]),))
     return fused
+
+
+def _out_channels(layer: nn.Module) -> int:
+    """Output channels of a backbone/neck layer (Conv, C3k2, SPPF, C2PSA)."""
+    if isinstance(layer, Conv):
+        return layer.conv.out_channels
+    return layer.cv2.conv.out_channels
 
 
 def build(scale: str = "n", nc: int = 80, init: str = "calibrated", seed: int = 0) -> DetectionModel:
@@ -472,5 +545,10 @@ def build(scale: str = "n", nc: int = 80, init: str = "calibrated", seed: int = 
     model = DetectionModel(scale, nc)
     if init == "calibrated":
         calibrated_init(model, seed)
+    elif init == "survey_b":
+        # SURVEY.md section 8(d) init (B) as written: gamma ~ U(0.5, 1.5), beta ~ N(0, 0.1) (running statistics from a seeded batch as
+        # above).  A random SiLU network with these BN parameters is in the chaotic phase (see calibrated_init's docstring):
+        # kept as a parity case to SHOW the amplification, with the control experiment next to it (tests/test_gpu_e2e.py).
+        calibrated_init(model, seed, gamma=(0.5, 1.5), beta=(0.0, 0.1))
     model.eval()
     return model

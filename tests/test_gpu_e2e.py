@@ -76,10 +76,11 @@ def test_raw_head_outputs_within_bf16_tolerance(engines, scale, B, H, W):
     e_box, e_cls = rel_l2(got[:, :64], want[:, :64]), rel_l2(got[:, 64:], want[:, 64:])
     f_box, f_cls = rel_l2(got[:, :64], want32[:, :64]), rel_l2(got[:, 64:], want32[:, 64:])
     print(f"head rel-L2 vs bf16-storage oracle: box {e_box:.3e} cls {e_cls:.3e}; vs fp32 oracle: box {f_box:.3e} cls {f_cls:.3e}")
-    # 2e-2 / 3e-2: two CORRECT bf16 implementations of this 40-layer-deep network (tcgen05 vs naive CUDA-core conv, below)
-    # already differ by 0.6 % because 1e-5-level accumulation-order differences flip bf16 roundings that are then amplified;
-    # the per-layer test (test_every_conv_of_the_plan_matches_torch) is the tight one (1 bf16 ulp per layer).
-    assert e_box <= 2e-2 and e_cls <= 2e-2, (e_box, e_cls)
+    # north_star tolerance: rel <= 1e-2 against the same-storage oracle (emulate_bf16_storage rounds to bf16 exactly where the
+    # CUDA path stores a tensor; what is left is summation order and the MUFU tanh / exp2 approximations).  Against the pure
+    # fp32 oracle the storage format alone costs ~1 % (emulated oracle vs fp32 oracle, measured on CPU), hence 3e-2 there.
+    # The per-layer test (test_every_conv_of_the_plan_matches_torch) is the amplification-free one (1 bf16 ulp per layer).
+    assert e_box <= 1e-2 and e_cls <= 1e-2, (e_box, e_cls)
     assert f_box <= 3e-2 and f_cls <= 3e-2, (f_box, f_cls)
 
 
@@ -153,7 +154,10 @@ def test_tune_cache_round_trip(engines, monkeypatch, tmp_path):
     stored = json.loads(cache.read_text())
     assert list(stored) == [nets[0]._tune_key]
     assert nets[0]._cached_variants is None and nets[1]._cached_variants is not None
-    assert nets[0].variants() == nets[1].variants() == [tuple(v) for v in stored[nets[0]._tune_key]]
+    by_name = stored[nets[0]._tune_key]          # stored by op name, keyed by device / SM count / plan configuration
+    assert nets[0].variants() == nets[1].variants()
+    assert all(tuple(by_name[o.name]) == v for o, v in zip(nets[1].ops, nets[1].variants()) if o.kind == "conv")
+    assert "NVIDIA" in nets[0]._tune_key and "/sm" in nets[0]._tune_key
 
 
 def match_detections(got: torch.Tensor, want: torch.Tensor, conf: float, margin: float = 0.03):

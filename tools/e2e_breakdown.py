@@ -9,7 +9,8 @@ from yolo_infer_b200.engine import YOLO
 scale = sys.argv[1] if len(sys.argv) > 1 else "n"
 B, S = 64, 640
 eng = YOLO.from_state_dict(T.synthetic_state_dict(scale, 80, seed=0), scale).to("cuda:0")
-eng.condition_synthetic_weights((S, S), batch=2, seed=0)
+from yolo_infer_b200.synth import condition_synthetic_weights
+condition_synthetic_weights(eng, (S, S), batch=2, seed=0)
 g = torch.Generator().manual_seed(0)
 host = [torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(3)]
 for i in range(4):

@@ -24,7 +24,8 @@ def main():
     from yolo_infer_b200 import topology as T
     from yolo_infer_b200.engine import YOLO
     eng = YOLO.from_state_dict(T.synthetic_state_dict(args.model, 80, seed=0), args.model).to("cuda:0")
-    eng.condition_synthetic_weights((384, 640), batch=2, seed=0)
+    from yolo_infer_b200.synth import condition_synthetic_weights
+    condition_synthetic_weights(eng, (384, 640), batch=2, seed=0)
     cap = None
     if args.video:
         import cv2

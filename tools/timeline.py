@@ -25,7 +25,8 @@ def main():
     from yolo_infer_b200.engine import YOLO
     dev = torch.device("cuda:0")
     eng = YOLO.from_state_dict(T.synthetic_state_dict(args.model, 80, seed=0), args.model).to(dev)
-    eng.condition_synthetic_weights((640, 640), batch=2, seed=0)
+    from yolo_infer_b200.synth import condition_synthetic_weights
+    condition_synthetic_weights(eng, (640, 640), batch=2, seed=0)
     B, S, NROT, NS = args.batch, 640, 4, args.streams
     g = torch.Generator().manual_seed(0)
     frames = [torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).to(dev) for _ in range(NROT)]

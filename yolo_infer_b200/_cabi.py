@@ -9,7 +9,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "_lib" / "liby11_b200.so"
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 ACT_NONE, ACT_SILU = 0, 1
 IMPL_TCGEN05, IMPL_SIMT_DEBUG = 0, 1
 RES_POST, RES_PRE_UP2 = 0, 1
@@ -68,6 +68,10 @@ class NmsParams(C.Structure):
                 ("max_wh", C.c_int32), ("agnostic", C.c_int32), ("multi_label", C.c_int32)]
 
 
+class Push(C.Structure):
+    _fields_ = [("done_counter", C.c_void_p), ("signal", C.c_void_p)]
+
+
 # name -> (restype, argtypes); mirrors include/y11.h one to one (tests/test_cabi_symbols.py checks the header)
 _P = C.c_void_p
 SIGNATURES = {
@@ -75,9 +79,11 @@ SIGNATURES = {
     "y11_last_error": (C.c_char_p, []),
     "y11_create": (C.c_int, [C.POINTER(_P), C.c_int]),
     "y11_destroy": (None, [_P]),
+    "y11_engine_error_code": (C.c_int, [_P]),
     "y11_letterbox": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "y11_letterbox_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "y11_nchw_f32_to_nhwc_bf16": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
+    "y11_nchw_f32_to_nhwc_bf16_auto": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "y11_plan_create": (C.c_int, [_P, C.POINTER(_P)]),
     "y11_plan_destroy": (None, [_P]),
     "y11_plan_add_conv": (C.c_int, [_P, C.POINTER(ConvDesc)]),
@@ -103,6 +109,11 @@ SIGNATURES = {
     "y11_decode_dense": (C.c_int, [_P, C.POINTER(HeadDesc), _P, _P]),
     "y11_postprocess_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "y11_detect_postprocess": (C.c_int, [_P, C.POINTER(HeadDesc), C.POINTER(NmsParams), _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "y11_detect_postprocess_push": (C.c_int, [_P, C.POINTER(HeadDesc), C.POINTER(NmsParams), _P, _P, _P, _P, _P, C.c_size_t,
+                                              C.POINTER(Push), _P]),
+    "y11_wait_signals": (C.c_int, [_P, _P, C.c_int, C.c_uint32, _P]),
+    "y11_detect_postprocess_timed": (C.c_int, [_P, C.POINTER(HeadDesc), C.POINTER(NmsParams), _P, _P, _P, _P, _P, C.c_size_t,
+                                               C.POINTER(C.c_float), _P]),
     "y11_nms_batched": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(NmsParams), _P, _P, _P, C.c_size_t, _P]),
     "y11_nms_workspace": (C.c_size_t, [C.c_int, C.c_int]),
 }

@@ -44,15 +44,28 @@ extern "C" int y11_create(y11_handle* out, int device) {
     return -2;
   }
   eng->encode_tiled = reinterpret_cast<y11_encode_tiled_fn>(fn);
-  Y11_CHECK_CUDA(cudaMalloc(&eng->dev_error_flag, sizeof(int)));
-  Y11_CHECK_CUDA(cudaMemset(eng->dev_error_flag, 0, sizeof(int)));
+  // pipeline-timeout code of the kernels' bounded mbarrier waits: mapped pinned memory, so that the host can still read it
+  // after a trapped kernel has poisoned the context (y11_engine_error_code)
+  e = cudaHostAlloc(reinterpret_cast<void**>(&eng->host_error_flag), sizeof(int), cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    *eng->host_error_flag = 0;
+    e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&eng->dev_error_flag), eng->host_error_flag, 0);
+  }
+  if (e != cudaSuccess) {
+    if (eng->host_error_flag) cudaFreeHost(eng->host_error_flag);
+    delete eng;
+    y11_set_error("y11_create: error-flag allocation failed (%s)", cudaGetErrorString(e));
+    return -2;
+  }
   *out = eng;
   return 0;
 }
 
+extern "C" int y11_engine_error_code(y11_handle h) { return (h && h->host_error_flag) ? *h->host_error_flag : 0; }
+
 extern "C" void y11_destroy(y11_handle h) {
   if (!h) return;
-  cudaFree(h->dev_error_flag);
+  if (h->host_error_flag) cudaFreeHost(h->host_error_flag);
   delete h;
 }
 
@@ -108,8 +121,14 @@ extern "C" int y11_plan_create(y11_handle h, y11_plan* out) {
   y11_plan_s* p = new y11_plan_s();
   p->eng = h;
   if (dyn_tiles_enabled()) {
-    Y11_CHECK_CUDA(cudaMalloc(&p->counters, 2 * kMaxPlanOps * sizeof(int)));
-    Y11_CHECK_CUDA(cudaMemset(p->counters, 0, 2 * kMaxPlanOps * sizeof(int)));
+    cudaError_t e = cudaMalloc(&p->counters, 2 * kMaxPlanOps * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(p->counters, 0, 2 * kMaxPlanOps * sizeof(int));
+    if (e != cudaSuccess) {
+      if (p->counters) cudaFree(p->counters);
+      delete p;
+      y11_set_error("y11_plan_create: tile-counter allocation failed (%s)", cudaGetErrorString(e));
+      return -2;
+    }
   }
   *out = p;
   return 0;

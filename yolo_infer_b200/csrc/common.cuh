@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/y11.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -40,10 +42,26 @@ struct y11_engine {
   int device;
   int num_sms;
   y11_encode_tiled_fn encode_tiled;
-  int* dev_error_flag;  // written by kernels before __trap()
+  int* dev_error_flag;   // device alias of host_error_flag: written by kernels before __trap()
+  int* host_error_flag;  // mapped pinned memory (readable after a trapped kernel poisoned the context)
 };
 
 static inline int y11_ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: opt a kernel in once for every device it is used
+// on (bit d of a per-call-site mask = done for device d; atomic, so engines on several GPUs / threads of one process are
+// safe).  The current device is the engine's (y11_create / the caller's cudaSetDevice).
+#define Y11_OPT_IN_SMEM(fn, bytes)                                                                         \
+  do {                                                                                                     \
+    static std::atomic<unsigned long long> _y11_done{0ull};                                                \
+    int _y11_dev = 0;                                                                                      \
+    Y11_CHECK_CUDA(cudaGetDevice(&_y11_dev));                                                              \
+    const unsigned long long _y11_bit = 1ull << (_y11_dev & 63);                                           \
+    if (!(_y11_done.load(std::memory_order_acquire) & _y11_bit)) {                                         \
+      Y11_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      _y11_done.fetch_or(_y11_bit, std::memory_order_release);                                             \
+    }                                                                                                      \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------- device
 #ifdef __CUDACC__
@@ -108,7 +126,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000ll) {  // ~2 s at 1.9 GHz
-      if (err_flag) atomicExch(err_flag, code);
+      if (err_flag) *reinterpret_cast<volatile int*>(err_flag) = code;  // mapped pinned host memory
       __threadfence_system();
       __trap();
     }

@@ -275,11 +275,7 @@ static int stem_launch_t(const y11_stem_desc* d, cudaStream_t s) {
   const int tiles_w = y11_ceil_div(d->Wout, PXB);
   const int row_p = 6 * PXB + 16;
   const size_t smem = (size_t)((2 * ROWS + 1) * row_p + std::max(PXB * (COUT + 8), COUT * 40)) * 2 + (U8 ? 16 : 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    Y11_CHECK_CUDA(cudaFuncSetAttribute(stem_kernel<COUT, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
-  }
+  Y11_OPT_IN_SMEM((stem_kernel<COUT, U8>), 96 * 1024);
   Y11_CHECK_CUDA(y11_launch_pdl(stem_kernel<COUT, U8>, dim3((unsigned)(tiles_w * (d->Hout / ROWS) * d->B)), dim3(PXB), smem, s, *d,
                                 PXB, tiles_w, ROWS));
   return 0;
@@ -463,11 +459,7 @@ int sppf_launch(const y11_sppf_desc* d, cudaStream_t s) {
   Y11_REQUIRE(d->c % 8 == 0 && d->io.c_off % 8 == 0 && d->io.c_total % 8 == 0, "sppf: alignment");
   const size_t smem = (size_t)2 * d->H * d->W * sizeof(uint4);
   Y11_REQUIRE(smem <= 200 * 1024, "sppf: plane %dx%d too large for shared memory", d->H, d->W);
-  static bool attr_set = false;
-  if (!attr_set) {
-    Y11_CHECK_CUDA(cudaFuncSetAttribute(sppf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  Y11_OPT_IN_SMEM(sppf_kernel, 200 * 1024);
   Y11_CHECK_CUDA(y11_launch_pdl(sppf_kernel, dim3((unsigned)(d->B * (d->c / 8))), dim3(256), smem, s, *d));
   return 0;
 }

@@ -900,12 +900,8 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   L->smem_bytes = kHeaderBytes + 1024u + p.b_res_bytes + (unsigned)stages * stage + staging;
   L->flops = 2.0 * d->B * d->Hout * d->Wout * (double)cout * cin * p.taps;
   (void)k_iters;
-  static bool attr_set = false;
-  if (!attr_set) {
-    Y11_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    Y11_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel_fat, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
-  }
+  Y11_OPT_IN_SMEM(conv_tc_kernel, 220 * 1024);
+  Y11_OPT_IN_SMEM(conv_tc_kernel_fat, 220 * 1024);
   return 0;
 }
 

@@ -210,11 +210,7 @@ int dwconv_tma_prepare(y11_engine* eng, const y11_dwconv_desc* d, DwTmaLaunch* L
   // far ahead as shared memory allows
   p.stages = (int)std::max(3u, std::min((uint32_t)kMaxStagesDw, (190u * 1024u) / p.stage_bytes));
   L->smem_bytes = 128u + (unsigned)p.stages * p.stage_bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
-    Y11_CHECK_CUDA(cudaFuncSetAttribute(dwconv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  Y11_OPT_IN_SMEM(dwconv_tma_kernel, 200 * 1024);
   return 0;
 }
 

@@ -394,9 +394,11 @@ struct NmsArgs {
   float class_offset;    // max_wh, or 0 when agnostic
   int max_det, max_nms;
   const float* scale;    // [B,5] gain,pad_x,pad_y,w0,h0 or nullptr
-  float* out_det;        // [B, max_det, 6] or nullptr
+  float* out_det;        // [B, max_det, 6] or nullptr  (may point into a PEER device's memory: result push)
   int* out_keep;         // [B, max_det] or nullptr
   int* out_count;        // [B]
+  int* done_counter;     // result push: device-local counter of finished CTAs (zero between launches) or nullptr
+  unsigned* signal;      // result push: system-scope counter bumped once per launch after every result write is visible
 };
 
 __global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
@@ -552,6 +554,36 @@ __global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
     __syncthreads();
   }
   if (tid == 0) g.out_count[b] = s_nk;
+  if (g.signal) {
+    // Result push: out_det / out_count live in another GPU's memory (NVLink peer mapping).  Every CTA makes its writes
+    // visible system-wide, the LAST one to finish bumps the consumer's signal - the consumer never sees the counter move
+    // before all B images of this launch have landed (threadFenceReduction pattern; fences are cumulative over the barrier).
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();
+      if (atomicAdd(g.done_counter, 1) == (int)gridDim.x - 1) {
+        *g.done_counter = 0;  // re-armed for the next launch (launches of one pipeline are stream-ordered)
+        __threadfence_system();
+        atomicAdd_system(g.signal, 1u);
+      }
+    }
+  }
+}
+
+// Consumer side of the result push: lane i parks until signals[i] has reached `target` (wrap-safe), bounded.
+__global__ void wait_signals_kernel(const volatile unsigned* signals, int n, unsigned target, int* err_flag) {
+  const int i = threadIdx.x;
+  if (i < n) {
+    const long long t0 = clock64();
+    while ((int)(signals[i] - target) < 0) {
+      __nanosleep(256);
+      if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer died
+        if (err_flag) *reinterpret_cast<volatile int*>(err_flag) = 201;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
 }
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -625,11 +657,7 @@ void carve(Workspace* w, void* base, int B, int cap, int nchunks, int kept_cap) 
 }
 
 int launch_sort_nms(const NmsArgs& a, int B, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    Y11_CHECK_CUDA(cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemKeys * 8));
-    attr_set = true;
-  }
+  Y11_OPT_IN_SMEM(sort_nms_kernel, kSmemKeys * 8);
   const int np2 = next_pow2(a.cap);
   // the kernel sorts in shared memory whenever THIS image's count fits, whatever the capacity is
   const size_t smem = (size_t)(np2 <= kSmemKeys ? np2 : kSmemKeys) * 8;
@@ -657,9 +685,9 @@ extern "C" size_t y11_postprocess_workspace(int B, int A, int nc, int multi_labe
   return w.total;
 }
 
-extern "C" int y11_detect_postprocess(y11_handle, const y11_head_desc* hd, const y11_nms_params* p, const float* scale, float* out_det,
-                                      int32_t* out_count, int32_t* out_ncand, void* workspace, size_t workspace_bytes, y11_stream s_) {
-  cudaStream_t s = static_cast<cudaStream_t>(s_);
+static int postprocess_impl(const y11_head_desc* hd, const y11_nms_params* p, const float* scale, float* out_det, int32_t* out_count,
+                            int32_t* out_ncand, void* workspace, size_t workspace_bytes, const y11_push* push, float* ms2,
+                            cudaStream_t s) {
   HeadParams hp;
   if (int e = fill_head(hd, &hp)) return e;
   Y11_REQUIRE(p->max_det >= 1, "postprocess: max_det=%d", p->max_det);
@@ -673,6 +701,11 @@ extern "C" int y11_detect_postprocess(y11_handle, const y11_head_desc* hd, const
   const double cc = std::min(std::max((double)p->conf, 1e-30), 1.0 - 1e-9);
   const float logit_lo = (float)(log(cc / (1.0 - cc)) - 1e-2);
   dim3 grid((unsigned)nchunks, (unsigned)hp.B);
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  if (ms2) {
+    for (auto& e : ev) Y11_CHECK_CUDA(cudaEventCreate(&e));
+    Y11_CHECK_CUDA(cudaEventRecord(ev[0], s));
+  }
   // single-label with A < 65536 (every real configuration): one pass with atomic slot reservation; the candidate count
   // cannot exceed the capacity (one candidate per anchor at most), so nothing depends on the arrival order
   const bool one_pass = !p->multi_label && hp.A < 65536 && cap >= hp.A;
@@ -688,6 +721,7 @@ extern "C" int y11_detect_postprocess(y11_handle, const y11_head_desc* hd, const
                                                   w.cscore, w.ccls, nullptr, nullptr, nullptr);
   }
   Y11_CHECK_CUDA(cudaGetLastError());
+  if (ms2) Y11_CHECK_CUDA(cudaEventRecord(ev[1], s));
   NmsArgs a;
   a.cbox = w.cbox; a.cscore = w.cscore; a.ccls = w.ccls; a.ncand = w.ncand; a.keys = w.keys; a.kbox = w.kbox; a.karea = w.karea;
   a.canchor = one_pass ? w.canchor : nullptr;
@@ -696,7 +730,46 @@ extern "C" int y11_detect_postprocess(y11_handle, const y11_head_desc* hd, const
   a.class_offset = p->agnostic ? 0.0f : (float)p->max_wh;
   a.max_det = p->max_det; a.max_nms = p->max_nms;
   a.scale = scale; a.out_det = out_det; a.out_keep = nullptr; a.out_count = out_count;
-  return launch_sort_nms(a, hp.B, s);
+  a.done_counter = push ? push->done_counter : nullptr;
+  a.signal = push ? push->signal : nullptr;
+  if (int e = launch_sort_nms(a, hp.B, s)) return e;
+  if (ms2) {
+    Y11_CHECK_CUDA(cudaEventRecord(ev[2], s));
+    Y11_CHECK_CUDA(cudaEventSynchronize(ev[2]));
+    Y11_CHECK_CUDA(cudaEventElapsedTime(&ms2[0], ev[0], ev[1]));
+    Y11_CHECK_CUDA(cudaEventElapsedTime(&ms2[1], ev[1], ev[2]));
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
+  return 0;
+}
+
+extern "C" int y11_detect_postprocess(y11_handle, const y11_head_desc* hd, const y11_nms_params* p, const float* scale, float* out_det,
+                                      int32_t* out_count, int32_t* out_ncand, void* workspace, size_t workspace_bytes, y11_stream s) {
+  return postprocess_impl(hd, p, scale, out_det, out_count, out_ncand, workspace, workspace_bytes, nullptr, nullptr,
+                          static_cast<cudaStream_t>(s));
+}
+
+extern "C" int y11_detect_postprocess_push(y11_handle, const y11_head_desc* hd, const y11_nms_params* p, const float* scale,
+                                           float* out_det, int32_t* out_count, int32_t* out_ncand, void* workspace,
+                                           size_t workspace_bytes, const y11_push* push, y11_stream s) {
+  Y11_REQUIRE(!push || (push->done_counter && push->signal), "postprocess_push: null counter/signal");
+  return postprocess_impl(hd, p, scale, out_det, out_count, out_ncand, workspace, workspace_bytes, push, nullptr,
+                          static_cast<cudaStream_t>(s));
+}
+
+extern "C" int y11_detect_postprocess_timed(y11_handle, const y11_head_desc* hd, const y11_nms_params* p, const float* scale,
+                                            float* out_det, int32_t* out_count, int32_t* out_ncand, void* workspace,
+                                            size_t workspace_bytes, float* ms_decode_nms, y11_stream s) {
+  Y11_REQUIRE(ms_decode_nms, "postprocess_timed: null ms");
+  return postprocess_impl(hd, p, scale, out_det, out_count, out_ncand, workspace, workspace_bytes, nullptr, ms_decode_nms,
+                          static_cast<cudaStream_t>(s));
+}
+
+extern "C" int y11_wait_signals(y11_handle h, const uint32_t* signals, int n, uint32_t target, y11_stream s) {
+  Y11_REQUIRE(h && signals && n >= 1 && n <= 32, "wait_signals: need 1..32 signals");
+  wait_signals_kernel<<<1, 32, 0, static_cast<cudaStream_t>(s)>>>(signals, n, target, h->dev_error_flag);
+  Y11_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 extern "C" size_t y11_nms_workspace(int B, int K) {
@@ -724,5 +797,6 @@ extern "C" int y11_nms_batched(y11_handle, const float* boxes, const float* scor
   a.class_offset = p->agnostic ? 0.0f : (float)p->max_wh;
   a.max_det = p->max_det; a.max_nms = p->max_nms;
   a.scale = nullptr; a.out_det = nullptr; a.out_keep = keep; a.out_count = keep_count;
+  a.done_counter = nullptr; a.signal = nullptr;
   return launch_sort_nms(a, B, static_cast<cudaStream_t>(s_));
 }

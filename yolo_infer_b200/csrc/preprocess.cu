@@ -10,6 +10,8 @@
 // HBM-bound: algorithmic bytes/image = h0*w0*3 (read) + H*W*3*2 (write).  One thread produces 8 consecutive
 // output pixels (24 channel values = 48 B of bf16, written as three 16-byte stores); consecutive threads cover
 // consecutive pixels, so both the source gathers and the stores of a warp are contiguous.
+#include <algorithm>
+
 #include "ops.h"
 
 using namespace y11;
@@ -136,9 +138,13 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const y11_image* __restr
 }
 
 // fp32 NCHW (tensor sources) -> bf16 NHWC with a divisor; 4 pixels per thread like above
-__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, int HW, float divisor, __nv_bfloat16* __restrict__ out) {
+// `dmax` != nullptr: LoadTensor's rule evaluated on the device - divide by 255 iff the maximum of the WHOLE tensor (left in
+// *dmax as the bits of a non-negative float by tensor_max_kernel) exceeds 1 + eps; otherwise `divisor` is used as given.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, int HW, float divisor, const unsigned* __restrict__ dmax,
+                                                           __nv_bfloat16* __restrict__ out) {
   const int qi = blockIdx.x * blockDim.x + threadIdx.x;
   if (qi >= HW / 4) return;
+  if (dmax) divisor = __uint_as_float(__ldg(dmax)) > 1.0f + 1.1920929e-07f ? 255.0f : 1.0f;
   const int b = blockIdx.y;
   const float* ip = in + (size_t)b * 3 * HW + (size_t)qi * 4;
   const float4 r = __ldg(reinterpret_cast<const float4*>(ip));
@@ -149,6 +155,18 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 #pragma unroll
   for (int i = 0; i < 3; ++i)
     op[i] = make_uint2(pack_bf16x2(__fdiv_rn(f[4 * i], divisor), __fdiv_rn(f[4 * i + 1], divisor)), pack_bf16x2(__fdiv_rn(f[4 * i + 2], divisor), __fdiv_rn(f[4 * i + 3], divisor)));
+}
+
+// max over a float tensor, clamped below at 0 (non-negative floats order like their bit patterns): *out = max(*out, bits)
+__global__ void __launch_bounds__(256) tensor_max_kernel(const float4* __restrict__ in, size_t n4, unsigned* __restrict__ out) {
+  float m = 0.0f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(in + i);
+    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out, __float_as_uint(m));
 }
 
 }  // namespace
@@ -173,7 +191,21 @@ extern "C" int y11_letterbox_u8(y11_handle, const y11_image* images, int B, int 
 extern "C" int y11_nchw_f32_to_nhwc_bf16(y11_handle, const float* in, int B, int H, int W, float divisor, void* out, y11_stream s) {
   Y11_REQUIRE((H * W) % 4 == 0, "nchw->nhwc: H*W must be a multiple of 4");
   dim3 grid((unsigned)((H * W / 4 + 255) / 256), (unsigned)B);
-  nchw_to_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(s)>>>(in, H * W, divisor, static_cast<__nv_bfloat16*>(out));
+  nchw_to_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(s)>>>(in, H * W, divisor, nullptr, static_cast<__nv_bfloat16*>(out));
+  Y11_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int y11_nchw_f32_to_nhwc_bf16_auto(y11_handle h, const float* in, int B, int H, int W, uint32_t* scratch_max, void* out,
+                                              y11_stream s_) {
+  Y11_REQUIRE(h && in && out && scratch_max, "nchw->nhwc(auto): null argument");
+  Y11_REQUIRE((H * W) % 4 == 0, "nchw->nhwc: H*W must be a multiple of 4");
+  cudaStream_t s = static_cast<cudaStream_t>(s_);
+  Y11_CHECK_CUDA(cudaMemsetAsync(scratch_max, 0, sizeof(uint32_t), s));
+  const size_t n4 = (size_t)B * 3 * H * W / 4;
+  tensor_max_kernel<<<(unsigned)std::min<size_t>((n4 + 255) / 256, (size_t)h->num_sms * 8), 256, 0, s>>>(
+      reinterpret_cast<const float4*>(in), n4, scratch_max);
+  dim3 grid((unsigned)((H * W / 4 + 255) / 256), (unsigned)B);
+  nchw_to_nhwc_kernel<<<grid, 256, 0, s>>>(in, H * W, 1.0f, scratch_max, static_cast<__nv_bfloat16*>(out));
   Y11_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -35,6 +35,7 @@ MAX_CACHED_PIPELINES = 16   # CUDA-graph pipeline instances kept per engine (one
 PREDICT_DEFAULTS = dict(conf=0.25, iou=0.7, max_det=300, imgsz=640, rect=True, agnostic_nms=False, classes=None,
                         half=False, verbose=True, save=False, show=False, stream=False, batch=1, device=None,
                         multi_label=False, max_nms=30000,
+                        devices=None,   # extension: list of CUDA device indices - the batch is image-sharded over them (one process)
                         graph=True)   # extension: False = launch the kernels one by one (no CUDA-graph pipeline) for file/array sources
 
 
@@ -106,7 +107,14 @@ class DetectionNet:
 
 
 def _load_state_dict(path: Path):
-    obj = torch.load(str(path), map_location="cpu", weights_only=True)
+    import pickle
+    try:
+        obj = torch.load(str(path), map_location="cpu", weights_only=True)
+    except (pickle.UnpicklingError, AttributeError, ModuleNotFoundError, RuntimeError) as e:
+        # an ultralytics checkpoint is a pickle of the whole DetectionModel object: unreadable without ultralytics
+        raise ValueError(f"{path}: not a plain state_dict file ({type(e).__name__}); pickled ultralytics model objects cannot be "
+                         "read without ultralytics - re-save the weights as a state_dict (ultralytics key names, SURVEY.md A.4), "
+                         "e.g. torch.save(YOLO(path).model.state_dict(), out)") from e
     if isinstance(obj, dict) and "state_dict" in obj:
         return obj["state_dict"], obj.get("scale"), obj.get("names"), obj.get("nc")
     if isinstance(obj, dict) and all(isinstance(v, torch.Tensor) for v in obj.values()):
@@ -144,13 +152,17 @@ class YOLO:
                 sd, scale, names, nc_ = _load_state_dict(p)
                 scale = scale or infer_scale(sd)
                 nc = nc_ or sd["model.23.cv3.0.2.weight"].shape[0]
-            elif stem.startswith("yolo11") and len(stem) >= 7 and stem[6] in T.SCALES:
-                # the reference would download pretrained weights here (core/model.py:106-110); there is no network
+            elif (stem.startswith("yolo11") and len(stem) >= 7 and stem[6] in T.SCALES
+                  and (init == "random" or os.environ.get("Y11_ALLOW_RANDOM_INIT", "0") != "0")):
+                # the reference would download pretrained weights here (core/model.py:106-110); there is no network, and
+                # silently answering with random weights would return garbage detections: explicit opt-in only
                 logger.warning("%s not found and cannot be downloaded offline: using random-init %s.yaml weights", model, stem[:7])
                 scale = stem[6]
                 sd = T.default_state_dict(scale, nc, seed)
             else:
-                raise FileNotFoundError(str(model))
+                raise FileNotFoundError(f"{model}: checkpoint not found (the reference would download it, core/model.py:106-110; "
+                                        "this path has no network access).  Pass an existing state_dict .pt, a yolo11{n,s,m,l,x}.yaml "
+                                        "for a random-init model, or opt in with init='random' / Y11_ALLOW_RANDOM_INIT=1")
         else:
             raise ValueError(f"unsupported model file {model!r}")
         self.scale = scale
@@ -174,6 +186,8 @@ class YOLO:
         self = cls.__new__(cls)
         YOLO.__init__(self, f"yolo11{scale or infer_scale(sd)}.yaml")
         self.nc = nc
+        if len(self.names) != nc:
+            self.names = {i: f"{i}" for i in range(nc)}
         self.model = DetectionNet(self.scale, nc, {k: v.detach().clone() for k, v in sd.items()}, self.names)
         return self
 
@@ -319,132 +333,95 @@ class YOLO:
     def forward(self, net: CompiledNet) -> None:
         net.run(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def result_buffers(self, B: int, max_det: int, rep: int = 0, flat: Optional[torch.Tensor] = None):
+        """(det [B,max_det,6] fp32, count [B] int32, ncand [B] int32, flat) where det and count are views of ONE flat buffer
+        ([B*max_det*6] fp32 followed by [B] int32) so that a multi-GPU caller moves a step's results as one piece.  `flat`:
+        use this buffer instead of an engine-owned one - it may live on ANOTHER GPU (an NVLink peer mapping): the NMS kernel
+        then writes its results straight into the gathering rank's memory (parallel.ResultExchange)."""
+        okey = ("post_out", B, max_det, rep, flat.data_ptr() if flat is not None else None)
+        out = self._ws.get(okey)
+        if out is None:
+            n = B * max_det * 6 + B
+            if flat is None:
+                flat = torch.zeros((n,), dtype=torch.float32, device=self.device)
+            assert flat.numel() == n and flat.dtype == torch.float32 and flat.is_contiguous()
+            out = (flat[: B * max_det * 6].view(B, max_det, 6), flat[B * max_det * 6:].view(torch.int32),
+                   torch.zeros((B,), dtype=torch.int32, device=self.device), flat)
+            self._ws[okey] = out
+        return out
+
     def postprocess(self, net: CompiledNet, scale_rows: Optional[torch.Tensor], conf: float, iou: float, max_det: int,
-                    agnostic: bool = False, multi_label: bool = False, max_nms: int = 30000):
-        """-> (det fp32 [B,max_det,6], count int32 [B], ncand int32 [B]) device tensors."""
+                    agnostic: bool = False, multi_label: bool = False, max_nms: int = 30000,
+                    out_flat: Optional[torch.Tensor] = None, push: Optional[Tuple[int, int]] = None):
+        """-> (det fp32 [B,max_det,6], count int32 [B], ncand int32 [B]) device tensors.
+        push = (done_counter device pointer, signal device pointer): see y11_detect_postprocess_push."""
         B = net.B
         nbytes = self._lib.y11_postprocess_workspace(B, net.A, self.nc, int(multi_label), max_nms)
         rep = getattr(net, "replica", 0)
         ws = self._workspace(("post", B, net.A, multi_label, rep), nbytes)
-        okey = ("post_out", B, max_det, rep)
-        out = self._ws.get(okey)
-        if out is None:
-            # det and count live in ONE flat buffer ([B*max_det*6] fp32 followed by [B] int32) so that a multi-GPU caller
-            # can gather a step's results with a single collective (parallel.gather_flat)
-            flat = torch.zeros((B * max_det * 6 + B,), dtype=torch.float32, device=self.device)
-            out = (flat[: B * max_det * 6].view(B, max_det, 6), flat[B * max_det * 6:].view(torch.int32),
-                   torch.zeros((B,), dtype=torch.int32, device=self.device), flat)
-            self._ws[okey] = out
-        det, count, ncand, _flat = out
+        det, count, ncand, _flat = self.result_buffers(B, max_det, rep, out_flat)
         hd = net.head_desc()
         p = cabi.NmsParams(conf, iou, max_det, max_nms, 7680, int(agnostic), int(multi_label))
         s = torch.cuda.current_stream(self.device).cuda_stream
-        cabi.check(self._lib.y11_detect_postprocess(self._engine, C.byref(hd), C.byref(p),
-                                                    scale_rows.data_ptr() if scale_rows is not None else None,
-                                                    det.data_ptr(), count.data_ptr(), ncand.data_ptr(), ws.data_ptr(),
-                                                    ws.numel(), C.c_void_p(s)), "y11_detect_postprocess")
+        srows = scale_rows.data_ptr() if scale_rows is not None else None
+        if push is not None:
+            pp = cabi.Push(push[0], push[1])
+            cabi.check(self._lib.y11_detect_postprocess_push(self._engine, C.byref(hd), C.byref(p), srows, det.data_ptr(),
+                                                             count.data_ptr(), ncand.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                             C.byref(pp), C.c_void_p(s)), "y11_detect_postprocess_push")
+        else:
+            cabi.check(self._lib.y11_detect_postprocess(self._engine, C.byref(hd), C.byref(p), srows, det.data_ptr(),
+                                                        count.data_ptr(), ncand.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                        C.c_void_p(s)), "y11_detect_postprocess")
         return det, count, ncand
+
+    def postprocess_timed(self, net: CompiledNet, scale_rows, conf: float, iou: float, max_det: int, multi_label: bool = False,
+                          max_nms: int = 30000) -> Tuple[float, float]:
+        """Measurement only: (ms of decode + compaction, ms of sort + NMS) of one post-processing pass on net's current head."""
+        B = net.B
+        nbytes = self._lib.y11_postprocess_workspace(B, net.A, self.nc, int(multi_label), max_nms)
+        ws = self._workspace(("post", B, net.A, multi_label, getattr(net, "replica", 0)), nbytes)
+        det, count, ncand, _ = self.result_buffers(B, max_det, getattr(net, "replica", 0))
+        hd = net.head_desc()
+        p = cabi.NmsParams(conf, iou, max_det, max_nms, 7680, 0, int(multi_label))
+        ms = (C.c_float * 2)()
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        cabi.check(self._lib.y11_detect_postprocess_timed(self._engine, C.byref(hd), C.byref(p),
+                                                          scale_rows.data_ptr() if scale_rows is not None else None, det.data_ptr(),
+                                                          count.data_ptr(), ncand.data_ptr(), ws.data_ptr(), ws.numel(), ms,
+                                                          C.c_void_p(s)), "y11_detect_postprocess_timed")
+        return float(ms[0]), float(ms[1])
 
     # ---- CUDA-graph pipeline for fixed-shape uint8 batches (throughput and batch-1 latency modes) ----------------
     def result_flat(self, net: CompiledNet, max_det: int) -> torch.Tensor:
-        """The flat [B*max_det*6 fp32 | B int32] buffer behind the (det, count) tensors `postprocess` returns for `net`."""
-        return self._ws[("post_out", net.B, max_det, getattr(net, "replica", 0))][3]
+        """The engine-owned flat [B*max_det*6 fp32 | B int32] buffer behind the (det, count) tensors `postprocess` returns."""
+        return self.result_buffers(net.B, max_det, getattr(net, "replica", 0))[3]
 
     def pipeline(self, B: int, h0: int, w0: int, imgsz=640, rect: bool = True, conf: float = 0.25, iou: float = 0.7,
                  max_det: int = 300, agnostic: bool = False, multi_label: bool = False, frames: Optional[torch.Tensor] = None,
-                 graph: bool = True, replica: int = 0) -> "GraphedPipeline":
-        """letterbox -> forward -> decode/NMS for B frames of h0 x w0, captured once as a CUDA graph (one replay per call).
-        `frames`: optional device uint8 [B,h0,w0,3] tensor to bind as the graph's input (zero-copy); otherwise the pipeline
-        owns a static input buffer that `run(src)` fills with one async copy (H2D from pinned memory or D2D)."""
+                 graph: bool = True, replica: int = 0, max_nms: int = 30000, kind: str = "u8",
+                 out_flat: Optional[torch.Tensor] = None, push: Optional[Tuple[int, int]] = None) -> "GraphedPipeline":
+        """preprocess -> forward -> decode/NMS for a fixed-shape batch, captured once as a CUDA graph (one replay per call).
+        kind "u8": B uint8 BGR frames of h0 x w0 (letterbox, or read directly by the stem when no resize is needed);
+        kind "f32": a float [B,3,h0,w0] tensor (LoadTensor semantics: /255 iff max > 1, decided on the device).
+        `frames`: optional device tensor to bind as the graph's input (zero-copy); otherwise the pipeline owns a static input
+        buffer that `run(src)` fills with one async copy (H2D from pinned memory or D2D).
+        `out_flat` / `push`: result buffer override and push signal (multi-GPU result push, see `postprocess`)."""
         self._ensure_device()
-        key = (B, h0, w0, imgsz if isinstance(imgsz, int) else tuple(imgsz), rect, conf, iou, max_det, agnostic, multi_label,
-               frames.data_ptr() if frames is not None else None, graph, replica)
+        key = (kind, B, h0, w0, imgsz if isinstance(imgsz, int) else tuple(imgsz), rect, conf, iou, max_det, agnostic, multi_label,
+               frames.data_ptr() if frames is not None else None, graph, replica, max_nms,
+               out_flat.data_ptr() if out_flat is not None else None, push)
         p = self._pipes.get(key) if hasattr(self, "_pipes") else None
         if p is None:
             if not hasattr(self, "_pipes"):
                 self._pipes = {}
             with torch.inference_mode(False):  # static buffers must stay writable from any mode
-                p = GraphedPipeline(self, B, h0, w0, imgsz, rect, conf, iou, max_det, agnostic, multi_label, frames, graph, replica)
+                p = GraphedPipeline(self, B, h0, w0, imgsz, rect, conf, iou, max_det, agnostic, multi_label, frames, graph, replica,
+                                    max_nms, kind, out_flat, push)
             if len(self._pipes) >= MAX_CACHED_PIPELINES:   # dicts keep insertion order: drop the oldest instance
                 self._pipes.pop(next(iter(self._pipes)))
             self._pipes[key] = p
         return p
-
-    # ---- synthetic-weight conditioning (benchmarks without checkpoints) ----------------------------------
-    def condition_synthetic_weights(self, hw: Tuple[int, int] = (640, 640), batch: int = 2, seed: int = 0, iters: int = 3,
-                                    act_rms: float = 1.0, box_std: float = 3.0, cls_std: float = 1.1,
-                                    cls_prior: float = 0.01) -> Dict[str, float]:
-        """Rescale each conv (its BN gamma, or the plain conv weight) so activations stay O(1) on random frames.
-
-        Random-init YOLO11 weights either collapse or explode through ~90 layers, which would make the decode/NMS stages
-        of a benchmark meaningless (zero or 8400 candidates per image).  This walks the plan in execution order; for conv
-        i it runs ops [0, i] on seeded uint8 frames, measures the rms (std for the two logit convs) of the op's output
-        buffer and scales that conv's packed weights towards the target, `iters` times.  The per-conv factors are then
-        written into the model's state_dict (so the oracle can load the very same weights) and everything is re-packed.
-        Uses the engine's own kernels plus torch reductions at init time only - nothing here is on the predict path.
-        """
-        self._ensure_device()
-        H, W = hw
-        with torch.cuda.device(self.device), torch.inference_mode():
-            net = self.compiled(batch, H, W, fold_upsample=False)
-            g = torch.Generator().manual_seed(seed)
-            frames = torch.randint(0, 256, (batch, H, W, 3), generator=g, dtype=torch.uint8).to(self.device)
-            geoms = [letterbox_geometry(H, W, (H, W), False)] * batch
-            self.preprocess_images(net, list(frames), geoms)
-            s = torch.cuda.current_stream(self.device).cuda_stream
-            factors: Dict[str, float] = {}
-            bias_shift: Dict[str, torch.Tensor] = {}
-            for i, op in enumerate(net.ops):
-                in_place = op.name.endswith(("attn.proj", "ffn.1"))  # out aliases the residual: must run exactly once
-                if op.kind not in ("conv", "dwconv", "stem") or op.name not in self._packed or in_place:
-                    net.run_range(i, i + 1, s)
-                    continue
-                pc = self._packed[op.name]
-                v = op.out
-                is_logit = op.name.endswith((".cv2.0.2", ".cv2.1.2", ".cv2.2.2", ".cv3.0.2", ".cv3.1.2", ".cv3.2.2"))
-                target = act_rms if not is_logit else (cls_std if ".cv3." in op.name else box_std)
-                total = 1.0
-                for _ in range(iters):
-                    net.run_range(i, i + 1, s)
-                    out = v.t[..., v.off:v.off + v.c].float()
-                    if is_logit:
-                        cur = float((out - out.mean((0, 1, 2), keepdim=True)).std())
-                    else:  # residual adds are part of the signal the next layer sees, so they stay in
-                        cur = float(out.pow(2).mean().sqrt())
-                    if not math.isfinite(cur) or cur <= 0:
-                        break
-                    f = min(max(target / cur, 0.05), 20.0)
-                    pc.w.mul_(f)
-                    if not is_logit:
-                        pc.b.mul_(f)
-                    total *= f
-                net.run_range(i, i + 1, s)
-                if is_logit and ".cv3." in op.name:
-                    # class logits: centre every channel on logit(prior) (random weights on positive-mean inputs give each
-                    # class its own offset of ~+-2, which would push most anchors over conf 0.25)
-                    out = v.t[..., v.off:v.off + self.nc].float()
-                    shift = math.log(cls_prior / (1 - cls_prior)) - out.mean((0, 1, 2))
-                    pc.b[: self.nc].add_(shift)
-                    bias_shift[op.name] = shift.cpu()
-                    net.run_range(i, i + 1, s)
-                factors[op.name] = total
-            torch.cuda.synchronize(self.device)
-        sd = self.model.state_dict()
-        for cp in T.conv_params(self.scale, self.nc):
-            f = factors.get(cp.prefix, 1.0)
-            if cp.bn:
-                sd[f"{cp.prefix}.bn.weight"] = sd[f"{cp.prefix}.bn.weight"] * f
-                sd[f"{cp.prefix}.bn.bias"] = sd[f"{cp.prefix}.bn.bias"] * f
-            else:
-                sd[f"{cp.prefix}.weight"] = sd[f"{cp.prefix}.weight"] * f
-                if cp.prefix in bias_shift:
-                    sd[f"{cp.prefix}.bias"] = sd[f"{cp.prefix}.bias"] + bias_shift[cp.prefix]
-        self.model = DetectionNet(self.scale, self.nc, sd, self.names)
-        getattr(self, "_pipes", {}).clear()
-        self._nets.clear()
-        with torch.cuda.device(self.device):
-            self._packed = pack_weights(self.scale, self.nc, sd, self.device)
-        return factors
 
     # ---- sources ----------------------------------------------------------------------------------
     @staticmethod
@@ -478,23 +455,66 @@ class YOLO:
             logger.debug("half=True: the B200 path always computes in bf16 with fp32 accumulation")
         if source is None:
             raise ValueError("predict: source is required")
+        if args["devices"] is not None and len(list(args["devices"])) > 1:
+            return self._predict_multi_device(source, list(args["devices"]), kwargs)
+        if args["devices"] is not None and len(list(args["devices"])) == 1 and args["device"] is None:
+            args["device"] = f"cuda:{int(list(args['devices'])[0])}"
         self._ensure_device(args["device"])
         imgsz = args["imgsz"]
         new_shape = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        pargs = dict(imgsz=imgsz, rect=bool(args["rect"]), conf=float(args["conf"]), iou=float(args["iou"]),
+                     max_det=int(args["max_det"]), agnostic=bool(args["agnostic_nms"]), multi_label=bool(args["multi_label"]),
+                     max_nms=int(args["max_nms"]), graph=bool(args["graph"]))
+        classes = torch.as_tensor(list(args["classes"])) if args["classes"] is not None else None
+
+        def finish(det, det_h, counts, speed, orig_imgs, paths, shapes):
+            """One Results per image; rows are sliced on first access (Results/Boxes keep a view descriptor)."""
+            results = []
+            for i, n in enumerate(counts):
+                img_i = orig_imgs[i] if orig_imgs is not None else None
+                path_i = paths[i] if paths is not None else f"image{i}.jpg"
+                if classes is None:
+                    results.append(Results(img_i, path_i, self.names, None, shapes[i], speed, None, (det, det_h, i, n)))
+                    continue
+                d, dh = det[i, :n], det_h[i, :n]
+                keep = torch.isin(dh[:, 5].long(), classes)
+                results.append(Results(img_i, path_i, self.names, d[keep.to(d.device)], shapes[i], speed, dh[keep]))
+            return results
+
+        # ---- float tensor sources [B,3,H,W] (the reference harness's input, benchmarks/speed_benchmark.py:100-102) ------------
+        if isinstance(source, torch.Tensor) and source.is_floating_point():
+            x = source[None] if source.ndim == 3 else source
+            if x.ndim != 4 or x.shape[1] != 3 or x.shape[2] % 32 or x.shape[3] % 32:
+                raise ValueError(f"tensor source must be [B,3,H,W] with H,W % 32 == 0, got {tuple(x.shape)}")
+            B, _, H, W = x.shape
+            with self._lock, torch.cuda.device(self.device), torch.inference_mode():
+                if x.dtype != torch.float32 or not x.is_contiguous():
+                    x = x.to(torch.float32).contiguous()
+                pipe = self.pipeline(B, H, W, kind="f32", **pargs)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                det, count, _ = pipe.run(x)
+                e1.record()
+                det, det_h, counts = self._fetch_results(det, count)
+                speed = pipe.speed(e0.elapsed_time(e1) / B)
+                self.last_speed = speed
+                results = finish(det, det_h, counts, speed, None, None, [(H, W)] * B)
+            if args["verbose"]:
+                logger.info("%d image(s) %dx%d (tensor): %.2f ms per image", B, H, W, sum(speed.values()))
+            return results
+
+        # ---- uint8 sources: files / BGR arrays / uint8 batch tensors ------------------------------------------------------
         orig_imgs = paths = None
-        if args["graph"] and not isinstance(source, torch.Tensor):
-            # files / BGR arrays of ONE shape (a video stream, a demo frame, a folder of equal-sized images): staged into a
-            # pinned uint8 batch and run through the same CUDA-graph pipeline as tensor batches - one replay per call
-            # instead of ~95 eager launches (reference call sites: demos/detection_demo.py:87-93, 190-196, 280-286)
-            preloaded = self._load_sources(source)
-            if len({im.shape for im in preloaded[0]}) == 1:
-                orig_imgs, paths = preloaded
-        else:
-            preloaded = None
-        if orig_imgs is not None or (isinstance(source, torch.Tensor) and source.dtype == torch.uint8):
-            # fixed-shape uint8 batch [B,H,W,3] BGR (pinned host or device): whole path replayed as ONE CUDA graph
-            if orig_imgs is None and (source.ndim != 4 or source.shape[-1] != 3):
+        if isinstance(source, torch.Tensor):
+            if source.dtype != torch.uint8 or source.ndim != 4 or source.shape[-1] != 3:
                 raise ValueError("uint8 tensor source must be [B,H,W,3] BGR")
+        else:
+            orig_imgs, paths = self._load_sources(source)
+        one_shape = orig_imgs is None or len({im.shape for im in orig_imgs}) == 1
+        if one_shape:
+            # a fixed-shape uint8 batch [B,H,W,3] BGR (pinned host or device; files / arrays of ONE shape - a video stream, a demo
+            # frame, a folder of equal-sized images - are staged into a pinned batch): the whole path is one CUDA-graph replay
+            # (reference call sites: demos/detection_demo.py:87-93, 190-196, 280-286); graph=False launches kernel by kernel
             with self._lock, torch.cuda.device(self.device), torch.inference_mode():
                 if orig_imgs is not None:   # stage the frames in a pinned batch (under the lock: the buffer is per engine)
                     key = ("pinned_frames", len(orig_imgs)) + tuple(orig_imgs[0].shape)
@@ -507,18 +527,14 @@ class YOLO:
                     for i, im in enumerate(orig_imgs):
                         stage_np[i] = im
                 B, h0, w0, _ = source.shape
-                pargs = (imgsz, bool(args["rect"]), float(args["conf"]), float(args["iou"]), int(args["max_det"]),
-                         bool(args["agnostic_nms"]), bool(args["multi_label"]))
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                if (not source.is_cuda) and B >= 32 and B % 8 == 0 and SPLIT_HOST_BATCH:
-                    # Host-fed batch: two half-batch pipelines on two streams.  The frames cross PCIe in order (one shared
-                    # copy stream), so the first half's network, decode and NMS run while the second half is still on the bus;
-                    # each half is itself chunked (H2D chunk c+1 under layers 0-4 of chunk c).
+                if (not source.is_cuda) and B >= 32 and B % 8 == 0 and SPLIT_HOST_BATCH and pargs["graph"]:
+                    # Host-fed batch as two half-batch pipelines on two streams (off by default: measured no gain)
                     Bh = B // 2
                     cur = torch.cuda.current_stream(self.device)
                     side = self._side_stream()
-                    pipes = [self.pipeline(Bh, h0, w0, *pargs, replica=r) for r in (0, 1)]
+                    pipes = [self.pipeline(Bh, h0, w0, replica=r, **pargs) for r in (0, 1)]
                     side.wait_stream(cur)
                     det0, count0, _ = pipes[0].run(source[:Bh])
                     with torch.cuda.stream(side):   # its uploads queue behind the first half's on the shared copy stream
@@ -526,66 +542,32 @@ class YOLO:
                     cur.wait_stream(side)
                     e1.record()
                     det, det_h, counts = self._fetch_results([det0, det1], [count0, count1])
+                    pipe = pipes[0]
                 else:
-                    pipe = self.pipeline(B, h0, w0, *pargs)
+                    pipe = self.pipeline(B, h0, w0, **pargs)
                     det, count, _ = pipe.run(source)
                     e1.record()
                     det, det_h, counts = self._fetch_results(det, count)
-                ms = e0.elapsed_time(e1) / B
-                speed = {"preprocess": 0.0, "inference": ms, "postprocess": 0.0}  # one graph: stages are not separable
+                # the stages of one graph replay are not separable call by call: the call's time is split by the stage shares
+                # measured once when the pipeline was built (GraphedPipeline.speed)
+                speed = pipe.speed(e0.elapsed_time(e1) / B)
                 self.last_speed = speed
-                results = []
-                classes = torch.as_tensor(list(args["classes"])) if args["classes"] is not None else None
-                for i in range(B):
-                    img_i = orig_imgs[i] if orig_imgs is not None else None
-                    path_i = paths[i] if paths is not None else f"image{i}.jpg"
-                    if classes is None:   # rows are sliced on first access (Results/Boxes keep a view descriptor)
-                        results.append(Results(img_i, path_i, self.names, None, (h0, w0), speed, None, (det, det_h, i, counts[i])))
-                        continue
-                    d, dh = det[i, : counts[i]], det_h[i, : counts[i]]
-                    keep = torch.isin(dh[:, 5].long(), classes)
-                    d, dh = d[keep.to(d.device)], dh[keep]
-                    results.append(Results(img_i, path_i, self.names, d, (h0, w0), speed, dh))
-                if args["verbose"]:
-                    logger.info("%d image(s) %dx%d: %.2f ms per image (letterbox + forward + decode + NMS, one CUDA graph)",
-                                B, h0, w0, ms)
+                results = finish(det, det_h, counts, speed, orig_imgs, paths, [(h0, w0)] * B)
+            if args["verbose"]:
+                logger.info("%d image(s) %dx%d: %.2f ms per image (preprocess + forward + decode + NMS)", B, h0, w0, sum(speed.values()))
             return results
+
+        # ---- mixed shapes (a dataset): kernel-by-kernel launches, square letterbox --------------------------------------------
         with self._lock, torch.cuda.device(self.device), torch.inference_mode():
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
-            if isinstance(source, torch.Tensor) and source.is_floating_point():
-                # LoadTensor semantics: whole tensor is one batch; /255 only if max > 1
-                x = source
-                if x.ndim == 3:
-                    x = x[None]
-                if x.ndim != 4 or x.shape[1] != 3 or x.shape[2] % 32 or x.shape[3] % 32:
-                    raise ValueError(f"tensor source must be [B,3,H,W] with H,W % 32 == 0, got {tuple(x.shape)}")
-                x = x.to(self.device, torch.float32, non_blocking=True).contiguous()
-                divisor = 255.0 if float(x.max()) > 1.0 + torch.finfo(torch.float32).eps else 1.0
-                B, _, H, W = x.shape
-                net = self.compiled(B, H, W)
-                self.preprocess_tensor(net, x, divisor)
-                orig_shapes = [(H, W)] * B
-                paths = [f"image{i}.jpg" for i in range(B)]
-                orig_imgs: List[Optional[np.ndarray]] = [None] * B
-            else:
-                if isinstance(source, torch.Tensor):  # device-resident uint8 frames [B,H,W,3] BGR (zero-copy path)
-                    if source.dtype != torch.uint8 or source.ndim != 4 or source.shape[-1] != 3:
-                        raise ValueError("uint8 tensor source must be [B,H,W,3] BGR")
-                    frames = [f for f in source.to(self.device).contiguous()]
-                    paths = [f"image{i}.jpg" for i in range(len(frames))]
-                    orig_imgs = [None] * len(frames)
-                else:
-                    imgs, paths = preloaded if preloaded is not None else self._load_sources(source)
-                    frames = [torch.from_numpy(im).pin_memory().to(self.device, non_blocking=True) for im in imgs]
-                    orig_imgs = list(imgs)
-                orig_shapes = [(int(f.shape[0]), int(f.shape[1])) for f in frames]
-                auto = bool(args["rect"]) and len(set(orig_shapes)) == 1
-                geoms = [letterbox_geometry(h, w, new_shape, auto) for h, w in orig_shapes]
-                H, W = geoms[0][4], geoms[0][5]
-                B = len(frames)
-                net = self.compiled(B, H, W)
-                self.preprocess_images(net, frames, geoms)
+            frames = [torch.from_numpy(im).pin_memory().to(self.device, non_blocking=True) for im in orig_imgs]
+            orig_shapes = [(int(f.shape[0]), int(f.shape[1])) for f in frames]
+            geoms = [letterbox_geometry(h, w, new_shape, False) for h, w in orig_shapes]
+            H, W = geoms[0][4], geoms[0][5]
+            B = len(frames)
+            net = self.compiled(B, H, W)
+            self.preprocess_images(net, frames, geoms)
             ev[1].record()
             self.forward(net)
             ev[2].record()
@@ -594,27 +576,66 @@ class YOLO:
                 gain, px, py = scale_geometry((H, W), (h0, w0))
                 rows.append([gain, float(px), float(py), float(w0), float(h0)])
             scale_rows = torch.tensor(rows, dtype=torch.float32).to(self.device, non_blocking=True)
-            det, count, ncand = self.postprocess(net, scale_rows, float(args["conf"]), float(args["iou"]), int(args["max_det"]),
-                                                 bool(args["agnostic_nms"]), bool(args["multi_label"]), int(args["max_nms"]))
+            det, count, ncand = self.postprocess(net, scale_rows, pargs["conf"], pargs["iou"], pargs["max_det"], pargs["agnostic"],
+                                                 pargs["multi_label"], pargs["max_nms"])
             ev[3].record()
             det, det_h, counts = self._fetch_results(det, count)  # one D2H; also the sync point of the call
             speed = {"preprocess": ev[0].elapsed_time(ev[1]) / B, "inference": ev[1].elapsed_time(ev[2]) / B,
                      "postprocess": ev[2].elapsed_time(ev[3]) / B}
             self.last_speed = speed
-            results = []
-            classes = torch.as_tensor(list(args["classes"])) if args["classes"] is not None else None
-            for i in range(B):
-                d, dh = det[i, : counts[i]], det_h[i, : counts[i]]
-                if classes is not None:
-                    keep = torch.isin(dh[:, 5].long(), classes)
-                    d, dh = d[keep.to(d.device)], dh[keep]
-                results.append(Results(orig_imgs[i], paths[i], self.names, d, orig_shapes[i], dict(speed), dh))
+            results = finish(det, det_h, counts, speed, orig_imgs, paths, orig_shapes)
         if args["verbose"]:
             logger.info("%d image(s) %dx%d: %.2f ms pre, %.2f ms inference, %.2f ms post per image", B, H, W,
                         speed["preprocess"], speed["inference"], speed["postprocess"])
         return results
 
     __call__ = predict
+
+    # ---- multi-GPU in ONE process: the README's "Multi-GPU ... inference" (/root/reference/README.md:13) as a library call -----
+    def _replica_on(self, index: int) -> "YOLO":
+        """An engine with the same weights on device `index` (weights are replicated once)."""
+        if self.device is not None and self.device.index == index and self._engine:
+            return self
+        reps = self.__dict__.setdefault("_replicas", {})
+        rep = reps.get(index)
+        if rep is None:
+            rep = YOLO.from_state_dict(self.model.state_dict(), self.scale, self.nc)
+            rep.names, rep.overrides = self.names, dict(self.overrides)
+            rep.to(f"cuda:{index}")
+            reps[index] = rep
+        return rep
+
+    def _predict_multi_device(self, source, devices: List[int], kwargs) -> List[Results]:
+        """Image-sharded predict over several GPUs of one box: the batch is split contiguously (parallel.shard_range), every
+        device runs the full single-device path on its slice from its own worker thread (own pinned staging buffers, own
+        copy / compute streams, own CUDA graphs), and the Results come back in source order.  No collective: the only
+        exchange is each device's one result D2H."""
+        from concurrent.futures import ThreadPoolExecutor
+        from .parallel import shard_range
+        devices = [int(d) for d in devices]
+        if len(set(devices)) != len(devices):
+            raise ValueError(f"devices must be distinct, got {devices}")
+        if isinstance(source, torch.Tensor):
+            n = source.shape[0] if source.ndim == 4 else 1
+            take = (lambda lo, hi: source[lo:hi]) if source.ndim == 4 else (lambda lo, hi: source)
+        else:
+            items = list(source) if isinstance(source, (list, tuple)) else [source]
+            n = len(items)
+            take = lambda lo, hi: items[lo:hi]
+        world = min(len(devices), n)
+        kw = {k: v for k, v in kwargs.items() if k not in ("devices", "device")}
+        pool = self.__dict__.get("_pool")
+        if pool is None or pool._max_workers < world:
+            pool = self.__dict__["_pool"] = ThreadPoolExecutor(max_workers=max(world, 8), thread_name_prefix="y11dev")
+
+        def work(r: int):
+            lo, hi = shard_range(n, r, world)
+            rep = self._replica_on(devices[r])
+            with torch.cuda.device(rep.device):
+                return rep.predict(take(lo, hi), **kw)
+
+        parts = list(pool.map(work, range(world)))
+        return [res for part in parts for res in part]
 
     # ---- out-of-scope surface: fail loudly, never silently fall back -----------------------------------
     def val(self, data=None, **kwargs):
@@ -645,45 +666,63 @@ class GraphedPipeline:
     """One fixed-shape instance of the whole hot path, replayed as CUDA graphs.
 
     All device buffers (input frames, letterbox descriptors, activations, post-processing workspace, results) are static,
-    so a call is: an async copy of the frames (skipped when the caller binds its own device tensor) + graph launches.
-    The launches inside are exactly the ones `YOLO.predict` issues; CUDA graphs only remove the per-launch CPU cost
-    (~96 launches for YOLO11n/s), which dominates at batch 1.
+    so a call is: an async copy of the input (skipped when the caller binds its own device tensor) + graph launches.
+    The launches inside are exactly the ones the kernel-by-kernel path issues; CUDA graphs only remove the per-launch CPU
+    cost (~96 launches for YOLO11n/s), which dominates at batch 1.
 
-    Host-fed batches (`frames is None`, B a multiple of 4, B >= 16) are CHUNKED: the frames cross PCIe in four pieces on a
-    copy stream, and letterbox + layers 0-4 of chunk c (one graph per chunk) run while chunk c+1 is still in flight; the
+    kind "u8"  : uint8 BGR frames [B,h0,w0,3] -> letterbox kernel (or read directly by the stem when no resize/pad is needed).
+    kind "f32" : float [B,3,H,W] tensors (ultralytics LoadTensor semantics; what the reference's SpeedBenchmark feeds):
+                 device-side max -> /255 rule -> bf16 NHWC, no letterbox, no host sync.
+
+    Host-fed uint8 batches (`frames is None`, B a multiple of 4, B >= 16) are CHUNKED: the frames cross PCIe in four pieces on
+    a copy stream, and preprocess + layers 0-4 of chunk c (one graph per chunk) run while chunk c+1 is still in flight; the
     rest of the network, decode and NMS run once on the whole batch.  The 78.6 MB upload of a 64-frame batch takes 1.42 ms
     against 2.6-3.9 ms of compute: unchunked it is simply added to every call.
     """
 
     def __init__(self, eng: YOLO, B: int, h0: int, w0: int, imgsz, rect: bool, conf: float, iou: float, max_det: int,
-                 agnostic: bool, multi_label: bool, frames: Optional[torch.Tensor], graph: bool, replica: int = 0):
-        self.eng, self.B, self.h0, self.w0 = eng, B, h0, w0
+                 agnostic: bool, multi_label: bool, frames: Optional[torch.Tensor], graph: bool, replica: int = 0,
+                 max_nms: int = 30000, kind: str = "u8", out_flat: Optional[torch.Tensor] = None,
+                 push: Optional[Tuple[int, int]] = None):
+        assert kind in ("u8", "f32")
+        self.eng, self.B, self.h0, self.w0, self.kind = eng, B, h0, w0, kind
         self.conf, self.iou, self.max_det, self.agnostic, self.multi_label = conf, iou, max_det, agnostic, multi_label
+        self.max_nms, self.out_flat, self.push = max_nms, out_flat, push
         dev = eng.device
         new_shape = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
-        geom = letterbox_geometry(h0, w0, new_shape, bool(rect))
-        self.H, self.W = geom[4], geom[5]
+        if kind == "u8":
+            geom = letterbox_geometry(h0, w0, new_shape, bool(rect))
+            self.H, self.W = geom[4], geom[5]
+        else:
+            geom = None
+            self.H, self.W = h0, w0          # tensor sources are used as they are (LoadTensor: H, W % 32 == 0)
         self.owns_input = frames is None
-        self.chunks = 4 if (self.owns_input and graph and B % 4 == 0 and B >= 16) else 1
-        if os.environ.get("Y11_CHUNKS"):   # experiment knob: chunk-major prefix also for device-resident frames
+        self.chunks = 4 if (kind == "u8" and self.owns_input and graph and B % 4 == 0 and B >= 16) else 1
+        if os.environ.get("Y11_CHUNKS") and kind == "u8":   # experiment knob: chunk-major prefix also for device-resident frames
             k = int(os.environ["Y11_CHUNKS"])
             self.chunks = k if (k >= 1 and B % k == 0 and graph) else self.chunks
         with torch.cuda.device(dev):
             self.net = eng.compiled(B, self.H, self.W, self.chunks, replica)
-            self.frames = frames if frames is not None else torch.zeros((B, h0, w0, 3), dtype=torch.uint8, device=dev)
-            assert self.frames.shape == (B, h0, w0, 3) and self.frames.dtype == torch.uint8 and self.frames.is_cuda
-            arr = (cabi.Image * B)()
-            for i in range(B):
-                f = self.frames[i]
-                arr[i] = cabi.Image(f.data_ptr(), h0, w0, f.stride(0), geom[1], geom[0], geom[2], geom[3])
-            self.desc = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
-            self.desc_stride = C.sizeof(cabi.Image)
-            # Frames already at network resolution (no resize, no padding): the stem reads the uint8 frames itself - bit for
-            # bit the letterbox kernel's conversion - and the letterbox launch with its bf16 round trip through HBM is skipped.
-            new_w, new_h, top, left = geom[0], geom[1], geom[2], geom[3]
-            self.fused_stem = bool(FUSE_U8_STEM and new_w == w0 and new_h == h0 and top == 0 and left == 0 and self.H == h0
-                                   and self.W == w0 and self.frames.data_ptr() % 4 == 0 and self.frames.stride(1) % 4 == 0
-                                   and self.frames.stride(0) % 4 == 0)
+            self.fused_stem = False
+            if kind == "u8":
+                self.frames = frames if frames is not None else torch.zeros((B, h0, w0, 3), dtype=torch.uint8, device=dev)
+                assert self.frames.shape == (B, h0, w0, 3) and self.frames.dtype == torch.uint8 and self.frames.is_cuda
+                arr = (cabi.Image * B)()
+                for i in range(B):
+                    f = self.frames[i]
+                    arr[i] = cabi.Image(f.data_ptr(), h0, w0, f.stride(0), geom[1], geom[0], geom[2], geom[3])
+                self.desc = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+                self.desc_stride = C.sizeof(cabi.Image)
+                # Frames already at network resolution (no resize, no padding): the stem reads the uint8 frames itself - bit
+                # for bit the letterbox kernel's conversion - and the letterbox launch with its bf16 round trip is skipped.
+                new_w, new_h, top, left = geom[0], geom[1], geom[2], geom[3]
+                self.fused_stem = bool(FUSE_U8_STEM and new_w == w0 and new_h == h0 and top == 0 and left == 0 and self.H == h0
+                                       and self.W == w0 and self.frames.data_ptr() % 4 == 0 and self.frames.stride(1) % 4 == 0
+                                       and self.frames.stride(0) % 4 == 0)
+            else:
+                self.frames = frames if frames is not None else torch.zeros((B, 3, h0, w0), dtype=torch.float32, device=dev)
+                assert self.frames.shape == (B, 3, h0, w0) and self.frames.dtype == torch.float32 and self.frames.is_cuda
+                self.max_scratch = torch.zeros((1,), dtype=torch.int32, device=dev)
             gain, px, py = scale_geometry((self.H, self.W), (h0, w0))
             self.scale_rows = torch.tensor([[gain, float(px), float(py), float(w0), float(h0)]] * B, dtype=torch.float32, device=dev)
             self.graphs: List[torch.cuda.CUDAGraph] = []
@@ -691,6 +730,7 @@ class GraphedPipeline:
             for fn in self._stage_fns:           # warm-up: allocates workspaces, sets function attributes
                 fn()
             torch.cuda.synchronize(dev)
+            self._measure_stage_shares()
             if graph:
                 for fn in self._stage_fns:
                     g = torch.cuda.CUDAGraph()
@@ -701,45 +741,76 @@ class GraphedPipeline:
                 self.copy_stream = eng.shared_copy_stream()
                 self.copy_events = [torch.cuda.Event() for _ in range(self.chunks)]
         post_launches = 4 if (multi_label or self.net.A >= 65536) else 2   # (count, scan, write | one-pass decode) + sort/NMS
-        # letterbox per chunk (none when the stem reads the frames) + plan + post-processing
-        self.launches = (0 if self.fused_stem else self.chunks) + self.net.n_launches + post_launches
+        pre_launches = 2 if kind == "f32" else (0 if self.fused_stem else self.chunks)   # max + convert | letterbox per chunk
+        self.launches = pre_launches + self.net.n_launches + post_launches
 
-    # ---- the enqueue functions: [chunk 0 prefix, ..., chunk K-1 prefix, rest]  (chunks == 1: a single stage) -------------
+    # ---- the stage closures -------------------------------------------------------------------------------------------------
+    def _pre(self, b0: int, nb: int):
+        eng, net = self.eng, self.net
+        s = torch.cuda.current_stream(eng.device).cuda_stream
+        if self.kind == "f32":
+            net.set_stem_source(None)
+            cabi.check(eng._lib.y11_nchw_f32_to_nhwc_bf16_auto(eng._engine, self.frames.data_ptr(), self.B, self.H, self.W,
+                                                               self.max_scratch.data_ptr(), net.input.data_ptr(), C.c_void_p(s)),
+                       "y11_nchw_f32_to_nhwc_bf16_auto")
+            return
+        if self.fused_stem:      # (re-)point the plan's stem op(s) at this pipeline's frames; no letterbox launch
+            net.set_stem_source(self.desc.data_ptr())
+            return
+        net.set_stem_source(None)
+        cabi.check(eng._lib.y11_letterbox(eng._engine, self.desc.data_ptr() + b0 * self.desc_stride, nb, self.H, self.W,
+                                          net.input[b0:b0 + nb].data_ptr(), C.c_void_p(s)), "y11_letterbox")
+
+    def _post(self):
+        self.det, self.count, self.ncand = self.eng.postprocess(self.net, self.scale_rows, self.conf, self.iou, self.max_det,
+                                                                self.agnostic, self.multi_label, self.max_nms, self.out_flat,
+                                                                self.push)
+
+    # the enqueue functions: [chunk 0 prefix, ..., chunk K-1 prefix, rest]  (chunks == 1: a single stage)
     def _stages(self):
         eng, net = self.eng, self.net
-
-        def letterbox(b0: int, nb: int):
-            if self.fused_stem:      # (re-)point the plan's stem op(s) at this pipeline's frames; no letterbox launch
-                net.set_stem_source(self.desc.data_ptr())
-                return
-            net.set_stem_source(None)
-            s = torch.cuda.current_stream(eng.device).cuda_stream
-            cabi.check(eng._lib.y11_letterbox(eng._engine, self.desc.data_ptr() + b0 * self.desc_stride, nb, self.H, self.W,
-                                              net.input[b0:b0 + nb].data_ptr(), C.c_void_p(s)), "y11_letterbox")
-
-        def post():
-            self.det, self.count, self.ncand = eng.postprocess(net, self.scale_rows, self.conf, self.iou, self.max_det,
-                                                               self.agnostic, self.multi_label)
-
         if self.chunks == 1:
             def whole():
-                letterbox(0, self.B)
+                self._pre(0, self.B)
                 eng.forward(net)
-                post()
+                self._post()
             return [whole]
         Bc = self.B // self.chunks
         fns = []
         for c, (first, last) in enumerate(net.prefix_ranges):
             def prefix(c=c, first=first, last=last):
-                letterbox(c * Bc, Bc)
+                self._pre(c * Bc, Bc)
                 net.run_ops(first, last, torch.cuda.current_stream(eng.device).cuda_stream)
             fns.append(prefix)
 
         def rest():
             net.run_ops(net.rest_first, net.n_ops, torch.cuda.current_stream(eng.device).cuda_stream)
-            post()
+            self._post()
         fns.append(rest)
         return fns
+
+    def _measure_stage_shares(self):
+        """One kernel-by-kernel pass with CUDA events between preprocess / network / decode+NMS: the shares by which
+        `speed()` splits the measured time of a graph replay into the reference's `Results.speed` keys
+        (/root/reference/core/validator.py:355-359 reads them)."""
+        dev = self.eng.device
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        self._pre(0, self.B)
+        ev[1].record()
+        self.eng.forward(self.net)
+        ev[2].record()
+        self._post()
+        ev[3].record()
+        torch.cuda.synchronize(dev)
+        t = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+        tot = sum(t) or 1.0
+        self.stage_share = {"preprocess": t[0] / tot, "inference": t[1] / tot, "postprocess": t[2] / tot}
+
+    def speed(self, ms_per_image: float) -> Dict[str, float]:
+        """ms per image of one call, split by the stage shares measured when the pipeline was built (with frames read
+        directly by the stem there is no separate preprocess launch: its share is 0 by construction)."""
+        return {k: ms_per_image * v for k, v in self.stage_share.items()}
 
     def _launch(self, i: int):
         if self.graphs:

@@ -34,14 +34,18 @@ AUTOTUNE = os.environ.get("Y11_AUTOTUNE", "1") != "0"
 # 8.67 -> 8.98 k img/s, but YOLO11n 34.3 -> 33.6 k and YOLO11s 20.9 -> 20.8 k (their three C3k blocks sit on small maps where
 # the extra fork/join edges cost more than the overlapped launch saves).
 C3K_LANES = os.environ.get("Y11_C3K_LANES", "auto")
-C3K_LANES_MAX_SMALL_B = int(os.environ.get("Y11_C3K_LANES_SMALL_B", "8"))   # "auto" also enables the lane for batches <= this (batch 1: n 0.505 -> 0.498 ms, s 0.691 -> 0.680 ms)
+C3K_LANES_MAX_SMALL_B = int(os.environ.get("Y11_C3K_LANES_SMALL_B", "8"))
+# C3k.cv1 and C3k.cv2 are two 1x1 convs over the SAME input: run them as ONE GEMM with concatenated output channels
+# (weights [cv2 | cv1] stacked at pack time, one launch instead of two, the input tile read once).  Y11_C3K_MERGE=0 restores
+# the two launches (and the side lane above).
+C3K_MERGE = os.environ.get("Y11_C3K_MERGE", "1") != "0"   # "auto" also enables the lane for batches <= this (batch 1: n 0.505 -> 0.498 ms, s 0.691 -> 0.680 ms)
 AUTOTUNE_REPS = int(os.environ.get("Y11_AUTOTUNE_REPS", "4"))
 # Y11_TUNE_CACHE=<file.json>: tuned variants are stored per (scale, nc, B, H, W, chunks, fold) and re-applied on the next
 # build instead of re-timing (a service restarts with the same plans; ncu sees the tuned plan without the tuning launches).
 TUNE_CACHE = os.environ.get("Y11_TUNE_CACHE")
 
 
-def _tune_cache_load() -> Dict[str, list]:
+def _tune_cache_load() -> Dict[str, dict]:
     import json
     try:
         with open(TUNE_CACHE) as f:
@@ -50,14 +54,21 @@ def _tune_cache_load() -> Dict[str, list]:
         return {}
 
 
-def _tune_cache_store(key: str, variants: list) -> None:
+def _tune_cache_store(key: str, variants: dict) -> None:
+    """Read-modify-write of the JSON file under an exclusive lock (torchrun ranks build their plans at the same time)."""
+    import fcntl
     import json
-    data = _tune_cache_load()
-    data[key] = variants
-    tmp = f"{TUNE_CACHE}.{os.getpid()}.tmp"
-    with open(tmp, "w") as f:
-        json.dump(data, f)
-    os.replace(tmp, TUNE_CACHE)
+    with open(f"{TUNE_CACHE}.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            data = _tune_cache_load()
+            data[key] = variants
+            tmp = f"{TUNE_CACHE}.{os.getpid()}.tmp"
+            with open(tmp, "w") as f:
+                json.dump(data, f)
+            os.replace(tmp, TUNE_CACHE)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 def upsample_folds(scale: str) -> Dict[int, Tuple[int, int, int, int]]:
@@ -160,6 +171,14 @@ def pack_weights(scale: str, nc: int, sd: Dict[str, torch.Tensor], device) -> Di
             packed[cp.prefix] = PackedConv(wp.view(c2p, -1).to(device, torch.bfloat16).contiguous(), bp.to(device), c1p, c2p,
                                            cp.k, cp.s, act)
     specs = T.layer_specs(scale)
+    for sp in specs:
+        if sp.kind == "C3k2" and sp.c3k:
+            for j in range(sp.n):
+                pre = f"model.{sp.index}.m.{j}"
+                a, b = packed[f"{pre}.cv2"], packed[f"{pre}.cv1"]      # output order [cv2 | cv1] (see CompiledNet._c3k)
+                if a.c1 == b.c1 and a.act == b.act and a.k == b.k == 1:
+                    packed[f"{pre}.cv12"] = PackedConv(torch.cat((a.w, b.w), 0).contiguous(), torch.cat((a.b, b.b), 0).contiguous(),
+                                                       a.c1, a.c2 + b.c2, 1, 1, a.act)
     for idx, (low, skip, _up, _cat) in upsample_folds(scale).items():
         # cv1 over Concat([up2(p), skip]) = up2(W[:, :c_up] . p + b)  +  W[:, c_up:] . skip      (then SiLU)
         full = packed[f"model.{idx}.cv1"]
@@ -227,6 +246,8 @@ class CompiledNet:
         assert H % 32 == 0 and W % 32 == 0, "network input must be a multiple of 32"
         assert chunks >= 1 and B % chunks == 0, (B, chunks)
         self.chunks = chunks
+        # fold_upsample=False asks for ONE OP PER REFERENCE CONV (the weight conditioning walks the plan by conv name)
+        self.merge_c3k = C3K_MERGE and fold_upsample is not False
         self.folds = upsample_folds(scale) if (FOLD_UPSAMPLE if fold_upsample is None else fold_upsample) else {}
         self.folds = {k: v for k, v in self.folds.items() if f"model.{k}.cv1#up" in packed}
         self._cur_B = B
@@ -244,17 +265,24 @@ class CompiledNet:
         self.no = 64 + pad16(nc)
         self.head: List[torch.Tensor] = []
         tune = AUTOTUNE and conv_impl == cabi.IMPL_TCGEN05
-        self._tune_key = f"{scale}/nc{nc}/B{B}/{H}x{W}/chunks{chunks}/fold{int(bool(self.folds))}"
-        self._cached_variants = _tune_cache_load().get(self._tune_key) if (tune and TUNE_CACHE) else None
+        props = torch.cuda.get_device_properties(device)
+        self._tune_key = (f"{props.name}/sm{props.multi_processor_count}/{scale}/nc{nc}/B{B}/{H}x{W}/chunks{chunks}/"
+                          f"fold{int(bool(self.folds))}/merge{int(self.merge_c3k)}/lanes{C3K_LANES}/impl{conv_impl}")
+        cached = _tune_cache_load().get(self._tune_key) if (tune and TUNE_CACHE) else None
+        # stored BY OP NAME (a chunk-major plan has one op of a name per chunk: same variant); a plan whose op names differ
+        # from the stored ones is re-tuned
+        self._cached_variants = cached if isinstance(cached, dict) else None
         self._build()
         self.A = sum(h.shape[1] * h.shape[2] for h in self.head)
+        if tune and self._cached_variants is not None and not all(o.name in self._cached_variants for o in self.ops if o.kind == "conv"):
+            self._cached_variants = None     # stale entry (different op list): tune again
         if tune and self._cached_variants is None:
             s = torch.cuda.current_stream(device).cuda_stream
             cabi.check(self.lib.y11_plan_autotune(self.plan, C.c_void_p(s), AUTOTUNE_REPS), "y11_plan_autotune")
             for t in self.buffers:      # the timing runs left garbage (in-place residual ops accumulate): start from zeros again
                 t.zero_()
             if TUNE_CACHE:
-                _tune_cache_store(self._tune_key, [list(v) for v in self.variants()])
+                _tune_cache_store(self._tune_key, {o.name: list(v) for o, v in zip(self.ops, self.variants()) if o.kind == "conv"})
 
     def __del__(self):
         try:
@@ -288,9 +316,7 @@ class CompiledNet:
         d.B, d.Hin, d.Win, d.Hout, d.Wout = x.B, x.H, x.W, out.H, out.W
         d.k, d.stride, d.act, d.out_f32, d.impl = pc.k, pc.s, pc.act, int(out_f32), self.conv_impl
         d.res_mode = res_mode
-        var = None
-        if self._cached_variants is not None and len(self.ops) < len(self._cached_variants):
-            var = self._cached_variants[len(self.ops)]
+        var = self._cached_variants.get(name) if self._cached_variants is not None else None
         if var is not None and var[2] > 0 and self.conv_impl == cabi.IMPL_TCGEN05:   # variant chosen by an earlier autotune run
             cabi.check(self.lib.y11_plan_add_conv_tuned(self.plan, C.byref(d), *[int(v) for v in var]), f"plan_add_conv_tuned({name})")
         else:
@@ -326,6 +352,16 @@ class CompiledNet:
         graph) next to the cv1 -> Bottleneck x2 chain: on the 20x20 / 40x40 maps every launch is latency bound and one of
         the block's seven is taken off the critical path."""
         c_ = int(out.c * 0.5)
+        if self.merge_c3k and f"{p}.cv12" in self.packed and c_ % 16 == 0:
+            # z = [m(cv1 x) | cv2 x | cv1 x]: ONE conv writes channels [c_, 3c_), cv3 reads [0, 2c_), the Bottleneck chain
+            # starts from the [2c_, 3c_) slice
+            z = self._new(x.H, x.W, 3 * c_)
+            self._conv(f"{p}.cv12", x, z.sub(c_, 2 * c_))
+            t1 = self._new(x.H, x.W, c_)
+            self._bottleneck(f"{p}.m.0", z.sub(2 * c_, c_), t1, 1.0)
+            self._bottleneck(f"{p}.m.1", t1, z.sub(0, c_), 1.0)
+            self._conv(f"{p}.cv3", z.sub(0, 2 * c_), out)
+            return
         z = self._new(x.H, x.W, 2 * c_)
         side = C3K_LANES == "1" or (C3K_LANES == "auto" and (self.scale in "mlx" or self.B <= C3K_LANES_MAX_SMALL_B))
         if side:
