@@ -370,6 +370,17 @@ def run_ours(args):
             gather_info["no_gather_ms_per_step"] = ctl_ms
             del ctl
     if args.skip_e2e:
+        if rank == 0 and args.per_op:
+            geoms = [letterbox_geometry(S, S, (S, S), True)] * B
+            eng.preprocess_images(net, list(loop.dev_batches[0]), geoms)
+            per_op = net.run_timed(stream.cuda_stream)
+            per_op = net.run_timed(stream.cuda_stream)
+            for m, o, v in sorted(zip(per_op, net.ops, net.variants()), key=lambda r: -r[0]):
+                tf = o.flops / (m / 1e3) / 1e12 if m > 0 else 0
+                gb = o.bytes_algo / (m / 1e3) / 1e9 if m > 0 else 0
+                var = f"  [{'lsu' if v[0] else 'tma'} {'epiW' if v[1] & 1 else 'epiC'}{'-fat' if v[1] & 2 else ''} {v[2]}cta/SM BN{v[3]}]" if v[2] > 0 else ""
+                print(f"{m:8.4f} ms  {o.kind:9s} {o.name:28s} {tf:8.1f} TFLOP/s {gb:8.1f} GB/s(algo){var}", file=sys.stderr)
+            print(f"network total {sum(per_op):.3f} ms; step {ms_step:.3f} ms", file=sys.stderr)
         if rank == 0:
             print(json.dumps({"profiling_only": True, "value": value, "ms_per_step": ms_step, "ms_per_step_blocks": blocks,
                               "launches_per_step": loop.launches, "mean_candidates_per_image": mean_cand}))

@@ -371,16 +371,21 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
         if (elect_one()) {
           const uint64_t ad0 = make_umma_desc_interleaved(ring_base + stage * stage_bytes, p.a_lbo, p.a_sbo);
           if (p.pad) {
-            // 3x3: nine taps, fully unrolled with compile-time offsets (cin <= 64, so one weight chunk per tap).  The issue
-            // thread runs ~10 cycles per dependent instruction: every instruction saved per MMA is worth it.
+            // 3x3: nine taps, fully unrolled with compile-time offsets.  The issue thread runs ~10 cycles per dependent
+            // instruction: every instruction saved per MMA is worth it.  cin in {16, 32, 64} is ONE weight chunk per tap
+            // (Cc == cin); cin = 48 (the 1.5x-wide scale) is three 16-channel chunks, each with its own resident weight slot.
+            const int cpt = p.chunks_per_tap;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               // tap (kh, kw) = the halo tile shifted by kh rows of (Tw+2) = 10 pixels and kw pixels, in 16-byte units
               const uint64_t ad = ad0 + (uint32_t)((tap / 3) * 10 + tap % 3);
-              const uint64_t bd = bd_res + (uint32_t)tap * b_step;
+              const uint64_t bd = bd_res + (uint32_t)(tap * cpt) * b_step;
               umma_bf16(tmem_acc, ad, bd, idesc, tap != 0);
               for (int kk = 1; kk < kk_n; ++kk)  // next 16 channels = two 8-channel planes further / +32 B in the weight row
                 umma_bf16(tmem_acc, ad + kk * k_step, bd + 2 * kk, idesc, 1);
+              for (int c = 1; c < cpt; ++c)      // further weight chunks of this tap: Cc channels = Cc/8 planes further
+                for (int kk = 0; kk < kk_n; ++kk)
+                  umma_bf16(tmem_acc, ad + (uint32_t)(c * kk_n + kk) * k_step, bd + (uint32_t)c * b_step + 2 * kk, idesc, 1);
             }
           } else {
             // 1x1: K = cin in weight chunks of Cc channels
@@ -688,9 +693,16 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     const size_t wbytes = (size_t)d->k * d->k * cin * cout * 2;
     const bool k3e = d->k == 3 && d->stride == 1 && cin <= 64 && d->Hout >= 32 && d->Wout >= 32;
     const bool k1e = d->k == 1 && (cin <= 32 || (cin % 32 != 0 && cin <= 112));  // TMA rows would be 32-64 B
-    const bool fits = cout <= 128 && wbytes <= 40 * 1024;
+    // resident-weight budget: 40 KB keeps 2-3 CTAs per SM; up to Y11_LSU_WMAX KB (default 80: the 3x3 64->64 layers, 72 KB) the
+    // mode is still OFFERED to the autotuner (1 CTA per SM, 4 halo stages) - those layers are bound by the L2->SM operand
+    // traffic of the tap-by-tap TMA mode (9 activation + 9 weight tiles per output tile, ~45 B/clk/SM against the ~43 B/clk/SM
+    // the L2 delivers chip-wide), and the halo mode moves a tenth of it; the heuristic default stays TMA above 40 KB
+    static const size_t wmax = [] { const char* e = getenv("Y11_LSU_WMAX"); return (size_t)(e ? atoi(e) : 80) * 1024; }();
+    const bool big = wbytes > 40 * 1024;
+    const bool fits = cout <= 128 && wbytes <= (tune.lsu == 1 ? wmax : (size_t)40 * 1024);
     const bool k3 = k3e && (mode & 1), k1 = k1e && (mode & 2);
-    L->lsu_eligible = (k3e || k1e) && fits;
+    L->lsu_eligible = (k3e || k1e) && cout <= 128 && wbytes <= wmax;
+    (void)big;
     p.halo = (k1 || k3) && fits;
     p.pad = (p.halo && k3) ? 1 : 0;
   }
