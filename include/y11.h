@@ -257,6 +257,30 @@ int y11_nms_batched(y11_handle h, const float* boxes, const float* scores, const
                     size_t workspace_bytes, y11_stream s);
 size_t y11_nms_workspace(int B, int K);
 
+/* ---- (4) result rasteriser  [a17 consumers / section 8f row 3: utils/visualization.py:18-106 draw_detections] ----------------
+ * Draws every image's detections (box outline, filled label background, label text `{name}: {conf:.2f}`, palette of
+ * visualization.py:get_color, painter's order) straight into uint8 BGR frames in device memory - bit-identical to the
+ * reference's cv2.rectangle / cv2.getTextSize / cv2.putText loop for line_thickness 1 or 2, FONT_HERSHEY_SIMPLEX at scale 0.5,
+ * thickness 1 (the defaults every call site uses); glyphs cut by the image border may differ in a few pixels. */
+typedef struct {
+  uint8_t* img;          /* device, BGR uint8 HWC, modified in place */
+  int32_t h, w, pitch;   /* pitch in bytes */
+  const float* det;      /* device, [max_det][6] = x1,y1,x2,y2,conf,cls rows of THIS image (y11_detect_postprocess layout) */
+  const int32_t* count;  /* device pointer to the number of valid rows, or NULL -> n */
+  int32_t n, max_det;
+} y11_draw_item;
+typedef struct {
+  const uint32_t* glyph_bits; /* device, [n_chars][2 pen phases][cell_h] row masks, bit x = column x of the cell */
+  const int32_t* advance;     /* device, [n_chars] pen advance in HALF pixels */
+  int32_t first_char, n_chars, cell_h, cell_w, base_y, pad_x;
+  int32_t text_h;             /* cv2.getTextSize(...)[0][1] of the font (12) */
+  const char* names;          /* device, [nc][name_stride] zero-padded class names */
+  int32_t nc, name_stride;
+} y11_font;
+/* items: DEVICE array of n_items descriptors; max_h / max_w: largest image extent among them (grid size). */
+int y11_draw_detections(y11_handle h, const y11_draw_item* items, int n_items, int max_h, int max_w, const y11_font* font,
+                        int line_thickness, y11_stream s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,17 @@ class NmsParams(C.Structure):
                 ("max_wh", C.c_int32), ("agnostic", C.c_int32), ("multi_label", C.c_int32)]
 
 
+class DrawItem(C.Structure):
+    _fields_ = [("img", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32), ("pitch", C.c_int32), ("det", C.c_void_p),
+                ("count", C.c_void_p), ("n", C.c_int32), ("max_det", C.c_int32)]
+
+
+class Font(C.Structure):
+    _fields_ = [("glyph_bits", C.c_void_p), ("advance", C.c_void_p), ("first_char", C.c_int32), ("n_chars", C.c_int32),
+                ("cell_h", C.c_int32), ("cell_w", C.c_int32), ("base_y", C.c_int32), ("pad_x", C.c_int32), ("text_h", C.c_int32),
+                ("names", C.c_void_p), ("nc", C.c_int32), ("name_stride", C.c_int32)]
+
+
 class Push(C.Structure):
     _fields_ = [("done_counter", C.c_void_p), ("signal", C.c_void_p)]
 
@@ -116,6 +127,7 @@ SIGNATURES = {
                                                C.POINTER(C.c_float), _P]),
     "y11_nms_batched": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(NmsParams), _P, _P, _P, C.c_size_t, _P]),
     "y11_nms_workspace": (C.c_size_t, [C.c_int, C.c_int]),
+    "y11_draw_detections": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(Font), C.c_int, _P]),
 }
 
 _lib = None

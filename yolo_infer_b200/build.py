@@ -13,7 +13,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "_lib"
 LIB = LIBDIR / "liby11_b200.so"
-SOURCES = ["api.cu", "preprocess.cu", "conv_tc.cu", "conv_simt.cu", "dwconv_tma.cu", "attention.cu", "postprocess.cu"]
+SOURCES = ["api.cu", "preprocess.cu", "conv_tc.cu", "conv_simt.cu", "dwconv_tma.cu", "attention.cu", "postprocess.cu", "draw.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
