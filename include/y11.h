@@ -281,6 +281,19 @@ typedef struct {
 int y11_draw_detections(y11_handle h, const y11_draw_item* items, int n_items, int max_h, int max_w, const y11_font* font,
                         int line_thickness, y11_stream s);
 
+/* ---- (5) GPU JPEG decode  [section 8f row 2: cv2.imread of utils/data_loader.py:42 / ultralytics LoadImagesAndVideos] -------------
+ * Compressed bytes in HOST memory -> BGR uint8 HWC frame in DEVICE memory (what y11_image.src points at), through nvJPEG
+ * (resolved with dlopen at first use; absent library -> these calls fail with a message, the rest of the ABI is unaffected).
+ * Not bit-identical to cv2.imread (different IDCT / chroma upsampling): tolerance stated in tests/test_gpu_decode.py.
+ * One decoder object per thread / stream of decodes. */
+typedef struct y11_jpeg_s* y11_jpeg;
+int y11_jpeg_create(y11_handle h, y11_jpeg* out);
+void y11_jpeg_destroy(y11_jpeg j);
+int y11_jpeg_info(y11_jpeg j, const uint8_t* data, size_t nbytes, int32_t* h, int32_t* w, int32_t* components);
+/* out_bgr: device [h][pitch] bytes; h, w must equal y11_jpeg_info's.  Enqueued on `s` (the Huffman stage runs on the host). */
+int y11_jpeg_decode(y11_jpeg j, const uint8_t* data, size_t nbytes, uint8_t* out_bgr, int32_t pitch, int32_t h, int32_t w,
+                    y11_stream s);
+
 #ifdef __cplusplus
 }
 #endif

