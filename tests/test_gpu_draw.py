@@ -27,7 +27,7 @@ def random_results(rng, n, h, w, names, margin):
 
 
 @pytest.mark.parametrize("thickness", [2, 1])
-@pytest.mark.parametrize("h,w,n", [(720, 1280, 60), (480, 640, 300), (853, 1280, 7), (64, 96, 3)])
+@pytest.mark.parametrize("h,w,n", [(720, 1280, 60), (480, 640, 300), (853, 1280, 7), (96, 352, 3)])
 def test_draw_detections_is_bit_identical_to_cv2_when_labels_are_inside_the_image(h, w, n, thickness):
     """Boxes anywhere, labels fully inside the frame (top margin >= 23 px, right margin): every pixel equals the reference loop."""
     rng = np.random.default_rng(h * 7 + n)

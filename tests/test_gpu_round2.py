@@ -337,3 +337,46 @@ def test_speed_benchmark_shaped_harness(eng_n, tmp_path):
     res = sb.benchmark_model_sizes(sizes=[str(path)], image_sizes=[320], batch_sizes=[1, 2])
     assert len(res["configurations"]) == 2 and res["summary"]["total_configurations"] == 2
     assert (tmp_path / "out" / "model_sizes_benchmark.json").exists() and Path(sb.generate_report()).exists()
+
+
+# ------------------------------------------------------------------------------------------------ val path against the oracle
+def test_val_rect_path_matches_the_oracle_val_path(oracle_models, tmp_path):
+    """`model.val` (core/validator.py:121-141): rect batches + multi-label NMS at conf 0.001 / iou 0.6 + ratio_pad un-letterboxing.
+    Ground truth = confident detections of the fp32 oracle; the SAME labels score the B200 path and the oracle path
+    (oracle/val_ref.py around the same-storage network): mAP50 / mAP50-95 must agree, and per image the predictions must match."""
+    import cv2
+    from oracle import val_ref as VR
+    from yolo_infer_b200.val import validate
+    _, sd = oracle_models("n")
+    eng = YOLO.from_state_dict(sd, "n").to("cuda:0")
+    fused, emul = fused_of(sd, "n"), fused_of(sd, "n", emul=True)
+    rng = np.random.default_rng(21)
+    sizes = [(360, 640), (480, 640), (640, 480), (427, 640), (500, 375), (640, 640), (300, 500)]
+    root = tmp_path / "ds"
+    (root / "images" / "val").mkdir(parents=True)
+    (root / "labels" / "val").mkdir(parents=True)
+    images, gts = [], []
+    for i, (h, w) in enumerate(sizes):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        cv2.imwrite(str(root / "images" / "val" / f"{i}.png"), img)
+        images.append(img)
+    labels = VR.val_predictions(fused, images, batch=4, conf=0.35, iou=0.6)
+    n_lab = 0
+    for i, ((h, w), d) in enumerate(zip(sizes, labels)):
+        rows = [f"{int(c)} {(x1 + x2) / 2 / w:.6f} {(y1 + y2) / 2 / h:.6f} {(x2 - x1) / w:.6f} {(y2 - y1) / h:.6f}" for x1, y1, x2, y2, s, c in d.tolist()]
+        n_lab += len(rows)
+        (root / "labels" / "val" / f"{i}.txt").write_text("\n".join(rows) + ("\n" if rows else ""))
+        gts.append(np.array([[c, x1, y1, x2, y2] for x1, y1, x2, y2, s, c in d.tolist()]).reshape(-1, 5))
+    assert n_lab >= 20
+    (root / "data.yaml").write_text(f"path: {root}\nval: images/val\nnames:\n" + "".join(f"  {k}: c{k}\n" for k in range(80)))
+    m = validate(eng, str(root / "data.yaml"), batch=4)
+    want_preds = VR.val_predictions(emul, images, batch=4)
+    # the labels file rounds coordinates to 1e-6 of the image size; score the oracle on the labels as read back from disk
+    from yolo_infer_b200.val import read_labels, load_dataset
+    files, _ = load_dataset(str(root / "data.yaml"))
+    gts_disk = [read_labels(f, w, h) for f, (h, w) in zip(sorted(files, key=lambda f: int(f.stem)), sizes)]
+    m50, m5095 = VR.mean_ap(want_preds, gts_disk)
+    print(f"val: B200 mAP50 {m.box.map50:.4f} mAP50-95 {m.box.map:.4f}; oracle path {m50:.4f} / {m5095:.4f}; images {m.n_images}, labels {m.n_labels}")
+    assert m.n_images == len(sizes) and m.n_labels == n_lab
+    assert abs(m.box.map50 - m50) <= 0.03 and abs(m.box.map - m5095) <= 0.03
+    assert m.box.map50 > 0.8

@@ -577,36 +577,56 @@ class YOLO:
                 logger.info("%d image(s) %dx%d: %.2f ms per image (preprocess + forward + decode + NMS)", B, h0, w0, sum(speed.values()))
             return results
 
-        # ---- mixed shapes (a dataset): kernel-by-kernel launches, square letterbox --------------------------------------------
+        # ---- mixed shapes: kernel-by-kernel launches, square letterbox (ultralytics: auto=False when shapes differ) ---------------
+        orig_shapes = [(int(im.shape[0]), int(im.shape[1])) for im in orig_imgs]
+        geoms = [letterbox_geometry(h, w, new_shape, False) for h, w in orig_shapes]
+        H, W = geoms[0][4], geoms[0][5]
+        rows = []
+        for (h0, w0) in orig_shapes:
+            gain, px, py = scale_geometry((H, W), (h0, w0))
+            rows.append([gain, float(px), float(py), float(w0), float(h0)])
+        results = self.predict_letterboxed(orig_imgs, [g[:4] for g in geoms], H, W, rows, paths=paths, classes=classes, **pargs)
+        if args["verbose"]:
+            sp = self.last_speed
+            logger.info("%d image(s) %dx%d: %.2f ms pre, %.2f ms inference, %.2f ms post per image", len(orig_imgs), H, W,
+                        sp["preprocess"], sp["inference"], sp["postprocess"])
+        return results
+
+    def predict_letterboxed(self, imgs: Sequence[np.ndarray], geoms: Sequence[Tuple[int, int, int, int]], H: int, W: int,
+                            scale_rows: Sequence[Sequence[float]], paths: Optional[Sequence[str]] = None, classes=None,
+                            conf: float = 0.25, iou: float = 0.7, max_det: int = 300, agnostic: bool = False,
+                            multi_label: bool = False, max_nms: int = 30000, **_unused) -> List[Results]:
+        """Kernel-by-kernel pass over BGR uint8 arrays with an EXPLICIT letterbox geometry per image - (new_w, new_h, top, left) on an
+        H x W canvas - and explicit un-letterbox rows [gain, pad_x, pad_y, w0, h0].  `predict` uses it for batches of mixed shapes;
+        the val path uses it for ultralytics' rect batches (val.rect_batches), whose geometry differs from predict's."""
+        self._ensure_device()
         with self._lock, torch.cuda.device(self.device), torch.inference_mode():
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
-            frames = [torch.from_numpy(im).pin_memory().to(self.device, non_blocking=True) for im in orig_imgs]
-            orig_shapes = [(int(f.shape[0]), int(f.shape[1])) for f in frames]
-            geoms = [letterbox_geometry(h, w, new_shape, False) for h, w in orig_shapes]
-            H, W = geoms[0][4], geoms[0][5]
+            frames = [torch.from_numpy(np.ascontiguousarray(im)).pin_memory().to(self.device, non_blocking=True) for im in imgs]
             B = len(frames)
             net = self.compiled(B, H, W)
-            self.preprocess_images(net, frames, geoms)
+            self.preprocess_images(net, frames, [(g[0], g[1], g[2], g[3], H, W) for g in geoms])
             ev[1].record()
             self.forward(net)
             ev[2].record()
-            rows = []
-            for (h0, w0) in orig_shapes:
-                gain, px, py = scale_geometry((H, W), (h0, w0))
-                rows.append([gain, float(px), float(py), float(w0), float(h0)])
-            scale_rows = torch.tensor(rows, dtype=torch.float32).to(self.device, non_blocking=True)
-            det, count, ncand = self.postprocess(net, scale_rows, pargs["conf"], pargs["iou"], pargs["max_det"], pargs["agnostic"],
-                                                 pargs["multi_label"], pargs["max_nms"])
+            rows = torch.tensor([list(map(float, r)) for r in scale_rows], dtype=torch.float32).to(self.device, non_blocking=True)
+            det, count, ncand = self.postprocess(net, rows, conf, iou, max_det, agnostic, multi_label, max_nms)
             ev[3].record()
             det, det_h, counts = self._fetch_results(det, count)  # one D2H; also the sync point of the call
             speed = {"preprocess": ev[0].elapsed_time(ev[1]) / B, "inference": ev[1].elapsed_time(ev[2]) / B,
                      "postprocess": ev[2].elapsed_time(ev[3]) / B}
             self.last_speed = speed
-            results = finish(det, det_h, counts, speed, orig_imgs, paths, orig_shapes)
-        if args["verbose"]:
-            logger.info("%d image(s) %dx%d: %.2f ms pre, %.2f ms inference, %.2f ms post per image", B, H, W,
-                        speed["preprocess"], speed["inference"], speed["postprocess"])
+            results = []
+            for i, n in enumerate(counts):
+                shape_i = (int(imgs[i].shape[0]), int(imgs[i].shape[1]))
+                path_i = paths[i] if paths is not None else f"image{i}.jpg"
+                if classes is None:
+                    results.append(Results(imgs[i], path_i, self.names, None, shape_i, speed, None, (det, det_h, i, n)))
+                    continue
+                d, dh = det[i, :n], det_h[i, :n]
+                keep = torch.isin(dh[:, 5].long(), classes)
+                results.append(Results(imgs[i], path_i, self.names, d[keep.to(d.device)], shape_i, speed, dh[keep]))
         return results
 
     __call__ = predict

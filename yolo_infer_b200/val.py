@@ -12,8 +12,12 @@ what lives here is the validator's book-keeping, which in ultralytics is CPU num
 * ``ap_per_class``: per class precision/recall curves over confidence-sorted predictions, AP by 101-point interpolation
   of the precision envelope (COCO), precision/recall reported at the confidence that maximises the smoothed mean F1.
 
-Differences from ultralytics, stated: batches are formed in file order (ultralytics sorts a rect dataloader by aspect ratio and
-pads with ``pad=0.5``); images of one batch with different shapes are letterboxed to the square ``imgsz``.
+Batching follows ultralytics' RECT val dataloader (``data/dataset.py: set_rectangle``, ``data/base.py: load_image``, the reference
+reaches it through ``model.val`` at ``core/validator.py:121-141``): images sorted by aspect ratio h/w, consecutive groups of
+``batch`` images share one canvas ``ceil([h, w] * imgsz / 32 + 0.5) * 32`` derived from the group's extreme aspect ratio, every
+image is resized so that its long side is ``imgsz`` (``ceil`` of the scaled size, bilinear) and centred on the canvas with
+border 114 (``LetterBox(auto=False, scaleup=False)``); predictions go back to original pixels with
+``scale_boxes(..., ratio_pad=((h1/h0, w1/w0), (left, top)))``.  ``rect=False`` keeps the square letterbox of ``predict``.
 """
 from __future__ import annotations
 
@@ -251,15 +255,68 @@ def read_labels(img: Path, w: int, h: int) -> np.ndarray:
     return out
 
 
+def rect_batches(shapes: Sequence[Tuple[int, int]], batch: int, imgsz: int = 640, stride: int = 32, pad: float = 0.5):
+    """ultralytics `YOLODataset.set_rectangle` restated.  shapes[i] = (h0, w0).  -> (order, canvases): `order` = image indices sorted by
+    aspect ratio h/w (stable), `canvases[k]` = (H, W) of batch k = images order[k*batch:(k+1)*batch]."""
+    s = np.asarray(shapes, np.float64).reshape(-1, 2)
+    ar = s[:, 0] / s[:, 1]
+    order = np.argsort(ar, kind="stable")
+    ar = ar[order]
+    n = len(order)
+    nb = (n + batch - 1) // batch
+    canvases = []
+    for k in range(nb):
+        ari = ar[k * batch:(k + 1) * batch]
+        mini, maxi = ari.min(), ari.max()
+        shp = [1.0, 1.0]
+        if maxi < 1:
+            shp = [maxi, 1.0]
+        elif mini > 1:
+            shp = [1.0, 1.0 / mini]
+        hw = np.ceil(np.asarray(shp) * imgsz / stride + pad).astype(int) * stride
+        canvases.append((int(hw[0]), int(hw[1])))
+    return [int(i) for i in order], canvases
+
+
+def rect_geometry(h0: int, w0: int, canvas: Tuple[int, int], imgsz: int = 640):
+    """Geometry of one image of a rect batch: ultralytics `load_image(rect_mode=True)` (long side -> imgsz, ceil) followed by
+    `LetterBox(canvas, auto=False, scaleup=False, center=True)`.  -> ((new_w, new_h, top, left), [gain, pad_x, pad_y, w0, h0])."""
+    import math
+    r = imgsz / max(h0, w0)
+    if r != 1:
+        w1, h1 = min(math.ceil(w0 * r), imgsz), min(math.ceil(h0 * r), imgsz)
+    else:
+        w1, h1 = w0, h0
+    H, W = canvas
+    r2 = min(min(H / h1, W / w1), 1.0)                    # scaleup=False
+    new_w, new_h = int(round(w1 * r2)), int(round(h1 * r2))
+    dw, dh = (W - new_w) / 2, (H - new_h) / 2
+    top, left = int(round(dh - 0.1)), int(round(dw - 0.1))
+    gain = (h1 / h0) * r2                                 # ratio_pad[0][0]: the HEIGHT ratio is applied to both axes
+    return (new_w, new_h, top, left), [gain, float(left), float(top), float(w0), float(h0)]
+
+
 def validate(engine, data, imgsz: int = 640, batch: int = 16, conf: float = 0.001, iou: float = 0.6, max_det: int = 300,
-             verbose: bool = False, **_ignored) -> DetMetrics:
-    """Run `engine.predict` (multi-label NMS, ultralytics val thresholds) over the dataset and score it."""
+             verbose: bool = False, rect: bool = True, **_ignored) -> DetMetrics:
+    """Run the engine (multi-label NMS, ultralytics val thresholds) over the dataset in rect batches and score it."""
     import cv2
     files, names = load_dataset(data)
     names = names or engine.names
     preds, gts = [], []
     speed = {"preprocess": 0.0, "inference": 0.0, "loss": 0.0, "postprocess": 0.0}
     t_read = 0.0
+    canvases = None
+    if rect:
+        t0 = time.perf_counter()
+        shapes = []
+        for f in files:                      # header-only read would do; the files are decoded again batch by batch below
+            im = cv2.imread(str(f))
+            if im is None:
+                raise FileNotFoundError(f"cannot read image {f}")
+            shapes.append(im.shape[:2])
+        t_read += time.perf_counter() - t0
+        order, canvases = rect_batches(shapes, batch, imgsz)
+        files = [files[i] for i in order]
     for i in range(0, len(files), batch):
         chunk = files[i:i + batch]
         t0 = time.perf_counter()
@@ -270,8 +327,14 @@ def validate(engine, data, imgsz: int = 640, batch: int = 16, conf: float = 0.00
                 raise FileNotFoundError(f"cannot read image {f}")
             imgs.append(im)
         t_read += time.perf_counter() - t0
-        # graph=False: a dataset has many distinct image sizes; a captured pipeline per size would cost more than it saves
-        res = engine.predict(imgs, conf=conf, iou=iou, max_det=max_det, imgsz=imgsz, multi_label=True, verbose=False, graph=False)
+        if rect:
+            H, W = canvases[i // batch]
+            gr = [rect_geometry(im.shape[0], im.shape[1], (H, W), imgsz) for im in imgs]
+            res = engine.predict_letterboxed(imgs, [g[0] for g in gr], H, W, [g[1] for g in gr], paths=[str(f) for f in chunk],
+                                             conf=conf, iou=iou, max_det=max_det, multi_label=True)
+        else:
+            # graph=False: a dataset has many distinct image sizes; a captured pipeline per size would cost more than it saves
+            res = engine.predict(imgs, conf=conf, iou=iou, max_det=max_det, imgsz=imgsz, multi_label=True, verbose=False, graph=False)
         for f, im, r in zip(chunk, imgs, res):
             preds.append(r.cpu().boxes.data.numpy())
             gts.append(read_labels(f, im.shape[1], im.shape[0]))
