@@ -322,12 +322,14 @@ def run_ours(args):
         for i in range(warmup):
             loop.step(i)
         barrier()
-        blocks, per_rank = [], []
+        blocks, per_rank, block_mhz = [], [], []
         with ClockSampler(local) as clocks:
             for rep in range(repeats):
                 barrier()
+                n0 = len(clocks.samples)
                 e0, e1 = loop.block(rep * steps, steps)
                 barrier()
+                block_mhz.append(statistics.median(clocks.samples[n0:]) if len(clocks.samples) > n0 else None)
                 mine = e0.elapsed_time(e1) / steps
                 if world > 1:
                     allms = [torch.zeros(1, device=dev) for _ in range(world)]
@@ -338,7 +340,9 @@ def run_ours(args):
                 blocks.append(max(ranks_ms))
                 per_rank.append(ranks_ms)
         med = sorted(range(len(blocks)), key=lambda k: blocks[k])[len(blocks) // 2]
-        return blocks[med], blocks, per_rank[med], clocks.summary()
+        summary = clocks.summary()
+        summary["sm_mhz_per_block"] = block_mhz      # back-to-back blocks heat the part up: the power cap shows here
+        return blocks[med], blocks, per_rank[med], summary
 
     B, S = args.batch, args.imgsz
     pk = peaks()
@@ -435,6 +439,7 @@ def run_ours(args):
                        "l2_policy": f"{loop.NROT} rotating input batches ({loop.NROT * B * S * S * 3 / 1e6:.0f} MB) + "
                                     f"{sum(b.numel() * b.element_size() for b in net.buffers) / 1e9:.2f} GB of activations per step (> 126 MB L2)"},
             "ms_per_step_blocks": blocks, "ms_per_step_spread": (max(blocks) - min(blocks)) / ms_step,
+            "value_best_block": world * B / (min(blocks) / 1e3),
             "ms_per_step_per_rank": ranks_ms,
             "timing": f"median of {len(blocks)} blocks of exactly {args.steps} steps (barrier + synchronize on both sides, CUDA events, max over ranks)",
             "clocks": clocks,

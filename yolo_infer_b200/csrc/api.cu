@@ -223,6 +223,10 @@ extern "C" int y11_plan_autotune(y11_plan p, y11_stream s_, int reps) {
           } else if (bn0 == 256) {
             cands.push_back(ConvTcTune{lsu, ew, cps, 128});  // 128x256 tiles need all of TMEM (1 CTA/SM): not always the best trade
           }
+          // ... and the other way round: 128x256 tiles for shorter-K layers whose heuristic tile is 128 wide (half the
+          // activation re-reads from L2; the layers on 20x20 / 40x40 maps run at the L2 -> SM bandwidth cap)
+          if (bn0 == 128 && d->out.c % 256 == 0 && d->in.c % 64 == 0 && cps == 2 && !(lsu && base.lsu_eligible))
+            cands.push_back(ConvTcTune{lsu, ew, 1, 256});
         }
     // time one variant: best of three trials of `reps` back-to-back launches (after one warm-up launch)
     auto time_variant = [&](const ConvTcLaunch& L, float* out_ms) -> int {

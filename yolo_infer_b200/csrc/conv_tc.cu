@@ -722,7 +722,10 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     const char* e = getenv("Y11_BN256");
     const int mode = e ? atoi(e) : 1;
     const long long k_total = (long long)cin * d->k * d->k;
-    if (mode && bn_cap >= 256 && cout % 256 == 0 && cin % 64 == 0 && k_total >= 1024) bn = 256;
+    // an explicit bn_max >= 256 (autotuner candidate / cached variant) asks for the wide tile on shorter K as well: the 1x1
+    // layers with 256-512 output channels re-read their activation tile once per 128-column N tile otherwise
+    const bool forced = tune.bn_max >= 256;
+    if (mode && bn_cap >= 256 && cout % 256 == 0 && cin % 64 == 0 && (k_total >= 1024 || forced)) bn = 256;
   }
   if (p.halo) bn = cout;
   p.BN = bn;
