@@ -67,6 +67,9 @@ def parse_args():
     ap.add_argument("--skip-condition", action="store_true",
                     help="profiling only: skip the init-time weight conditioning pass (keeps the launch list short under ncu)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling only: value loop only")
+    ap.add_argument("--weights-cache", default=None,
+                    help="profiling only: file to keep the conditioned state_dict in, so that the ncu passes start from the conditioned "
+                         "weights (realistic candidate counts in decode / NMS) without the ~1000 launches of the conditioning pass")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying CUDA graphs")
     ap.add_argument("--latency-iters", type=int, default=200, help="batch-1 latency samples (0 = skip)")
     ap.add_argument("--dump-ops", default=None, help="write the plan's op list (kind, name, algorithmic flops/bytes, launch variant) "
@@ -312,9 +315,14 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     def make_engine(scale: str):
+        cache = Path(f"{args.weights_cache}.{scale}.pt") if args.weights_cache else None
+        if cache is not None and cache.exists():
+            return YOLO.from_state_dict(torch.load(cache, weights_only=True), scale).to(dev)
         eng = YOLO.from_state_dict(T.synthetic_state_dict(scale, 80, seed=0), scale).to(dev)
         if not args.skip_condition:
             condition_synthetic_weights(eng, (S, S), batch=2, seed=0)
+            if cache is not None and rank == 0:
+                torch.save({k: v.cpu() for k, v in eng.model.state_dict().items()}, cache)
         return eng
 
     def measure_value(loop: ResidentLoop, steps: int, warmup: int, repeats: int):
@@ -635,10 +643,33 @@ def pre_post_rooflines(eng, net, loop, B, S, pk, mean_cand, mean_det):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE JSON line: everything else that lands on file descriptor 1 while the run lasts (NCCL's version
+    # banner is printed by the C library, past sys.stdout) is sent to stderr, and the descriptor is restored for the line itself
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    buf = []
+    import builtins
+    real_print = builtins.print
+
+    def capture(*a, **k):
+        if k.get("file") in (None, sys.stdout):
+            buf.append(" ".join(str(x) for x in a))
+        else:
+            real_print(*a, **k)
+    builtins.print = capture
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        builtins.print = real_print
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+        for line in buf:
+            real_print(line, flush=True)
 
 
 if __name__ == "__main__":

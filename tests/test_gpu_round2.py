@@ -192,7 +192,8 @@ def test_result_push_two_pipelines_equal_single_pipeline(eng_n):
 
 def _rank_main(rank, world, port, out_dir):
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      NCCL_DEBUG_FILE="/dev/stderr")
     sys.path.insert(0, str(ROOT))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -211,7 +212,7 @@ def _rank_main(rank, world, port, out_dir):
         for _ in range(3):      # several steps: slots are reused under back-pressure
             res = sp.predict(frames)
         modes[mode] = (sp.x.mode, [r.boxes.data.clone() for r in res])
-    local = [r.boxes.data.cpu() for r in eng.predict(frames, conf=0.25, iou=0.7, verbose=False)]
+    local = [r.boxes.data.cpu() for r in eng.predict(frames, conf=0.25, iou=0.7, imgsz=S, verbose=False)]
     torch.save({"modes": modes, "local": local}, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()

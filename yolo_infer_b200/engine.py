@@ -32,6 +32,9 @@ SPLIT_HOST_BATCH = os.environ.get("Y11_SPLIT_HOST", "0") != "0"
 # Y11_FUSE_STEM=0: always run the letterbox kernel, even for frames that need neither resizing nor padding
 FUSE_U8_STEM = os.environ.get("Y11_FUSE_STEM", "1") != "0"
 MAX_CACHED_PIPELINES = 16   # CUDA-graph pipeline instances kept per engine (one per source shape x thresholds)
+# Plans and CUDA graphs are BUILT by one thread at a time, process-wide: a stream capture must not overlap another thread's
+# allocations / launches (the engines of a multi-device predict build their pipelines from one worker thread per device).
+_BUILD_LOCK = threading.RLock()
 PREDICT_DEFAULTS = dict(conf=0.25, iou=0.7, max_det=300, imgsz=640, rect=True, agnostic_nms=False, classes=None,
                         half=False, verbose=True, save=False, show=False, stream=False, batch=1, device=None,
                         multi_label=False, max_nms=30000,
@@ -250,7 +253,7 @@ class YOLO:
             key = key + ("fold", fold_upsample)
         net = self._nets.get(key)
         if net is None:
-            with torch.cuda.device(self.device):
+            with _BUILD_LOCK, torch.cuda.device(self.device):
                 net = CompiledNet(self._engine, self.scale, self.nc, self._packed, B, H, W, self.device, self.conv_impl, chunks,
                                   fold_upsample)
                 net.replica = replica
@@ -268,6 +271,12 @@ class YOLO:
         if getattr(self, "_side", None) is None or self._side.device != self.device:
             self._side = torch.cuda.Stream(self.device)
         return self._side
+
+    def capture_stream(self) -> torch.cuda.Stream:
+        """The stream CUDA-graph captures of this engine run on (one per engine, on the engine's device)."""
+        if getattr(self, "_capture", None) is None or self._capture.device != self.device:
+            self._capture = torch.cuda.Stream(self.device)
+        return self._capture
 
     def shared_copy_stream(self) -> torch.cuda.Stream:
         """One upload stream per engine: host->device copies of concurrently running pipelines stay in submission order."""
@@ -416,7 +425,7 @@ class YOLO:
         if p is None:
             if not hasattr(self, "_pipes"):
                 self._pipes = {}
-            with torch.inference_mode(False):  # static buffers must stay writable from any mode
+            with _BUILD_LOCK, torch.inference_mode(False):  # static buffers must stay writable from any mode
                 p = GraphedPipeline(self, B, h0, w0, imgsz, rect, conf, iou, max_det, agnostic, multi_label, frames, graph, replica,
                                     max_nms, kind, out_flat, push)
             if len(self._pipes) >= MAX_CACHED_PIPELINES:   # dicts keep insertion order: drop the oldest instance
@@ -639,10 +648,13 @@ class YOLO:
         reps = self.__dict__.setdefault("_replicas", {})
         rep = reps.get(index)
         if rep is None:
-            rep = YOLO.from_state_dict(self.model.state_dict(), self.scale, self.nc)
-            rep.names, rep.overrides = self.names, dict(self.overrides)
-            rep.to(f"cuda:{index}")
-            reps[index] = rep
+            with _BUILD_LOCK:
+                rep = reps.get(index)
+                if rep is None:
+                    rep = YOLO.from_state_dict(self.model.state_dict(), self.scale, self.nc)
+                    rep.names, rep.overrides = self.names, dict(self.overrides)
+                    rep.to(f"cuda:{index}")
+                    reps[index] = rep
         return rep
 
     def _predict_multi_device(self, source, devices: List[int], kwargs) -> List[Results]:
@@ -774,7 +786,10 @@ class GraphedPipeline:
             if graph:
                 for fn in self._stage_fns:
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    # an explicit capture stream ON THIS DEVICE: torch.cuda.graph's default capture stream is created once per
+                    # process, on whichever device captured first - a capture for an engine on another GPU would switch the
+                    # current device to that one and launch this device's kernels outside the capture
+                    with torch.cuda.graph(g, stream=eng.capture_stream(), capture_error_mode="thread_local"):
                         fn()
                     self.graphs.append(g)
             if self.chunks > 1:
