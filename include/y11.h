@@ -97,6 +97,19 @@ typedef struct {
   int32_t k, stride, act, out_f32;
   int32_t impl; /* Y11_IMPL_TCGEN05 (product) | Y11_IMPL_SIMT_DEBUG (bring-up cross-check only) */
   int32_t res_mode; /* Y11_RES_POST | Y11_RES_PRE_UP2 (ignored when res.ptr == NULL) */
+  /* FP8 (e4m3) operands - the Blackwell counterpart of the reference's int8 post-training quantizers
+   * (optimization/quantization/quantizers.py:24-310, reached through create_quantizer(...).optimize()):
+   *   in_fp8  != 0 : `in` is an e4m3 tensor (1 byte per channel, views counted in channels = bytes) and `w` holds e4m3 weights
+   *                  [cout][k*k*cin]; the MMA is tcgen05.mma.kind::f8f6f4 (K = 32 per instruction, fp32 accumulate in TMEM);
+   *                  cin % 32 == 0;
+   *   cscale       : fp32 [cout] multiplier of the accumulator BEFORE the bias (activation scale x per-channel weight scale);
+   *                  NULL = 1;
+   *   out_fp8 != 0 : the result (after activation / residual) is multiplied by out_scale (= 1 / activation scale of the
+   *                  consumer) and stored as e4m3 with saturation (cvt.rn.satfinite); cout % 32 == 0; excludes out_f32.
+   * All three default to 0 / NULL = the bf16 path. */
+  int32_t in_fp8, out_fp8;
+  const float* cscale;
+  float out_scale;
 } y11_conv_desc;
 
 /* Stem conv: 3 -> cout, 3x3 stride 2, input is the dense 3-channel bf16 NHWC letterbox output. */

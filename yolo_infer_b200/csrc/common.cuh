@@ -171,6 +171,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with e4m3 operands (kind::f8f6f4: K = 32 bytes per instruction, fp32 accumulate).
+__device__ __forceinline__ void umma_e4m3(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives once all previously issued MMAs of this thread have completed (implies fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -209,6 +218,18 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128.
 __device__ __forceinline__ uint32_t make_idesc_bf16_m128(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// kind::f8f6f4 instruction descriptor: D=f32, A=B=e4m3 (format code 0), both K-major, M=128.
+__device__ __forceinline__ uint32_t make_idesc_e4m3_m128(uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// four fp32 -> four e4m3 bytes (byte i = value i), round to nearest even, saturating at +-448
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  return (uint32_t)lo | ((uint32_t)hi << 16);
 }
 
 // ---- programmatic dependent launch (PDL) ----------------------------------------------------------

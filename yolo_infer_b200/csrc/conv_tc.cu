@@ -95,18 +95,31 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 
 // 16 accumulator columns of one tile row: +bias, (+pre-activation term), SiLU, (+residual), convert, and the swizzled
 // 16-byte stores into the staging row at `dst`; `unit0` = index of the first 16-byte unit of these columns in the row.
+template <bool kQ>  // kQ: the e4m3 paths (dequantisation scale, e4m3 stores) are compiled in; false = the bf16 kernels, unchanged
 __device__ __forceinline__ void epi16(const ConvTcParams& p, const uint32_t (&v)[16], const uint4 r0, const uint4 r1, int n,
                                       uint32_t dst, uint32_t unit0, uint32_t swz) {
   using namespace y11;
   float f[16];
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+  if (kQ && p.cscale) {  // fp8 operands: accumulator * (activation scale * weight scale of the channel) + bias
+    const float4* c4 = reinterpret_cast<const float4*>(p.cscale + n);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 bb = __ldg(b4 + i);
-    f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x;
-    f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
-    f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
-    f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
+    for (int i = 0; i < 4; ++i) {
+      const float4 bb = __ldg(b4 + i), cc = __ldg(c4 + i);
+      f[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]), cc.x, bb.x);
+      f[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), cc.y, bb.y);
+      f[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), cc.z, bb.z);
+      f[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), cc.w, bb.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 bb = __ldg(b4 + i);
+      f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x;
+      f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
+      f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
+      f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
+    }
   }
   const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
   if (p.res_pre) {  // up2(W_up . p) of a folded Upsample+Concat: part of the pre-activation sum
@@ -127,7 +140,12 @@ __device__ __forceinline__ void epi16(const ConvTcParams& p, const uint32_t (&v)
       f[2 * i + 1] += bf16_hi(rr[i]);
     }
   }
-  if (p.out_f32) {
+  if (kQ && p.out_esz == 1) {  // e4m3: 16 channels = ONE 16-byte unit of the staging row
+    const float o = p.oscale;
+    st_shared_v4(dst + (((unit0 >> 1) ^ swz) << 4), pack_e4m3x4(f[0] * o, f[1] * o, f[2] * o, f[3] * o),
+                 pack_e4m3x4(f[4] * o, f[5] * o, f[6] * o, f[7] * o), pack_e4m3x4(f[8] * o, f[9] * o, f[10] * o, f[11] * o),
+                 pack_e4m3x4(f[12] * o, f[13] * o, f[14] * o, f[15] * o));
+  } else if (p.out_f32) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       st_shared_v4(dst + (((2u * unit0 + i) ^ swz) << 4), __float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]),
@@ -144,7 +162,7 @@ __device__ __forceinline__ void epi16(const ConvTcParams& p, const uint32_t (&v)
 // tcgen05.ld in flight, 64-channel store chunks = half the fences / barriers / TMA stores per tile; needs > 64 registers,
 // i.e. 2 CTAs/SM).  The ncu source view of the store-heavy 1x1 layers showed the epilogue chain - tcgen05.wait::ld,
 // fence.proxy.async, the CTA-wide barrier - as the top stall sites with the issue slots half idle.
-template <int kCpw>
+template <int kCpw, bool kQ>
 __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvTcParams& p) {
   using namespace y11;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -350,8 +368,9 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
     // version ran the loop inside `if (lane == 0)`: in a divergent region the compiler cannot prove operands warp-uniform
     // and wrapped every UTCHMMA in an ELECT/R2UR/BRA.U.ANY sequence - ~50 instructions and ~500 cycles per MMA, which
     // made the issue thread the bottleneck of every short-K layer: ncu source view, profiles/r01c_summary.md.)
-    const uint32_t idesc = make_idesc_bf16_m128(p.BN);
-    const int kk_n = p.Cc / 16;
+    const bool f8 = kQ && p.in_fp8;
+    const uint32_t idesc = f8 ? make_idesc_e4m3_m128(p.BN) : make_idesc_bf16_m128(p.BN);
+    const int kk_n = f8 ? p.Cc / 32 : p.Cc / 16;  // one MMA = 32 bytes of K: 16 bf16 or 32 e4m3 elements
     uint32_t stage = 0, phase = 0;  // ring position, advanced incrementally (no div/mod per stage)
     int ti = 0;
     if (p.halo) mbar_wait(bres_bar, 0, p.err_flag, 105);
@@ -421,6 +440,9 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
                   started = 1u;
                 }
               }
+            } else if (f8) {
+              umma_e4m3(tmem_acc, ad, bd, idesc, k != 0);
+              for (int kk = 1; kk < kk_n; ++kk) umma_e4m3(tmem_acc, ad + 2 * kk, bd + 2 * kk, idesc, 1);
             } else {
               umma_bf16(tmem_acc, ad, bd, idesc, k != 0);
               for (int kk = 1; kk < kk_n; ++kk)  // +32 B (= 16 bf16 of K) inside the swizzle row per UMMA
@@ -510,8 +532,8 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
             if (lane == 0) mbar_arrive(acce_bar + 8 * grp);
           }
           const int n = nt * p.BN + col;
-          epi16(p, va, ra0, ra1, n, dst, (uint32_t)(st * kCpw) / 8u, swz);
-          if (two) epi16(p, vb, rb0, rb1, n + 16, dst, (uint32_t)(st * kCpw + 16) / 8u, swz);
+          epi16<kQ>(p, va, ra0, ra1, n, dst, (uint32_t)(st * kCpw) / 8u, swz);
+          if (two) epi16<kQ>(p, vb, rb0, rb1, n + 16, dst, (uint32_t)(st * kCpw + 16) / 8u, swz);
         }
         fence_async_smem();  // my generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
@@ -535,7 +557,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
     const int r = quad * 32 + lane;
     const int tw = r % p.Tw, th = (r / p.Tw) % p.Th, tn = r / (p.Tw * p.Th);
     const bool leader = ew == 0 && lane == 0;
-    const uint32_t esz = p.out_f32 ? 4u : 2u;
+    const uint32_t esz = kQ ? (uint32_t)p.out_esz : (p.out_f32 ? 4u : 2u);
     const int halves = p.cw / kCpw;                        // 1 or 2 warps per row share a chunk
     const uint32_t pitch = (uint32_t)p.cw * esz;           // staging row pitch: 32 / 64 / 128 B
     const uint32_t swz = (r / (128u / pitch)) & (pitch / 16u - 1u);  // TMA SWIZZLE_{32,64,128}B pattern for row r
@@ -585,8 +607,8 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
           tmem_ld_wait();
           if (lane == 0 && (ew == 0 || ew == 3)) TRACE(2 + (ew == 3), 2);
           const int n = nt * p.BN + col;
-          epi16(p, va, ra0, ra1, n, dst, (uint32_t)(half * kCpw) / 8u, swz);
-          if (two) epi16(p, vb, rb0, rb1, n + 16, dst, (uint32_t)(half * kCpw + 16) / 8u, swz);
+          epi16<kQ>(p, va, ra0, ra1, n, dst, (uint32_t)(half * kCpw) / 8u, swz);
+          if (two) epi16<kQ>(p, vb, rb0, rb1, n + 16, dst, (uint32_t)(half * kCpw + 16) / 8u, swz);
           fence_async_smem();  // my generic-proxy smem writes -> visible to the TMA (async proxy)
           if (lane == 0 && (ew == 0 || ew == 3)) TRACE(2 + (ew == 3), 3);
         }
@@ -624,12 +646,17 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
 
 __global__ void __launch_bounds__(kThreads, 3)
 conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcParams p) {
-  conv_tc_body<16>(maps, p);
+  conv_tc_body<16, false>(maps, p);
+}
+// e4m3 variant (operands and / or output in fp8): same body with the quantised paths compiled in; 2 CTAs per SM
+__global__ void __launch_bounds__(kThreads, 2)
+conv_tc_kernel_q(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcParams p) {
+  conv_tc_body<16, true>(maps, p);
 }
 // "fat" epilogue variant: up to 102 registers per thread, 2 CTAs per SM
 __global__ void __launch_bounds__(kThreads, 2)
 conv_tc_kernel_fat(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcParams p) {
-  conv_tc_body<32>(maps, p);
+  conv_tc_body<32, false>(maps, p);
 }
 
 int encode_map(y11_engine* eng, CUtensorMap* m, CUtensorMapDataType dt, int rank, void* base, const cuuint64_t* gdim,
@@ -669,9 +696,13 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   Y11_REQUIRE((d->k == 1 && d->stride == 1) || (d->k == 2 && d->stride == 1) || (d->k == 3 && (d->stride == 1 || d->stride == 2)),
               "conv_tc: unsupported k=%d stride=%d", d->k, d->stride);
   const int cin = d->in.c, cout = d->out.c;
+  const int in_esz = d->in_fp8 ? 1 : 2, out_esz = d->out_f32 ? 4 : d->out_fp8 ? 1 : 2;
   Y11_REQUIRE(cin % 16 == 0 && cout % 16 == 0, "conv_tc: cin=%d cout=%d must be multiples of 16", cin, cout);
-  Y11_REQUIRE(d->in.c_total % 8 == 0 && d->in.c_off % 8 == 0, "conv_tc: input view must be 16-byte aligned");
-  Y11_REQUIRE(d->out.c_off % (d->out_f32 ? 4 : 8) == 0 && d->out.c_total % (d->out_f32 ? 4 : 8) == 0,
+  Y11_REQUIRE(!(d->out_f32 && d->out_fp8), "conv_tc: out_f32 and out_fp8 exclude each other");
+  Y11_REQUIRE(!d->in_fp8 || (cin % 32 == 0 && d->k != 2), "conv_tc: e4m3 input needs cin %% 32 == 0 (cin=%d) and k in {1,3}", cin);
+  Y11_REQUIRE(!d->out_fp8 || cout % 32 == 0, "conv_tc: e4m3 output needs cout %% 32 == 0 (cout=%d)", cout);
+  Y11_REQUIRE((d->in.c_total * in_esz) % 16 == 0 && (d->in.c_off * in_esz) % 16 == 0, "conv_tc: input view must be 16-byte aligned");
+  Y11_REQUIRE((d->out.c_off * out_esz) % 16 == 0 && (d->out.c_total * out_esz) % 16 == 0,
               "conv_tc: output view must be 16-byte aligned");
   Y11_REQUIRE(!d->res.ptr || (d->res.c_off % 8 == 0 && d->res.c_total % 8 == 0), "conv_tc: residual view alignment");
   if (d->stride == 1) Y11_REQUIRE(d->Hout == d->Hin && d->Wout == d->Win, "conv_tc: stride-1 shape mismatch");
@@ -691,8 +722,9 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     const char* e = getenv("Y11_HALO");
     const int mode = tune.lsu >= 0 ? (tune.lsu ? 3 : 0) : (e ? atoi(e) : 3);  // bit 0: 3x3 halo tiles, bit 1: 1x1
     const size_t wbytes = (size_t)d->k * d->k * cin * cout * 2;
-    const bool k3e = d->k == 3 && d->stride == 1 && cin <= 64 && d->Hout >= 32 && d->Wout >= 32;
-    const bool k1e = d->k == 1 && (cin <= 32 || (cin % 32 != 0 && cin <= 112));  // TMA rows would be 32-64 B
+    const bool bf16_io = !d->in_fp8 && !d->out_fp8;   // the cp.async producer / un-swizzled layouts are bf16 only
+    const bool k3e = bf16_io && d->k == 3 && d->stride == 1 && cin <= 64 && d->Hout >= 32 && d->Wout >= 32;
+    const bool k1e = bf16_io && d->k == 1 && (cin <= 32 || (cin % 32 != 0 && cin <= 112));  // TMA rows would be 32-64 B
     // resident-weight budget: 40 KB keeps 2-3 CTAs per SM; up to Y11_LSU_WMAX KB (default 80: the 3x3 64->64 layers, 72 KB) the
     // mode is still OFFERED to the autotuner (1 CTA per SM, 4 halo stages) - those layers are bound by the L2->SM operand
     // traffic of the tap-by-tap TMA mode (9 activation + 9 weight tiles per output tile, ~45 B/clk/SM against the ~43 B/clk/SM
@@ -725,23 +757,29 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     // an explicit bn_max >= 256 (autotuner candidate / cached variant) asks for the wide tile on shorter K as well: the 1x1
     // layers with 256-512 output channels re-read their activation tile once per 128-column N tile otherwise
     const bool forced = tune.bn_max >= 256;
-    if (mode && bn_cap >= 256 && cout % 256 == 0 && cin % 64 == 0 && (k_total >= 1024 || forced)) bn = 256;
+    if (mode && bn_cap >= 256 && cout % 256 == 0 && (cin * in_esz) % 128 == 0 && (k_total >= 1024 || forced)) bn = 256;
   }
   if (p.halo) bn = cout;
   p.BN = bn;
   p.n_tiles = cout / bn;
-  p.Cc = (cin % 64 == 0) ? 64 : (cin % 32 == 0) ? 32 : 16;
+  // K chunk per pipeline stage = one swizzle row: 128 / 64 / 32 bytes of channels
+  if (d->in_fp8) p.Cc = (cin % 128 == 0) ? 128 : (cin % 64 == 0) ? 64 : 32;
+  else p.Cc = (cin % 64 == 0) ? 64 : (cin % 32 == 0) ? 32 : 16;
   p.cin = cin;
+  p.in_fp8 = d->in_fp8 ? 1 : 0;
+  p.out_esz = out_esz;
+  p.cscale = d->cscale;
+  p.oscale = d->out_fp8 ? d->out_scale : 1.0f;
   p.chunks_per_tap = cin / p.Cc;
   p.taps = d->k * d->k;
   p.ksize = d->k;
   p.stride = d->stride;
-  const uint32_t swz_bytes = p.Cc * 2;
+  const uint32_t swz_bytes = p.Cc * in_esz;
   p.sbo = 8 * swz_bytes;
-  p.layout_type = (p.Cc == 64) ? 2u : (p.Cc == 32) ? 4u : 6u;  // SWIZZLE_128B / 64B / 32B
-  const CUtensorMapSwizzle swz = (p.Cc == 64)   ? CU_TENSOR_MAP_SWIZZLE_128B
-                                 : (p.Cc == 32) ? CU_TENSOR_MAP_SWIZZLE_64B
-                                                : CU_TENSOR_MAP_SWIZZLE_32B;
+  p.layout_type = (swz_bytes == 128) ? 2u : (swz_bytes == 64) ? 4u : 6u;  // SWIZZLE_128B / 64B / 32B
+  const CUtensorMapSwizzle swz = (swz_bytes == 128)  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (swz_bytes == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                     : CU_TENSOR_MAP_SWIZZLE_32B;
   p.a_slot = 128u * swz_bytes;
   p.b_slot = ((uint32_t)bn * swz_bytes + 1023u) & ~1023u;
   if (p.halo) {
@@ -781,10 +819,13 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     p.epi_warp = ok && (mode & 1);
     // fat: bf16 outputs only (64 fp32 channels would be 256-byte staging rows), and the chunk grid must tile BN
     p.fat = (mode & 2) && !d->out_f32 && bn > 32 && (bn % 64 == 0 || p.n_tiles == 1);
+    p.quant = (d->in_fp8 || d->out_fp8 || d->cscale) ? 1 : 0;
+    if (p.quant) { p.epi_warp = 0; p.fat = 0; }  // e4m3 kernel: CTA-wide epilogue (32-byte staging rows for e4m3 stores)
   }
   // epilogue chunk width: 32 output channels per TMA store when the tile allows it, else 16 (fp32 rows: 16 in warp mode);
   // 64 in fat mode
   int cw = (bn % 32 == 0) ? 32 : 16;
+  if (d->out_fp8) Y11_REQUIRE(bn % 32 == 0, "conv_tc: e4m3 output needs an N tile that is a multiple of 32 (BN=%d)", bn);
   if (p.epi_warp && d->out_f32) cw = 16;
   if (p.fat) cw = 64;
   if (p.n_tiles > 1) Y11_REQUIRE(bn % cw == 0, "conv_tc: BN=%d not a multiple of the chunk width", bn);
@@ -792,7 +833,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   // staging for the TMA-store epilogue: CTA-wide mode = ring of 2 whole-tile buffers (3 and 4 measured no faster and cost
   // load stages); warp mode = 2 private 32-row buffers per epilogue warp
   p.nstg = 2;
-  const uint32_t opitch_b = (uint32_t)cw * (d->out_f32 ? 4u : 2u);
+  const uint32_t opitch_b = (uint32_t)cw * (uint32_t)out_esz;
   // CTA-wide mode: nstg whole-tile (128-row) buffers; warp mode: nstg private 32-row buffers for each of the 8 warps
   uint32_t staging = (uint32_t)p.nstg * 128u * opitch_b;
   if (p.epi_warp) {
@@ -812,7 +853,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   int cps = 3;
   if (const char* e = getenv("Y11_CTAS_PER_SM")) cps = std::max(1, std::min(4, atoi(e)));
   if (tune.cps > 0) cps = std::max(1, std::min(4, tune.cps));
-  if (p.fat) cps = std::min(cps, 2);  // conv_tc_kernel_fat is compiled for 2 CTAs per SM (up to 102 registers)
+  if (p.fat || p.quant) cps = std::min(cps, 2);  // conv_tc_kernel_fat / _q are compiled for 2 CTAs per SM (up to 102 registers)
   int cols = 64;  // >= 2 accumulator stages of max(BN, 32) columns (a partial last chunk may read up to 16 spare columns)
   while (cols < 2 * bn) cols *= 2;
   while (cps > 1 && cps * cols > 512) --cps;
@@ -846,34 +887,37 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
 
   // activation tensor maps
   const size_t ct = d->in.c_total;
-  __nv_bfloat16* in_base = static_cast<__nv_bfloat16*>(d->in.ptr) + d->in.c_off;
+  const size_t ie = (size_t)in_esz;
+  char* in_base = static_cast<char*>(d->in.ptr) + (size_t)d->in.c_off * ie;
   const cuuint32_t box[4] = {(cuuint32_t)p.Cc, (cuuint32_t)p.Tw, (cuuint32_t)p.Th, (cuuint32_t)p.Tn};
   const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType it = d->in_fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : bf;
   if (d->stride == 1) {
     const cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
-    const cuuint64_t gstr[3] = {ct * 2, ct * 2 * d->Win, ct * 2 * d->Win * d->Hin};
-    if (int e = encode_map(eng, &L->maps.a[0], bf, 4, in_base, gdim, gstr, box, swz)) return e;
+    const cuuint64_t gstr[3] = {ct * ie, ct * ie * d->Win, ct * ie * d->Win * d->Hin};
+    if (int e = encode_map(eng, &L->maps.a[0], it, 4, in_base, gdim, gstr, box, swz)) return e;
     L->maps.a[1] = L->maps.a[2] = L->maps.a[3] = L->maps.a[0];
   } else {
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw) {
         const cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)((d->Win - pw + 1) / 2), (cuuint64_t)((d->Hin - ph + 1) / 2),
                                     (cuuint64_t)d->B};
-        const cuuint64_t gstr[3] = {ct * 2 * 2, ct * 2 * d->Win * 2, ct * 2 * d->Win * d->Hin};
-        __nv_bfloat16* base = in_base + ((size_t)ph * d->Win + pw) * ct;
-        if (int e = encode_map(eng, &L->maps.a[ph * 2 + pw], bf, 4, base, gdim, gstr, box, swz)) return e;
+        const cuuint64_t gstr[3] = {ct * ie * 2, ct * ie * d->Win * 2, ct * ie * d->Win * d->Hin};
+        char* base = in_base + ((size_t)ph * d->Win + pw) * ct * ie;
+        if (int e = encode_map(eng, &L->maps.a[ph * 2 + pw], it, 4, base, gdim, gstr, box, swz)) return e;
       }
   }
   {
     const cuuint64_t K = (cuuint64_t)p.taps * cin;
     const cuuint64_t gdim[2] = {K, (cuuint64_t)cout};
-    const cuuint64_t gstr[1] = {K * 2};
+    const cuuint64_t gstr[1] = {K * ie};
     const cuuint32_t bbox[2] = {(cuuint32_t)p.Cc, (cuuint32_t)bn};
-    if (int e = encode_map(eng, &L->maps.b, bf, 2, const_cast<void*>(d->w), gdim, gstr, bbox, swz)) return e;
+    if (int e = encode_map(eng, &L->maps.b, it, 2, const_cast<void*>(d->w), gdim, gstr, bbox, swz)) return e;
   }
   {
     // output view: 16-channel boxes (32 B bf16 / 64 B fp32 per pixel), swizzled staging, clipped at the tensor edge
-    const size_t esz = d->out_f32 ? 4 : 2;
+    const size_t esz = (size_t)out_esz;
+    const CUtensorMapDataType ot = d->out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : d->out_fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : bf;
     const size_t oct = d->out.c_total;
     char* obase = static_cast<char*>(d->out.ptr) + (size_t)d->out.c_off * esz;
     const cuuint64_t gdim[4] = {(cuuint64_t)cout, (cuuint64_t)d->Wout, (cuuint64_t)d->Hout, (cuuint64_t)d->B};
@@ -881,14 +925,12 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     const cuuint32_t obox[4] = {(cuuint32_t)p.cw, (cuuint32_t)p.Tw, (cuuint32_t)p.Th, (cuuint32_t)p.Tn};
     const uint32_t opitch = (uint32_t)p.cw * (uint32_t)esz;
     const CUtensorMapSwizzle oswz = opitch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : opitch == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-    if (int e = encode_map(eng, &L->maps.out, d->out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : bf, 4, obase, gdim, gstr, obox,
-                           oswz))
+    if (int e = encode_map(eng, &L->maps.out, ot, 4, obase, gdim, gstr, obox, oswz))
       return e;
     L->maps.outq = L->maps.out;
     if (p.epi_warp) {
       const cuuint32_t qbox[4] = {(cuuint32_t)p.cw, (cuuint32_t)qbw, (cuuint32_t)qbh, (cuuint32_t)qbn};
-      if (int e = encode_map(eng, &L->maps.outq, d->out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : bf, 4, obase, gdim, gstr, qbox,
-                             oswz))
+      if (int e = encode_map(eng, &L->maps.outq, ot, 4, obase, gdim, gstr, qbox, oswz))
         return e;
     }
   }
@@ -917,11 +959,12 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   (void)k_iters;
   Y11_OPT_IN_SMEM(conv_tc_kernel, 220 * 1024);
   Y11_OPT_IN_SMEM(conv_tc_kernel_fat, 220 * 1024);
+  Y11_OPT_IN_SMEM(conv_tc_kernel_q, 220 * 1024);
   return 0;
 }
 
 int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t s) {
-  Y11_CHECK_CUDA(y11_launch_pdl(L->p.fat ? conv_tc_kernel_fat : conv_tc_kernel, dim3(L->grid), dim3(kThreads), L->smem_bytes, s,
-                                L->maps, L->p));
+  auto* kern = L->p.quant ? conv_tc_kernel_q : L->p.fat ? conv_tc_kernel_fat : conv_tc_kernel;
+  Y11_CHECK_CUDA(y11_launch_pdl(kern, dim3(L->grid), dim3(kThreads), L->smem_bytes, s, L->maps, L->p));
   return 0;
 }

@@ -46,6 +46,11 @@ struct ConvTcParams {
   int32_t res_pre;  // 1: residual is a half-resolution map added BEFORE the activation (Y11_RES_PRE_UP2)
   const float* bias;
   int32_t act;
+  int32_t quant;         // conv_tc_kernel_q: any of the e4m3 paths below is in use
+  int32_t in_fp8;        // A and B operands are e4m3 (tcgen05.mma.kind::f8f6f4, K = 32 per instruction)
+  int32_t out_esz;       // bytes per output element: 4 (fp32 logits), 2 (bf16), 1 (e4m3)
+  const float* cscale;   // per-output-channel multiplier of the accumulator before the bias (fp8 dequantisation) or nullptr
+  float oscale;          // multiplier before the e4m3 conversion of the output
   uint64_t kmask;       // bit (k_iter * Cc/16 + kk): that 16-element K step has non-zero weights (TMA path, k == 2)
   int32_t kmask_on;
   int* err_flag;
