@@ -543,6 +543,24 @@ def run_ours(args):
             except Exception as e:   # never lose the headline line to an extra
                 line[f"value_{sc}"] = {"error": f"{type(e).__name__}: {e}"}
 
+    # ---- opt-in FP8 (e4m3) mode of the same engine (quant.py): value only, NOT the headline (north_star numerics are bf16) ----
+    if world == 1 and args.extras and not args.no_graph:
+        try:
+            from yolo_infer_b200.quant import calibrate_activation_scales
+            hb = synth_frames(B, S, 4321).to(dev)
+            scales = calibrate_activation_scales(eng, [hb[:8]])
+            eng.enable_fp8(scales)
+            l8 = ResidentLoop(eng, args, B, S, dev, rank, world, "none")
+            ms8, bl8, _, _ = measure_value(l8, min(args.steps, 10), 3, 3)
+            line["value_fp8"] = {"value": B / (ms8 / 1e3), "unit": UNIT, "ms_per_step": ms8, "ms_per_step_blocks": bl8, "e4m3_convs": len(scales),
+                                 "workload": f"YOLO11{args.model}, same loop as `value`, with the {len(scales)} single-reader hidden tensors "
+                                             "(Bottleneck, Detect box towers) stored as e4m3 and their consumers on tcgen05.mma.kind::f8f6f4; "
+                                             "opt-in (create_quantizer('fp8', model).optimize(loader)), parity vs the quantised oracle in tests/test_gpu_fp8.py"}
+            del l8
+            eng.disable_fp8()
+        except Exception as e:
+            line["value_fp8"] = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sd = {k: v.cpu() for k, v in eng.model.state_dict().items()}
         ips, ms, cores, sample = cpu_reference_arm(args, sd, steps=2, warmup=1, batch=min(16, B))

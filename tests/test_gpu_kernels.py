@@ -513,6 +513,60 @@ def test_multi_label_more_candidates_than_max_nms(ctx):
         assert (got[:, :4] - want[b][:, :4]).abs().max() <= 1e-3
 
 
+@pytest.mark.parametrize("case", ["clustered", "ties", "few"])
+def test_progressive_topk_stages_equal_sorting_everything(ctx, case):
+    """Long multi-label candidate lists are processed as score-ordered prefixes (stage 1: exact top 8192, stage 2: top max_nms,
+    then the whole list) - csrc/postprocess.cu `topk_stage`.  Whatever stage finishes an image, the result must be the oracle's
+    (= sorting everything): `clustered` = every box overlaps one of a few sites, so stage 1 keeps fewer than max_det boxes and the
+    image goes on to stage 2; `ties` = tens of thousands of identical scores at the selection threshold (saturated logits), wider
+    than both compact buffers, so the image falls through to the full-list path; `few` = below 8192 rows (stage 1 takes all)."""
+    B, nc = 2, 80
+    g = torch.Generator().manual_seed({"clustered": 1, "ties": 2, "few": 3}[case])
+    dims = [(40, 40), (20, 20), (10, 10)]
+    feats = [(torch.randn(B, h, w, 64 + nc, generator=g) * 2) for (h, w) in dims]
+    for f in feats:
+        if case == "clustered":
+            f[..., :64] = 0.0
+            f[..., 15:64:16] = 12.0           # every side's DFL expectation = 15 bins: huge boxes, all overlapping their neighbours
+            f[..., 64:] -= 3.0
+            f[..., 64 + 10:] = -20.0          # ten live classes: ~20 000 rows per image, a handful of survivors per class
+        elif case == "ties":
+            f[..., 64:] = 30.0                # sigmoid saturates: every (anchor, class) score is exactly 1.0
+        else:
+            f[..., 64:] -= 9.5                # a few thousand pairs above conf 0.001
+    feats = [f.to(ctx.dev) for f in feats]
+    hd = head_desc(feats, nc, B)
+    A = sum(h * w for h, w in dims)
+    y = torch.zeros((B, 84, A), device=ctx.dev)
+    cabi.check(ctx.lib.y11_decode_dense(ctx.h, C.byref(hd), y.data_ptr(), ctx.stream()))
+    conf, iou, max_det, max_nms = 0.001, 0.6, 300, 30000
+    det = torch.zeros((B, max_det, 6), device=ctx.dev)
+    cnt = torch.zeros((B,), dtype=torch.int32, device=ctx.dev)
+    ncand = torch.zeros((B,), dtype=torch.int32, device=ctx.dev)
+    ws = torch.empty(ctx.lib.y11_postprocess_workspace(B, A, nc, 1, max_nms), dtype=torch.uint8, device=ctx.dev)
+    p = cabi.NmsParams(conf, iou, max_det, max_nms, 7680, 0, 1)
+    for _ in range(2):     # twice: the stage buffers and flags are reused from call to call
+        cabi.check(ctx.lib.y11_detect_postprocess(ctx.h, C.byref(hd), C.byref(p), None, det.data_ptr(), cnt.data_ptr(),
+                                                  ncand.data_ptr(), ws.data_ptr(), ws.numel(), ctx.stream()))
+    torch.cuda.synchronize()
+    want = P.non_max_suppression(y.cpu(), conf, iou, multi_label=True, max_det=max_det, max_nms=max_nms)
+    nmin = int(ncand.min())
+    if case == "few":
+        assert 0 < nmin and int(ncand.max()) < 8192
+    elif case == "clustered":
+        assert nmin > 8192
+    else:
+        assert nmin > 65536
+    for b in range(B):
+        n = int(cnt[b])
+        assert n == want[b].shape[0]
+        if case == "clustered":
+            assert n < max_det           # stage 1 could not finish this image
+        got = det[b, :n].cpu()
+        assert torch.equal(got[:, 4:], want[b][:, 4:])
+        assert (got[:, :4] - want[b][:, :4]).abs().max() <= 1e-3
+
+
 @pytest.mark.parametrize("multi_label", [False, True])
 def test_fused_postprocess_matches_oracle_nms(ctx, multi_label):
     """decode -> compaction -> sort -> NMS -> scale_boxes, vs oracle non_max_suppression on the GPU's own dense decode

@@ -399,6 +399,10 @@ struct NmsArgs {
   int* out_count;        // [B]
   int* done_counter;     // result push: device-local counter of finished CTAs (zero between launches) or nullptr
   unsigned* signal;      // result push: system-scope counter bumped once per launch after every result write is visible
+  // progressive top-K (see select_* kernels): the candidate list handed in is the score-ordered PREFIX of a longer list
+  const int* skip;       // [B] or nullptr: image already final (an earlier stage kept max_det boxes) -> leave its results alone
+  int* done_out;         // [B] or nullptr: 1 = this stage's result is final for the image
+  const int* total;      // [B] or nullptr: length of the full candidate list the prefix was selected from
 };
 
 __global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
@@ -418,7 +422,9 @@ __global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
 
   const int b = blockIdx.x, tid = threadIdx.x;
   const size_t ob = (size_t)b * g.cap;
-  const int n = min(g.ncand[b], g.cap);
+  const bool skipped = g.skip && g.skip[b];   // CTA-uniform: an earlier stage already produced this image's final result
+  const bool overflow = g.ncand[b] < 0;        // the selection did not fit its buffer (huge score tie): a later stage takes it
+  const int n = (skipped || overflow) ? 0 : min(g.ncand[b], g.cap);
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   unsigned long long* keys = (np2 <= kSmemKeys) ? s_keys : g.keys + (size_t)b * g.keys_stride;
@@ -553,7 +559,12 @@ __global__ void __launch_bounds__(kNmsThreads) sort_nms_kernel(NmsArgs g) {
     }
     __syncthreads();
   }
-  if (tid == 0) g.out_count[b] = s_nk;
+  if (tid == 0) {
+    if (!skipped && !overflow) g.out_count[b] = s_nk;
+    // final iff max_det boxes were kept, or the prefix was the whole list, or it reached the max_nms ranks NMS may look at
+    if (g.done_out)
+      g.done_out[b] = skipped ? 1 : overflow ? 0 : (s_nk >= g.max_det || !g.total || n >= min(g.total[b], g.max_nms)) ? 1 : 0;
+  }
   if (g.signal) {
     // Result push: out_det / out_count live in another GPU's memory (NVLink peer mapping).  Every CTA makes its writes
     // visible system-wide, the LAST one to finish bumps the consumer's signal - the consumer never sees the counter move
@@ -584,6 +595,137 @@ __global__ void wait_signals_kernel(const volatile unsigned* signals, int n, uns
     }
   }
   __threadfence_system();
+}
+
+// ------------------------------------------------------------------------------------------------ progressive top-K
+// Validation runs NMS at conf 0.001 with multi-label candidates: up to nc * A = 2.7 M (anchor, class) rows per 1280x1280 image.
+// Sorting all of them in one CTA took 300 ms per batch (profiles/r02_post_scale_m1280.json); greedy NMS in score order only
+// ever needs the score-ordered PREFIX it walks before max_det boxes are kept (and never more than max_nms rows).  So:
+//   stage 1: exact top-K1 (K1 = 8192) by a multi-CTA radix select on the monotone score keys (three histogram passes of
+//            11 + 11 + 10 bits), ORDER-PRESERVING compaction of every row with key >= threshold (ties included, so the prefix
+//            is exactly the first `count` rows of the stable descending sort), then the usual sort + NMS CTA on <= 16 K rows;
+//   stage 2: only for images whose stage 1 kept fewer than max_det boxes although rows were left: the same with K = max_nms.
+// Results are bit-identical to sorting everything (same keys, same tie order, same NMS arithmetic).
+constexpr int kSelBits0 = 11, kSelBits1 = 11, kSelBits2 = 10;
+constexpr int kSelBins = 2048;
+constexpr int kSelChunk = 1024;   // candidates per compaction chunk
+
+__device__ __forceinline__ unsigned score_key(float s) {
+  const unsigned u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // monotone map float -> unsigned (same as the sort key's high word)
+}
+
+struct SelState {   // per image
+  unsigned prefix;  // key bits decided so far (left aligned at the current pass)
+  int remaining;    // rows still to take among the keys that match the prefix
+  int all;          // 1: the list has at most K rows - take everything
+};
+
+__global__ void select_init_kernel(const int* __restrict__ ncand, const int* __restrict__ skip, int K, int cap, SelState* __restrict__ st,
+                                   int* __restrict__ hist) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) hist[b * kSelBins + i] = 0;
+  if (threadIdx.x == 0) {
+    const int n = min(ncand[b], cap);
+    st[b].prefix = 0u;
+    st[b].remaining = min(K, n);
+    st[b].all = (n <= K || (skip && skip[b])) ? 1 : 0;
+  }
+}
+
+// pass p: histogram of the next bit field over the rows whose higher bits equal the prefix
+__global__ void __launch_bounds__(256) select_hist_kernel(const float* __restrict__ cscore, const int* __restrict__ ncand,
+                                                          const int* __restrict__ skip, const SelState* __restrict__ st, int cap,
+                                                          int shift, int bits, int hi_shift, int* __restrict__ hist) {
+  __shared__ int s_h[kSelBins];
+  const int b = blockIdx.y;
+  if ((skip && skip[b]) || st[b].all) return;
+  const int n = min(ncand[b], cap);
+  const int i0 = blockIdx.x * 256 * 16;
+  if (i0 >= n) return;
+  for (int i = threadIdx.x; i < kSelBins; i += 256) s_h[i] = 0;
+  __syncthreads();
+  const unsigned prefix = st[b].prefix, mask = (1u << bits) - 1u;
+  const float* sc = cscore + (size_t)b * cap;
+  for (int i = i0 + threadIdx.x; i < min(n, i0 + 256 * 16); i += 256) {
+    const unsigned u = score_key(sc[i]);
+    if (hi_shift >= 32 || (u >> hi_shift) == prefix) atomicAdd(&s_h[(u >> shift) & mask], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (1 << bits); i += 256)
+    if (s_h[i]) atomicAdd(&hist[b * kSelBins + i], s_h[i]);
+}
+
+// pick the bin in which the `remaining`-th largest key lies; one CTA per image; clears the histogram for the next pass
+__global__ void __launch_bounds__(1024) select_find_kernel(SelState* __restrict__ st, int bits, int* __restrict__ hist) {
+  __shared__ int s_c[kSelBins];
+  const int b = blockIdx.x, nb = 1 << bits;
+  if (st[b].all) return;
+  for (int i = threadIdx.x; i < nb; i += 1024) s_c[i] = hist[b * kSelBins + i];
+  __syncthreads();
+  if (threadIdx.x == 0) {   // 2048 bins: a serial walk from the top costs ~2 us, once per pass per image
+    int need = st[b].remaining, bin = nb - 1, above = 0;
+    for (; bin > 0; --bin) {
+      if (above + s_c[bin] >= need) break;
+      above += s_c[bin];
+    }
+    st[b].prefix = (st[b].prefix << bits) | (unsigned)bin;
+    st[b].remaining = need - above;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += 1024) hist[b * kSelBins + i] = 0;
+}
+
+// MODE 0: rows with key >= threshold per chunk.  MODE 1: copy them, in list order, behind the chunk's offset.
+template <int MODE>
+__global__ void __launch_bounds__(256) select_compact_kernel(const float4* __restrict__ cbox, const float* __restrict__ cscore,
+                                                             const float* __restrict__ ccls, const int* __restrict__ ncand,
+                                                             const int* __restrict__ skip, const SelState* __restrict__ st, int cap,
+                                                             int nchunks, int cap2, int* __restrict__ chunk_cnt,
+                                                             const int* __restrict__ chunk_off, float4* __restrict__ sbox,
+                                                             float* __restrict__ sscore, float* __restrict__ scls) {
+  __shared__ int s_warp[8];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (skip && skip[b]) {
+    if (MODE == 0 && threadIdx.x == 0) chunk_cnt[b * nchunks + blockIdx.x] = 0;
+    return;
+  }
+  const int n = min(ncand[b], cap);
+  const unsigned thr = st[b].all ? 0u : st[b].prefix;
+  const size_t ob = (size_t)b * cap;
+  int run = MODE == 1 ? chunk_off[b * nchunks + blockIdx.x] : 0;
+  int total = 0;
+  for (int r = 0; r < kSelChunk / 256; ++r) {   // 4 rounds of 256 rows, in order
+    const int i = blockIdx.x * kSelChunk + r * 256 + threadIdx.x;
+    const bool take = i < n && score_key(cscore[ob + i]) >= thr;
+    const unsigned bal = __ballot_sync(0xffffffffu, take);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, round_total = 0;
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) before += s_warp[w];
+      round_total += s_warp[w];
+    }
+    if (MODE == 1 && take) {
+      const int pos = run + before + __popc(bal & ((1u << lane) - 1u));
+      if (pos < cap2) {
+        const size_t o2 = (size_t)b * cap2 + pos;
+        sbox[o2] = cbox[ob + i];
+        sscore[o2] = cscore[ob + i];
+        scls[o2] = ccls[ob + i];
+      }
+    }
+    run += round_total;
+    total += round_total;
+    __syncthreads();
+  }
+  if (MODE == 0 && threadIdx.x == 0) chunk_cnt[b * nchunks + blockIdx.x] = total;
+}
+
+// after the scan: images whose selection overflowed the compact buffer (a huge score tie) go to the next stage / full path
+__global__ void select_finish_kernel(int* __restrict__ sel_n, const int* __restrict__ sel_raw, int cap2, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && sel_raw[b] > cap2) sel_n[b] = -1;
 }
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -624,8 +766,16 @@ struct Workspace {
   float4* cbox; float* cscore; float* ccls; int* canchor; int* chunk_cnt; int* chunk_off; int* ncand;
   unsigned long long* keys; float4* kbox; float* karea;
   int cap, keys_stride, nchunks;
+  // progressive top-K (lists longer than kSelMinCap rows)
+  float4* sbox; float* sscore; float* scls; int* sel_n; int* sel_raw; int* sel_cnt; int* sel_off; int* hist; int* done_a; int* done_b;
+  SelState* sel_state;
+  int sel_chunks, cap2_max;
   size_t total;
 };
+constexpr int kSelMinCap = 32768;     // shorter candidate lists are sorted directly
+constexpr int kSelK1 = 8192;          // stage-1 prefix length
+constexpr int kSelCap2A = 16384;      // stage-1 compact buffer (room for ties; sorted in shared memory)
+constexpr int kSelCap2B = 65536;      // stage-2 compact buffer (K = max_nms = 30000 by default)
 
 // Candidate capacity per image.  Multi-label (val mode, conf 0.001): room for EVERY (anchor, class) pair up to 4 M, so
 // that "keep the max_nms best by score" (ultralytics non_max_suppression) is exact - the list is sorted by score before
@@ -653,7 +803,51 @@ void carve(Workspace* w, void* base, int B, int cap, int nchunks, int kept_cap) 
   w->keys = (unsigned long long*)take(w->keys_stride > kSmemKeys ? (size_t)B * w->keys_stride * 8 : 0);
   w->kbox = (float4*)take((size_t)B * kept_cap * 16);
   w->karea = (float*)take((size_t)B * kept_cap * 4);
+  const bool sel = cap > kSelMinCap;
+  w->cap2_max = sel ? kSelCap2B : 0;
+  w->sel_chunks = sel ? y11_ceil_div(cap, kSelChunk) : 0;
+  w->sbox = (float4*)take((size_t)B * w->cap2_max * 16);
+  w->sscore = (float*)take((size_t)B * w->cap2_max * 4);
+  w->scls = (float*)take((size_t)B * w->cap2_max * 4);
+  w->sel_cnt = (int*)take((size_t)B * w->sel_chunks * 4);
+  w->sel_off = (int*)take((size_t)B * w->sel_chunks * 4);
+  w->hist = (int*)take(sel ? (size_t)B * kSelBins * 4 : 0);
+  w->sel_state = (SelState*)take(sel ? (size_t)B * sizeof(SelState) : 0);
+  w->sel_n = (int*)take((size_t)B * 4);
+  w->sel_raw = (int*)take((size_t)B * 4);
+  w->done_a = (int*)take((size_t)B * 4);
+  w->done_b = (int*)take((size_t)B * 4);
   w->total = o;
+}
+
+// One stage of the progressive top-K: exact selection of the K best rows (ties at the threshold included) of every image not
+// yet final, order-preserving compaction into the compact buffers (stride cap2), then sort + NMS on that prefix.
+int launch_sort_nms(const NmsArgs& a, int B, cudaStream_t s);
+int topk_stage(const Workspace& w, const NmsArgs& full, int B, int K, int cap2, const int* skip, int* done_out, cudaStream_t s) {
+  select_init_kernel<<<B, 256, 0, s>>>(w.ncand, skip, K, w.cap, w.sel_state, w.hist);
+  const dim3 hgrid((unsigned)y11_ceil_div(w.cap, 256 * 16), (unsigned)B);
+  const int bits[3] = {kSelBits0, kSelBits1, kSelBits2};
+  int shift = 32;
+  for (int pass = 0; pass < 3; ++pass) {
+    const int hi_shift = shift;            // bits above this pass's field must equal the prefix (32 = no constraint)
+    shift -= bits[pass];
+    select_hist_kernel<<<hgrid, 256, 0, s>>>(w.cscore, w.ncand, skip, w.sel_state, w.cap, shift, bits[pass], hi_shift, w.hist);
+    select_find_kernel<<<B, 1024, 0, s>>>(w.sel_state, bits[pass], w.hist);
+  }
+  const dim3 cgrid((unsigned)w.sel_chunks, (unsigned)B);
+  select_compact_kernel<0><<<cgrid, 256, 0, s>>>(w.cbox, w.cscore, w.ccls, w.ncand, skip, w.sel_state, w.cap, w.sel_chunks, cap2, w.sel_cnt,
+                                                 w.sel_off, w.sbox, w.sscore, w.scls);
+  scan_chunks_kernel<<<B, 1024, 0, s>>>(w.sel_cnt, w.sel_off, w.sel_chunks, cap2, w.sel_n, w.sel_raw);
+  select_compact_kernel<1><<<cgrid, 256, 0, s>>>(w.cbox, w.cscore, w.ccls, w.ncand, skip, w.sel_state, w.cap, w.sel_chunks, cap2, w.sel_cnt,
+                                                 w.sel_off, w.sbox, w.sscore, w.scls);
+  select_finish_kernel<<<y11_ceil_div(B, 256), 256, 0, s>>>(w.sel_n, w.sel_raw, cap2, B);
+  Y11_CHECK_CUDA(cudaGetLastError());
+  NmsArgs a = full;
+  a.cbox = w.sbox; a.cscore = w.sscore; a.ccls = w.scls; a.ncand = w.sel_n; a.canchor = nullptr;
+  a.cap = cap2; a.keys_stride = next_pow2(cap2);
+  a.skip = skip; a.done_out = done_out; a.total = w.ncand;
+  a.done_counter = nullptr; a.signal = nullptr;   // the result push is signalled by the LAST launch of the call only
+  return launch_sort_nms(a, B, s);
 }
 
 int launch_sort_nms(const NmsArgs& a, int B, cudaStream_t s) {
@@ -730,6 +924,15 @@ static int postprocess_impl(const y11_head_desc* hd, const y11_nms_params* p, co
   a.class_offset = p->agnostic ? 0.0f : (float)p->max_wh;
   a.max_det = p->max_det; a.max_nms = p->max_nms;
   a.scale = scale; a.out_det = out_det; a.out_keep = nullptr; a.out_count = out_count;
+  a.skip = nullptr; a.done_out = nullptr; a.total = nullptr;
+  a.done_counter = nullptr; a.signal = nullptr;
+  if (!one_pass && cap > kSelMinCap) {
+    // long lists (multi-label validation, A >= 65536): sort + NMS on score-ordered prefixes instead of on everything
+    const int k1 = std::min(kSelK1, p->max_nms);
+    if (int e = topk_stage(w, a, hp.B, k1, kSelCap2A, nullptr, w.done_a, s)) return e;
+    if (int e = topk_stage(w, a, hp.B, std::min(p->max_nms, kSelCap2B / 2), kSelCap2B, w.done_a, w.done_b, s)) return e;
+    a.skip = w.done_b;   // what is still open after both stages (a score tie wider than the buffers): the full list, as before
+  }
   a.done_counter = push ? push->done_counter : nullptr;
   a.signal = push ? push->signal : nullptr;
   if (int e = launch_sort_nms(a, hp.B, s)) return e;
@@ -798,5 +1001,6 @@ extern "C" int y11_nms_batched(y11_handle, const float* boxes, const float* scor
   a.max_det = p->max_det; a.max_nms = p->max_nms;
   a.scale = nullptr; a.out_det = nullptr; a.out_keep = keep; a.out_count = keep_count;
   a.done_counter = nullptr; a.signal = nullptr;
+  a.skip = nullptr; a.done_out = nullptr; a.total = nullptr;
   return launch_sort_nms(a, B, static_cast<cudaStream_t>(s_));
 }

@@ -213,6 +213,9 @@ class YOLO:
         with torch.cuda.device(dev):
             cabi.check(self._lib.y11_create(C.byref(self._engine), dev.index), "y11_create")
             self._packed = pack_weights(self.scale, self.nc, self.model.state_dict(), dev)
+            if getattr(self, "fp8_scales", None):
+                from .network import pack_fp8
+                pack_fp8(self.scale, self.nc, self.model.state_dict(), self._packed, self.fp8_scales, dev)
         return self
 
     def cuda(self) -> "YOLO":
@@ -255,10 +258,30 @@ class YOLO:
         if net is None:
             with _BUILD_LOCK, torch.cuda.device(self.device):
                 net = CompiledNet(self._engine, self.scale, self.nc, self._packed, B, H, W, self.device, self.conv_impl, chunks,
-                                  fold_upsample)
+                                  fold_upsample, getattr(self, "fp8_scales", None))
                 net.replica = replica
             self._nets[key] = net
         return net
+
+    # ---- FP8 (e4m3) mode: the Blackwell counterpart of the reference's int8 post-training quantizers (quant.py) -----------------
+    def enable_fp8(self, act_scales: Dict[str, float]) -> None:
+        """act_scales: {producer conv name -> activation scale of its output tensor} for the edges of `network.fp8_pairs`: those
+        tensors are stored as e4m3(value / scale) and their consumers run with e4m3 weights on tcgen05.mma.kind::f8f6f4.
+        Plans and pipelines are rebuilt on next use."""
+        from .network import pack_fp8
+        self._ensure_device()
+        self.fp8_scales = {k: float(v) for k, v in act_scales.items()}
+        with torch.cuda.device(self.device):
+            for k in [k for k in self._packed if k.endswith("#fp8")]:
+                del self._packed[k]
+            pack_fp8(self.scale, self.nc, self.model.state_dict(), self._packed, self.fp8_scales, self.device)
+        getattr(self, "_pipes", {}).clear()
+        self._nets.clear()
+
+    def disable_fp8(self) -> None:
+        self.fp8_scales = None
+        getattr(self, "_pipes", {}).clear()
+        self._nets.clear()
 
     def _workspace(self, key, nbytes: int) -> torch.Tensor:
         t = self._ws.get(key)

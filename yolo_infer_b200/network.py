@@ -108,6 +108,8 @@ class PackedConv:
     act: int
     depthwise: bool = False
     alg_k: int = 0           # algorithmic K per output (e.g. 9*cin of the 3x3 conv a repacked 2x2 space-to-depth conv stands for)
+    in_fp8: bool = False     # w holds e4m3 bytes (uint8 tensor); the input tensor is e4m3 as well
+    cscale: Optional[torch.Tensor] = None   # fp32 [cout]: input activation scale x per-channel weight scale (fp8 dequantisation)
 
 
 def fold(sd: Dict[str, torch.Tensor], cp: T.ConvParam) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -191,6 +193,51 @@ def pack_weights(scale: str, nc: int, sd: Dict[str, torch.Tensor], device) -> Di
     return packed
 
 
+E4M3_MAX = 448.0
+
+
+def fp8_pairs(scale: str, nc: int = 80) -> List[Tuple[str, str, bool]]:
+    """(producer, consumer, consumer_writes_fp8) for every conv -> conv edge whose intermediate tensor has NO other reader, so that it
+    can live in HBM as e4m3: the hidden tensor of every Bottleneck (cv1 -> cv2) and the two hidden tensors of the Detect box
+    tower (cv2.l.0 -> cv2.l.1 -> cv2.l.2).  Edges whose tensor has fewer than 32 channels (or not a multiple of 32) are left in
+    bf16 (tcgen05.mma.kind::f8f6f4 consumes 32 channels per instruction)."""
+    cps = {c.prefix: c for c in T.conv_params(scale, nc)}
+    out = []
+    for name, c in cps.items():
+        if name.endswith(".cv1") and c.k == 3 and c.g == 1 and ".m." in name:
+            cons = name[:-1] + "2"
+            if cons in cps and cps[cons].k == 3 and c.c2 % 32 == 0:
+                out.append((name, cons, False))
+    for l in range(3):
+        a, b, c = (f"model.23.cv2.{l}.{j}" for j in range(3))
+        if cps[a].c2 % 32 == 0:
+            out.append((a, b, cps[b].c2 % 32 == 0))
+            if cps[b].c2 % 32 == 0:
+                out.append((b, c, False))
+    return out
+
+
+def pack_fp8(scale: str, nc: int, sd: Dict[str, torch.Tensor], packed: Dict[str, PackedConv], act_scales: Dict[str, float], device) -> None:
+    """Adds `<consumer>#fp8` entries: BN-folded weights quantised to e4m3 with one scale per output channel (amax / 448),
+    K-major like the bf16 packing; cscale[n] = activation scale of the input tensor x weight scale of channel n."""
+    cps = {c.prefix: c for c in T.conv_params(scale, nc)}
+    for prod, cons, _ in fp8_pairs(scale, nc):
+        if prod not in act_scales:
+            continue
+        cp = cps[cons]
+        w, b = fold(sd, cp)
+        s_w = (w.abs().amax(dim=(1, 2, 3)) / E4M3_MAX).clamp_min(1e-12)
+        q = (w / s_w.view(-1, 1, 1, 1)).clamp(-E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn)
+        c2p = pad16(cp.c2)
+        wq = torch.zeros((c2p, cp.k, cp.k, cp.c1), dtype=torch.uint8)
+        wq[: cp.c2] = q.permute(0, 2, 3, 1).contiguous().view(torch.uint8)
+        bp, cs = torch.zeros(c2p), torch.zeros(c2p)
+        bp[: cp.c2] = b
+        cs[: cp.c2] = s_w * float(act_scales[prod])
+        packed[f"{cons}#fp8"] = PackedConv(wq.view(c2p, -1).to(device).contiguous(), bp.to(device), cp.c1, c2p, cp.k, cp.s,
+                                           cabi.ACT_SILU if cp.act else cabi.ACT_NONE, in_fp8=True, cscale=cs.to(device))
+
+
 @dataclass
 class V:
     """A channel-slice view of an NHWC buffer."""
@@ -240,12 +287,17 @@ class CompiledNet:
     PREFIX_LAYERS = 5   # yaml layers 0-4 (stem .. first stride-8 C3k2): the high-resolution, memory-heavy part
 
     def __init__(self, engine, scale: str, nc: int, packed: Dict[str, PackedConv], B: int, H: int, W: int, device,
-                 conv_impl: int = cabi.IMPL_TCGEN05, chunks: int = 1, fold_upsample: Optional[bool] = None):
+                 conv_impl: int = cabi.IMPL_TCGEN05, chunks: int = 1, fold_upsample: Optional[bool] = None,
+                 fp8: Optional[Dict[str, float]] = None):
         """chunks > 1: layers 0-4 are emitted once per batch chunk (chunk-major), so that a host-fed pipeline can run chunk c
         while chunk c+1 is still on the PCIe bus (engine.GraphedPipeline); the rest of the network runs on the whole batch."""
         assert H % 32 == 0 and W % 32 == 0, "network input must be a multiple of 32"
         assert chunks >= 1 and B % chunks == 0, (B, chunks)
         self.chunks = chunks
+        # fp8: {producer conv -> activation scale of its output}: those tensors are stored as e4m3 and their consumers run on
+        # tcgen05.mma.kind::f8f6f4 (see fp8_pairs / quant.py); None = the bf16 network
+        self.fp8 = dict(fp8) if (fp8 and conv_impl == cabi.IMPL_TCGEN05 and fold_upsample is not False) else {}
+        self.fp8_out = {p: c_out for p, _, c_out in fp8_pairs(scale, nc)} if self.fp8 else {}
         # fold_upsample=False asks for ONE OP PER REFERENCE CONV (the weight conditioning walks the plan by conv name)
         self.merge_c3k = C3K_MERGE and fold_upsample is not False
         self.folds = upsample_folds(scale) if (FOLD_UPSAMPLE if fold_upsample is None else fold_upsample) else {}
@@ -267,7 +319,7 @@ class CompiledNet:
         tune = AUTOTUNE and conv_impl == cabi.IMPL_TCGEN05
         props = torch.cuda.get_device_properties(device)
         self._tune_key = (f"{props.name}/sm{props.multi_processor_count}/{scale}/nc{nc}/B{B}/{H}x{W}/chunks{chunks}/"
-                          f"fold{int(bool(self.folds))}/merge{int(self.merge_c3k)}/lanes{C3K_LANES}/impl{conv_impl}")
+                          f"fold{int(bool(self.folds))}/merge{int(self.merge_c3k)}/lanes{C3K_LANES}/impl{conv_impl}/fp8{len(self.fp8)}")
         cached = _tune_cache_load().get(self._tune_key) if (tune and TUNE_CACHE) else None
         # stored BY OP NAME (a chunk-major plan has one op of a name per chunk: same variant); a plan whose op names differ
         # from the stored ones is re-tuned
@@ -302,12 +354,23 @@ class CompiledNet:
         cp = pad16(c)
         return V(self._alloc(h, w, cp), 0, cp)
 
+    def _new8(self, h: int, w: int, c: int) -> V:
+        """An e4m3 tensor (one byte per channel; c % 32 == 0)."""
+        assert c % 32 == 0
+        return V(self._alloc(h, w, c, torch.uint8), 0, c)
+
+    def _fp8_edge(self, prod: str, cons: str) -> bool:
+        return prod in self.fp8 and f"{cons}#fp8" in self.packed
+
     # ---- op emitters --------------------------------------------------------------------------
-    def _conv(self, name: str, x: V, out: V, res: Optional[V] = None, out_f32: bool = False, res_mode: int = cabi.RES_POST):
+    def _conv(self, name: str, x: V, out: V, res: Optional[V] = None, out_f32: bool = False, res_mode: int = cabi.RES_POST,
+              out_fp8_scale: Optional[float] = None):
+        """out_fp8_scale: store the result as e4m3(value / out_fp8_scale) (out is a uint8 buffer)."""
         pc = self.packed[name]
         assert not pc.depthwise
         assert x.c == pc.c1, (name, x.c, pc.c1)
         assert out.c == pc.c2, (name, out.c, pc.c2)
+        assert pc.in_fp8 == (x.t.dtype == torch.uint8) and (out_fp8_scale is not None) == (out.t.dtype == torch.uint8), name
         d = cabi.ConvDesc()
         d.inp, d.out = x.cview(), out.cview()
         d.res = res.cview() if res is not None else cabi.NULL_VIEW
@@ -316,6 +379,10 @@ class CompiledNet:
         d.B, d.Hin, d.Win, d.Hout, d.Wout = x.B, x.H, x.W, out.H, out.W
         d.k, d.stride, d.act, d.out_f32, d.impl = pc.k, pc.s, pc.act, int(out_f32), self.conv_impl
         d.res_mode = res_mode
+        d.in_fp8 = int(pc.in_fp8)
+        d.cscale = pc.cscale.data_ptr() if pc.cscale is not None else None
+        d.out_fp8 = int(out_fp8_scale is not None)
+        d.out_scale = 1.0 / out_fp8_scale if out_fp8_scale is not None else 1.0
         var = self._cached_variants.get(name) if self._cached_variants is not None else None
         if var is not None and var[2] > 0 and self.conv_impl == cabi.IMPL_TCGEN05:   # variant chosen by an earlier autotune run
             cabi.check(self.lib.y11_plan_add_conv_tuned(self.plan, C.byref(d), *[int(v) for v in var]), f"plan_add_conv_tuned({name})")
@@ -324,8 +391,8 @@ class CompiledNet:
         px = x.B * out.H * out.W
         res_bytes = 0 if res is None else res.B * res.H * res.W * pc.c2 * 2
         self.ops.append(OpRecord("conv", name, 2.0 * px * pc.c2 * (pc.alg_k or pc.c1 * pc.k * pc.k),
-                                 x.B * x.H * x.W * pc.c1 * 2 + pc.w.numel() * 2 + px * pc.c2 * (4 if out_f32 else 2)
-                                 + res_bytes, out, x, res, res_mode))
+                                 x.B * x.H * x.W * pc.c1 * x.t.element_size() + pc.w.numel() * pc.w.element_size()
+                                 + px * pc.c2 * out.t.element_size() + res_bytes, out, x, res, res_mode))
 
     def _dw(self, name: str, x: V, out: V, res: Optional[V] = None):
         pc = self.packed[name]
@@ -341,6 +408,12 @@ class CompiledNet:
 
     # ---- modules ------------------------------------------------------------------------------
     def _bottleneck(self, p: str, x: V, out: V, e: float):
+        if self._fp8_edge(f"{p}.cv1", f"{p}.cv2"):
+            # the hidden tensor has one writer and one reader: it lives in HBM as e4m3 and cv2 runs on the fp8 tensor-core path
+            hidden = self._new8(x.H, x.W, int(out.c * e))
+            self._conv(f"{p}.cv1", x, hidden, out_fp8_scale=self.fp8[f"{p}.cv1"])
+            self._conv(f"{p}.cv2#fp8", hidden, out, res=x)
+            return
         hidden = self._new(x.H, x.W, int(out.c * e))
         self._conv(f"{p}.cv1", x, hidden)
         self._conv(f"{p}.cv2", hidden, out, res=x)  # shortcut: c1 == c2 everywhere in YOLO11
@@ -452,11 +525,13 @@ class CompiledNet:
         head = self._alloc(x.H, x.W, self.no, torch.float32)
         self.head.append(head)
         cabi.check(self.lib.y11_plan_set_lane(self.plan, lane_box), "plan_set_lane")
-        t1 = self._new(x.H, x.W, c2)
-        t2 = self._new(x.H, x.W, c2)
-        self._conv(f"{p}.cv2.{l}.0", x, t1)
-        self._conv(f"{p}.cv2.{l}.1", t1, t2)
-        self._conv(f"{p}.cv2.{l}.2", t2, V(head, 0, 64), out_f32=True)
+        n0, n1, n2 = (f"{p}.cv2.{l}.{j}" for j in range(3))
+        q01, q12 = self._fp8_edge(n0, n1), self._fp8_edge(n1, n2)
+        t1 = self._new8(x.H, x.W, c2) if q01 else self._new(x.H, x.W, c2)
+        t2 = self._new8(x.H, x.W, c2) if q12 else self._new(x.H, x.W, c2)
+        self._conv(n0, x, t1, out_fp8_scale=self.fp8[n0] if q01 else None)
+        self._conv(n1 + "#fp8" if q01 else n1, t1, t2, out_fp8_scale=self.fp8[n1] if q12 else None)
+        self._conv(n2 + "#fp8" if q12 else n2, t2, V(head, 0, 64), out_f32=True)
         cabi.check(self.lib.y11_plan_set_lane(self.plan, lane_cls), "plan_set_lane")
         u1 = self._new(x.H, x.W, x.c)
         u2 = self._new(x.H, x.W, c3)
