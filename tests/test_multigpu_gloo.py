@@ -59,3 +59,51 @@ def test_gather_equals_single_process_world2(n_items):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _exchange_worker(rank, world, port, q):
+    """ResultExchange in its collective (fallback) mode on gloo/CPU: slots, out_flat, the gather and split_flat - the same host logic
+    bench.py and parallel.ShardedPredictor drive on NCCL when the NVLink result push is unavailable."""
+    from yolo_infer_b200.parallel import ResultExchange
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B, MD, slots = 3, 4, 2
+    n_flat = B * MD * 6 + B
+    x = ResultExchange(None, None, n_flat, slots, torch.device("cpu"), mode="nccl")
+    ok = x.mode == "nccl" and x.world == world and x.push_ptrs(0) is None
+    x.arm()
+    gathered = torch.empty(world * n_flat)
+    for step in range(4):
+        slot = step % slots
+        g = torch.Generator().manual_seed(100 * step + rank)
+        det = torch.rand(B, MD, 6, generator=g)
+        cnt = torch.randint(0, MD + 1, (B,), generator=g, dtype=torch.int32)
+        x.before_produce(slot, None, backpressure=True)
+        x.out_flat(slot).copy_(torch.cat((det.reshape(-1), cnt.view(torch.float32))))
+        x.after_produce(slot, None, gathered)
+        x.wait_all(slot, None)
+        gd, gc = split_flat(gathered.view(world, -1), B, MD)
+        for r in range(world):
+            g = torch.Generator().manual_seed(100 * step + r)
+            d = torch.rand(B, MD, 6, generator=g)
+            c = torch.randint(0, MD + 1, (B,), generator=g, dtype=torch.int32)
+            ok = ok and torch.equal(gd[r * B:(r + 1) * B], d) and torch.equal(gc[r * B:(r + 1) * B], c)
+        x.release(slot)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, bool(ok)))
+
+
+def test_result_exchange_collective_mode_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

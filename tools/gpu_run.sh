@@ -1,7 +1,22 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_fp8.py tests/test_gpu_kernels.py -m gpu -q -s --timeout 600 -rf -k "fp8 or progressive or multi_label or nms" > gpurun_out/c9_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/c9_pytest.log
-grep -E "passed|failed|FAILED|FP8:|Error|error" gpurun_out/c9_pytest.log | head -30
-timeout 600 python tools/post_scale.py > gpurun_out/r02_post_scale_m1280_topk.json 2> gpurun_out/c9_post.err; cat gpurun_out/r02_post_scale_m1280_topk.json; tail -3 gpurun_out/c9_post.err
-timeout 600 python tools/post_scale.py --cls-prior 0.00005 > gpurun_out/r02_post_scale_m1280_sparse_topk.json 2>> gpurun_out/c9_post.err; cat gpurun_out/r02_post_scale_m1280_sparse_topk.json
+N=$(nvidia-smi -L | wc -l)
+echo "gpus: $N"
+for n in 8 4 2; do
+  if [ $n -le $N ]; then
+    timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/r02_bench_yolo11s_b64_${n}gpu.json 2> gpurun_out/c11_bench_${n}gpu.err; echo "N=$n rc=$?"
+    python -c "
+import json
+d=json.loads([l for l in open('gpurun_out/r02_bench_yolo11s_b64_${n}gpu.json') if l.startswith('{')][-1])
+print('N=${n}: value',round(d['value']),'ms',round(d['ms_per_step'],3),'blocks',[round(x,3) for x in d['ms_per_step_blocks']],'ranks',[round(x,3) for x in d['ms_per_step_per_rank']])
+print('   e2e',round(d['e2e']['value']),'gather',d['gather']['mode'],'no_gather_ms',d['gather'].get('no_gather_ms_per_step'),'clocks',d['clocks']['sm_mhz'],d['clocks']['reasons'])
+"
+  fi
+done
+timeout 500 python bench.py --extras "" --no-cpu-baseline > gpurun_out/c11_bench_1gpu.json 2> gpurun_out/c11_bench_1gpu.err
+python -c "
+import json
+d=json.load(open('gpurun_out/c11_bench_1gpu.json'))
+print('N=1: value',round(d['value']),'ms',round(d['ms_per_step'],3),'blocks',[round(x,3) for x in d['ms_per_step_blocks']],'e2e',round(d['e2e']['value']))
+"

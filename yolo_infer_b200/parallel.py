@@ -149,10 +149,13 @@ class ResultExchange:
 
     def arm(self) -> None:
         """After every pipeline has been built (their warm-up passes bumped the signals): remember the signal values."""
-        torch.cuda.synchronize(self.device)
+        cuda = torch.device(self.device).type == "cuda"
+        if cuda:
+            torch.cuda.synchronize(self.device)
         if self.world > 1:
             dist.barrier(group=self.group)
-            torch.cuda.synchronize(self.device)
+            if cuda:
+                torch.cuda.synchronize(self.device)
         words = self.buf.view(torch.int32)
         self.base = words[self.o_sig:self.o_sig + self.slots * self.world].cpu().tolist()
         self.base_free = words[self.o_free:self.o_free + self.slots].cpu().tolist()
