@@ -405,16 +405,17 @@ def run_ours(args):
     if world == 1:
         def step_e2e(i: int):
             res = eng.predict(host_batches[i % loop.NROT], conf=CONF, iou=IOU, max_det=MAX_DET, imgsz=S, verbose=False)
-            return [r.cpu().boxes.data for r in res]   # Results.cpu(): host rows of every image
-        e2e_api = ("YOLO.predict(pinned uint8 [B,H,W,3] host tensor) -> List[Results] -> Results.cpu(); H2D in 4 chunks overlapped "
-                   "with layers 0-4 of the previous chunk, one D2H of all results")
+            first = res[0].cpu().boxes.data                 # a Results as the reference's callers take it ...
+            return res.det_host, res.counts, first          # ... and the whole batch's host rows (the call's one D2H)
+        e2e_api = ("YOLO.predict(pinned uint8 [B,H,W,3] host tensor) -> sequence of Results (built on access; the batch's host rows "
+                   "are read as one tensor); H2D in 4 chunks overlapped with layers 0-4 of the previous chunk, one D2H of all results")
     else:
         from yolo_infer_b200.parallel import ShardedPredictor
         sp = ShardedPredictor(eng, B, S, S, S, True, CONF, IOU, MAX_DET, mode=args.gather)
 
         def step_e2e(i: int):
             res = sp.predict(host_batches[i % loop.NROT])   # rank 0: Results of the GLOBAL batch (world * B images)
-            return [r.boxes.data for r in res]
+            return (res.det_host, res.counts, res[0].boxes.data) if len(res) else ()
         e2e_api = (f"parallel.ShardedPredictor.predict(pinned uint8 [B,H,W,3] local shard) on every rank; rank 0 returns the Results of "
                    f"all {world * B} images (gather = {sp.x.mode}) inside the timed region")
     for i in range(min(args.warmup, 3)):
@@ -430,7 +431,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * B / (float(t2) / 1e3)
-    d2h = (sum(o.numel() * 4 for o in out) + len(out) * 4) if out else 0
+    d2h = (out[0].numel() * 4 + len(out[1]) * 4) if out else 0
     if world > 1:
         t3 = torch.tensor([float(d2h)], device=dev)
         dist.all_reduce(t3, op=dist.ReduceOp.MAX)

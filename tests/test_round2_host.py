@@ -159,3 +159,16 @@ def test_harness_system_probes_keep_the_reference_keys():
     s = SpeedBenchmark._calculate_summary([{"fps": 10.0, "throughput": 40.0}, {"fps": 20.0, "throughput": 20.0}])
     assert s == {"best_fps": 20.0, "worst_fps": 10.0, "avg_fps": 15.0, "best_throughput": 40.0, "worst_throughput": 20.0,
                  "avg_throughput": 30.0, "total_configurations": 2}
+
+
+def test_results_batch_is_a_lazy_sequence_of_results():
+    from yolo_infer_b200.results import ResultsBatch
+    det = torch.arange(3 * 4 * 6, dtype=torch.float32).view(3, 4, 6)
+    rb = ResultsBatch(None, det, [2, 0, 4], {0: "a"}, (480, 640), paths=["p0", "p1", "p2"])
+    assert len(rb) == 3 and not rb._items                        # nothing built yet
+    assert len(rb[0].boxes) == 2 and rb[0].path == "p0" and rb[0].orig_shape == (480, 640)
+    assert not rb[1].boxes and len(rb[-1].boxes) == 4 and rb[0] is rb[0]
+    assert [len(r.boxes) for r in rb] == [2, 0, 4] and [len(r.boxes) for r in rb[1:]] == [0, 4]
+    assert torch.equal(rb[2].boxes.xyxy, det[2, :, :4]) and torch.equal(rb[2].cpu().boxes.conf, det[2, :, 4])
+    with pytest.raises(IndexError):
+        rb[3]

@@ -21,7 +21,7 @@ import torch
 from . import _cabi as cabi
 from . import topology as T
 from .network import CompiledNet, pack_weights
-from .results import Results
+from .results import Results, ResultsBatch
 
 logger = logging.getLogger(__name__)
 
@@ -501,7 +501,9 @@ class YOLO:
         classes = torch.as_tensor(list(args["classes"])) if args["classes"] is not None else None
 
         def finish(det, det_h, counts, speed, orig_imgs, paths, shapes):
-            """One Results per image; rows are sliced on first access (Results/Boxes keep a view descriptor)."""
+            """One Results per image, built on first access (ResultsBatch); rows are sliced lazily too."""
+            if classes is None:
+                return ResultsBatch(det, det_h, counts, self.names, shapes, paths, orig_imgs, speed)
             results = []
             for i, n in enumerate(counts):
                 img_i = orig_imgs[i] if orig_imgs is not None else None

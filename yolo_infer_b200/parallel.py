@@ -227,7 +227,8 @@ class ShardedPredictor:
                                                out_flat=self.x.out_flat(s), push=self.x.push_ptrs(s)))
             self.gathered = (torch.empty((self.x.world * n_flat,), dtype=torch.float32, device=eng.device)
                              if self.x.mode == "nccl" else None)
-            self.pin = torch.empty((self.x.world, n_flat), dtype=torch.float32).pin_memory() if self.x.rank == 0 else None
+            self.pins = ([torch.empty((self.x.world, n_flat), dtype=torch.float32).pin_memory() for _ in range(slots)]
+                         if self.x.rank == 0 else None)
         self.x.arm()
         self.step = 0
 
@@ -249,15 +250,14 @@ class ShardedPredictor:
             if x.rank != 0:
                 st.synchronize()
                 return []
-            self.pin.copy_(src, non_blocking=True)
+            pin = self.pins[slot]
+            pin.copy_(src, non_blocking=True)
             x.release(slot)
             st.synchronize()
-            det, count = split_flat(self.pin, self.B, self.max_det)
-            counts = count.tolist()
-            det_h = det.clone()
-            speed = {"preprocess": 0.0, "inference": 0.0, "postprocess": 0.0}
-            return [Results(None, f"image{i}.jpg", eng.names, det_h[i, :n], (self.h0, self.w0), speed, det_h[i, :n])
-                    for i, n in enumerate(counts)]
+            det, count = split_flat(pin, self.B, self.max_det)     # views of the slot's pinned buffer: valid until the slot's next use
+            from .results import ResultsBatch
+            return ResultsBatch(None, det, count.tolist(), eng.names, (self.h0, self.w0),
+                                speed={"preprocess": 0.0, "inference": 0.0, "postprocess": 0.0})
 
 
 def C_void(v: int):

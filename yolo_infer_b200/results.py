@@ -9,7 +9,8 @@ rows sorted by confidence descending; n <= max_det.  Tensors stay on the device 
 """
 from __future__ import annotations
 
-from typing import Dict, Iterator, Optional, Tuple
+from collections.abc import Sequence
+from typing import Dict, Iterator, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -161,3 +162,44 @@ class Results:
 
     def __repr__(self) -> str:
         return f"Results(path={self.path!r}, orig_shape={self.orig_shape}, boxes={len(self.boxes)})"
+
+
+
+class ResultsBatch(Sequence):
+    """What `predict` returns for a fixed-shape batch: a read-only sequence of `Results` (``len``, indexing, slicing, iteration -
+    everything the reference's callers do with the list ultralytics returns: ``results[0]``, ``for r in results``) whose items are
+    built on first access.  The batch's detections live in ONE device tensor and ONE host mirror (the call's single D2H), so a
+    throughput loop over hundreds of images does not pay for hundreds of Python objects it never looks at; `det` / `counts`
+    give the whole batch at once (rows beyond counts[i] are stale)."""
+
+    def __init__(self, det: Optional[torch.Tensor], det_host: torch.Tensor, counts: List[int], names: Dict[int, str],
+                 orig_shapes, paths=None, orig_imgs=None, speed: Optional[Dict[str, float]] = None):
+        self.det, self.det_host, self.counts, self.names = det, det_host, counts, names
+        self._shapes, self._paths, self._imgs, self.speed = orig_shapes, paths, orig_imgs, speed
+        self._items: Dict[int, Results] = {}
+
+    def __len__(self) -> int:
+        return len(self.counts)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        r = self._items.get(i)
+        if r is None:
+            shape = self._shapes[i] if isinstance(self._shapes, list) else self._shapes
+            path = self._paths[i] if self._paths is not None else f"image{i}.jpg"
+            img = self._imgs[i] if self._imgs is not None else None
+            n = self.counts[i]
+            if self.det is not None:
+                r = Results(img, path, self.names, None, shape, self.speed, None, (self.det, self.det_host, i, n))
+            else:
+                r = Results(img, path, self.names, self.det_host[i, :n], shape, self.speed, self.det_host[i, :n])
+            self._items[i] = r
+        return r
+
+    def __repr__(self) -> str:
+        return f"ResultsBatch(n={len(self)}, detections={sum(self.counts)})"
