@@ -381,3 +381,23 @@ def test_val_rect_path_matches_the_oracle_val_path(oracle_models, tmp_path):
     assert m.n_images == len(sizes) and m.n_labels == n_lab
     assert abs(m.box.map50 - m50) <= 0.03 and abs(m.box.map - m5095) <= 0.03
     assert m.box.map50 > 0.8
+
+
+def test_stream_mode_equals_one_call_at_a_time(eng_n):
+    """`predict(batches, stream=True)`: a generator with two batches in flight; every batch's results equal the synchronous call's,
+    in order, for an odd number of batches, pinned-host and device sources."""
+    eng, _ = eng_n
+    g = torch.Generator().manual_seed(8)
+    batches = [torch.randint(0, 256, (16, 160, 256, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(5)]
+    want = [[r.boxes.data.cpu().clone() for r in eng.predict(b, conf=0.3, verbose=False)] for b in batches]
+    for src in (batches, [b.cuda() for b in batches]):
+        got = []
+        for res in eng.predict(iter(src), stream=True, conf=0.3, verbose=False):
+            assert len(res) == 16
+            got.append([r.boxes.data.cpu().clone() for r in res])
+        assert len(got) == 5
+        for a, b in zip(got, want):
+            for x, y in zip(a, b):
+                assert torch.equal(x, y)
+    with pytest.raises(ValueError):
+        list(eng.predict([torch.zeros(2, 3, 64, 64)], stream=True))
