@@ -93,6 +93,55 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// tcgen05.mma with the two shared-memory descriptors given as (low, high) 32-bit halves: the low word (start address, LBO)
+// is what changes between UMMAs, the high word (SBO, version, swizzle mode) is a per-kernel constant.
+template <bool kF8>
+__device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                          uint32_t accumulate) {
+  if (kF8) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// one TMA pipeline stage = KK UMMAs, +32 B (= 2 descriptor units) inside the swizzle row per UMMA
+template <int KK, bool kQ>
+__device__ __forceinline__ void tma_issue(uint32_t tmem_acc, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc0,
+                                          bool f8) {
+  if (kQ && f8) {
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) umma_lohi<true>(tmem_acc, a_lo + 2u * kk, hi, b_lo + 2u * kk, hi, idesc, kk ? 1u : acc0);
+  } else {
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) umma_lohi<false>(tmem_acc, a_lo + 2u * kk, hi, b_lo + 2u * kk, hi, idesc, kk ? 1u : acc0);
+  }
+}
+// one 3x3 halo tile with ONE weight chunk per tap (cin = 16 * KK): 9 * KK UMMAs with compile-time tap offsets
+template <int KK>
+__device__ __forceinline__ void halo3_issue(uint32_t tmem_acc, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t b_step,
+                                            uint32_t k_step, uint32_t idesc) {
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const uint32_t at = a_lo + (uint32_t)((tap / 3) * 10 + tap % 3);
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk)
+      umma_lohi<false>(tmem_acc, at + (uint32_t)kk * k_step, a_hi, b_lo + 2u * kk, b_hi, idesc, (tap | kk) ? 1u : 0u);
+    b_lo += b_step;
+  }
+}
+
 // 16 accumulator columns of one tile row: +bias, (+pre-activation term), SiLU, (+residual), convert, and the swizzled
 // 16-byte stores into the staging row at `dst`; `unit0` = index of the first 16-byte unit of these columns in the row.
 template <bool kQ>  // kQ: the e4m3 paths (dequantisation scale, e4m3 stores) are compiled in; false = the bf16 kernels, unchanged
@@ -368,92 +417,112 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
     // version ran the loop inside `if (lane == 0)`: in a divergent region the compiler cannot prove operands warp-uniform
     // and wrapped every UTCHMMA in an ELECT/R2UR/BRA.U.ANY sequence - ~50 instructions and ~500 cycles per MMA, which
     // made the issue thread the bottleneck of every short-K layer: ncu source view, profiles/r01c_summary.md.)
+    // Round 2 (timeline of this warp, tools/trace_narrow.py): the generic loops - runtime K-step counts, descriptors rebuilt
+    // from constant-bank parameters per stage, the kmask / e4m3 branches inside the K loop - still cost 150-250 cycles per
+    // UMMA (2 UMMAs + commit of a 32-channel stage: 500 cycles; the 18 UMMAs of a 3x3 32->16 halo tile: 3300), i.e. the issue
+    // thread was slower than the tensor pipe (64 cycles for a 128x128x16 UMMA).  The loops are now specialised on the number
+    // of UMMAs per stage (compile-time unrolled, immediate descriptor offsets) and carry the 32-bit descriptor LOW words as
+    // running warp-uniform values; the HIGH words are per-kernel constants.  Same issue order -> bit-identical results.
     const bool f8 = kQ && p.in_fp8;
     const uint32_t idesc = f8 ? make_idesc_e4m3_m128(p.BN) : make_idesc_bf16_m128(p.BN);
     const int kk_n = f8 ? p.Cc / 32 : p.Cc / 16;  // one MMA = 32 bytes of K: 16 bf16 or 32 e4m3 elements
     uint32_t stage = 0, phase = 0;  // ring position, advanced incrementally (no div/mod per stage)
     int ti = 0;
     if (p.halo) mbar_wait(bres_bar, 0, p.err_flag, 105);
-    const uint64_t bd_res = make_umma_desc(tiles_base, p.sbo, p.layout_type);
-    const uint32_t b_step = p.b_slot >> 4, k_step = (2u * p.a_lbo) >> 4;
-    for (;; ++ti) {
-      if (tq_take((uint32_t)ti) < 0) break;
-      const int as = ti & 1;
-      mbar_wait(acce_bar + 8 * as, ((ti >> 1) & 1) ^ 1, p.err_flag, 104);  // epilogue has drained this accumulator stage
-      if (lane == 0) TRACE(1, 1);
-      const uint32_t tmem_acc = tmem_base + as * acc_stride;
-      if (p.halo) {
-        mbar_wait(full_bar + 8 * stage, phase, p.err_flag, 102);
+    const uint32_t n_stages = (uint32_t)p.stages;
+    const uint32_t stage_units = stage_bytes >> 4;
+    // swizzled K-major descriptor (weights everywhere, activations in TMA mode): lo = addr>>4 | LBO(1)<<16, hi = SBO>>4 | version | layout
+    const uint32_t sw_hi = (p.sbo >> 4) | (1u << 14) | (p.layout_type << 29);
+    const uint32_t ring_lo0 = ((ring_base & 0x3FFFFu) >> 4) | (1u << 16);
+    if (p.halo) {
+      // un-swizzled activation tile: lo = addr>>4 | (LBO>>4)<<16, hi = SBO>>4 | version
+      const uint32_t a_hi = (p.a_sbo >> 4) | (1u << 14);
+      const uint32_t a_lo0 = ((ring_base & 0x3FFFFu) >> 4) | ((p.a_lbo >> 4) << 16);
+      const uint32_t b_lo0 = ((tiles_base & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t b_step = p.b_slot >> 4, k_step = (2u * p.a_lbo) >> 4;
+      const int cpt = p.chunks_per_tap;
+      const int mode = (p.pad && cpt == 1 && !f8) ? kk_n : 0;  // 1 / 2 / 4: specialised 3x3 loop (cin = 16 / 32 / 64)
+      uint32_t a_lo = a_lo0, fb = full_bar, eb = empty_bar;
+      for (;; ++ti) {
+        if (tq_take((uint32_t)ti) < 0) break;
+        const int as = ti & 1;
+        mbar_wait(acce_bar + 8 * as, ((ti >> 1) & 1) ^ 1, p.err_flag, 104);  // epilogue has drained this accumulator stage
+        if (lane == 0) TRACE(1, 1);
+        const uint32_t tmem_acc = tmem_base + as * acc_stride;
+        mbar_wait(fb, phase, p.err_flag, 102);
         if (lane == 0) TRACE(1, 2);
         fence_async_smem();  // cp.async wrote through the generic proxy; the MMA reads through the async proxy
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t ad0 = make_umma_desc_interleaved(ring_base + stage * stage_bytes, p.a_lbo, p.a_sbo);
-          if (p.pad) {
-            // 3x3: nine taps, fully unrolled with compile-time offsets.  The issue thread runs ~10 cycles per dependent
-            // instruction: every instruction saved per MMA is worth it.  cin in {16, 32, 64} is ONE weight chunk per tap
-            // (Cc == cin); cin = 48 (the 1.5x-wide scale) is three 16-channel chunks, each with its own resident weight slot.
-            const int cpt = p.chunks_per_tap;
-#pragma unroll
+          // 3x3: tap (kh, kw) = the halo tile shifted by kh rows of (Tw+2) = 10 pixels and kw pixels, in 16-byte units; the next
+          // 16 channels = two 8-channel planes further (k_step) / +32 B in the weight row
+          if (mode == 2) halo3_issue<2>(tmem_acc, a_lo, a_hi, b_lo0, sw_hi, b_step, k_step, idesc);
+          else if (mode == 4) halo3_issue<4>(tmem_acc, a_lo, a_hi, b_lo0, sw_hi, b_step, k_step, idesc);
+          else if (mode == 1) halo3_issue<1>(tmem_acc, a_lo, a_hi, b_lo0, sw_hi, b_step, k_step, idesc);
+          else if (p.pad) {
+            // cin = 48 (the 1.5x-wide scale): three 16-channel weight chunks per tap, each with its own resident weight slot
             for (int tap = 0; tap < 9; ++tap) {
-              // tap (kh, kw) = the halo tile shifted by kh rows of (Tw+2) = 10 pixels and kw pixels, in 16-byte units
-              const uint64_t ad = ad0 + (uint32_t)((tap / 3) * 10 + tap % 3);
-              const uint64_t bd = bd_res + (uint32_t)(tap * cpt) * b_step;
-              umma_bf16(tmem_acc, ad, bd, idesc, tap != 0);
-              for (int kk = 1; kk < kk_n; ++kk)  // next 16 channels = two 8-channel planes further / +32 B in the weight row
-                umma_bf16(tmem_acc, ad + kk * k_step, bd + 2 * kk, idesc, 1);
-              for (int c = 1; c < cpt; ++c)      // further weight chunks of this tap: Cc channels = Cc/8 planes further
+              const uint32_t at = a_lo + (uint32_t)((tap / 3) * 10 + tap % 3);
+              for (int c = 0; c < cpt; ++c)
                 for (int kk = 0; kk < kk_n; ++kk)
-                  umma_bf16(tmem_acc, ad + (uint32_t)(c * kk_n + kk) * k_step, bd + (uint32_t)c * b_step + 2 * kk, idesc, 1);
+                  umma_lohi<false>(tmem_acc, at + (uint32_t)(c * kk_n + kk) * k_step, a_hi,
+                                   b_lo0 + (uint32_t)(tap * cpt + c) * b_step + 2u * kk, sw_hi, idesc, (tap | c | kk) != 0);
             }
           } else {
             // 1x1: K = cin in weight chunks of Cc channels
-            for (int c = 0; c < p.chunks_per_tap; ++c) {
-              const uint64_t ad = ad0 + (uint32_t)(c * kk_n) * k_step;
-              const uint64_t bd = bd_res + (uint32_t)c * b_step;
-              umma_bf16(tmem_acc, ad, bd, idesc, c != 0);
-              for (int kk = 1; kk < kk_n; ++kk) umma_bf16(tmem_acc, ad + kk * k_step, bd + 2 * kk, idesc, 1);
-            }
+            for (int c = 0; c < cpt; ++c)
+              for (int kk = 0; kk < kk_n; ++kk)
+                umma_lohi<false>(tmem_acc, a_lo + (uint32_t)(c * kk_n + kk) * k_step, a_hi, b_lo0 + (uint32_t)c * b_step + 2u * kk,
+                                 sw_hi, idesc, (c | kk) != 0);
           }
-          umma_commit(empty_bar + 8 * stage);
+          umma_commit(eb);
           umma_commit(accf_bar + 8 * as);
         }
         __syncwarp();
         if (lane == 0) TRACE(1, 3);
-        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
-      } else {
+        if (++stage == n_stages) { stage = 0; phase ^= 1; a_lo = a_lo0; fb = full_bar; eb = empty_bar; }
+        else { a_lo += stage_units; fb += 8; eb += 8; }
+      }
+    } else {
+      const uint32_t b_off = p.a_slot >> 4;  // weights of a stage follow its activation box
+      const int mode = p.kmask_on ? 0 : kk_n;
+      uint32_t a_lo = ring_lo0, fb = full_bar, eb = empty_bar;
+      for (;; ++ti) {
+        if (tq_take((uint32_t)ti) < 0) break;
+        const int as = ti & 1;
+        mbar_wait(acce_bar + 8 * as, ((ti >> 1) & 1) ^ 1, p.err_flag, 104);  // epilogue has drained this accumulator stage
+        if (lane == 0) TRACE(1, 1);
+        const uint32_t tmem_acc = tmem_base + as * acc_stride;
+        const uint32_t accf = accf_bar + 8 * as;
         uint32_t started = 0u;  // kmask mode: the first MMA actually issued for this tile overwrites the accumulator
         for (int k = 0; k < k_iters; ++k) {
-          mbar_wait(full_bar + 8 * stage, phase, p.err_flag, 102);
+          mbar_wait(fb, phase, p.err_flag, 102);
           if (lane == 0) TRACE(1, 2);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t a_src = ring_base + stage * stage_bytes;
-            const uint64_t ad = make_umma_desc(a_src, p.sbo, p.layout_type);
-            const uint64_t bd = make_umma_desc(a_src + p.a_slot, p.sbo, p.layout_type);
-            if (p.kmask_on) {
+            const uint32_t b_lo = a_lo + b_off;
+            if (mode == 4) tma_issue<4, kQ>(tmem_acc, a_lo, b_lo, sw_hi, idesc, k != 0, f8);
+            else if (mode == 2) tma_issue<2, kQ>(tmem_acc, a_lo, b_lo, sw_hi, idesc, k != 0, f8);
+            else if (mode == 1) tma_issue<1, kQ>(tmem_acc, a_lo, b_lo, sw_hi, idesc, k != 0, f8);
+            else if (mode == 8) tma_issue<8, kQ>(tmem_acc, a_lo, b_lo, sw_hi, idesc, k != 0, f8);
+            else {
               // structurally sparse K (the 2x2 space-to-depth form of a 3x3 stride-2 conv has 7 of 16 all-zero
               // 16-channel blocks): issue only the K steps whose weights are not all zero
+              const uint32_t bits = (uint32_t)(p.kmask >> (k * kk_n));
               for (int kk = 0; kk < kk_n; ++kk) {
-                if ((p.kmask >> (k * kk_n + kk)) & 1ull) {
-                  umma_bf16(tmem_acc, ad + 2 * kk, bd + 2 * kk, idesc, started);
+                if ((bits >> kk) & 1u) {
+                  umma_lohi<false>(tmem_acc, a_lo + 2u * kk, sw_hi, b_lo + 2u * kk, sw_hi, idesc, started);
                   started = 1u;
                 }
               }
-            } else if (f8) {
-              umma_e4m3(tmem_acc, ad, bd, idesc, k != 0);
-              for (int kk = 1; kk < kk_n; ++kk) umma_e4m3(tmem_acc, ad + 2 * kk, bd + 2 * kk, idesc, 1);
-            } else {
-              umma_bf16(tmem_acc, ad, bd, idesc, k != 0);
-              for (int kk = 1; kk < kk_n; ++kk)  // +32 B (= 16 bf16 of K) inside the swizzle row per UMMA
-                umma_bf16(tmem_acc, ad + 2 * kk, bd + 2 * kk, idesc, 1);
             }
-            umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs retire
-            if (k == k_iters - 1) umma_commit(accf_bar + 8 * as);  // accumulator complete
+            umma_commit(eb);                        // frees the smem slot once these MMAs retire
+            if (k == k_iters - 1) umma_commit(accf);  // accumulator complete
           }
           __syncwarp();
           if (lane == 0) TRACE(1, 3);
-          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; a_lo = ring_lo0; fb = full_bar; eb = empty_bar; }
+          else { a_lo += stage_units; fb += 8; eb += 8; }
         }
       }
     }
