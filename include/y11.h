@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define Y11_ABI_VERSION 5
+#define Y11_ABI_VERSION 6
 
 typedef struct y11_engine* y11_handle;
 typedef struct y11_plan_s* y11_plan;
@@ -176,6 +176,23 @@ int y11_plan_add_stem(y11_plan p, const y11_stem_desc* d);
  * stem ops its slice of the descriptor array), NULL -> the bf16 letterbox output given at y11_plan_add_stem.  Takes effect
  * for launches (and graph captures) made after the call. */
 int y11_plan_set_stem_source(y11_plan p, const y11_image* images);
+/* Class-emit mode of a Detect class-logit conv (cv3.<l>.2, fp32 out, no activation) [a12 + the conf filter of a13, fused
+ * into the conv epilogue].  In single-label prediction the reference reduces the nc class scores of an anchor to
+ * (max score, first class attaining it) and keeps the anchor iff max score > conf (ultralytics non_max_suppression).  With
+ * emit set, op `op_index` does exactly that on the accumulator rows it already holds in TMEM: it does NOT write its
+ * [B, H*W, nc] fp32 logits; every row whose maximum logit exceeds `logit_threshold` (a conservative bound: sigmoid(x) > conf
+ * implies x > logit_threshold) is appended to its image's list as {anchor index, class, bits of the max logit, 0}.
+ * y11_detect_postprocess_list consumes the lists.  `count` is zeroed whenever op 0 of the plan is launched.  e == NULL or
+ * e->list == NULL: back to storing logits.  Takes effect for launches (and graph captures) made after the call. */
+typedef struct {
+  void* list;             /* device, int32x4 [B][cap] */
+  int32_t* count;         /* device, int32 [B]; the same array for every emitting op of a plan */
+  int32_t cap;            /* entries per image (>= anchors per image) */
+  int32_t nc;             /* classes = valid output columns */
+  int32_t anchor_offset;  /* anchor index of this level's pixel (0, 0) */
+  float logit_threshold;
+} y11_cls_emit;
+int y11_plan_set_cls_emit(y11_plan p, int op_index, const y11_cls_emit* e);
 int y11_plan_add_dwconv(y11_plan p, const y11_dwconv_desc* d);
 int y11_plan_add_sppf(y11_plan p, const y11_sppf_desc* d);
 int y11_plan_add_upsample(y11_plan p, const y11_upsample_desc* d);
@@ -254,6 +271,16 @@ typedef struct {
 int y11_detect_postprocess_push(y11_handle h, const y11_head_desc* hd, const y11_nms_params* p, const float* scale,
                                 float* out_det, int32_t* out_count, int32_t* out_ncand, void* workspace,
                                 size_t workspace_bytes, const y11_push* push, y11_stream s);
+
+/* Same post-processing, fed by the pre-candidate lists of class-emit convs (y11_plan_set_cls_emit) instead of a scan of the
+ * class logits: per list entry the accurate score, the conf test, DFL decode of the anchor's box logits (hd->head[l][..0:64],
+ * which the box towers still write) - then the identical sort + NMS.  Single-label only (p->multi_label must be 0).  Results
+ * are bit-identical to y11_detect_postprocess on the logits the convs would have stored.  push may be NULL. */
+int y11_detect_postprocess_list(y11_handle h, const y11_head_desc* hd, const y11_nms_params* p, const void* list,
+                                const int32_t* list_count, int32_t list_cap, const float* scale, float* out_det,
+                                int32_t* out_count, int32_t* out_ncand, void* workspace, size_t workspace_bytes,
+                                const y11_push* push, y11_stream s);
+
 /* Consumer side: enqueue a one-warp kernel that parks until signals[i] >= target (wrap-safe) for all i < n (n <= 32). */
 int y11_wait_signals(y11_handle h, const uint32_t* signals, int n, uint32_t target, y11_stream s);
 /* Measurement only: same launches with CUDA events between them; ms_decode_nms[0] = decode + compaction, [1] = sort + NMS.

@@ -401,3 +401,99 @@ def test_stream_mode_equals_one_call_at_a_time(eng_n):
                 assert torch.equal(x, y)
     with pytest.raises(ValueError):
         list(eng.predict([torch.zeros(2, 3, 64, 64)], stream=True))
+
+
+# ------------------------------------------------------------------------------------------------ class-emit conv epilogue
+@pytest.mark.parametrize("conf", [0.25, 0.001, 0.6])
+def test_class_emit_epilogue_equals_decode_of_stored_logits(eng_n, conf):
+    """Single-label: the class-logit convs reduce each anchor to (max logit, class) and list the candidates in their epilogue
+    (y11_plan_set_cls_emit + y11_detect_postprocess_list) instead of storing [B,A,nc] fp32 logits for a scan kernel.  Detections,
+    counts and candidate counts must equal the stored-logits path bit for bit."""
+    eng, _ = eng_n
+    B, H, W = 4, 320, 448
+    g = torch.Generator().manual_seed(11)
+    frames = [torch.randint(0, 256, (H, W, 3), dtype=torch.uint8, generator=g).cuda() for _ in range(B)]
+    net = eng.compiled(B, H, W)
+    geoms = [(W, H, 0, 0, H, W)] * B
+    with torch.cuda.device(eng.device):
+        eng.preprocess_images(net, frames, geoms)
+        eng.forward(net)                       # stored logits
+        a = [t.clone() for t in eng.postprocess(net, None, conf, 0.7, 300)]
+        eng.forward(net, cls_emit=conf)        # class-emit epilogue
+        assert net.emit_conf == conf
+        b = [t.clone() for t in eng.postprocess(net, None, conf, 0.7, 300)]
+        n_list = net.emit_count.clone()
+        eng.forward(net)                       # and back: the plan stores logits again
+        assert net.emit_conf is None
+        c = [t.clone() for t in eng.postprocess(net, None, conf, 0.7, 300)]
+        torch.cuda.synchronize()
+    assert conf > 0.25 or int(a[2].sum()) > 0, "no candidates: the comparison would be empty"
+    for x, y, z in zip(a, b, c):
+        assert torch.equal(x, y) and torch.equal(x, z)
+    assert bool((n_list >= a[2]).all()) and bool((n_list <= net.A).all())   # the list is a superset of the candidates
+
+
+def test_class_emit_epilogue_class_ties_and_saturation():
+    """The class of an anchor is the FIRST class whose sigmoid score equals the maximum score: equal logits, logits that differ
+    below fp32 sigmoid resolution, and saturated logits (sigmoid == 1.0) must all resolve as the stored-logits decode does."""
+    from gpu_utils import Ctx
+    ctx = Ctx()
+    dev = ctx.dev
+    B, H, W, cin, nc = 2, 16, 16, 32, 80
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, H, W, cin, generator=g).to(torch.bfloat16)
+    # weights: class c responds to input channel c % cin with a gain that creates exact and near ties
+    w = torch.zeros(nc, cin)
+    for c in range(nc):
+        w[c, c % cin] = 1.0
+    b = torch.zeros(nc)
+    b[3], b[40] = 20.0, 20.0            # saturation: sigmoid(20 + small) == 1.0 for both -> class 3 wins wherever they lead
+    b[10], b[11] = 2.0, 2.0 + 1e-7      # below sigmoid resolution at 2
+    xd, wd, bd = x.to(dev), w.to(torch.bfloat16).to(dev), b.to(dev)
+    A = H * W
+    no = 64 + nc
+    head = torch.zeros(B, H, W, no, device=dev, dtype=torch.float32)
+    head[..., :64] = torch.randn(B, H, W, 64, generator=g).to(dev)
+    d = cabi.ConvDesc()
+    d.inp = cabi.View(xd.data_ptr(), cin, 0, cin)
+    d.out = cabi.View(head.data_ptr(), no, 64, nc)
+    d.w, d.bias = wd.data_ptr(), bd.data_ptr()
+    d.B, d.Hin, d.Win, d.Hout, d.Wout = B, H, W, H, W
+    d.k, d.stride, d.act, d.out_f32, d.impl = 1, 1, 0, 1, cabi.IMPL_TCGEN05
+    lib = ctx.lib
+    hd = cabi.HeadDesc()
+    hd.head[0], hd.hl[0], hd.wl[0], hd.stride[0] = head.data_ptr(), H, W, 8.0
+    hd.nl, hd.B, hd.nc, hd.row_stride = 1, B, nc, no
+    p = cabi.NmsParams(0.25, 0.7, 100, 30000, 7680, 0, 0)
+    ws = torch.empty(lib.y11_postprocess_workspace(B, A, nc, 0, 30000), dtype=torch.uint8, device=dev)
+    outs = []
+    for variant in ((-1, 0, -1, -1), (-1, 1, -1, -1), (-1, 2, 2, -1)):      # CTA-wide, warp-independent, fat epilogue
+        for emit in (False, True):
+            plan = ctx.plan()
+            cabi.check(lib.y11_plan_add_conv_tuned(plan, C.byref(d), *variant), "add_conv_tuned")
+            det = torch.zeros(B, 100, 6, device=dev)
+            cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+            ncand = torch.zeros(B, dtype=torch.int32, device=dev)
+            if emit:
+                lst = torch.zeros(B, A, 4, dtype=torch.int32, device=dev)
+                lcnt = torch.zeros(B, dtype=torch.int32, device=dev)
+                e = cabi.ClsEmit(lst.data_ptr(), lcnt.data_ptr(), A, nc, 0, float(np.log(0.25 / 0.75) - 1e-2))
+                cabi.check(lib.y11_plan_set_cls_emit(plan, 0, C.byref(e)), "set_cls_emit")
+                head[..., 64:] = float("nan")      # the class logits must not be needed
+            cabi.check(lib.y11_plan_run(plan, ctx.stream()), "run")
+            if emit:
+                cabi.check(lib.y11_detect_postprocess_list(ctx.h, C.byref(hd), C.byref(p), lst.data_ptr(), lcnt.data_ptr(), A, None,
+                                                           det.data_ptr(), cnt.data_ptr(), ncand.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                           None, ctx.stream()), "postprocess_list")
+            else:
+                cabi.check(lib.y11_detect_postprocess(ctx.h, C.byref(hd), C.byref(p), None, det.data_ptr(), cnt.data_ptr(),
+                                                      ncand.data_ptr(), ws.data_ptr(), ws.numel(), ctx.stream()), "postprocess")
+            torch.cuda.synchronize()
+            outs.append((det.cpu(), cnt.cpu(), ncand.cpu()))
+    ref = outs[0]
+    assert int(ref[2].sum()) > 0
+    cls_seen = set(ref[0][..., 5][ref[0][..., 4] > 0].to(torch.int64).tolist())
+    assert 3 in cls_seen                                   # saturated ties (sigmoid == 1.0 for classes 3 and 40) occur
+    for o in outs[1:]:
+        for x_, y_ in zip(ref, o):
+            assert torch.equal(x_, y_)

@@ -1,13 +1,6 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-T=${TAG:-d2}
-timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "conv" > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${T}_pytest.log
-timeout 600 python bench.py --extras "" --no-cpu-baseline --skip-e2e --latency-iters 0 --per-op > gpurun_out/${T}_bench_s.json 2> gpurun_out/${T}_bench_s.err; echo "bench rc=$?"
-python - <<PY
-import json
-d=json.loads([l for l in open('gpurun_out/${T}_bench_s.json') if l.startswith('{')][-1])
-print('value',round(d['value']),'ms',round(d['ms_per_step'],3),'blocks',[round(x,3) for x in d.get('ms_per_step_blocks',[])], 'clk', d.get('clocks',{}).get('sm_mhz_per_block'))
-r=d.get('roofline',{}); print('frac',r.get('frac'),'serialised',r.get('serialised'))
-PY
-Y11_LIB=$PWD/yolo_infer_b200/_lib/liby11_trace.so timeout 300 python tools/trace_narrow.py > gpurun_out/${T}_trace.log 2>&1; echo "trace rc=$?"
+T=${TAG:-d8}
+timeout 1500 python -m pytest tests/test_gpu_round2.py -x -q -m gpu -k "class_emit" > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/${T}_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/${T}_smoke.log

@@ -9,7 +9,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "_lib" / "liby11_b200.so"
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 ACT_NONE, ACT_SILU = 0, 1
 IMPL_TCGEN05, IMPL_SIMT_DEBUG = 0, 1
 RES_POST, RES_PRE_UP2 = 0, 1
@@ -84,6 +84,11 @@ class Push(C.Structure):
     _fields_ = [("done_counter", C.c_void_p), ("signal", C.c_void_p)]
 
 
+class ClsEmit(C.Structure):
+    _fields_ = [("list", C.c_void_p), ("count", C.c_void_p), ("cap", C.c_int32), ("nc", C.c_int32),
+                ("anchor_offset", C.c_int32), ("logit_threshold", C.c_float)]
+
+
 # name -> (restype, argtypes); mirrors include/y11.h one to one (tests/test_cabi_symbols.py checks the header)
 _P = C.c_void_p
 SIGNATURES = {
@@ -123,6 +128,9 @@ SIGNATURES = {
     "y11_detect_postprocess": (C.c_int, [_P, C.POINTER(HeadDesc), C.POINTER(NmsParams), _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "y11_detect_postprocess_push": (C.c_int, [_P, C.POINTER(HeadDesc), C.POINTER(NmsParams), _P, _P, _P, _P, _P, C.c_size_t,
                                               C.POINTER(Push), _P]),
+    "y11_detect_postprocess_list": (C.c_int, [_P, C.POINTER(HeadDesc), C.POINTER(NmsParams), _P, _P, C.c_int32, _P, _P, _P, _P, _P,
+                                              C.c_size_t, C.POINTER(Push), _P]),
+    "y11_plan_set_cls_emit": (C.c_int, [_P, C.c_int, C.POINTER(ClsEmit)]),
     "y11_wait_signals": (C.c_int, [_P, _P, C.c_int, C.c_uint32, _P]),
     "y11_detect_postprocess_timed": (C.c_int, [_P, C.POINTER(HeadDesc), C.POINTER(NmsParams), _P, _P, _P, _P, _P, C.c_size_t,
                                                C.POINTER(C.c_float), _P]),

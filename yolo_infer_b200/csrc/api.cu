@@ -105,6 +105,8 @@ struct y11_plan_s {
   cudaEvent_t* events = nullptr;
   int n_events = 0;
   int* counters = nullptr;  // 2 ints per op: dynamic-tile-scheduler state of the tcgen05 convs (conv_tc.cu)
+  int* emit_count = nullptr;  // class-emit mode (y11_plan_set_cls_emit): per-image list counters, zeroed when op 0 is launched
+  int emit_B = 0;
 };
 constexpr int kMaxPlanOps = 1024;
 
@@ -255,6 +257,8 @@ extern "C" int y11_plan_autotune(y11_plan p, y11_stream s_, int reps) {
       ConvTcLaunch L;
       if (conv_tc_prepare(p->eng, d, &L, &c)) continue;  // variant not feasible for this layer
       L.p.tile_counter = base.p.tile_counter;
+      L.p.emit = base.p.emit; L.p.emit_nc = base.p.emit_nc; L.p.emit_aoff = base.p.emit_aoff; L.p.emit_cap = base.p.emit_cap;
+      L.p.emit_thr = base.p.emit_thr; L.p.emit_list = base.p.emit_list; L.p.emit_count = base.p.emit_count;
       bool dup = false;
       for (const ConvTcTune& v : seen)
         dup |= v.lsu == L.variant.lsu && v.epi_warp == L.variant.epi_warp && v.cps == L.variant.cps && v.bn_max == L.variant.bn_max;
@@ -293,6 +297,43 @@ extern "C" int y11_plan_set_stem_source(y11_plan p, const y11_image* images) {
     op->d.stem.u8_src = images ? 1 : 0;
     first += (size_t)op->d.stem.B;
   }
+  return 0;
+}
+
+// Class-emit mode of a Detect class-logit conv (cv3.l.2): see y11.h.  Like y11_plan_set_stem_source this edits the launch
+// parameters of an existing op; a CUDA-graph capture records whatever is set at capture time.
+extern "C" int y11_plan_set_cls_emit(y11_plan p, int op_index, const y11_cls_emit* e) {
+  Y11_REQUIRE(p && op_index >= 0 && op_index < (int)p->ops.size(), "plan_set_cls_emit: bad op index %d", op_index);
+  PlanOp* op = p->ops[op_index];
+  Y11_REQUIRE(op->kind == OP_CONV_TC, "plan_set_cls_emit: op %d is not a tcgen05 conv", op_index);
+  ConvTcParams& q = op->tc.p;   // (op->tc is re-assigned below: q stays a reference to the same member)
+  if (!e || !e->list) {
+    q.emit = 0; q.emit_list = nullptr; q.emit_count = nullptr;
+    bool any = false;
+    for (PlanOp* o : p->ops) any |= o->kind == OP_CONV_TC && o->tc.p.emit;
+    if (!any) { p->emit_count = nullptr; p->emit_B = 0; }
+    return 0;
+  }
+  Y11_REQUIRE(e->count && e->cap > 0 && e->nc > 0 && e->nc <= op->d.conv.out.c, "plan_set_cls_emit: bad list / class count");
+  Y11_REQUIRE(q.out_f32 && q.act == Y11_ACT_NONE && !q.res && !q.quant && op->d.conv.out.c <= 128,
+              "plan_set_cls_emit: op %d is not an fp32 logit conv of <= 128 channels", op_index);
+  if (!q.emit && (q.n_tiles != 1 || !q.epi_warp)) {
+    // an epilogue thread must see all columns of its row (one N tile), and the warp-independent epilogue keeps all eight
+    // epilogue warps busy in emit mode (the CTA-wide one scans with four): re-prepare the op in that variant where the tile allows
+    ConvTcTune t = op->tc.variant;
+    t.bn_max = -1;
+    t.epi_warp = op->tc.epi_warp_possible ? 1 : 0;
+    ConvTcLaunch L;
+    if (int rc = conv_tc_prepare(p->eng, &op->d.conv, &L, &t)) return rc;
+    L.p.tile_counter = q.tile_counter;
+    Y11_REQUIRE(L.p.n_tiles == 1, "plan_set_cls_emit: op %d does not fit one N tile", op_index);
+    op->tc = L;
+  }
+  Y11_REQUIRE(!p->emit_count || p->emit_count == e->count, "plan_set_cls_emit: one counter array per plan");
+  q.emit = 1; q.emit_nc = e->nc; q.emit_aoff = e->anchor_offset; q.emit_cap = e->cap; q.emit_thr = e->logit_threshold;
+  q.emit_list = static_cast<int4*>(e->list); q.emit_count = e->count;
+  p->emit_count = e->count;
+  p->emit_B = q.B;
   return 0;
 }
 
@@ -394,6 +435,7 @@ extern "C" int y11_plan_run_range(y11_plan p, int first, int last, y11_stream s)
 extern "C" int y11_plan_run_ops(y11_plan p, int first, int last, y11_stream s_) {
   Y11_REQUIRE(p && first >= 0 && last <= (int)p->ops.size() && first <= last, "plan_run_ops: bad range");
   cudaStream_t s0 = static_cast<cudaStream_t>(s_);
+  if (first == 0 && p->emit_count) Y11_CHECK_CUDA(cudaMemsetAsync(p->emit_count, 0, (size_t)p->emit_B * sizeof(int), s0));
   for (const SchedItem& it : p->sched) {
     switch (it.kind) {
       case S_OP:

@@ -207,6 +207,49 @@ __device__ __forceinline__ void epi16(const ConvTcParams& p, const uint32_t (&v)
   }
 }
 
+// ---- class-emit epilogue (ConvTcParams::emit) ----------------------------------------------------------------------------
+// The reference takes, per anchor, the maximum of the SIGMOID scores and the first class that attains it.  sigmoid is monotone,
+// so the maximum logit gives the score; two different logits share a class rank only when their fp32 sigmoids are equal, which
+// needs them closer than 1e-2 (below 8) or both in the saturating range - only then is the accurate sigmoid evaluated here.
+__device__ __forceinline__ float emit_sigmoid(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+__device__ __forceinline__ void emit_scan16(const ConvTcParams& p, const uint32_t (&v)[16], int col0, float& best, int& cls) {
+  const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 bb = __ldg(b4 + i);
+    const float f[4] = {__uint_as_float(v[4 * i + 0]) + bb.x, __uint_as_float(v[4 * i + 1]) + bb.y,
+                        __uint_as_float(v[4 * i + 2]) + bb.z, __uint_as_float(v[4 * i + 3]) + bb.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int col = col0 + 4 * i + k;
+      const float x = f[k];
+      if (col < p.emit_nc && x > best) {
+        // up to 10, logits more than 1e-2 apart have sigmoids >= 7 fp32 ulps apart (sigmoid'(10) = 4.5e-5): only closer pairs
+        // and the saturating range need the accurate comparison
+        const bool near = x - best <= 1e-2f || best > 10.0f;
+        if (!(near && emit_sigmoid(x) == emit_sigmoid(best))) cls = col;  // same sigmoid as an earlier class: that one keeps the rank
+        best = x;
+      }
+    }
+  }
+}
+// called by all 32 lanes of a converged warp; the lanes that list a row of the same image share one atomicAdd
+__device__ __forceinline__ void emit_row(const ConvTcParams& p, bool valid, int on, int oh, int ow, float best, int cls) {
+  const bool c = valid && best > p.emit_thr;
+  const unsigned m = __ballot_sync(0xffffffffu, c);
+  if (c) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned peers = __match_any_sync(m, on);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if ((int)lane == leader) base = atomicAdd(p.emit_count + on, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const int slot = base + __popc(peers & ((1u << lane) - 1u));
+    if (slot < p.emit_cap)
+      p.emit_list[(size_t)on * p.emit_cap + slot] = make_int4(p.emit_aoff + oh * p.Wout + ow, cls, __float_as_int(best), 0);
+  }
+}
+
 // kCpw = accumulator columns an epilogue warp drains per step: 16 (3 CTAs/SM, 64 registers) or 32 ("fat" epilogue: two
 // tcgen05.ld in flight, 64-channel store chunks = half the fences / barriers / TMA stores per tile; needs > 64 registers,
 // i.e. 2 CTAs/SM).  The ncu source view of the store-heavy 1x1 layers showed the epilogue chain - tcgen05.wait::ld,
@@ -569,6 +612,21 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
       mbar_wait(accf_bar + 8 * grp, (ti >> 1) & 1, p.err_flag, 103);
       tc_fence_after();
       const uint32_t taddr = tmem_base + grp * acc_stride + (static_cast<uint32_t>(quad * 32) << 16);
+      if (p.emit) {  // class-emit mode: row maximum + class instead of a store
+        float best = -INFINITY;
+        int cls = 0;
+        for (int col = 0; col < p.BN; col += 16) {
+          uint32_t va[16];
+          tmem_ld16(taddr + col, va);
+          tmem_ld_wait();
+          emit_scan16(p, va, col, best, cls);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acce_bar + 8 * grp);
+        emit_row(p, valid, on, oh, ow, best, cls);
+        continue;
+      }
       for (int c = 0; c < n_chunks; ++c) {
         const uint32_t buf = my_stage + sb * wbuf_bytes;
         if (lane == 0) {  // the last store that used this buffer (two chunks ago / the previous one) has finished reading it
@@ -656,6 +714,23 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
       if (lane == 0 && (ew == 0 || ew == 3)) TRACE(2 + (ew == 3), 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * acc_stride + (static_cast<uint32_t>(quad * 32) << 16);
+      if (p.emit) {  // class-emit mode: the first warp of each lane quadrant scans all columns of its 32 rows; nothing is stored
+        if (half == 0) {
+          float best = -INFINITY;
+          int cls = 0;
+          for (int col = 0; col < p.BN; col += 16) {
+            uint32_t va[16];
+            tmem_ld16(taddr + col, va);
+            tmem_ld_wait();
+            emit_scan16(p, va, col, best, cls);
+          }
+          emit_row(p, valid, on, oh, ow, best, cls);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acce_bar + 8 * as);
+        continue;
+      }
       for (int c = 0; c < n_chunks; ++c) {
         const int col = c * p.cw + half * kCpw;          // column inside the tile's accumulator
         const uint32_t dst = staging_base + sb * stg_bytes + row_addr;

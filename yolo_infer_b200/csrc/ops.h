@@ -66,6 +66,16 @@ struct ConvTcParams {
   int32_t in_ct, Hin, Win;
   uint32_t b_res_bytes; // resident weight region (all taps), loaded once per CTA
   uint32_t a_lbo, a_sbo;
+  // class-emit epilogue (Detect cv3.l.2 in single-label prediction, y11_plan_set_cls_emit): instead of storing the fp32 class
+  // logits, every output row (= anchor) keeps the maximum logit and its class, and rows above the threshold are appended to the
+  // image's pre-candidate list {anchor, class, logit bits, 0}
+  int32_t emit;            // 1: emit mode (the output tensor is not written)
+  int32_t emit_nc;         // valid columns (classes)
+  int32_t emit_aoff;       // anchor index of this level's first pixel
+  int32_t emit_cap;        // list entries per image
+  float emit_thr;          // conservative logit threshold: sigmoid(x) > conf  =>  x > emit_thr
+  int4* emit_list;         // [B][emit_cap]
+  int* emit_count;         // [B]
 };
 
 // Per-layer launch variant.  -1 = the built-in heuristic (which an environment knob may override globally); the plan

@@ -332,6 +332,49 @@ decode_onepass_kernel(HeadParams hp, float conf, float logit_lo, int cap, float4
   }
 }
 
+// Single-label with class-emit convs (y11_plan_set_cls_emit): the conv epilogues already reduced every anchor's class logits
+// to (maximum logit, class) and listed the anchors above the conservative threshold.  This is phase 2 of decode_onepass_kernel
+// on that list: accurate sigmoid, conf test, DFL box of the candidates (4 lanes per entry), one atomicAdd per warp for the
+// output slots.  Same arithmetic, same helpers -> bit-identical candidates (the list order is free: the sort key breaks
+// score ties by anchor).
+__global__ void __launch_bounds__(256)
+decode_list_kernel(HeadParams hp, float conf, int cap, const int4* __restrict__ list, const int* __restrict__ list_count, int list_cap,
+                   float4* __restrict__ cbox, float* __restrict__ cscore, float* __restrict__ ccls, int* __restrict__ canchor,
+                   int* __restrict__ ncand, int* __restrict__ ncand_raw) {
+  const int b = blockIdx.y;
+  const int n = min(list_count[b], list_cap);
+  const int lane = threadIdx.x & 31, sub = threadIdx.x & 3;
+  const int e0 = blockIdx.x * kChunk + (threadIdx.x >> 2);
+  if (blockIdx.x * kChunk + (threadIdx.x >> 5) * 8 >= n) return;  // whole warps beyond the list leave
+  const bool have = e0 < n;
+  const int4 ent = list[(size_t)b * list_cap + (have ? e0 : 0)];
+  const int a = ent.x;
+  const float best = __int_as_float(ent.z);
+  const AnchorRef ar = anchor_ref(hp, b, a);
+  const float score = sigmoidf_acc(best);
+  const bool cand = have && score > conf;
+  const unsigned cb = __ballot_sync(0xffffffffu, cand && sub == 0);
+  int wbase = 0;
+  if (cb) {
+    if (lane == 0) {
+      wbase = atomicAdd(&ncand[b], __popc(cb));
+      if (ncand_raw) atomicAdd(&ncand_raw[b], __popc(cb));
+    }
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+  }
+  if (!cand) return;  // whole 4-lane groups leave together
+  const unsigned gmask = 0xFu << (lane & ~3);
+  const int pos = wbase + __popc(cb & ((1u << (lane & ~3)) - 1u));
+  const float4 box = xywh2xyxy_rn(decode_box(ar, sub, lane, gmask));
+  if (sub == 0 && pos < cap) {
+    const size_t ob = (size_t)b * cap;
+    cbox[ob + pos] = box;
+    cscore[ob + pos] = score;
+    ccls[ob + pos] = (float)ent.y;
+    canchor[ob + pos] = a;
+  }
+}
+
 // exclusive scan of chunk counts, one CTA per image
 __global__ void __launch_bounds__(1024) scan_chunks_kernel(const int* __restrict__ chunk_cnt, int* __restrict__ chunk_off, int nchunks,
                                                            int cap, int* __restrict__ ncand, int* __restrict__ ncand_raw) {
@@ -879,9 +922,15 @@ extern "C" size_t y11_postprocess_workspace(int B, int A, int nc, int multi_labe
   return w.total;
 }
 
+struct EmitList {  // pre-candidate lists of class-emit convs (y11_detect_postprocess_list)
+  const int4* list;
+  const int* count;
+  int cap;
+};
+
 static int postprocess_impl(const y11_head_desc* hd, const y11_nms_params* p, const float* scale, float* out_det, int32_t* out_count,
                             int32_t* out_ncand, void* workspace, size_t workspace_bytes, const y11_push* push, float* ms2,
-                            cudaStream_t s) {
+                            cudaStream_t s, const EmitList* el = nullptr) {
   HeadParams hp;
   if (int e = fill_head(hd, &hp)) return e;
   Y11_REQUIRE(p->max_det >= 1, "postprocess: max_det=%d", p->max_det);
@@ -903,7 +952,15 @@ static int postprocess_impl(const y11_head_desc* hd, const y11_nms_params* p, co
   // single-label with A < 65536 (every real configuration): one pass with atomic slot reservation; the candidate count
   // cannot exceed the capacity (one candidate per anchor at most), so nothing depends on the arrival order
   const bool one_pass = !p->multi_label && hp.A < 65536 && cap >= hp.A;
-  if (one_pass) {
+  if (el) {
+    Y11_REQUIRE(one_pass, "postprocess_list: single-label with fewer than 65536 anchors only");
+    Y11_REQUIRE(el->list && el->count && el->cap > 0, "postprocess_list: null list");
+    Y11_CHECK_CUDA(cudaMemsetAsync(w.ncand, 0, (size_t)hp.B * sizeof(int), s));
+    if (out_ncand) Y11_CHECK_CUDA(cudaMemsetAsync(out_ncand, 0, (size_t)hp.B * sizeof(int), s));
+    dim3 lgrid((unsigned)y11_ceil_div(std::min(el->cap, hp.A), kChunk), (unsigned)hp.B);
+    decode_list_kernel<<<lgrid, 256, 0, s>>>(hp, p->conf, cap, el->list, el->count, el->cap, w.cbox, w.cscore, w.ccls, w.canchor,
+                                             w.ncand, out_ncand);
+  } else if (one_pass) {
     Y11_CHECK_CUDA(cudaMemsetAsync(w.ncand, 0, (size_t)hp.B * sizeof(int), s));
     if (out_ncand) Y11_CHECK_CUDA(cudaMemsetAsync(out_ncand, 0, (size_t)hp.B * sizeof(int), s));
     decode_onepass_kernel<<<grid, 256, 0, s>>>(hp, p->conf, logit_lo, cap, w.cbox, w.cscore, w.ccls, w.canchor, w.ncand, out_ncand);
@@ -958,6 +1015,18 @@ extern "C" int y11_detect_postprocess_push(y11_handle, const y11_head_desc* hd, 
   Y11_REQUIRE(!push || (push->done_counter && push->signal), "postprocess_push: null counter/signal");
   return postprocess_impl(hd, p, scale, out_det, out_count, out_ncand, workspace, workspace_bytes, push, nullptr,
                           static_cast<cudaStream_t>(s));
+}
+
+extern "C" int y11_detect_postprocess_list(y11_handle, const y11_head_desc* hd, const y11_nms_params* p, const void* list,
+                                           const int32_t* list_count, int32_t list_cap, const float* scale, float* out_det,
+                                           int32_t* out_count, int32_t* out_ncand, void* workspace, size_t workspace_bytes,
+                                           const y11_push* push, y11_stream s) {
+  Y11_REQUIRE(hd && p && out_det && out_count, "y11_detect_postprocess_list: null argument");
+  Y11_REQUIRE(!p->multi_label, "y11_detect_postprocess_list: single-label only");
+  Y11_REQUIRE(!push || (push->done_counter && push->signal), "y11_detect_postprocess_list: null push field");
+  const EmitList el{static_cast<const int4*>(list), list_count, list_cap};
+  return postprocess_impl(hd, p, scale, out_det, out_count, out_ncand, workspace, workspace_bytes, push, nullptr,
+                          static_cast<cudaStream_t>(s), &el);
 }
 
 extern "C" int y11_detect_postprocess_timed(y11_handle, const y11_head_desc* hd, const y11_nms_params* p, const float* scale,

@@ -364,7 +364,11 @@ class YOLO:
         cabi.check(self._lib.y11_nchw_f32_to_nhwc_bf16(self._engine, x.data_ptr(), net.B, net.H, net.W, divisor,
                                                        net.input.data_ptr(), C.c_void_p(s)), "y11_nchw_f32_to_nhwc_bf16")
 
-    def forward(self, net: CompiledNet) -> None:
+    def forward(self, net: CompiledNet, cls_emit: Optional[float] = None) -> None:
+        """cls_emit = conf of a single-label post-processing that follows: the class-logit convs then list (anchor, class,
+        max logit) of the anchors that can pass conf instead of storing logits (CompiledNet.set_cls_emit; `postprocess` picks the
+        lists up).  None (default): logits are stored - `raw_head`, multi-label and dense decode need them."""
+        net.set_cls_emit(cls_emit)
         net.run(torch.cuda.current_stream(self.device).cuda_stream)
 
     def result_buffers(self, B: int, max_det: int, rep: int = 0, flat: Optional[torch.Tensor] = None):
@@ -398,7 +402,16 @@ class YOLO:
         p = cabi.NmsParams(conf, iou, max_det, max_nms, 7680, int(agnostic), int(multi_label))
         s = torch.cuda.current_stream(self.device).cuda_stream
         srows = scale_rows.data_ptr() if scale_rows is not None else None
-        if push is not None:
+        if net.emit_conf is not None:
+            # the plan ran in class-emit mode (CompiledNet.set_cls_emit): the class logits were reduced in the conv epilogues
+            assert not multi_label and net.emit_conf == conf, "class-emit plan used with different post-processing parameters"
+            pp = cabi.Push(push[0], push[1]) if push is not None else None
+            cabi.check(self._lib.y11_detect_postprocess_list(self._engine, C.byref(hd), C.byref(p), net.emit_list.data_ptr(),
+                                                             net.emit_count.data_ptr(), net.A, srows, det.data_ptr(),
+                                                             count.data_ptr(), ncand.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                             C.byref(pp) if pp is not None else None, C.c_void_p(s)),
+                       "y11_detect_postprocess_list")
+        elif push is not None:
             pp = cabi.Push(push[0], push[1])
             cabi.check(self._lib.y11_detect_postprocess_push(self._engine, C.byref(hd), C.byref(p), srows, det.data_ptr(),
                                                              count.data_ptr(), ncand.data_ptr(), ws.data_ptr(), ws.numel(),
@@ -645,7 +658,7 @@ class YOLO:
             net = self.compiled(B, H, W)
             self.preprocess_images(net, frames, [(g[0], g[1], g[2], g[3], H, W) for g in geoms])
             ev[1].record()
-            self.forward(net)
+            self.forward(net, None if multi_label else conf)
             ev[2].record()
             rows = torch.tensor([list(map(float, r)) for r in scale_rows], dtype=torch.float32).to(self.device, non_blocking=True)
             det, count, ncand = self.postprocess(net, rows, conf, iou, max_det, agnostic, multi_label, max_nms)
@@ -823,6 +836,7 @@ class GraphedPipeline:
         self.eng, self.B, self.h0, self.w0, self.kind = eng, B, h0, w0, kind
         self.conf, self.iou, self.max_det, self.agnostic, self.multi_label = conf, iou, max_det, agnostic, multi_label
         self.max_nms, self.out_flat, self.push = max_nms, out_flat, push
+        self._emit = None if multi_label else conf     # class-emit mode of the class-logit convs (CompiledNet.set_cls_emit)
         dev = eng.device
         new_shape = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
         if kind == "u8":
@@ -886,6 +900,8 @@ class GraphedPipeline:
     def _pre(self, b0: int, nb: int):
         eng, net = self.eng, self.net
         s = torch.cuda.current_stream(eng.device).cuda_stream
+        # single-label: the class-logit convs emit (max logit, class) lists instead of logits (plans are shared: set it per launch)
+        net.set_cls_emit(self._emit)
         if self.kind == "f32":
             net.set_stem_source(None)
             cabi.check(eng._lib.y11_nchw_f32_to_nhwc_bf16_auto(eng._engine, self.frames.data_ptr(), self.B, self.H, self.W,
@@ -910,7 +926,7 @@ class GraphedPipeline:
         if self.chunks == 1:
             def whole():
                 self._pre(0, self.B)
-                eng.forward(net)
+                eng.forward(net, self._emit)
                 self._post()
             return [whole]
         Bc = self.B // self.chunks
@@ -922,6 +938,7 @@ class GraphedPipeline:
             fns.append(prefix)
 
         def rest():
+            net.set_cls_emit(self._emit)
             net.run_ops(net.rest_first, net.n_ops, torch.cuda.current_stream(eng.device).cuda_stream)
             self._post()
         fns.append(rest)
@@ -936,7 +953,7 @@ class GraphedPipeline:
         ev[0].record()
         self._pre(0, self.B)
         ev[1].record()
-        self.eng.forward(self.net)
+        self.eng.forward(self.net, self._emit)
         ev[2].record()
         self._post()
         ev[3].record()

@@ -43,6 +43,9 @@ AUTOTUNE_REPS = int(os.environ.get("Y11_AUTOTUNE_REPS", "4"))
 # Y11_TUNE_CACHE=<file.json>: tuned variants are stored per (scale, nc, B, H, W, chunks, fold) and re-applied on the next
 # build instead of re-timing (a service restarts with the same plans; ncu sees the tuned plan without the tuning launches).
 TUNE_CACHE = os.environ.get("Y11_TUNE_CACHE")
+# Single-label pipelines: max-class reduction + conf pre-filter in the epilogue of the class-logit convs instead of an fp32
+# [B,A,nc] logit tensor and a scan kernel (CompiledNet.set_cls_emit).  Y11_FUSE_CLS=0 keeps the stored-logits path everywhere.
+FUSE_CLS_DECODE = os.environ.get("Y11_FUSE_CLS", "1") != "0"
 
 
 def _tune_cache_load() -> Dict[str, dict]:
@@ -316,6 +319,10 @@ class CompiledNet:
         self.input = self._alloc(H, W, 3)                      # bf16 NHWC, written by the letterbox kernel
         self.no = 64 + pad16(nc)
         self.head: List[torch.Tensor] = []
+        self.cls_ops: List[Tuple[int, int]] = []          # (op index, anchor offset) of the class-logit convs cv3.l.2
+        self.emit_list: Optional[torch.Tensor] = None     # class-emit mode (set_cls_emit): int32 [B, A, 4] pre-candidate lists
+        self.emit_count: Optional[torch.Tensor] = None
+        self.emit_conf: Optional[float] = None
         tune = AUTOTUNE and conv_impl == cabi.IMPL_TCGEN05
         props = torch.cuda.get_device_properties(device)
         self._tune_key = (f"{props.name}/sm{props.multi_processor_count}/{scale}/nc{nc}/B{B}/{H}x{W}/chunks{chunks}/"
@@ -542,6 +549,7 @@ class CompiledNet:
         self._dw(f"{p}.cv3.{l}.1.0", u2, u3)
         self._conv(f"{p}.cv3.{l}.1.1", u3, u4)
         self._conv(f"{p}.cv3.{l}.2", u4, V(head, 64, pad16(self.nc)), out_f32=True)
+        self.cls_ops.append((len(self.ops) - 1, sum(h.shape[1] * h.shape[2] for h in self.head[:-1])))   # (op index, anchor offset)
         cabi.check(self.lib.y11_plan_set_lane(self.plan, 0), "plan_set_lane")
         self.head_lanes += [lane_box, lane_cls]
 
@@ -673,6 +681,31 @@ class CompiledNet:
     def run_range(self, first: int, last: int, stream: int) -> None:
         cabi.check(self.lib.y11_plan_run_range(self.plan, first, last, C.c_void_p(stream)), "y11_plan_run_range")
 
+    def set_cls_emit(self, conf: Optional[float]) -> bool:
+        """Single-label prediction at threshold `conf`: the three class-logit convs (cv3.l.2) reduce every anchor to (maximum
+        logit, class) in their epilogue and list the anchors that can pass `conf` instead of storing [B,A,nc] fp32 logits
+        (y11_plan_set_cls_emit); `engine.postprocess` then consumes `self.emit_list` / `self.emit_count`.  None: back to stored
+        logits (multi-label, raw-head consumers).  Returns whether emit mode is on.  Like `set_stem_source` it edits the plan,
+        i.e. it holds for launches and graph captures made after the call."""
+        if conf is None or self.A >= 65536 or self.conv_impl != cabi.IMPL_TCGEN05 or not FUSE_CLS_DECODE:
+            if self.emit_conf is not None:
+                for op, _ in self.cls_ops:
+                    cabi.check(self.lib.y11_plan_set_cls_emit(self.plan, op, None), "y11_plan_set_cls_emit")
+                self.emit_conf = None
+            return False
+        if self.emit_conf == conf:
+            return True
+        if self.emit_list is None:
+            self.emit_list = torch.zeros((self.B, self.A, 4), dtype=torch.int32, device=self.device)
+            self.emit_count = torch.zeros((self.B,), dtype=torch.int32, device=self.device)
+        cc = min(max(float(conf), 1e-30), 1.0 - 1e-9)
+        thr = math.log(cc / (1.0 - cc)) - 1e-2      # sigmoid(x) > conf  =>  x > logit(conf) - slack (as y11_detect_postprocess)
+        for op, aoff in self.cls_ops:
+            e = cabi.ClsEmit(self.emit_list.data_ptr(), self.emit_count.data_ptr(), self.A, self.nc, aoff, thr)
+            cabi.check(self.lib.y11_plan_set_cls_emit(self.plan, op, C.byref(e)), "y11_plan_set_cls_emit")
+        self.emit_conf = conf
+        return True
+
     def set_stem_source(self, images_dev_ptr: Optional[int]) -> None:
         """Point the stem at a device array of `y11_image` descriptors of frames ALREADY at network resolution (the stem then
         reads the uint8 frames itself and no letterbox launch is needed), or back at `self.input` (None)."""
@@ -703,6 +736,7 @@ class CompiledNet:
 
     def raw_head(self) -> torch.Tensor:
         """[B, 64+nc, A] fp32 in ultralytics' layout (test helper; a torch view/permute, not a kernel)."""
+        assert self.emit_conf is None, "the plan last ran in class-emit mode: no class logits were stored (forward(net) first)"
         parts = []
         for h in self.head:
             x = torch.cat((h[..., :64], h[..., 64:64 + self.nc]), -1)
