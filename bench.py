@@ -667,10 +667,15 @@ def pre_post_rooflines(eng, net, loop, B, S, pk, mean_cand, mean_det):
     d_ms, n_ms = statistics.median(dms), statistics.median(nms_)
     A = pnet.A
     K = mean_cand
-    dec_bytes = B * (80 * A * 4 + K * (64 * 4 + 28))          # class logits of every anchor once + DFL logits and one row per candidate
+    fused_cls = pnet.emit_conf is not None
+    if fused_cls:   # class-emit conv epilogues: the decode kernel reads one 16-byte list entry + the DFL logits per listed anchor
+        dec_bytes = B * K * (16 + 64 * 4 + 28)
+    else:
+        dec_bytes = B * (80 * A * 4 + K * (64 * 4 + 28))      # class logits of every anchor once + DFL logits and one row per candidate
     nms_bytes = B * (K * 32 + mean_det * (24 + 28))             # candidate rows + kept rows (the bit masks live in shared memory)
     post = {"bound": "hbm",
-            "decode": {"kernel": "decode_onepass_kernel", "ms": d_ms, "bytes": dec_bytes, "achieved": dec_bytes / (d_ms / 1e3) / 1e9,
+            "decode": {"kernel": "decode_list_kernel (class maximum + conf pre-filter run in the cv3.l.2 conv epilogues)" if fused_cls
+                       else "decode_onepass_kernel", "ms": d_ms, "bytes": dec_bytes, "achieved": dec_bytes / (d_ms / 1e3) / 1e9,
                        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": dec_bytes / (d_ms / 1e3) / 1e9 / pk["hbm_gbs"]},
             "sort_nms": {"kernel": "sort_nms_kernel", "ms": n_ms, "bytes": nms_bytes, "achieved": nms_bytes / (n_ms / 1e3) / 1e9,
                          "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": nms_bytes / (n_ms / 1e3) / 1e9 / pk["hbm_gbs"],

@@ -289,6 +289,12 @@ int y11_detect_postprocess_timed(y11_handle h, const y11_head_desc* hd, const y1
                                  float* out_det, int32_t* out_count, int32_t* out_ncand, void* workspace,
                                  size_t workspace_bytes, float* ms_decode_nms, y11_stream s);
 
+/* Measurement only: y11_detect_postprocess_list with CUDA events between its launches ([0] = list decode, [1] = sort + NMS). */
+int y11_detect_postprocess_list_timed(y11_handle h, const y11_head_desc* hd, const y11_nms_params* p, const void* list,
+                                      const int32_t* list_count, int32_t list_cap, const float* scale, float* out_det,
+                                      int32_t* out_count, int32_t* out_ncand, void* workspace, size_t workspace_bytes,
+                                      float* ms_decode_nms, y11_stream s);
+
 /* NMS only, batched, on caller-provided candidates (the bit-exact test against torchvision.ops.nms):
  * boxes fp32 [B, K, 4] xyxy (class offset NOT yet applied), scores fp32 [B,K], cls fp32 [B,K],
  * n int32 [B] valid candidates per image.  keep: int32 [B, max_det] candidate indices in score order. */

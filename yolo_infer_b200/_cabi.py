@@ -130,6 +130,8 @@ SIGNATURES = {
                                               C.POINTER(Push), _P]),
     "y11_detect_postprocess_list": (C.c_int, [_P, C.POINTER(HeadDesc), C.POINTER(NmsParams), _P, _P, C.c_int32, _P, _P, _P, _P, _P,
                                               C.c_size_t, C.POINTER(Push), _P]),
+    "y11_detect_postprocess_list_timed": (C.c_int, [_P, C.POINTER(HeadDesc), C.POINTER(NmsParams), _P, _P, C.c_int32, _P, _P, _P, _P, _P,
+                                                    C.c_size_t, C.POINTER(C.c_float), _P]),
     "y11_plan_set_cls_emit": (C.c_int, [_P, C.c_int, C.POINTER(ClsEmit)]),
     "y11_wait_signals": (C.c_int, [_P, _P, C.c_int, C.c_uint32, _P]),
     "y11_detect_postprocess_timed": (C.c_int, [_P, C.POINTER(HeadDesc), C.POINTER(NmsParams), _P, _P, _P, _P, _P, C.c_size_t,

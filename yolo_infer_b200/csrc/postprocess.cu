@@ -1037,6 +1037,17 @@ extern "C" int y11_detect_postprocess_timed(y11_handle, const y11_head_desc* hd,
                           static_cast<cudaStream_t>(s));
 }
 
+extern "C" int y11_detect_postprocess_list_timed(y11_handle, const y11_head_desc* hd, const y11_nms_params* p, const void* list,
+                                                 const int32_t* list_count, int32_t list_cap, const float* scale, float* out_det,
+                                                 int32_t* out_count, int32_t* out_ncand, void* workspace, size_t workspace_bytes,
+                                                 float* ms_decode_nms, y11_stream s) {
+  Y11_REQUIRE(hd && p && out_det && out_count && ms_decode_nms, "y11_detect_postprocess_list_timed: null argument");
+  Y11_REQUIRE(!p->multi_label, "y11_detect_postprocess_list_timed: single-label only");
+  const EmitList el{static_cast<const int4*>(list), list_count, list_cap};
+  return postprocess_impl(hd, p, scale, out_det, out_count, out_ncand, workspace, workspace_bytes, nullptr, ms_decode_nms,
+                          static_cast<cudaStream_t>(s), &el);
+}
+
 extern "C" int y11_wait_signals(y11_handle h, const uint32_t* signals, int n, uint32_t target, y11_stream s) {
   Y11_REQUIRE(h && signals && n >= 1 && n <= 32, "wait_signals: need 1..32 signals");
   wait_signals_kernel<<<1, 32, 0, static_cast<cudaStream_t>(s)>>>(signals, n, target, h->dev_error_flag);

@@ -433,6 +433,14 @@ class YOLO:
         p = cabi.NmsParams(conf, iou, max_det, max_nms, 7680, 0, int(multi_label))
         ms = (C.c_float * 2)()
         s = torch.cuda.current_stream(self.device).cuda_stream
+        if net.emit_conf is not None:      # the plan last ran in class-emit mode: time the list path on its lists
+            assert not multi_label and net.emit_conf == conf
+            cabi.check(self._lib.y11_detect_postprocess_list_timed(self._engine, C.byref(hd), C.byref(p), net.emit_list.data_ptr(),
+                                                                   net.emit_count.data_ptr(), net.A,
+                                                                   scale_rows.data_ptr() if scale_rows is not None else None,
+                                                                   det.data_ptr(), count.data_ptr(), ncand.data_ptr(), ws.data_ptr(),
+                                                                   ws.numel(), ms, C.c_void_p(s)), "y11_detect_postprocess_list_timed")
+            return float(ms[0]), float(ms[1])
         cabi.check(self._lib.y11_detect_postprocess_timed(self._engine, C.byref(hd), C.byref(p),
                                                           scale_rows.data_ptr() if scale_rows is not None else None, det.data_ptr(),
                                                           count.data_ptr(), ncand.data_ptr(), ws.data_ptr(), ws.numel(), ms,
