@@ -42,7 +42,7 @@ def nhwc(x_nchw: torch.Tensor, c_total=None, c_off=0, dtype=torch.bfloat16):
 
 
 def conv_case(ctx: Ctx, B, H, W, cin, cout, k, stride, act, res=False, out_f32=False, in_off=0, in_extra=0, out_off=0,
-              out_extra=0, impl=cabi.IMPL_TCGEN05, seed=0, res_mode=cabi.RES_POST, tune=None, repeats=1):
+              out_extra=0, impl=cabi.IMPL_TCGEN05, seed=0, res_mode=cabi.RES_POST, tune=None, repeats=1, return_variant=False):
     """Runs one conv op; returns (got NCHW fp32, want NCHW fp32 computed by torch fp32 on the same bf16 inputs)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     dev = ctx.dev
@@ -79,8 +79,12 @@ def conv_case(ctx: Ctx, B, H, W, cin, cout, k, stride, act, res=False, out_f32=F
         cabi.check(ctx.lib.y11_plan_add_conv(p, C.byref(d)), "add_conv")
     else:   # explicit launch variant (lsu, epi_warp, ctas_per_sm, bn_max) instead of the per-layer heuristic
         cabi.check(ctx.lib.y11_plan_add_conv_tuned(p, C.byref(d), *tune), "add_conv_tuned")
+    var = (C.c_int32 * 4)()
+    cabi.check(ctx.lib.y11_plan_op_variant(p, 0, var), "op_variant")
     ctx.run(p, repeats)
     got = out[..., out_off:out_off + cout].float().permute(0, 3, 1, 2)
     untouched = torch.cat((out[..., :out_off].flatten(), out[..., out_off + cout:].flatten()))
     assert torch.all(untouched == -3.0), "conv wrote outside its channel slice"
+    if return_variant:
+        return got, tuple(var)       # (lsu, epi_warp bits, ctas_per_sm, bn) actually used
     return got, want

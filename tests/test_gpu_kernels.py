@@ -195,6 +195,32 @@ def test_conv_launch_variants_are_bit_identical(ctx, shape):
     assert n == 48
 
 
+PAIR_SHAPES = [
+    # B, H, W, cin, cout, k, s, act, res
+    (4, 20, 20, 128, 256, 1, 1, True, True),     # 1x1, BN 256 (forced), residual; (4,4,8) tiles, 13 M tiles: odd -> phantom peer tile
+    (2, 40, 40, 256, 256, 3, 1, True, False),    # 3x3 long K, BN 256: 25 M tiles
+    (2, 40, 40, 128, 128, 3, 2, True, False),    # stride 2, BN 128
+    (3, 24, 20, 64, 128, 3, 1, True, True),      # ragged tiles, BN 128 / 64
+    (2, 16, 16, 64, 64, 1, 1, False, False),     # BN 64, fp32-free plain
+]
+
+
+@pytest.mark.parametrize("shape", PAIR_SHAPES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_cta_pair_variant_is_bit_identical(ctx, shape):
+    """tcgen05.mma.cta_group::2 variant (conv_tc_kernel_pair: a cluster of two CTAs computes a 256-row tile, each CTA holding
+    half of the weight tile): matches torch and is BIT-identical to the default 1-CTA variant, for every N tile it accepts."""
+    B, H, W, cin, cout, k, s_, act, res = shape
+    base, want = conv_case(ctx, B, H, W, cin, cout, k, s_, act, res)
+    close_bf16(base, want)
+    n = 0
+    for cps in (1, 2):
+        for bn in (-1, 256, 128, 64):
+            got, var = conv_case(ctx, B, H, W, cin, cout, k, s_, act, res, tune=(0, 8, cps, bn), repeats=2, return_variant=True)
+            assert torch.equal(got, base), (cps, bn, (got - base).abs().max().item())
+            n += 1 if (var[1] & 8) else 0
+    assert n >= 4, "the pair kernel was never selected"
+
+
 def test_conv_2x2_space_to_depth_form(ctx):
     """k = 2 (taps {-1,0}^2, top/left zero padding): what a 3x3 stride-2 conv becomes on a space-to-depth input.  Checked
     (a) as a plain 2x2 conv against torch and (b) end to end: stem-style s2d repacking of a 3x3/2 conv == the 3x3/2 conv."""

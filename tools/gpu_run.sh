@@ -1,7 +1,20 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-T=${TAG:-d9}
-timeout 900 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench rc=$?"
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_ref.json 2> gpurun_out/${T}_bench_ref.err; echo "ref rc=$?"
-tail -c 600 gpurun_out/${T}_bench_ref.json
+T=${TAG:-d14}
+for st in 1 2; do for f in 1 0; do
+Y11_PAIR=$f timeout 600 python bench.py --streams $st --extras "" --no-cpu-baseline --skip-e2e --latency-iters 0 > gpurun_out/${T}_s${st}_p$f.json 2> gpurun_out/${T}_s${st}_p$f.err
+python - <<PY
+import json
+d=json.loads([l for l in open('gpurun_out/${T}_s${st}_p$f.json') if l.startswith('{')][-1])
+print('streams $st pair $f: value',round(d['value']),'ms',round(d['ms_per_step'],3),'blocks',[round(x,3) for x in d.get('ms_per_step_blocks',[])])
+PY
+done; done
+for f in 1 0; do
+Y11_PAIR=$f timeout 600 python bench.py --model m --extras "" --no-cpu-baseline --skip-e2e --latency-iters 0 > gpurun_out/${T}_m_p$f.json 2> gpurun_out/${T}_m_p$f.err
+python - <<PY
+import json
+d=json.loads([l for l in open('gpurun_out/${T}_m_p$f.json') if l.startswith('{')][-1])
+print('model m pair $f: value',round(d['value']),'ms',round(d['ms_per_step'],3),'blocks',[round(x,3) for x in d.get('ms_per_step_blocks',[])])
+PY
+done

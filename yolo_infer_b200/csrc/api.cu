@@ -230,6 +230,18 @@ extern "C" int y11_plan_autotune(y11_plan p, y11_stream s_, int reps) {
           if (bn0 == 128 && d->out.c % 256 == 0 && d->in.c % 64 == 0 && cps == 2 && !(lsu && base.lsu_eligible))
             cands.push_back(ConvTcTune{lsu, ew, 1, 256});
         }
+    // CTA-pair variant (tcgen05.mma.cta_group::2, conv_tc_kernel_pair): half the weight-tile traffic per SM, 256-row tiles;
+    // prepare declines it where it does not apply (halo / e4m3 / k = 2 layers) and the duplicate filter below drops those
+    {
+      static const bool pair_on = [] { const char* e = getenv("Y11_PAIR"); return e ? atoi(e) != 0 : true; }();
+      if (pair_on && !(base.p.halo) && bn0 >= 64) {
+        for (int cps = 2; cps >= 1; --cps) {
+          cands.push_back(ConvTcTune{0, 8, cps, -1});
+          if (d->out.c % 256 == 0 && bn0 != 256) cands.push_back(ConvTcTune{0, 8, cps, 256});
+          if (bn0 == 256) cands.push_back(ConvTcTune{0, 8, cps, 128});
+        }
+      }
+    }
     // time one variant: best of three trials of `reps` back-to-back launches (after one warm-up launch)
     auto time_variant = [&](const ConvTcLaunch& L, float* out_ms) -> int {
       if (int e = conv_tc_launch(&L, s)) return e;

@@ -128,6 +128,26 @@ __device__ __forceinline__ void tma_issue(uint32_t tmem_acc, uint32_t a_lo, uint
     for (int kk = 0; kk < KK; ++kk) umma_lohi<false>(tmem_acc, a_lo + 2u * kk, hi, b_lo + 2u * kk, hi, idesc, kk ? 1u : acc0);
   }
 }
+// All K stages of one tile in TMA mode, run by ONE thread: wait for the stage, KK UMMAs, release the stage; accumulator-full
+// commit after the last stage.
+struct TmaTileArgs {
+  uint32_t tmem_acc, ring_lo0, b_off, hi, idesc, stage_units, n_stages, full_bar, empty_bar, accf;
+  int k_iters;
+  int* err_flag;
+};
+template <int KK, bool kQ>
+__device__ __forceinline__ void tma_tile_issue(const TmaTileArgs& t, uint32_t stage, uint32_t phase, bool f8) {
+  uint32_t a_lo = t.ring_lo0 + stage * t.stage_units, fb = t.full_bar + 8 * stage, eb = t.empty_bar + 8 * stage;
+  for (int k = 0; k < t.k_iters; ++k) {
+    y11::mbar_wait(fb, phase, t.err_flag, 102);
+    y11::tc_fence_after();
+    tma_issue<KK, kQ>(t.tmem_acc, a_lo, a_lo + t.b_off, t.hi, t.idesc, k != 0, f8);
+    y11::umma_commit(eb);  // frees the smem slot once these MMAs retire
+    if (++stage == t.n_stages) { stage = 0; phase ^= 1; a_lo = t.ring_lo0; fb = t.full_bar; eb = t.empty_bar; }
+    else { a_lo += t.stage_units; fb += 8; eb += 8; }
+  }
+  y11::umma_commit(t.accf);  // accumulator complete
+}
 // one 3x3 halo tile with ONE weight chunk per tap (cin = 16 * KK): 9 * KK UMMAs with compile-time tap offsets
 template <int KK>
 __device__ __forceinline__ void halo3_issue(uint32_t tmem_acc, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t b_step,
@@ -529,7 +549,6 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
     } else {
       const uint32_t b_off = p.a_slot >> 4;  // weights of a stage follow its activation box
       const int mode = p.kmask_on ? 0 : kk_n;
-      uint32_t a_lo = ring_lo0, fb = full_bar, eb = empty_bar;
       for (;; ++ti) {
         if (tq_take((uint32_t)ti) < 0) break;
         const int as = ti & 1;
@@ -537,20 +556,23 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
         if (lane == 0) TRACE(1, 1);
         const uint32_t tmem_acc = tmem_base + as * acc_stride;
         const uint32_t accf = accf_bar + 8 * as;
-        uint32_t started = 0u;  // kmask mode: the first MMA actually issued for this tile overwrites the accumulator
-        for (int k = 0; k < k_iters; ++k) {
-          mbar_wait(fb, phase, p.err_flag, 102);
-          if (lane == 0) TRACE(1, 2);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t b_lo = a_lo + b_off;
-            if (mode == 4) tma_issue<4, kQ>(tmem_acc, a_lo, b_lo, sw_hi, idesc, k != 0, f8);
-            else if (mode == 2) tma_issue<2, kQ>(tmem_acc, a_lo, b_lo, sw_hi, idesc, k != 0, f8);
-            else if (mode == 1) tma_issue<1, kQ>(tmem_acc, a_lo, b_lo, sw_hi, idesc, k != 0, f8);
-            else if (mode == 8) tma_issue<8, kQ>(tmem_acc, a_lo, b_lo, sw_hi, idesc, k != 0, f8);
-            else {
-              // structurally sparse K (the 2x2 space-to-depth form of a 3x3 stride-2 conv has 7 of 16 all-zero
-              // 16-channel blocks): issue only the K steps whose weights are not all zero
+        // ONE elected lane walks all K stages of the tile (wait, UMMAs, commit): no per-stage elect / warp re-convergence
+        // between the last UMMA of a stage and the first of the next - with BN = 256 the pipe's queue does not cover that gap
+        if (elect_one()) {
+          const TmaTileArgs ta{tmem_acc, ring_lo0, b_off, sw_hi, idesc, stage_units, n_stages, full_bar, empty_bar, accf,
+                               k_iters, p.err_flag};
+          if (mode == 4) tma_tile_issue<4, kQ>(ta, stage, phase, f8);
+          else if (mode == 2) tma_tile_issue<2, kQ>(ta, stage, phase, f8);
+          else if (mode == 1) tma_tile_issue<1, kQ>(ta, stage, phase, f8);
+          else if (mode == 8) tma_tile_issue<8, kQ>(ta, stage, phase, f8);
+          else {
+            // structurally sparse K (the 2x2 space-to-depth form of a 3x3 stride-2 conv has 7 of 16 all-zero
+            // 16-channel blocks): issue only the K steps whose weights are not all zero
+            uint32_t st = stage, ph = phase, started = 0u;
+            for (int k = 0; k < k_iters; ++k) {
+              mbar_wait(full_bar + 8 * st, ph, p.err_flag, 102);
+              tc_fence_after();
+              const uint32_t a_lo = ring_lo0 + st * stage_units, b_lo = a_lo + b_off;
               const uint32_t bits = (uint32_t)(p.kmask >> (k * kk_n));
               for (int kk = 0; kk < kk_n; ++kk) {
                 if ((bits >> kk) & 1u) {
@@ -558,15 +580,18 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
                   started = 1u;
                 }
               }
+              umma_commit(empty_bar + 8 * st);  // frees the smem slot once these MMAs retire
+              if (++st == n_stages) { st = 0; ph ^= 1; }
             }
-            umma_commit(eb);                        // frees the smem slot once these MMAs retire
-            if (k == k_iters - 1) umma_commit(accf);  // accumulator complete
+            umma_commit(accf);  // accumulator complete
           }
-          __syncwarp();
-          if (lane == 0) TRACE(1, 3);
-          if (++stage == n_stages) { stage = 0; phase ^= 1; a_lo = ring_lo0; fb = full_bar; eb = empty_bar; }
-          else { a_lo += stage_units; fb += 8; eb += 8; }
         }
+        __syncwarp();
+        if (lane == 0) TRACE(1, 3);
+        // ring position after this tile, the same in every lane
+        uint32_t adv = stage + (uint32_t)k_iters;
+        while (adv >= n_stages) { adv -= n_stages; phase ^= 1; }
+        stage = adv;
       }
     }
   } else if (p.epi_warp) {
@@ -788,6 +813,272 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
   if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// ================================================================================================================
+// 2-CTA variant (round 2): tcgen05.mma.cta_group::2 - a CTA PAIR (cluster of two, one CTA per SM of a TPC) computes a 256-row
+// x BN tile.  Each CTA loads its own 128-row activation box and HALF of the weight tile (BN/2 rows), the leader CTA's MMA warp
+// issues one UMMA for the pair (M = 256; D rows 0-127 land in the leader's TMEM, 128-255 in the peer's), each CTA drains and
+// stores its own rows.  Why: the 1-CTA tiles are bound by SHARED-MEMORY bandwidth, not by the tensor pipe - per K stage of a
+// 128 x 256 tile the TMA writes 48 KB and the UMMAs read 48 KB, 96 KB / 128 B/clk = 750 cycles against 512 cycles of math
+// (timeline: 676 cycles per stage, 61-72 % tensor-pipe utilisation in ncu).  With the weight tile split across the pair each
+// SM writes + reads 2 x 32 KB per stage (500 cycles), and 5 stages of 32 KB fit instead of 3 of 48 KB.
+// Scope: TMA producer, bf16, k in {1, 3}, stride 1 / 2, CTA-wide epilogue.  Same per-element K order -> bit-identical results.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const void* tmap, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void* tmap, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once all MMAs issued so far have completed) on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc_bf16_m256(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
+}
+
+template <int KK>
+__device__ __forceinline__ void pair_issue(uint32_t tmem_acc, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+  for (int kk = 0; kk < KK; ++kk) umma2_lohi(tmem_acc, a_lo + 2u * kk, hi, b_lo + 2u * kk, hi, idesc, kk ? 1u : acc0);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel_pair(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcParams p) {
+  using namespace y11;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t tiles_base = (smem_base + kHeaderBytes + 1023u) & ~1023u;
+  const uint32_t full_bar = smem_base;                    // kMaxStages x 8 B (used in the leader CTA)
+  const uint32_t empty_bar = smem_base + 8 * kMaxStages;  // kMaxStages x 8 B (one per CTA)
+  const uint32_t accf_bar = smem_base + 16 * kMaxStages;  // 2 x 8 B  accumulator full  (MMA -> epilogue, one per CTA)
+  const uint32_t acce_bar = accf_bar + 16;                // 2 x 8 B  accumulator empty (both epilogues -> leader's MMA warp)
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_raw + 16 * kMaxStages + 48);
+  const uint32_t stage_bytes = p.a_slot + p.b_slot;
+  const uint32_t ring_base = tiles_base;
+  const uint32_t staging_base = ring_base + p.stages * stage_bytes;  // 2 buffers x stg_bytes
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs, owns the full / accumulator-empty barriers)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);   // the leader producer's arrive.expect_tx; both CTAs' TMA loads complete bytes on it
+      mbar_init(empty_bar + 8 * s, 1);  // the pair's tcgen05.commit, multicast to both CTAs
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(accf_bar + 8 * a, 1);
+      mbar_init(acce_bar + 8 * a, 2 * kEpiWarps);  // the epilogue warps of BOTH CTAs
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.b);
+    prefetch_tmap(&maps.out);
+    if (p.stride == 2) {
+      prefetch_tmap(&maps.a[1]);
+      prefetch_tmap(&maps.a[2]);
+      prefetch_tmap(&maps.a[3]);
+    }
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem))),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything of this CTA can signal them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t acc_stride = p.tmem_cols >> 1;
+  pdl_wait();
+  pdl_trigger();
+
+  const int k_iters = p.taps * p.chunks_per_tap;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_pairs = ((m_tiles + 1) >> 1) * p.n_tiles;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  // pair tile -> (N tile, this CTA's M tile); an odd last M tile leaves the peer with an all-out-of-bounds tile (n0 >= B: the
+  // TMA loads zero-fill, the store is clipped, the residual reads are guarded)
+  auto decode = [&](int pt, int& nt, int& w0, int& h0, int& n0) {
+    uint32_t t = (uint32_t)pt, q;
+    q = fast_div(t, p.mg_ntiles); nt = (int)(t - q * p.n_tiles); t = 2u * q + rank;
+    if ((int)t >= m_tiles) { w0 = 0; h0 = 0; n0 = p.tiles_n * p.Tn; return; }
+    q = fast_div(t, p.mg_tw); w0 = (int)(t - q * p.tiles_w) * p.Tw; t = q;
+    q = fast_div(t, p.mg_th); h0 = (int)(t - q * p.tiles_h) * p.Th; t = q;
+    n0 = (int)t * p.Tn;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    const uint32_t full0 = mapa_u32(full_bar, 0);  // the leader's full barriers, as a cluster address
+    uint32_t stage = 0, phase = 0;
+    for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
+      int nt, w0, h0, n0;
+      decode(pt, nt, w0, h0, n0);
+      for (int tap = 0; tap < p.taps; ++tap) {
+        int mi = 0, cw, ch;
+        if (p.ksize == 1) {
+          cw = w0; ch = h0;
+        } else if (p.stride == 1) {
+          cw = w0 + tap % 3 - 1; ch = h0 + tap / 3 - 1;
+        } else {
+          const int kh = tap / 3, kw = tap % 3;
+          mi = ((kh == 1) ? 0 : 2) + ((kw == 1) ? 0 : 1);
+          cw = w0 - (kw == 0); ch = h0 - (kh == 0);
+        }
+        for (int c = 0; c < p.chunks_per_tap; ++c) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1, p.err_flag, 111);
+          if (elect_one()) {
+            const uint32_t a_dst = ring_base + stage * stage_bytes;
+            if (rank == 0) mbar_expect_tx(full_bar + 8 * stage, 2u * p.tx_bytes);  // this CTA's and the peer's bytes
+            tma_load_4d_2sm(a_dst, &maps.a[mi], full0 + 8 * stage, c * p.Cc, cw, ch, n0);
+            tma_load_2d_2sm(a_dst + p.a_slot, &maps.b, full0 + 8 * stage, tap * p.cin + c * p.Cc, nt * p.BN + (int)rank * (p.BN >> 1));
+          }
+          __syncwarp();
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16_m256(p.BN);
+      const int kk_n = p.Cc / 16;
+      const uint32_t n_stages = (uint32_t)p.stages, stage_units = stage_bytes >> 4, b_off = p.a_slot >> 4;
+      const uint32_t sw_hi = (p.sbo >> 4) | (1u << 14) | (p.layout_type << 29);
+      const uint32_t ring_lo0 = ((ring_base & 0x3FFFFu) >> 4) | (1u << 16);
+      uint32_t stage = 0, phase = 0;
+      int ti = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += n_clusters, ++ti) {
+        const int as = ti & 1;
+        mbar_wait(acce_bar + 8 * as, ((ti >> 1) & 1) ^ 1, p.err_flag, 114);  // both epilogues have drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + as * acc_stride;
+        if (elect_one()) {
+          uint32_t st = stage, ph = phase;
+          uint32_t a_lo = ring_lo0 + st * stage_units;
+          for (int k = 0; k < k_iters; ++k) {
+            mbar_wait(full_bar + 8 * st, ph, p.err_flag, 112);
+            tc_fence_after();
+            if (kk_n == 4) pair_issue<4>(tmem_acc, a_lo, a_lo + b_off, sw_hi, idesc, k != 0);
+            else if (kk_n == 2) pair_issue<2>(tmem_acc, a_lo, a_lo + b_off, sw_hi, idesc, k != 0);
+            else pair_issue<1>(tmem_acc, a_lo, a_lo + b_off, sw_hi, idesc, k != 0);
+            umma2_commit_both(empty_bar + 8 * st);  // frees the stage in BOTH CTAs once these MMAs retire
+            if (++st == n_stages) { st = 0; ph ^= 1; a_lo = ring_lo0; }
+            else a_lo += stage_units;
+          }
+          umma2_commit_both(accf_bar + 8 * as);  // accumulator complete, in both CTAs
+        }
+        __syncwarp();
+        uint32_t adv = stage + (uint32_t)k_iters;
+        while (adv >= n_stages) { adv -= n_stages; phase ^= 1; }
+        stage = adv;
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- epilogue (warps 2..9, both CTAs): as the CTA-wide
+    // epilogue of conv_tc_body, on this CTA's 128 rows
+    const int ew = warp - 2;
+    const int half = ew >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int tw = r % p.Tw, th = (r / p.Tw) % p.Th, tn = r / (p.Tw * p.Th);
+    const bool leader = ew == 0 && lane == 0;
+    const uint32_t esz = p.out_f32 ? 4u : 2u;
+    const int halves = p.cw / 16;
+    const uint32_t pitch = (uint32_t)p.cw * esz;
+    const uint32_t swz = (r / (128u / pitch)) & (pitch / 16u - 1u);
+    const uint32_t stg_bytes = 128u * pitch;
+    const uint32_t row_addr = r * pitch;
+    const int n_chunks = (p.BN + p.cw - 1) / p.cw;
+    const bool active = half < halves;
+    const uint32_t acce0 = mapa_u32(acce_bar, 0);  // the leader's accumulator-empty barriers
+    int ti = 0;
+    uint32_t sb = 0;
+    for (int pt = cluster_id; pt < total_pairs; pt += n_clusters, ++ti) {
+      int nt, w0, h0, n0;
+      decode(pt, nt, w0, h0, n0);
+      const int ow = w0 + tw, oh = h0 + th, on = n0 + tn;
+      const bool valid = (r < p.Tw * p.Th * p.Tn) && ow < p.Wout && oh < p.Hout && on < p.B;
+      const size_t pix = (static_cast<size_t>(on) * p.Hout + oh) * p.Wout + ow;
+      const size_t rpix = p.res_pre ? (static_cast<size_t>(on) * (p.Hout >> 1) + (oh >> 1)) * (p.Wout >> 1) + (ow >> 1) : pix;
+      const __nv_bfloat16* res_row = static_cast<const __nv_bfloat16*>(p.res) + rpix * p.res_ct + p.res_co + nt * p.BN;
+      const int as = ti & 1;
+      mbar_wait(accf_bar + 8 * as, (ti >> 1) & 1, p.err_flag, 113);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * acc_stride + (static_cast<uint32_t>(quad * 32) << 16);
+      for (int c = 0; c < n_chunks; ++c) {
+        const int col = c * p.cw + half * 16;
+        const uint32_t dst = staging_base + sb * stg_bytes + row_addr;
+        if (active && col < p.BN) {
+          uint4 ra0 = make_uint4(0, 0, 0, 0), ra1 = ra0;
+          if (p.res && valid) {
+            ra0 = *reinterpret_cast<const uint4*>(res_row + col);
+            ra1 = *reinterpret_cast<const uint4*>(res_row + col + 8);
+          }
+          uint32_t va[16];
+          tmem_ld16(taddr + col, va);
+          tmem_ld_wait();
+          epi16<false>(p, va, ra0, ra1, nt * p.BN + col, dst, (uint32_t)(half * 16) / 8u, swz);
+          fence_async_smem();
+        }
+        if (leader) bulk_wait_read0();
+        named_bar_sync(1, kEpiWarps * 32);
+        if (leader) {
+          tma_store_4d(&maps.out, staging_base + sb * stg_bytes, nt * p.BN + c * p.cw, w0, h0, n0);
+          bulk_commit();
+        }
+        sb ^= 1u;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acce0 + 8 * as);
+    }
+    if (leader) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA leaves (or frees its TMEM) while the other may still signal it or use the pair's accumulators
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 3)
 conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcParams p) {
   conv_tc_body<16, false>(maps, p);
@@ -926,6 +1217,10 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
                                                      : CU_TENSOR_MAP_SWIZZLE_32B;
   p.a_slot = 128u * swz_bytes;
   p.b_slot = ((uint32_t)bn * swz_bytes + 1023u) & ~1023u;
+  // CTA-pair variant (tune.epi_warp bit 3): each CTA of the pair holds half of the weight tile
+  p.pair = tune.epi_warp >= 0 && (tune.epi_warp & 8) && !p.halo && !d->in_fp8 && !d->out_fp8 && !d->cscale && d->k != 2 &&
+           bn >= 64 && bn % 32 == 0 && p.tiles_w * p.tiles_h * p.tiles_n >= 2;
+  if (p.pair) p.b_slot = ((uint32_t)(bn / 2) * swz_bytes + 1023u) & ~1023u;
   if (p.halo) {
     p.n_pos = (p.Tw + 2 * p.pad) * (p.Th + 2 * p.pad) * p.Tn;
     const uint32_t plane = (uint32_t)(p.pad ? p.n_pos : 128) * 16u;  // one 8-channel plane: 16 B per position
@@ -938,7 +1233,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     p.in_ct = d->in.c_total; p.Hin = d->Hin; p.Win = d->Win;
     p.mg_ncg = ((1ull << 42) + (cin / 8) - 1) / (cin / 8);
   }
-  p.tx_bytes = (uint32_t)(p.Tw * p.Th * p.Tn) * swz_bytes + (uint32_t)bn * swz_bytes;
+  p.tx_bytes = (uint32_t)(p.Tw * p.Th * p.Tn) * swz_bytes + (uint32_t)(p.pair ? bn / 2 : bn) * swz_bytes;
   const int k_iters = p.taps * p.chunks_per_tap;
   const uint32_t stage = p.halo ? p.a_slot : p.a_slot + p.b_slot;
   // Warp-independent epilogue: possible when the tile has exactly 128 rows and every 32-row quarter (one TMEM lane
@@ -964,7 +1259,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     // fat: bf16 outputs only (64 fp32 channels would be 256-byte staging rows), and the chunk grid must tile BN
     p.fat = (mode & 2) && !d->out_f32 && bn > 32 && (bn % 64 == 0 || p.n_tiles == 1);
     p.quant = (d->in_fp8 || d->out_fp8 || d->cscale) ? 1 : 0;
-    if (p.quant) { p.epi_warp = 0; p.fat = 0; }  // e4m3 kernel: CTA-wide epilogue (32-byte staging rows for e4m3 stores)
+    if (p.quant || p.pair) { p.epi_warp = 0; p.fat = 0; }  // the pair kernel has the CTA-wide epilogue only  // e4m3 kernel: CTA-wide epilogue (32-byte staging rows for e4m3 stores)
   }
   // epilogue chunk width: 32 output channels per TMA store when the tile allows it, else 16 (fp32 rows: 16 in warp mode);
   // 64 in fat mode
@@ -997,7 +1292,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   int cps = 3;
   if (const char* e = getenv("Y11_CTAS_PER_SM")) cps = std::max(1, std::min(4, atoi(e)));
   if (tune.cps > 0) cps = std::max(1, std::min(4, tune.cps));
-  if (p.fat || p.quant) cps = std::min(cps, 2);  // conv_tc_kernel_fat / _q are compiled for 2 CTAs per SM (up to 102 registers)
+  if (p.fat || p.quant || p.pair) cps = std::min(cps, 2);  // conv_tc_kernel_fat / _q are compiled for 2 CTAs per SM (up to 102 registers)
   int cols = 64;  // >= 2 accumulator stages of max(BN, 32) columns (a partial last chunk may read up to 16 spare columns)
   while (cols < 2 * bn) cols *= 2;
   while (cps > 1 && cps * cols > 512) --cps;
@@ -1055,7 +1350,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     const cuuint64_t K = (cuuint64_t)p.taps * cin;
     const cuuint64_t gdim[2] = {K, (cuuint64_t)cout};
     const cuuint64_t gstr[1] = {K * ie};
-    const cuuint32_t bbox[2] = {(cuuint32_t)p.Cc, (cuuint32_t)bn};
+    const cuuint32_t bbox[2] = {(cuuint32_t)p.Cc, (cuuint32_t)(p.pair ? bn / 2 : bn)};
     if (int e = encode_map(eng, &L->maps.b, it, 2, const_cast<void*>(d->w), gdim, gstr, bbox, swz)) return e;
   }
   {
@@ -1097,17 +1392,27 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   }
   const unsigned total_tiles = (unsigned)(p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles);
   L->grid = std::min(total_tiles, (unsigned)(eng->num_sms * cps));
-  L->variant = ConvTcTune{p.halo, p.epi_warp | (p.fat << 1), cps, bn};
+  if (p.pair) {
+    const unsigned m_tiles = (unsigned)(p.tiles_w * p.tiles_h * p.tiles_n);
+    const unsigned total_pairs = ((m_tiles + 1) / 2) * (unsigned)p.n_tiles;
+    L->grid = 2u * std::min(total_pairs, (unsigned)((eng->num_sms / 2) * cps));
+  }
+  L->variant = ConvTcTune{p.halo, p.epi_warp | (p.fat << 1) | (p.pair << 3), cps, bn};
   L->smem_bytes = kHeaderBytes + 1024u + p.b_res_bytes + (unsigned)stages * stage + staging;
   L->flops = 2.0 * d->B * d->Hout * d->Wout * (double)cout * cin * p.taps;
   (void)k_iters;
   Y11_OPT_IN_SMEM(conv_tc_kernel, 220 * 1024);
   Y11_OPT_IN_SMEM(conv_tc_kernel_fat, 220 * 1024);
   Y11_OPT_IN_SMEM(conv_tc_kernel_q, 220 * 1024);
+  Y11_OPT_IN_SMEM(conv_tc_kernel_pair, 220 * 1024);
   return 0;
 }
 
 int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t s) {
+  if (L->p.pair) {
+    Y11_CHECK_CUDA(y11_launch_pdl_pair(conv_tc_kernel_pair, dim3(L->grid), dim3(kThreads), L->smem_bytes, s, L->maps, L->p));
+    return 0;
+  }
   auto* kern = L->p.quant ? conv_tc_kernel_q : L->p.fat ? conv_tc_kernel_fat : conv_tc_kernel;
   Y11_CHECK_CUDA(y11_launch_pdl(kern, dim3(L->grid), dim3(kThreads), L->smem_bytes, s, L->maps, L->p));
   return 0;

@@ -20,6 +20,26 @@ static inline cudaError_t y11_launch_pdl(void (*kernel)(KArgs...), dim3 grid, di
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// Same, as clusters of two CTAs (the cta_group::2 conv variant): gridDim.x must be even.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t y11_launch_pdl_pair(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = 2;
+  at[1].val.clusterDim.y = 1;
+  at[1].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // ---- tcgen05 implicit-GEMM conv (conv_tc.cu) ---------------------------------------------------
 struct ConvTcMaps {
   CUtensorMap a[4];  // activation views: [0] for stride 1; [ph*2+pw] parity sub-grids for stride 2
@@ -34,6 +54,7 @@ struct ConvTcParams {
   int32_t n_tiles;                    // Cout tiles of BN columns
   int32_t BN, Cc, chunks_per_tap, taps, ksize, stride, stages, tmem_cols;
   int32_t epi_warp;  // warp-independent epilogue: each warp stores its own 32-row sub-box (tile must decompose)
+  int32_t pair;      // conv_tc_kernel_pair: a CTA pair computes a 256-row tile with tcgen05.mma.cta_group::2 (b_slot / tx_bytes are per CTA)
   int32_t fat;       // conv_tc_kernel_fat: 32 accumulator columns per epilogue warp step, 64-channel store chunks, 2 CTAs/SM
   int32_t nstg;  // staging buffers per warp of the warp-independent epilogue (1 or 2); the CTA-wide epilogue uses 2
   int32_t cw;  // epilogue chunk width in output channels (16 or 32) = inner box of the output tensor map
@@ -82,7 +103,7 @@ struct ConvTcParams {
 // autotuner (y11_plan_autotune) times the feasible combinations of a layer on its real buffers and keeps the fastest.
 struct ConvTcTune {
   int32_t lsu;       // 0: TMA producer even where the cp.async (LSU) producer is eligible; 1/-1: LSU where eligible
-  int32_t epi_warp;  // bit 0: warp-independent epilogue, bit 1: fat epilogue (conv_tc_kernel_fat)
+  int32_t epi_warp;  // bit 0: warp-independent epilogue, bit 1: fat epilogue (conv_tc_kernel_fat), bit 3: CTA-pair kernel (cta_group::2)
   int32_t cps;       // persistent CTAs per SM (1..4)
   int32_t bn_max;    // largest N tile to consider (16..256)
 };
