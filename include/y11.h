@@ -110,6 +110,14 @@ typedef struct {
   int32_t in_fp8, out_fp8;
   const float* cscale;
   float out_scale;
+  /* k == 2 only.  s2d_block = c != 0 (c in {32, 64}): `in` is a space-to-depth tensor of 4 blocks of c channels in the PERMUTED
+   * block order [(dy,dx)] = [(1,0), (1,1), (0,1), (0,0)] (y11_stem_desc.s2d == 2), and only the channel blocks a tap can touch are
+   * loaded - the 3x3 stride-2 conv this stands for reads 1, 2, 2 and 4 of the 4 blocks at its four block taps, and the permuted
+   * order makes each of those sets ONE contiguous channel range: tap (-1,-1) -> block 1, (-1,0) -> blocks 0-1, (0,-1) -> blocks
+   * 1-2, (0,0) -> blocks 0-3.  `w` is then packed per K stage of 64 channels: bf16 [cout][n_stages * 64], stages ordered
+   * (tap = ty*2+tx ascending; within a tap, 64-channel chunks from channel lo*c upward), zero where a channel's (dy,dx) does
+   * not belong to the tap.  9/16 of the activation bytes of the plain k = 2 form (10/16 for c = 32). */
+  int32_t s2d_block;
 } y11_conv_desc;
 
 /* Stem conv: 3 -> cout, 3x3 stride 2, input is the dense 3-channel bf16 NHWC letterbox output. */
@@ -123,7 +131,7 @@ typedef struct {
    * channel block (dy*2 + dx) of pixel (y, x) is output pixel (2y+dy, 2x+dx); `out` then describes that tensor
    * (out.c = 4*cout).  The following 3x3 stride-2 layer becomes a 2x2 stride-1 conv over 4*cout channels, whose
    * 128-byte-or-longer pixel rows the TMA unit can stream (32-byte rows through four parity maps could not). */
-  int32_t s2d;
+  int32_t s2d;   /* 1: block order (dy*2 + dx);  2: permuted block order [(1,0), (1,1), (0,1), (0,0)] (see y11_conv_desc.s2d_block) */
   /* u8_src != 0: read the frames directly (`in` is ignored): images = DEVICE array of B y11_image descriptors whose frames
    * are already at network resolution (h0 == new_h == Hin, w0 == new_w == Win, top == left == 0, src 4-byte aligned, pitch a
    * multiple of 4).  The conversion (BGR->RGB, x*(1/255), bf16) is bit-identical to y11_letterbox's for such frames, so the

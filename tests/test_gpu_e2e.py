@@ -343,7 +343,11 @@ def test_every_conv_of_the_plan_matches_torch(engines, oracle_models, scale, B, 
             w = pc.w.float().t().reshape(pc.c2, 1, 3, 3)
             want = torch.nn.functional.conv2d(xin, w, pc.b, padding=1, groups=pc.c2)
         else:
-            w = pc.w.float().view(pc.c2, pc.k, pc.k, pc.c1).permute(0, 3, 1, 2)
+            if pc.k == 2:
+                from yolo_infer_b200.network import dense_k2_weights
+                w = dense_k2_weights(pc).permute(0, 3, 1, 2)     # also from the compact per-stage packing (s, m: s2d_block)
+            else:
+                w = pc.w.float().view(pc.c2, pc.k, pc.k, pc.c1).permute(0, 3, 1, 2)
             if pc.k == 2:   # space-to-depth form of model.1: taps at {-1, 0}^2 = zero padding on the top/left only
                 want = torch.nn.functional.conv2d(torch.nn.functional.pad(xin, (1, 0, 1, 0)), w, pc.b)
             else:

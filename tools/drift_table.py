@@ -76,7 +76,11 @@ def main():
         got = v.t[..., v.off:v.off + v.c].float().permute(0, 3, 1, 2).cpu()
         if op.kind == "stem" and got.shape[1] != want[op.name].shape[1]:      # space-to-depth stem buffer
             c = want[op.name].shape[1]
-            got = got.view(B, 2, 2, c, got.shape[2], got.shape[3]).permute(0, 3, 4, 1, 5, 2).reshape(B, c, 2 * got.shape[2], 2 * got.shape[3])
+            got = got.view(B, 4, c, got.shape[2], got.shape[3])
+            if eng._packed["model.1"].s2d_block:       # permuted block order of the compact 2x2 form: back to dy*2+dx
+                from yolo_infer_b200.network import S2D_PERM
+                got = got[:, [S2D_PERM.index((dy, dx)) for dy in (0, 1) for dx in (0, 1)]]
+            got = got.reshape(B, 2, 2, c, got.shape[3], got.shape[4]).permute(0, 3, 4, 1, 5, 2).reshape(B, c, 2 * got.shape[3], 2 * got.shape[4])
         w = want[op.name]
         overwritten = any(o2.out is not None and o2.out.t.data_ptr() == v.t.data_ptr() and o2.out.off < v.off + v.c and v.off < o2.out.off + o2.out.c
                           for o2 in net.ops[i + 1:])

@@ -32,7 +32,7 @@ class ConvDesc(C.Structure):
     _fields_ = [("inp", View), ("out", View), ("res", View), ("w", C.c_void_p), ("bias", C.c_void_p),
                 ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32),
                 ("k", C.c_int32), ("stride", C.c_int32), ("act", C.c_int32), ("out_f32", C.c_int32), ("impl", C.c_int32), ("res_mode", C.c_int32),
-                ("in_fp8", C.c_int32), ("out_fp8", C.c_int32), ("cscale", C.c_void_p), ("out_scale", C.c_float)]
+                ("in_fp8", C.c_int32), ("out_fp8", C.c_int32), ("cscale", C.c_void_p), ("out_scale", C.c_float), ("s2d_block", C.c_int32)]
 
 
 class StemDesc(C.Structure):

@@ -243,13 +243,16 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
     const int oy = oh0 + r;
     // plain NHWC: pixel (oy, ox).  space-to-depth: pixel (oy/2, ox/2) of the half-size map, channel block (oy&1)*2 + (ox&1)
     const size_t row0 = d.s2d ? ((size_t)n * (d.Hout >> 1) + (oy >> 1)) * (d.Wout >> 1) : ((size_t)n * d.Hout + oy) * d.Wout;
-    const int blk_y = d.s2d ? (oy & 1) * 2 * COUT : 0;
+    // block of pixel parity (dy, dx): dy*2 + dx, or (s2d == 2) the permuted order [(1,0), (1,1), (0,1), (0,0)]: dy ? dx : 3 - dx
+    const int dy = oy & 1;
 #pragma unroll
     for (int i = lane; i < 32 * VPP; i += 32) {
       const int px = i / VPP, v = i % VPP;
       const int ox = ow0 + warp * 32 + px;
       if (ox < d.Wout) {
-        const size_t off = d.s2d ? (row0 + (ox >> 1)) * d.out.c_total + blk_y + (ox & 1) * COUT : (row0 + ox) * d.out.c_total;
+        const int dx = ox & 1;
+        const int blk = d.s2d == 2 ? (dy ? dx : 3 - dx) : dy * 2 + dx;
+        const size_t off = d.s2d ? (row0 + (ox >> 1)) * d.out.c_total + blk * COUT : (row0 + ox) * d.out.c_total;
         *reinterpret_cast<uint4*>(ob + off + v * 8) = *reinterpret_cast<const uint4*>(so + px * OP + v * 8);
       }
     }

@@ -345,7 +345,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
   pdl_wait();
   pdl_trigger();
 
-  const int k_iters = p.taps * p.chunks_per_tap;
+  const int k_iters = p.n_kt ? p.n_kt : p.taps * p.chunks_per_tap;
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
 #ifdef Y11_TRACE
   int trc = 0;
@@ -443,7 +443,21 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
       q = fast_div(t, p.mg_tw); const int w0 = (t - q * p.tiles_w) * p.Tw; t = q;
       q = fast_div(t, p.mg_th); const int h0 = (t - q * p.tiles_h) * p.Th; t = q;
       const int n0 = t * p.Tn;
-      for (int tap = 0; tap < p.taps; ++tap) {
+      for (int k = 0; k < p.n_kt; ++k) {  // compact k = 2 form: only the channel blocks a block tap can touch
+        const uint32_t e = p.kt[k];
+        const int tap = (int)(e & 3u), c0 = (int)(e >> 2) * 16;
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1, p.err_flag, 101);
+        if (elect_one()) {
+          const uint32_t fb = full_bar + 8 * stage;
+          const uint32_t a_dst = ring_base + stage * stage_bytes;
+          mbar_expect_tx(fb, p.tx_bytes);
+          tma_load_4d(a_dst, &maps.a[0], fb, c0, w0 + (tap & 1) - 1, h0 + (tap >> 1) - 1, n0);
+          tma_load_2d(a_dst + p.a_slot, &maps.b, fb, k * p.Cc, nt * p.BN);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+      }
+      for (int tap = 0; tap < (p.n_kt ? 0 : p.taps); ++tap) {
         int mi = 0, cw, ch;
         if (p.ksize == 1) {
           cw = w0; ch = h0;
@@ -1207,6 +1221,18 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   p.oscale = d->out_fp8 ? d->out_scale : 1.0f;
   p.chunks_per_tap = cin / p.Cc;
   p.taps = d->k * d->k;
+  if (d->s2d_block) {
+    const int c = d->s2d_block;
+    Y11_REQUIRE(d->k == 2 && (c == 32 || c == 64) && cin == 4 * c && !d->in_fp8, "conv_tc: s2d_block=%d needs k = 2 and cin = 4 * block (cin=%d)", c, cin);
+    p.Cc = 64;
+    p.chunks_per_tap = cin / 64;
+    // permuted block order [(1,0), (1,1), (0,1), (0,0)]: block range a tap (ty, tx) can touch
+    static const int lo[4] = {1, 0, 1, 0}, hi[4] = {2, 2, 3, 4};
+    for (int tap = 0; tap < 4; ++tap) {
+      const int c0 = lo[tap] * c, n = ((hi[tap] - lo[tap]) * c + 63) / 64;
+      for (int j = 0; j < n; ++j) p.kt[p.n_kt++] = (uint16_t)(tap | (((c0 + 64 * j) / 16) << 2));
+    }
+  }
   p.ksize = d->k;
   p.stride = d->stride;
   const uint32_t swz_bytes = p.Cc * in_esz;
@@ -1347,7 +1373,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
       }
   }
   {
-    const cuuint64_t K = (cuuint64_t)p.taps * cin;
+    const cuuint64_t K = p.n_kt ? (cuuint64_t)p.n_kt * p.Cc : (cuuint64_t)p.taps * cin;
     const cuuint64_t gdim[2] = {K, (cuuint64_t)cout};
     const cuuint64_t gstr[1] = {K * ie};
     const cuuint32_t bbox[2] = {(cuuint32_t)p.Cc, (cuuint32_t)(p.pair ? bn / 2 : bn)};
@@ -1375,7 +1401,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   }
   if (d->k == 2 && !p.halo) {
     // zero-block scan of the weights (one-off, at plan-build time): K step (k_iter, kk) = 16 consecutive K elements
-    const int k_total = p.taps * cin, steps = k_total / 16;
+    const int k_total = p.n_kt ? p.n_kt * p.Cc : p.taps * cin, steps = k_total / 16;
     if (steps <= 64) {
       std::vector<__nv_bfloat16> hw((size_t)cout * k_total);
       Y11_CHECK_CUDA(cudaMemcpy(hw.data(), d->w, hw.size() * sizeof(__nv_bfloat16), cudaMemcpyDeviceToHost));

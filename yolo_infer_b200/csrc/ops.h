@@ -72,6 +72,10 @@ struct ConvTcParams {
   int32_t out_esz;       // bytes per output element: 4 (fp32 logits), 2 (bf16), 1 (e4m3)
   const float* cscale;   // per-output-channel multiplier of the accumulator before the bias (fp8 dequantisation) or nullptr
   float oscale;          // multiplier before the e4m3 conversion of the output
+  // compact k = 2 form (y11_conv_desc.s2d_block): K stage k loads channels [16*(kt[k]>>2), +Cc) at block tap (kt[k] & 3);
+  // n_kt = number of K stages (0: the regular tap x chunk walk)
+  int32_t n_kt;
+  uint16_t kt[16];
   uint64_t kmask;       // bit (k_iter * Cc/16 + kk): that 16-element K step has non-zero weights (TMA path, k == 2)
   int32_t kmask_on;
   int* err_flag;

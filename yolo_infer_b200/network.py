@@ -23,6 +23,8 @@ from . import topology as T
 
 BN_EPS = 1e-3
 S2D_STEM = True   # stem output in space-to-depth form, model.1 as a 2x2 stride-1 conv (see pack_weights)
+# model.1 in the compact 2x2 form for 32- / 64-channel stems (s, m, l): permuted block order, only the blocks a tap touches are loaded
+S2D_COMPACT = os.environ.get("Y11_S2D_COMPACT", "1") != "0"
 # Upsample -> Concat -> C3k2.cv1 (yaml layers 11-13 and 14-16) without the upsampled / concatenated tensors: a 1x1 conv
 # commutes with nearest upsampling, so cv1's weights are split by input channel, W_up . p (+bias) runs at LOW resolution and
 # enters the conv over the skip tensor as a pre-activation term (Y11_RES_PRE_UP2).  Y11_FOLD_UP=0 restores the copy ops.
@@ -113,6 +115,27 @@ class PackedConv:
     alg_k: int = 0           # algorithmic K per output (e.g. 9*cin of the 3x3 conv a repacked 2x2 space-to-depth conv stands for)
     in_fp8: bool = False     # w holds e4m3 bytes (uint8 tensor); the input tensor is e4m3 as well
     cscale: Optional[torch.Tensor] = None   # fp32 [cout]: input activation scale x per-channel weight scale (fp8 dequantisation)
+    s2d_block: int = 0       # k == 2, compact form: space-to-depth input with blocks of this many channels in the permuted order
+
+
+S2D_PERM = [(1, 0), (1, 1), (0, 1), (0, 0)]     # permuted space-to-depth block order of the compact 2x2 form: block index -> (dy, dx)
+
+
+def compact_k2_stages(c: int) -> List[Tuple[int, int]]:
+    """K stages (tap = ty*2+tx, first channel) of the compact 2x2 form for blocks of c channels (y11_conv_desc.s2d_block)."""
+    lo, hi = [1, 0, 1, 0], [2, 2, 3, 4]
+    return [(tap, lo[tap] * c + 64 * j) for tap in range(4) for j in range(((hi[tap] - lo[tap]) * c + 63) // 64)]
+
+
+def dense_k2_weights(pc: "PackedConv") -> torch.Tensor:
+    """[cout, 2, 2, 4c] fp32 weights of a k = 2 conv over its (possibly permuted-block) space-to-depth input, from either packing."""
+    if not pc.s2d_block:
+        return pc.w.float().view(pc.c2, 2, 2, pc.c1)
+    w = torch.zeros(pc.c2, 4, pc.c1, device=pc.w.device)
+    wc = pc.w.float().view(pc.c2, -1, 64)
+    for k, (tap, c0) in enumerate(compact_k2_stages(pc.s2d_block)):
+        w[:, tap, c0:c0 + 64] += wc[:, k]          # stages of one tap never overlap
+    return w.view(pc.c2, 2, 2, pc.c1)
 
 
 def fold(sd: Dict[str, torch.Tensor], cp: T.ConvParam) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -165,6 +188,25 @@ def pack_weights(scale: str, nc: int, sd: Dict[str, torch.Tensor], device) -> Di
                             kh, kw = 2 * (ty - 1) + dy + 1, 2 * (tx - 1) + dx + 1
                             if 0 <= kh <= 2 and 0 <= kw <= 2:
                                 wp[:, ty, tx, dy * 2 + dx, :] = w[:, :, kh, kw]
+            if S2D_COMPACT and cp.c1 in (32, 64):
+                # Compact form (y11_conv_desc.s2d_block): the stem writes its blocks in the order [(1,0), (1,1), (0,1), (0,0)], in
+                # which the blocks each tap can touch - 1, 2, 2 and 4 of the 4 - are contiguous channel ranges; only those are loaded.
+                c = cp.c1
+                stages = []
+                for tap, c0 in compact_k2_stages(c):
+                    ty, tx = tap // 2, tap % 2
+                    st = torch.zeros(cp.c2, 64)
+                    for i in range(64):
+                        ch = c0 + i
+                        dy, dx = S2D_PERM[ch // c]
+                        kh, kw = 2 * (ty - 1) + dy + 1, 2 * (tx - 1) + dx + 1
+                        if 0 <= kh <= 2 and 0 <= kw <= 2:
+                            st[:, i] = w[:, ch % c, kh, kw]
+                    stages.append(st)
+                wc = torch.cat(stages, 1)
+                packed[cp.prefix] = PackedConv(wc.to(device, torch.bfloat16).contiguous(), b.to(device).contiguous(), 4 * c, cp.c2, 2, 1,
+                                               act, alg_k=9 * c, s2d_block=c)
+                continue
             packed[cp.prefix] = PackedConv(wp.view(cp.c2, -1).to(device, torch.bfloat16).contiguous(), b.to(device).contiguous(),
                                            4 * cp.c1, cp.c2, 2, 1, act, alg_k=9 * cp.c1)
         else:
@@ -390,6 +432,7 @@ class CompiledNet:
         d.cscale = pc.cscale.data_ptr() if pc.cscale is not None else None
         d.out_fp8 = int(out_fp8_scale is not None)
         d.out_scale = 1.0 / out_fp8_scale if out_fp8_scale is not None else 1.0
+        d.s2d_block = pc.s2d_block
         var = self._cached_variants.get(name) if self._cached_variants is not None else None
         if var is not None and var[2] > 0 and self.conv_impl == cabi.IMPL_TCGEN05:   # variant chosen by an earlier autotune run
             cabi.check(self.lib.y11_plan_add_conv_tuned(self.plan, C.byref(d), *[int(v) for v in var]), f"plan_add_conv_tuned({name})")
@@ -604,6 +647,8 @@ class CompiledNet:
                 pc = self.packed["model.0"]
                 nb = inp.shape[0]
                 s2d = int(o.c == 4 * sp.c2)          # o is then the [H/4, W/4, 4*c2] space-to-depth tensor
+                if s2d and self.packed["model.1"].s2d_block:
+                    s2d = 2                          # permuted block order (compact 2x2 form of model.1)
                 d = cabi.StemDesc(inp.data_ptr(), o.cview(), pc.w.data_ptr(), pc.b.data_ptr(), nb, H, W, H // 2, W // 2, s2d)
                 cabi.check(self.lib.y11_plan_add_stem(self.plan, C.byref(d)), "plan_add_stem")
                 self.ops.append(OpRecord("stem", "model.0", 2.0 * nb * (H // 2) * (W // 2) * sp.c2 * 27,
