@@ -213,12 +213,13 @@ def test_conv_cta_pair_variant_is_bit_identical(ctx, shape):
     base, want = conv_case(ctx, B, H, W, cin, cout, k, s_, act, res)
     close_bf16(base, want)
     n = 0
-    for cps in (1, 2):
-        for bn in (-1, 256, 128, 64):
-            got, var = conv_case(ctx, B, H, W, cin, cout, k, s_, act, res, tune=(0, 8, cps, bn), repeats=2, return_variant=True)
-            assert torch.equal(got, base), (cps, bn, (got - base).abs().max().item())
-            n += 1 if (var[1] & 8) else 0
-    assert n >= 4, "the pair kernel was never selected"
+    for ew in (8, 10):              # bit 3: pair kernel; bit 1: its fat epilogue (conv_tc_kernel_pair_fat)
+        for cps in (1, 2):
+            for bn in (-1, 256, 128, 64):
+                got, var = conv_case(ctx, B, H, W, cin, cout, k, s_, act, res, tune=(0, ew, cps, bn), repeats=2, return_variant=True)
+                assert torch.equal(got, base), (ew, cps, bn, (got - base).abs().max().item())
+                n += 1 if (var[1] & 8) else 0
+    assert n >= 8, "the pair kernel was never selected"
 
 
 def test_conv_2x2_space_to_depth_form(ctx):

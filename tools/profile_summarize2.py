@@ -22,11 +22,13 @@ def ncu_csv(path):
     return list(csv.DictReader(io.StringIO(text[text.index('"ID"'):])))
 
 
-out = [f"# {TAG}: ncu summary (commands: tools/profile_round2.sh; B200, 1 GPU, batch 64, 640x640, `--clock-control none`, conditioned "
+out = [f"# {TAG}: ncu summary (commands: tools/profile_round2.sh / profile_round2b.sh; B200, 1 GPU, batch 64, 640x640, `--clock-control none`, conditioned "
        "synthetic weights, kernels launched one by one in plan order)\n"]
 traffic = {"what": "dram__bytes_read.sum + dram__bytes_write.sum summed over the conv_tc_kernel launches of ONE step, per model; raw rows "
                    f"profiles/{TAG}_conv_dram_M.csv, per-layer join profiles/{TAG}_layers_M.md"}
 for m in "sn":
+    if not (G / f"{TAG}_launches_yolo11{m}_b64.csv").exists():     # tools/profile_round2b.sh profiles YOLO11s only
+        continue
     rows = ncu_csv(G / f"{TAG}_launches_yolo11{m}_b64.csv")
     first = next(i for i, r in enumerate(rows) if "letterbox" in r["Kernel Name"] or "stem_kernel" in r["Kernel Name"])
     per, n_pass = defaultdict(lambda: [0, 0.0]), 0

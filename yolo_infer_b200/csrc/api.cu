@@ -235,11 +235,12 @@ extern "C" int y11_plan_autotune(y11_plan p, y11_stream s_, int reps) {
     {
       static const bool pair_on = [] { const char* e = getenv("Y11_PAIR"); return e ? atoi(e) != 0 : true; }();
       if (pair_on && !(base.p.halo) && bn0 >= 64) {
-        for (int cps = 2; cps >= 1; --cps) {
-          cands.push_back(ConvTcTune{0, 8, cps, -1});
-          if (d->out.c % 256 == 0 && bn0 != 256) cands.push_back(ConvTcTune{0, 8, cps, 256});
-          if (bn0 == 256) cands.push_back(ConvTcTune{0, 8, cps, 128});
-        }
+        for (int cps = 2; cps >= 1; --cps)
+          for (int ew = 8; ew <= 10; ew += 2) {  // plain and fat epilogue
+            cands.push_back(ConvTcTune{0, ew, cps, -1});
+            if (d->out.c % 256 == 0 && bn0 != 256) cands.push_back(ConvTcTune{0, ew, cps, 256});
+            if (bn0 == 256) cands.push_back(ConvTcTune{0, ew, cps, 128});
+          }
       }
     }
     // time one variant: best of three trials of `reps` back-to-back launches (after one warm-up launch)

@@ -134,6 +134,7 @@ struct TmaTileArgs {
   uint32_t tmem_acc, ring_lo0, b_off, hi, idesc, stage_units, n_stages, full_bar, empty_bar, accf;
   int k_iters;
   int* err_flag;
+  uint32_t bres_lo, b_step;  // resident weights (bres_lo != 0): descriptor low word of K stage 0 and the step between stages
 };
 template <int KK, bool kQ>
 __device__ __forceinline__ void tma_tile_issue(const TmaTileArgs& t, uint32_t stage, uint32_t phase, bool f8) {
@@ -141,7 +142,7 @@ __device__ __forceinline__ void tma_tile_issue(const TmaTileArgs& t, uint32_t st
   for (int k = 0; k < t.k_iters; ++k) {
     y11::mbar_wait(fb, phase, t.err_flag, 102);
     y11::tc_fence_after();
-    tma_issue<KK, kQ>(t.tmem_acc, a_lo, a_lo + t.b_off, t.hi, t.idesc, k != 0, f8);
+    tma_issue<KK, kQ>(t.tmem_acc, a_lo, t.bres_lo ? t.bres_lo + (uint32_t)k * t.b_step : a_lo + t.b_off, t.hi, t.idesc, k != 0, f8);
     y11::umma_commit(eb);  // frees the smem slot once these MMAs retire
     if (++stage == t.n_stages) { stage = 0; phase ^= 1; a_lo = t.ring_lo0; fb = t.full_bar; eb = t.empty_bar; }
     else { a_lo += t.stage_units; fb += 8; eb += 8; }
@@ -286,7 +287,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
   const uint32_t acce_bar = accf_bar + 16;                // 2 x 8 B  accumulator empty (epilogue -> MMA)
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_raw + 16 * kMaxStages + 48);
   // TMA mode : stages x [A tap box | B tap tile];  halo mode: [resident B, all taps] then stages x [A halo tile]
-  const uint32_t stage_bytes = p.halo ? p.a_slot : p.a_slot + p.b_slot;
+  const uint32_t stage_bytes = (p.halo || p.bres) ? p.a_slot : p.a_slot + p.b_slot;
   const uint32_t ring_base = tiles_base + p.b_res_bytes;
   const uint32_t staging_base = ring_base + p.stages * stage_bytes;  // 2 buffers x stg_bytes
   const uint32_t bres_bar = acce_bar + 16;               // halo mode: resident weights landed
@@ -433,6 +434,11 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
     }
   } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (converged warp, one elected lane issues)
+    if (p.bres && lane == 0) {  // resident weights: every K stage of the single N tile, once per CTA
+      const int nb = p.n_kt ? p.n_kt : p.taps * p.chunks_per_tap;
+      mbar_expect_tx(bres_bar, (uint32_t)(nb * p.BN) * (uint32_t)(p.Cc * 2));
+      for (int i = 0; i < nb; ++i) tma_load_2d(tiles_base + i * p.b_slot, &maps.b, bres_bar, i * p.Cc, 0);
+    }
     uint32_t stage = 0, phase = 0, qi = 0;
     for (int tile = blockIdx.x; ; ++qi) {
       tq_publish(qi, tile);
@@ -452,7 +458,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
           const uint32_t a_dst = ring_base + stage * stage_bytes;
           mbar_expect_tx(fb, p.tx_bytes);
           tma_load_4d(a_dst, &maps.a[0], fb, c0, w0 + (tap & 1) - 1, h0 + (tap >> 1) - 1, n0);
-          tma_load_2d(a_dst + p.a_slot, &maps.b, fb, k * p.Cc, nt * p.BN);
+          if (!p.bres) tma_load_2d(a_dst + p.a_slot, &maps.b, fb, k * p.Cc, nt * p.BN);
         }
         __syncwarp();
         if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
@@ -478,7 +484,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
             const uint32_t a_dst = ring_base + stage * stage_bytes;
             mbar_expect_tx(fb, p.tx_bytes);
             tma_load_4d(a_dst, &maps.a[mi], fb, c * p.Cc, cw, ch, n0);
-            tma_load_2d(a_dst + p.a_slot, &maps.b, fb, tap * p.cin + c * p.Cc, nt * p.BN);
+            if (!p.bres) tma_load_2d(a_dst + p.a_slot, &maps.b, fb, tap * p.cin + c * p.Cc, nt * p.BN);
           }
           __syncwarp();
           if (lane == 0) TRACE(0, 2);
@@ -505,7 +511,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
     const int kk_n = f8 ? p.Cc / 32 : p.Cc / 16;  // one MMA = 32 bytes of K: 16 bf16 or 32 e4m3 elements
     uint32_t stage = 0, phase = 0;  // ring position, advanced incrementally (no div/mod per stage)
     int ti = 0;
-    if (p.halo) mbar_wait(bres_bar, 0, p.err_flag, 105);
+    if (p.halo || p.bres) mbar_wait(bres_bar, 0, p.err_flag, 105);
     const uint32_t n_stages = (uint32_t)p.stages;
     const uint32_t stage_units = stage_bytes >> 4;
     // swizzled K-major descriptor (weights everywhere, activations in TMA mode): lo = addr>>4 | LBO(1)<<16, hi = SBO>>4 | version | layout
@@ -573,8 +579,9 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
         // ONE elected lane walks all K stages of the tile (wait, UMMAs, commit): no per-stage elect / warp re-convergence
         // between the last UMMA of a stage and the first of the next - with BN = 256 the pipe's queue does not cover that gap
         if (elect_one()) {
+          const uint32_t bres_lo = p.bres ? (((tiles_base & 0x3FFFFu) >> 4) | (1u << 16)) : 0u;
           const TmaTileArgs ta{tmem_acc, ring_lo0, b_off, sw_hi, idesc, stage_units, n_stages, full_bar, empty_bar, accf,
-                               k_iters, p.err_flag};
+                               k_iters, p.err_flag, bres_lo, p.b_slot >> 4};
           if (mode == 4) tma_tile_issue<4, kQ>(ta, stage, phase, f8);
           else if (mode == 2) tma_tile_issue<2, kQ>(ta, stage, phase, f8);
           else if (mode == 1) tma_tile_issue<1, kQ>(ta, stage, phase, f8);
@@ -586,7 +593,8 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
             for (int k = 0; k < k_iters; ++k) {
               mbar_wait(full_bar + 8 * st, ph, p.err_flag, 102);
               tc_fence_after();
-              const uint32_t a_lo = ring_lo0 + st * stage_units, b_lo = a_lo + b_off;
+              const uint32_t a_lo = ring_lo0 + st * stage_units;
+              const uint32_t b_lo = bres_lo ? bres_lo + (uint32_t)k * (p.b_slot >> 4) : a_lo + b_off;
               const uint32_t bits = (uint32_t)(p.kmask >> (k * kk_n));
               for (int kk = 0; kk < kk_n; ++kk) {
                 if ((bits >> kk) & 1u) {
@@ -890,8 +898,8 @@ __device__ __forceinline__ void pair_issue(uint32_t tmem_acc, uint32_t a_lo, uin
   for (int kk = 0; kk < KK; ++kk) umma2_lohi(tmem_acc, a_lo + 2u * kk, hi, b_lo + 2u * kk, hi, idesc, kk ? 1u : acc0);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel_pair(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcParams p) {
+template <int kCpw>  // accumulator columns an epilogue warp drains per step (32 = fat epilogue, 64-channel store chunks)
+__device__ __forceinline__ void conv_tc_pair_body(const ConvTcMaps& maps, const ConvTcParams& p) {
   using namespace y11;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
@@ -1028,7 +1036,7 @@ conv_tc_kernel_pair(const __grid_constant__ ConvTcMaps maps, const __grid_consta
     }
   } else {
     // -------------------------------------------------------------------- epilogue (warps 2..9, both CTAs): as the CTA-wide
-    // epilogue of conv_tc_body, on this CTA's 128 rows
+    // epilogue of conv_tc_body (incl. its fat form), on this CTA's 128 rows
     const int ew = warp - 2;
     const int half = ew >> 2;
     const int quad = warp & 3;
@@ -1036,7 +1044,7 @@ conv_tc_kernel_pair(const __grid_constant__ ConvTcMaps maps, const __grid_consta
     const int tw = r % p.Tw, th = (r / p.Tw) % p.Th, tn = r / (p.Tw * p.Th);
     const bool leader = ew == 0 && lane == 0;
     const uint32_t esz = p.out_f32 ? 4u : 2u;
-    const int halves = p.cw / 16;
+    const int halves = p.cw / kCpw;
     const uint32_t pitch = (uint32_t)p.cw * esz;
     const uint32_t swz = (r / (128u / pitch)) & (pitch / 16u - 1u);
     const uint32_t stg_bytes = 128u * pitch;
@@ -1059,18 +1067,26 @@ conv_tc_kernel_pair(const __grid_constant__ ConvTcMaps maps, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * acc_stride + (static_cast<uint32_t>(quad * 32) << 16);
       for (int c = 0; c < n_chunks; ++c) {
-        const int col = c * p.cw + half * 16;
+        const int col = c * p.cw + half * kCpw;
         const uint32_t dst = staging_base + sb * stg_bytes + row_addr;
         if (active && col < p.BN) {
-          uint4 ra0 = make_uint4(0, 0, 0, 0), ra1 = ra0;
+          const bool two = kCpw == 32 && col + 16 < p.BN;
+          uint4 ra0 = make_uint4(0, 0, 0, 0), ra1 = ra0, rb0 = ra0, rb1 = ra0;
           if (p.res && valid) {
             ra0 = *reinterpret_cast<const uint4*>(res_row + col);
             ra1 = *reinterpret_cast<const uint4*>(res_row + col + 8);
+            if (two) {
+              rb0 = *reinterpret_cast<const uint4*>(res_row + col + 16);
+              rb1 = *reinterpret_cast<const uint4*>(res_row + col + 24);
+            }
           }
-          uint32_t va[16];
+          uint32_t va[16], vb[16];
           tmem_ld16(taddr + col, va);
+          if (two) tmem_ld16(taddr + col + 16, vb);
           tmem_ld_wait();
-          epi16<false>(p, va, ra0, ra1, nt * p.BN + col, dst, (uint32_t)(half * 16) / 8u, swz);
+          const int n = nt * p.BN + col;
+          epi16<false>(p, va, ra0, ra1, n, dst, (uint32_t)(half * kCpw) / 8u, swz);
+          if (two) epi16<false>(p, vb, rb0, rb1, n + 16, dst, (uint32_t)(half * kCpw + 16) / 8u, swz);
           fence_async_smem();
         }
         if (leader) bulk_wait_read0();
@@ -1091,6 +1107,15 @@ conv_tc_kernel_pair(const __grid_constant__ ConvTcMaps maps, const __grid_consta
   __syncthreads();
   cluster_sync_all();  // neither CTA leaves (or frees its TMEM) while the other may still signal it or use the pair's accumulators
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+conv_tc_kernel_pair(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcParams p) {
+  conv_tc_pair_body<16>(maps, p);
+}
+__global__ void __launch_bounds__(kThreads, 2)
+conv_tc_kernel_pair_fat(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcParams p) {
+  conv_tc_pair_body<32>(maps, p);
 }
 
 __global__ void __launch_bounds__(kThreads, 3)
@@ -1244,9 +1269,22 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   p.a_slot = 128u * swz_bytes;
   p.b_slot = ((uint32_t)bn * swz_bytes + 1023u) & ~1023u;
   // CTA-pair variant (tune.epi_warp bit 3): each CTA of the pair holds half of the weight tile
-  p.pair = tune.epi_warp >= 0 && (tune.epi_warp & 8) && !p.halo && !d->in_fp8 && !d->out_fp8 && !d->cscale && d->k != 2 &&
+  // heuristic (no explicit variant): the long-K 3x3 layers on 128 x 256 tiles, which the autotuner moved to the pair kernel on
+  // every scale measured (they are shared-memory-bandwidth bound as single CTAs)
+  static const bool pair_default = [] { const char* e = getenv("Y11_PAIR"); return e ? atoi(e) != 0 : true; }();
+  const bool want_pair = tune.epi_warp >= 0 ? (tune.epi_warp & 8) != 0 : (pair_default && d->k == 3 && bn == 256);
+  p.pair = want_pair && !p.halo && !d->in_fp8 && !d->out_fp8 && !d->cscale && d->k != 2 &&
            bn >= 64 && bn % 32 == 0 && p.tiles_w * p.tiles_h * p.tiles_n >= 2;
   if (p.pair) p.b_slot = ((uint32_t)(bn / 2) * swz_bytes + 1023u) & ~1023u;
+  // Resident weights in TMA mode: a layer with ONE N tile whose whole weight matrix is small keeps it in shared memory for
+  // the CTA's lifetime instead of re-fetching a B tile with every K stage of every tile (model.1: 8 KB of the 24 KB per stage;
+  // the store-heavy 1x1 layers on the large maps: a third to a half of their L2 -> shared-memory traffic).
+  {
+    static const int bres_kb = [] { const char* e = getenv("Y11_BRES_KB"); return e ? atoi(e) : 40; }();
+    const int nk = p.n_kt ? p.n_kt : p.taps * p.chunks_per_tap;
+    p.bres = !p.halo && !p.pair && !d->in_fp8 && cout == bn && (size_t)nk * p.b_slot <= (size_t)bres_kb * 1024;
+    if (p.bres) p.b_res_bytes = (uint32_t)nk * p.b_slot;
+  }
   if (p.halo) {
     p.n_pos = (p.Tw + 2 * p.pad) * (p.Th + 2 * p.pad) * p.Tn;
     const uint32_t plane = (uint32_t)(p.pad ? p.n_pos : 128) * 16u;  // one 8-channel plane: 16 B per position
@@ -1259,9 +1297,9 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     p.in_ct = d->in.c_total; p.Hin = d->Hin; p.Win = d->Win;
     p.mg_ncg = ((1ull << 42) + (cin / 8) - 1) / (cin / 8);
   }
-  p.tx_bytes = (uint32_t)(p.Tw * p.Th * p.Tn) * swz_bytes + (uint32_t)(p.pair ? bn / 2 : bn) * swz_bytes;
+  p.tx_bytes = (uint32_t)(p.Tw * p.Th * p.Tn) * swz_bytes + (p.bres ? 0u : (uint32_t)(p.pair ? bn / 2 : bn) * swz_bytes);
   const int k_iters = p.taps * p.chunks_per_tap;
-  const uint32_t stage = p.halo ? p.a_slot : p.a_slot + p.b_slot;
+  const uint32_t stage = (p.halo || p.bres) ? p.a_slot : p.a_slot + p.b_slot;
   // Warp-independent epilogue: possible when the tile has exactly 128 rows and every 32-row quarter (one TMEM lane
   // quadrant) is itself a (qbw x qbh x qbn) box of pixels, so that each warp can TMA-store its own rows.
   int qbw = 0, qbh = 0, qbn = 0;
@@ -1285,7 +1323,8 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     // fat: bf16 outputs only (64 fp32 channels would be 256-byte staging rows), and the chunk grid must tile BN
     p.fat = (mode & 2) && !d->out_f32 && bn > 32 && (bn % 64 == 0 || p.n_tiles == 1);
     p.quant = (d->in_fp8 || d->out_fp8 || d->cscale) ? 1 : 0;
-    if (p.quant || p.pair) { p.epi_warp = 0; p.fat = 0; }  // the pair kernel has the CTA-wide epilogue only  // e4m3 kernel: CTA-wide epilogue (32-byte staging rows for e4m3 stores)
+    if (p.quant) { p.epi_warp = 0; p.fat = 0; }
+    if (p.pair) p.epi_warp = 0;  // the pair kernel has the CTA-wide epilogue (plain or fat)  // e4m3 kernel: CTA-wide epilogue (32-byte staging rows for e4m3 stores)
   }
   // epilogue chunk width: 32 output channels per TMA store when the tile allows it, else 16 (fp32 rows: 16 in warp mode);
   // 64 in fat mode
@@ -1327,6 +1366,10 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   if (p.halo) {  // resident weights + at least two halo tiles must fit
     while (cps > 1 && budget_of(cps) < fixed + 2 * stage) --cps;
     Y11_REQUIRE(budget_of(cps) >= fixed + 2 * stage, "conv_tc: halo tile does not fit in shared memory");
+  }
+  if (p.bres) {  // resident weights + at least three activation stages must fit
+    while (cps > 1 && budget_of(cps) < fixed + 3 * stage) --cps;
+    Y11_REQUIRE(budget_of(cps) >= fixed + 2 * stage, "conv_tc: resident weights do not fit in shared memory");
   }
   const uint32_t budget = budget_of(cps);
   int stages = budget > fixed ? (int)((budget - fixed) / stage) : 0;
@@ -1431,12 +1474,14 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   Y11_OPT_IN_SMEM(conv_tc_kernel_fat, 220 * 1024);
   Y11_OPT_IN_SMEM(conv_tc_kernel_q, 220 * 1024);
   Y11_OPT_IN_SMEM(conv_tc_kernel_pair, 220 * 1024);
+  Y11_OPT_IN_SMEM(conv_tc_kernel_pair_fat, 220 * 1024);
   return 0;
 }
 
 int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t s) {
   if (L->p.pair) {
-    Y11_CHECK_CUDA(y11_launch_pdl_pair(conv_tc_kernel_pair, dim3(L->grid), dim3(kThreads), L->smem_bytes, s, L->maps, L->p));
+    Y11_CHECK_CUDA(y11_launch_pdl_pair(L->p.fat ? conv_tc_kernel_pair_fat : conv_tc_kernel_pair, dim3(L->grid), dim3(kThreads),
+                                       L->smem_bytes, s, L->maps, L->p));
     return 0;
   }
   auto* kern = L->p.quant ? conv_tc_kernel_q : L->p.fat ? conv_tc_kernel_fat : conv_tc_kernel;

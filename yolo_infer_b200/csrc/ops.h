@@ -54,6 +54,7 @@ struct ConvTcParams {
   int32_t n_tiles;                    // Cout tiles of BN columns
   int32_t BN, Cc, chunks_per_tap, taps, ksize, stride, stages, tmem_cols;
   int32_t epi_warp;  // warp-independent epilogue: each warp stores its own 32-row sub-box (tile must decompose)
+  int32_t bres;      // TMA mode with RESIDENT weights: all K stages of the (single) N tile are loaded once per CTA, stages carry activations only
   int32_t pair;      // conv_tc_kernel_pair: a CTA pair computes a 256-row tile with tcgen05.mma.cta_group::2 (b_slot / tx_bytes are per CTA)
   int32_t fat;       // conv_tc_kernel_fat: 32 accumulator columns per epilogue warp step, 64-channel store chunks, 2 CTAs/SM
   int32_t nstg;  // staging buffers per warp of the warp-independent epilogue (1 or 2); the CTA-wide epilogue uses 2
