@@ -186,13 +186,13 @@ def test_conv_launch_variants_are_bit_identical(ctx, shape):
     close_bf16(base, want)
     n = 0
     for lsu in (0, 1):
-        for ew in (0, 1, 2, 3):     # bit 0: per-warp epilogue, bit 1: fat epilogue (conv_tc_kernel_fat, 64-channel chunks)
+        for ew in (0, 1, 2, 3, 4, 6):     # bit 0: per-warp epilogue, bit 1: fat epilogue (64-channel chunks), bit 2: resident weights
             for cps in (2, 3):
                 for bn in (-1, 64, 32):
                     got, _ = conv_case(ctx, B, H, W, cin, cout, k, s_, act, res, tune=(lsu, ew, cps, bn))
                     assert torch.equal(got, base), (lsu, ew, cps, bn, (got - base).abs().max().item())
                     n += 1
-    assert n == 48
+    assert n == 72
 
 
 PAIR_SHAPES = [

@@ -1,13 +1,12 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-T=${TAG:-d16}
+T=${TAG:-d18}
 timeout 900 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "conv" > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/${T}_pytest.log
-for f in 40 0; do
-Y11_BRES_KB=$f timeout 600 python bench.py --extras "" --no-cpu-baseline --skip-e2e --latency-iters 0 --per-op > gpurun_out/${T}_bench_s_b$f.json 2> gpurun_out/${T}_bench_s_b$f.err; echo "bench bres=$f rc=$?"
+timeout 600 python bench.py --extras "" --no-cpu-baseline --skip-e2e --latency-iters 0 --per-op > gpurun_out/${T}_bench_s.json 2> gpurun_out/${T}_bench_s.err; echo "bench rc=$?"
 python - <<PY
 import json
-d=json.loads([l for l in open('gpurun_out/${T}_bench_s_b$f.json') if l.startswith('{')][-1])
+d=json.loads([l for l in open('gpurun_out/${T}_bench_s.json') if l.startswith('{')][-1])
 print('value',round(d['value']),'ms',round(d['ms_per_step'],3),'blocks',[round(x,3) for x in d.get('ms_per_step_blocks',[])])
 PY
-done
+grep -c bres gpurun_out/${T}_bench_s.err

@@ -29,7 +29,7 @@ for o, i in zip(ops, ids):
     t = m.get("gpu__time_duration.sum", 0.0)
     t_us = t / 1e3 if t > 1e3 else t
     v = o["variant"]
-    var = f"{'lsu' if v[0] else 'tma'} {'epiW' if v[1] & 1 else 'epiC'}{'-fat' if v[1] & 2 else ''}{'-pair' if v[1] & 8 else ''} {v[2]}cta BN{v[3]}"
+    var = f"{'lsu' if v[0] else 'tma'} {'epiW' if v[1] & 1 else 'epiC'}{'-fat' if v[1] & 2 else ''}{'-bres' if v[1] & 4 else ''}{'-pair' if v[1] & 8 else ''} {v[2]}cta BN{v[3]}"
     tr += rd; tw += wr; ta += o["bytes_algo"]; tt += t_us
     print(f"| {o['name']} | {var} | {t_us:.1f} | {rd / 1e6:.1f} | {wr / 1e6:.1f} | {o['bytes_algo'] / 1e6:.1f} | {(rd + wr) / o['bytes_algo']:.2f} |")
 print(f"\ntotals: {len(ops)} conv_tc launches, {tt:.1f} us, DRAM read {tr / 1e9:.3f} GB + write {tw / 1e9:.3f} GB, algorithmic {ta / 1e9:.3f} GB")

@@ -230,6 +230,11 @@ extern "C" int y11_plan_autotune(y11_plan p, y11_stream s_, int reps) {
           if (bn0 == 128 && d->out.c % 256 == 0 && d->in.c % 64 == 0 && cps == 2 && !(lsu && base.lsu_eligible))
             cands.push_back(ConvTcTune{lsu, ew, 1, 256});
         }
+    // resident weights (epi_warp bit 2) for single-N-tile TMA layers that walk several tiles per CTA
+    if (!base.p.halo && d->out.c == bn0 && tiles0 >= 4ll * p->eng->num_sms) {
+      for (int ew = 4; ew <= 7; ++ew)
+        for (int cps = 3; cps >= 2; --cps) cands.push_back(ConvTcTune{0, ew, cps, -1});
+    }
     // CTA-pair variant (tcgen05.mma.cta_group::2, conv_tc_kernel_pair): half the weight-tile traffic per SM, 256-row tiles;
     // prepare declines it where it does not apply (halo / e4m3 / k = 2 layers) and the duplicate filter below drops those
     {

@@ -1280,9 +1280,16 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   // the CTA's lifetime instead of re-fetching a B tile with every K stage of every tile (model.1: 8 KB of the 24 KB per stage;
   // the store-heavy 1x1 layers on the large maps: a third to a half of their L2 -> shared-memory traffic).
   {
-    static const int bres_kb = [] { const char* e = getenv("Y11_BRES_KB"); return e ? atoi(e) : 40; }();
+    // Measured (A/B per layer, YOLO11s B=64): it pays where a CTA walks many tiles and the weights are small enough to leave the
+    // CTAs-per-SM count and the epilogue staging alone (model.2.cv2 166 -> 144 us); on maps with one or two tiles per CTA the
+    // up-front load is exposed latency, and 32-40 KB of resident weights cost a CTA slot or the fat epilogue (model.1, model.4.cv1).
+    static const int bres_kb = [] { const char* e = getenv("Y11_BRES_KB"); return e ? atoi(e) : 24; }();
     const int nk = p.n_kt ? p.n_kt : p.taps * p.chunks_per_tap;
-    p.bres = !p.halo && !p.pair && !d->in_fp8 && cout == bn && (size_t)nk * p.b_slot <= (size_t)bres_kb * 1024;
+    const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+    // explicit variant (autotuner candidate / cached choice): bit 2 of epi_warp says it; heuristic otherwise
+    const bool fits = !p.halo && !p.pair && !d->in_fp8 && cout == bn;
+    if (tune.epi_warp >= 0) p.bres = fits && (tune.epi_warp & 4) && (size_t)nk * p.b_slot <= (size_t)64 * 1024;
+    else p.bres = fits && (size_t)nk * p.b_slot <= (size_t)bres_kb * 1024 && m_tiles >= 8ll * 3 * eng->num_sms;
     if (p.bres) p.b_res_bytes = (uint32_t)nk * p.b_slot;
   }
   if (p.halo) {
@@ -1466,7 +1473,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     const unsigned total_pairs = ((m_tiles + 1) / 2) * (unsigned)p.n_tiles;
     L->grid = 2u * std::min(total_pairs, (unsigned)((eng->num_sms / 2) * cps));
   }
-  L->variant = ConvTcTune{p.halo, p.epi_warp | (p.fat << 1) | (p.pair << 3), cps, bn};
+  L->variant = ConvTcTune{p.halo, p.epi_warp | (p.fat << 1) | (p.bres << 2) | (p.pair << 3), cps, bn};
   L->smem_bytes = kHeaderBytes + 1024u + p.b_res_bytes + (unsigned)stages * stage + staging;
   L->flops = 2.0 * d->B * d->Hout * d->Wout * (double)cout * cin * p.taps;
   (void)k_iters;
