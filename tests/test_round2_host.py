@@ -172,3 +172,34 @@ def test_results_batch_is_a_lazy_sequence_of_results():
     assert torch.equal(rb[2].boxes.xyxy, det[2, :, :4]) and torch.equal(rb[2].cpu().boxes.conf, det[2, :, 4])
     with pytest.raises(IndexError):
         rb[3]
+
+
+def test_compact_space_to_depth_packing_equals_the_3x3_stride2_conv():
+    """model.1 on the permuted space-to-depth stem output (network.S2D_PERM, y11_conv_desc.s2d_block): the per-stage packed weights,
+    expanded back to a dense 2x2 kernel (network.dense_k2_weights), applied to the permuted space-to-depth tensor with top/left zero
+    padding, must equal the original 3x3 stride-2 conv - pure torch on the CPU, for both supported block sizes."""
+    import torch
+    from yolo_infer_b200 import network as N
+    from yolo_infer_b200 import topology as T
+    for scale, c in (("s", 32), ("m", 64)):
+        sd = T.synthetic_state_dict(scale, seed=3)
+        packed = N.pack_weights(scale, 80, sd, torch.device("cpu"))
+        pc = packed["model.1"]
+        assert pc.k == 2 and pc.s2d_block == c and pc.c1 == 4 * c
+        stages = N.compact_k2_stages(c)
+        assert len(stages) == (5 if c == 32 else 9) and pc.w.shape == (pc.c2, 64 * len(stages))
+        cp = next(p for p in T.conv_params(scale, 80) if p.prefix == "model.1")
+        w3, b3 = N.fold(sd, cp)
+        w3 = w3.to(torch.bfloat16).float()                                  # the packing rounds the folded weights to bf16
+        g = torch.Generator().manual_seed(4)
+        x = torch.randn(2, c, 24, 32, generator=g)                          # a stem output [B, c, H, W]
+        want = torch.nn.functional.conv2d(x, w3, b3, stride=2, padding=1)
+        # permuted space-to-depth form: [B, 4c, H/2, W/2], block i holds pixels (2y+dy, 2x+dx) with (dy, dx) = S2D_PERM[i]
+        xs = torch.cat([x[:, :, dy::2, dx::2] for dy, dx in N.S2D_PERM], 1)
+        w2 = N.dense_k2_weights(pc).permute(0, 3, 1, 2)                       # [cout, 4c, 2, 2]
+        got = torch.nn.functional.conv2d(torch.nn.functional.pad(xs, (1, 0, 1, 0)), w2, pc.b)
+        assert got.shape == want.shape
+        assert float((got - want).abs().max()) <= 1e-4 * float(want.abs().max())
+        # only the blocks a tap can touch carry weights: 9 of the 16 (tap, block) pairs
+        nz = (w2.view(pc.c2, 4, c, 2, 2).abs().sum((0, 2)) > 0).sum().item()
+        assert nz == 9
