@@ -732,7 +732,8 @@ class CompiledNet:
         (y11_plan_set_cls_emit); `engine.postprocess` then consumes `self.emit_list` / `self.emit_count`.  None: back to stored
         logits (multi-label, raw-head consumers).  Returns whether emit mode is on.  Like `set_stem_source` it edits the plan,
         i.e. it holds for launches and graph captures made after the call."""
-        if conf is None or self.A >= 65536 or self.conv_impl != cabi.IMPL_TCGEN05 or not FUSE_CLS_DECODE:
+        if (conf is None or self.A >= 65536 or self.conv_impl != cabi.IMPL_TCGEN05 or not FUSE_CLS_DECODE
+                or pad16(self.nc) > 128):        # more than one N tile of class logits: a row is split over CTAs, keep the scan kernel
             if self.emit_conf is not None:
                 for op, _ in self.cls_ops:
                     cabi.check(self.lib.y11_plan_set_cls_emit(self.plan, op, None), "y11_plan_set_cls_emit")
