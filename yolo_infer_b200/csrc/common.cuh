@@ -97,6 +97,57 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per issued instruction) -------------
+// A pair lives in one 64-bit register (lo = first element).  Every op rounds each element exactly like its scalar form
+// (fma.rn / mul.rn / add.rn, no flush to zero), so code that moves from the scalar to the packed form keeps its results bit
+// for bit; what it saves is issue slots, which is what bounds the depthwise conv and the conv / stem epilogues.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// one 32-bit word of two bf16 -> the pair as fp32
+__device__ __forceinline__ f32x2 f2_from_bf16x2(uint32_t v) { return f2_pack(bf16_lo(v), bf16_hi(v)); }
+__device__ __forceinline__ uint32_t f2_to_bf16x2(f32x2 v) {
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+#ifndef Y11_SILU_EX2
+// silu() of both elements: FMUL2 + 2 MUFU + FFMA2 instead of 2 x (FMUL + MUFU + FFMA); same bits as silu()
+__device__ __forceinline__ f32x2 silu2(f32x2 x) {
+  const f32x2 h = f2_mul(x, f2_pack(0.5f, 0.5f));
+  float hl, hh, tl, th;
+  f2_unpack(h, hl, hh);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(tl) : "f"(hl));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh));
+  return f2_fma(h, f2_pack(tl, th), h);
+}
+#else
+__device__ __forceinline__ f32x2 silu2(f32x2 x) {
+  float lo, hi;
+  f2_unpack(x, lo, hi);
+  return f2_pack(silu(lo), silu(hi));
+}
+#endif
+
 // ---- mbarrier -----------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

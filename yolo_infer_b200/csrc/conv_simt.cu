@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
         float c[4] = {bias[nb][0], bias[nb][1], bias[nb][0], bias[nb][1]};
         mma_bf16_16816_s(c, af[0], bw[nb][0][0], bw[nb][0][1]);
         mma_bf16_16816_s(c, af[1], bw[nb][1][0], bw[nb][1][1]);
-        *reinterpret_cast<uint32_t*>(so + (mt * 16 + g) * OP + nb * 8 + 2 * t) = pack_bf16x2(silu(c[0]), silu(c[1]));
-        *reinterpret_cast<uint32_t*>(so + (mt * 16 + g + 8) * OP + nb * 8 + 2 * t) = pack_bf16x2(silu(c[2]), silu(c[3]));
+        *reinterpret_cast<uint32_t*>(so + (mt * 16 + g) * OP + nb * 8 + 2 * t) = f2_to_bf16x2(silu2(f2_pack(c[0], c[1])));
+        *reinterpret_cast<uint32_t*>(so + (mt * 16 + g + 8) * OP + nb * 8 + 2 * t) = f2_to_bf16x2(silu2(f2_pack(c[2], c[3])));
       }
     }
     __syncwarp();
@@ -324,17 +324,19 @@ __global__ void __launch_bounds__(256) dwconv_kernel(y11_dwconv_desc d, int stri
   const int y0 = (int)(rest % strips) * R;
   const size_t n = rest / strips;
   // constants first (they do not depend on the previous kernel): weights [9][c] tap-major, bias
-  float w[9][4], acc[R][4];
+  // (round 2: the channel pairs are packed fp32 pairs - FFMA2 / FMUL2 / FADD2, half the arithmetic instructions, same bits)
+  f32x2 w[9][2], acc[R][2];
   {
     const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(d.w) + g * 4;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const uint2 u = __ldg(reinterpret_cast<const uint2*>(wp + (size_t)tap * d.in.c));
-      w[tap][0] = bf16_lo(u.x); w[tap][1] = bf16_hi(u.x); w[tap][2] = bf16_lo(u.y); w[tap][3] = bf16_hi(u.y);
+      w[tap][0] = f2_from_bf16x2(u.x);
+      w[tap][1] = f2_from_bf16x2(u.y);
     }
     const float4 b = __ldg(reinterpret_cast<const float4*>(d.bias + g * 4));
 #pragma unroll
-    for (int r = 0; r < R; ++r) { acc[r][0] = b.x; acc[r][1] = b.y; acc[r][2] = b.z; acc[r][3] = b.w; }
+    for (int r = 0; r < R; ++r) { acc[r][0] = f2_pack(b.x, b.y); acc[r][1] = f2_pack(b.z, b.w); }
   }
   pdl_wait();
   pdl_trigger();
@@ -360,16 +362,13 @@ __global__ void __launch_bounds__(256) dwconv_kernel(y11_dwconv_desc d, int stri
 #pragma unroll
     for (int kw = 0; kw < 3; ++kw) {
       const bool ok = row_ok && (kw == 1 || (kw == 0 ? xl != 0 : xr != 0));
-      const uint32_t vx = ok ? v[r][kw].x : 0u, vy = ok ? v[r][kw].y : 0u;
-      const float f0 = bf16_lo(vx), f1 = bf16_hi(vx), f2 = bf16_lo(vy), f3 = bf16_hi(vy);
+      const f32x2 f01 = f2_from_bf16x2(ok ? v[r][kw].x : 0u), f23 = f2_from_bf16x2(ok ? v[r][kw].y : 0u);
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const int orow = r - kh;  // input row y0+r-1 is tap kh of output row y0+r-kh
         if (orow >= 0 && orow < R) {
-          acc[orow][0] = fmaf(f0, w[kh * 3 + kw][0], acc[orow][0]);
-          acc[orow][1] = fmaf(f1, w[kh * 3 + kw][1], acc[orow][1]);
-          acc[orow][2] = fmaf(f2, w[kh * 3 + kw][2], acc[orow][2]);
-          acc[orow][3] = fmaf(f3, w[kh * 3 + kw][3], acc[orow][3]);
+          acc[orow][0] = f2_fma(f01, w[kh * 3 + kw][0], acc[orow][0]);
+          acc[orow][1] = f2_fma(f23, w[kh * 3 + kw][1], acc[orow][1]);
         }
       }
     }
@@ -379,17 +378,15 @@ __global__ void __launch_bounds__(256) dwconv_kernel(y11_dwconv_desc d, int stri
     const int y = y0 + r;
     if (y >= d.H) break;
     const size_t pix = (img + y) * d.W + x;
-    float o[4] = {acc[r][0], acc[r][1], acc[r][2], acc[r][3]};
-    if (d.act == Y11_ACT_SILU) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = silu(o[i]);
-    }
+    f32x2 o0 = acc[r][0], o1 = acc[r][1];
+    if (d.act == Y11_ACT_SILU) { o0 = silu2(o0); o1 = silu2(o1); }
     if (d.res.ptr) {
       const uint2 rr = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(d.res.ptr) + pix * d.res.c_total + d.res.c_off + g * 4);
-      o[0] += bf16_lo(rr.x); o[1] += bf16_hi(rr.x); o[2] += bf16_lo(rr.y); o[3] += bf16_hi(rr.y);
+      o0 = f2_add(o0, f2_from_bf16x2(rr.x));
+      o1 = f2_add(o1, f2_from_bf16x2(rr.y));
     }
     *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(d.out.ptr) + pix * d.out.c_total + d.out.c_off + g * 4) =
-        make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+        make_uint2(f2_to_bf16x2(o0), f2_to_bf16x2(o1));
   }
 }
 

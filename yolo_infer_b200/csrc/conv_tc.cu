@@ -169,62 +169,58 @@ template <bool kQ>  // kQ: the e4m3 paths (dequantisation scale, e4m3 stores) ar
 __device__ __forceinline__ void epi16(const ConvTcParams& p, const uint32_t (&v)[16], const uint4 r0, const uint4 r1, int n,
                                       uint32_t dst, uint32_t unit0, uint32_t swz) {
   using namespace y11;
-  float f[16];
+  // Round 2: the 16 columns are handled as 8 packed fp32 pairs (FADD2 / FMUL2 / FFMA2): bias, SiLU and the residual cost half
+  // the issue slots; every element goes through the same IEEE operations as before, so the results are bit-identical.
+  f32x2 f[8];
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
   if (kQ && p.cscale) {  // fp8 operands: accumulator * (activation scale * weight scale of the channel) + bias
     const float4* c4 = reinterpret_cast<const float4*>(p.cscale + n);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 bb = __ldg(b4 + i), cc = __ldg(c4 + i);
-      f[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]), cc.x, bb.x);
-      f[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), cc.y, bb.y);
-      f[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), cc.z, bb.z);
-      f[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), cc.w, bb.w);
+      f[2 * i + 0] = f2_fma(f2_pack(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1])), f2_pack(cc.x, cc.y), f2_pack(bb.x, bb.y));
+      f[2 * i + 1] = f2_fma(f2_pack(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), f2_pack(cc.z, cc.w), f2_pack(bb.z, bb.w));
     }
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 bb = __ldg(b4 + i);
-      f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x;
-      f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
-      f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
-      f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
+      f[2 * i + 0] = f2_add(f2_pack(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1])), f2_pack(bb.x, bb.y));
+      f[2 * i + 1] = f2_add(f2_pack(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), f2_pack(bb.z, bb.w));
     }
   }
   const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
   if (p.res_pre) {  // up2(W_up . p) of a folded Upsample+Concat: part of the pre-activation sum
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      f[2 * i] += bf16_lo(rr[i]);
-      f[2 * i + 1] += bf16_hi(rr[i]);
-    }
+    for (int i = 0; i < 8; ++i) f[i] = f2_add(f[i], f2_from_bf16x2(rr[i]));
   }
   if (p.act == Y11_ACT_SILU) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = silu(f[i]);
+    for (int i = 0; i < 8; ++i) f[i] = silu2(f[i]);
   }
   if (p.res && !p.res_pre) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      f[2 * i] += bf16_lo(rr[i]);
-      f[2 * i + 1] += bf16_hi(rr[i]);
-    }
+    for (int i = 0; i < 8; ++i) f[i] = f2_add(f[i], f2_from_bf16x2(rr[i]));
   }
   if (kQ && p.out_esz == 1) {  // e4m3: 16 channels = ONE 16-byte unit of the staging row
     const float o = p.oscale;
-    st_shared_v4(dst + (((unit0 >> 1) ^ swz) << 4), pack_e4m3x4(f[0] * o, f[1] * o, f[2] * o, f[3] * o),
-                 pack_e4m3x4(f[4] * o, f[5] * o, f[6] * o, f[7] * o), pack_e4m3x4(f[8] * o, f[9] * o, f[10] * o, f[11] * o),
-                 pack_e4m3x4(f[12] * o, f[13] * o, f[14] * o, f[15] * o));
+    float g[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f2_unpack(f[i], g[2 * i], g[2 * i + 1]);
+    st_shared_v4(dst + (((unit0 >> 1) ^ swz) << 4), pack_e4m3x4(g[0] * o, g[1] * o, g[2] * o, g[3] * o),
+                 pack_e4m3x4(g[4] * o, g[5] * o, g[6] * o, g[7] * o), pack_e4m3x4(g[8] * o, g[9] * o, g[10] * o, g[11] * o),
+                 pack_e4m3x4(g[12] * o, g[13] * o, g[14] * o, g[15] * o));
   } else if (p.out_f32) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      st_shared_v4(dst + (((2u * unit0 + i) ^ swz) << 4), __float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]),
-                   __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3]));
+    for (int i = 0; i < 4; ++i) {
+      float a, b, c, d;
+      f2_unpack(f[2 * i], a, b);
+      f2_unpack(f[2 * i + 1], c, d);
+      st_shared_v4(dst + (((2u * unit0 + i) ^ swz) << 4), __float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d));
+    }
   } else {
-    st_shared_v4(dst + (((unit0 + 0u) ^ swz) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                 pack_bf16x2(f[6], f[7]));
-    st_shared_v4(dst + (((unit0 + 1u) ^ swz) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
-                 pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+    st_shared_v4(dst + (((unit0 + 0u) ^ swz) << 4), f2_to_bf16x2(f[0]), f2_to_bf16x2(f[1]), f2_to_bf16x2(f[2]), f2_to_bf16x2(f[3]));
+    st_shared_v4(dst + (((unit0 + 1u) ^ swz) << 4), f2_to_bf16x2(f[4]), f2_to_bf16x2(f[5]), f2_to_bf16x2(f[6]), f2_to_bf16x2(f[7]));
   }
 }
 

@@ -148,6 +148,8 @@ struct DwTmaParams {
   const void* res;
   int32_t res_ct, res_co;
   int* err_flag;
+  uint64_t mg_chunks, mg_tw, mg_th;  // fast_div magics of the tile decomposition
+  int32_t dbg;  // probe builds (-DY11_DW_PROBE) only: bit 0 = skip the arithmetic, bit 1 = skip the loads
 };
 struct DwTmaLaunch {
   CUtensorMap tmap;
