@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
     const int total = n_rows * gpr;
     const uint32_t gmagic = 0xffffffffu / (uint32_t)gpr + 1u;  // i / gpr == umulhi(i, gmagic) for the few thousand i of a tile
     const float r255 = 1.0f / 255.0f;
+    const float c255 = -8388608.0f * r255;  // exact (a power-of-two multiple of r255)
     constexpr int kFly = 4;
     for (int i0 = tid; i0 < total; i0 += kFly * nt) {
       uint32_t w[kFly][3];
@@ -154,14 +155,19 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
           uint2 o[3] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
           if (ok[q]) {
             // source bytes B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3  ->  elements R0 G0 B0 R1 G1 B1 R2 G2 B2 R3 G3 B3
-            float f[12];
+            // byte -> x/255 without the conversion unit (round 2: I2F.U8 shares the quarter-rate pipe with the SiLU tanh):
+            // PRMT builds the float 2^23 + byte (byte in the low mantissa bits of 0x4B000000), one FFMA2 per pair computes
+            // (2^23 + b) * r - 2^23 * r with a single rounding = RN(b * r), the same bits as __fmul_rn((float)b, r)
+            f32x2 f2[6];
 #pragma unroll
-            for (int e = 0; e < 12; ++e) {
-              const int sb = 3 * (e / 3) + 2 - (e % 3);  // source byte of element e (compile-time after unrolling)
-              f[e] = __fmul_rn((float)((w[q][sb >> 2] >> (8 * (sb & 3))) & 0xffu), r255);
+            for (int e = 0; e < 12; e += 2) {
+              const int sb0 = 3 * (e / 3) + 2 - (e % 3), sb1 = 3 * ((e + 1) / 3) + 2 - ((e + 1) % 3);  // source bytes (compile-time)
+              const uint32_t v0 = __byte_perm(w[q][sb0 >> 2], 0x4B000000u, 0x7540u | (uint32_t)(sb0 & 3));
+              const uint32_t v1 = __byte_perm(w[q][sb1 >> 2], 0x4B000000u, 0x7540u | (uint32_t)(sb1 & 3));
+              f2[e / 2] = f2_fma(f2_pack(__uint_as_float(v0), __uint_as_float(v1)), f2_pack(r255, r255), f2_pack(c255, c255));
             }
 #pragma unroll
-            for (int v = 0; v < 3; ++v) o[v] = make_uint2(pack_bf16x2(f[4 * v], f[4 * v + 1]), pack_bf16x2(f[4 * v + 2], f[4 * v + 3]));
+            for (int v = 0; v < 3; ++v) o[v] = make_uint2(f2_to_bf16x2(f2[2 * v]), f2_to_bf16x2(f2[2 * v + 1]));
           }
           uint2* dst = reinterpret_cast<uint2*>(s_in + r * row_p + 12 * gi - 4);
           dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
@@ -216,6 +222,27 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
   constexpr int VPP = COUT / 8;  // 16-byte vectors per pixel
   __nv_bfloat16* so = s_o + warp * 32 * OP;
   __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(d.out.ptr) + d.out.c_off;
+  // Write-out plan of this lane, constant over the rows of the tile (round 2: the per-store index arithmetic - pixel / vector
+  // split, block selection, 64-bit multiplies - was 17 instructions per 16-byte store).  Vector j of the lane is 16-byte unit
+  // v = lane % VPP of pixel lane / VPP + j * (32 / VPP) of the warp's 32 (VPP divides 32 for 16 / 32 / 64 output channels; 96
+  // keeps the generic loop): its shared and global offsets are those of vector 0 plus j times a constant step, and the global
+  // offset is row_base(oy) + (oy odd ? goff1 : goff0) + j * gstep.
+  // space-to-depth: pixel (oy/2, ox/2) of the half-size map, channel block dy*2 + dx, or (s2d == 2) the permuted order
+  // [(1,0), (1,1), (0,1), (0,0)]: dy ? dx : 3 - dx; the pixel step 32 / VPP is even, so dx is the same for all j
+  constexpr bool kPlan = 32 % VPP == 0;
+  constexpr int PSTEP = kPlan ? 32 / VPP : 1;
+  const int px0 = lane / VPP, v0 = lane % VPP, ox0 = ow0 + warp * 32 + px0, dx0 = ox0 & 1;
+  const uint32_t soff0 = (uint32_t)(px0 * OP + v0 * 8);
+  int goff0, goff1, gstep;
+  if (d.s2d) {
+    const int b0 = d.s2d == 2 ? 3 - dx0 : dx0, b1 = d.s2d == 2 ? dx0 : 2 + dx0;
+    goff0 = (ox0 >> 1) * d.out.c_total + b0 * COUT + v0 * 8;
+    goff1 = (ox0 >> 1) * d.out.c_total + b1 * COUT + v0 * 8;
+    gstep = (PSTEP / 2) * d.out.c_total;
+  } else {
+    goff0 = goff1 = ox0 * d.out.c_total + v0 * 8;
+    gstep = PSTEP * d.out.c_total;
+  }
   for (int r = 0; r < ROWS; ++r) {
     const __nv_bfloat16* base = s_in + 2 * r * row_p;
 #pragma unroll
@@ -241,19 +268,25 @@ __global__ void __launch_bounds__(160) stem_kernel(y11_stem_desc d, int PXB, int
     __syncwarp();
     // coalesced write-out of this warp's 32 pixels: 16 bytes per lane, consecutive lanes -> consecutive bytes of a pixel row
     const int oy = oh0 + r;
-    // plain NHWC: pixel (oy, ox).  space-to-depth: pixel (oy/2, ox/2) of the half-size map, channel block (oy&1)*2 + (ox&1)
     const size_t row0 = d.s2d ? ((size_t)n * (d.Hout >> 1) + (oy >> 1)) * (d.Wout >> 1) : ((size_t)n * d.Hout + oy) * d.Wout;
-    // block of pixel parity (dy, dx): dy*2 + dx, or (s2d == 2) the permuted order [(1,0), (1,1), (0,1), (0,0)]: dy ? dx : 3 - dx
+    __nv_bfloat16* orow = ob + row0 * d.out.c_total;
     const int dy = oy & 1;
+    if (kPlan) {
+      __nv_bfloat16* og = orow + (dy ? goff1 : goff0);
 #pragma unroll
-    for (int i = lane; i < 32 * VPP; i += 32) {
-      const int px = i / VPP, v = i % VPP;
-      const int ox = ow0 + warp * 32 + px;
-      if (ox < d.Wout) {
-        const int dx = ox & 1;
-        const int blk = d.s2d == 2 ? (dy ? dx : 3 - dx) : dy * 2 + dx;
-        const size_t off = d.s2d ? (row0 + (ox >> 1)) * d.out.c_total + blk * COUT : (row0 + ox) * d.out.c_total;
-        *reinterpret_cast<uint4*>(ob + off + v * 8) = *reinterpret_cast<const uint4*>(so + px * OP + v * 8);
+      for (int j = 0; j < VPP; ++j)
+        if (ox0 + j * PSTEP < d.Wout) *reinterpret_cast<uint4*>(og + j * gstep) = *reinterpret_cast<const uint4*>(so + soff0 + j * (PSTEP * OP));
+    } else {
+#pragma unroll
+      for (int i = lane; i < 32 * VPP; i += 32) {
+        const int px = i / VPP, v = i % VPP;
+        const int ox = ow0 + warp * 32 + px;
+        if (ox < d.Wout) {
+          const int dx = ox & 1;
+          const int blk = d.s2d == 2 ? (dy ? dx : 3 - dx) : dy * 2 + dx;
+          const size_t off = d.s2d ? (size_t)(ox >> 1) * d.out.c_total + blk * COUT : (size_t)ox * d.out.c_total;
+          *reinterpret_cast<uint4*>(orow + off + v * 8) = *reinterpret_cast<const uint4*>(so + px * OP + v * 8);
+        }
       }
     }
     __syncwarp();
