@@ -435,7 +435,7 @@ def run_ours(args):
         e2e_sync_value = B / (e2e_ms / 1e3)
         list(eng.predict((host_batches[i % loop.NROT] for i in range(3)), stream=True, conf=CONF, iou=IOU, max_det=MAX_DET, imgsz=S, verbose=False))
         barrier()
-        n_stream = max(e2e_steps, 10)
+        n_stream = max(args.steps, 10)     # exactly --steps batches (pipeline fill and drain included in the timed region)
         t0 = time.perf_counter()
         for res in eng.predict((host_batches[i % loop.NROT] for i in range(n_stream)), stream=True, conf=CONF, iou=IOU, max_det=MAX_DET,
                                imgsz=S, verbose=False):
