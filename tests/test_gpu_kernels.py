@@ -340,8 +340,9 @@ def test_stem_reading_uint8_frames_equals_letterbox_then_stem(ctx, H, W):
 
 
 @pytest.mark.parametrize("act,res,H,W,c", [(True, False, 20, 28, 64), (False, True, 20, 28, 64), (True, True, 14, 20, 64),
-                                           (True, False, 1, 8, 64),
-                                           # TMA-ring kernel (W >= 32, H >= 16; ragged tiles in the last two): 2/4/8-row groups, 80 channels
+                                           # register kernel (maps narrower than 18 pixels or lower than 8 rows)
+                                           (True, False, 1, 8, 64), (False, True, 7, 16, 64), (True, True, 20, 12, 128),
+                                           # TMA-ring kernel (W >= 18, H >= 8: the three cases above and these; ragged tiles): 2/4/8-row groups, 80 channels
                                            # (surplus threads), two 128-channel chunks, residual, many tiles per CTA
                                            (True, False, 16, 32, 64), (False, True, 32, 48, 128), (True, True, 24, 64, 80),
                                            (True, False, 16, 32, 256), (True, False, 8 * 20, 16 * 12, 32), (True, True, 40, 40, 128), (False, False, 20, 36, 64)])
