@@ -174,6 +174,8 @@ VARIANT_SHAPES = [
     (4, 20, 20, 128, 128, 1, 1, True, True),     # TMA 1x1, (4,4,8) tiles
     (2, 16, 16, 64, 128, 3, 1, True, False),     # TMA 3x3
     (2, 32, 32, 64, 128, 3, 2, True, False),     # stride 2
+    (2, 40, 36, 64, 64, 3, 1, True, True),       # TMA-halo eligible (3x3 stride 1, cin = 64): ragged tiles, residual
+    (3, 32, 32, 64, 32, 3, 1, True, False),      # TMA-halo eligible, N = 32
 ]
 
 
@@ -185,14 +187,15 @@ def test_conv_launch_variants_are_bit_identical(ctx, shape):
     base, want = conv_case(ctx, B, H, W, cin, cout, k, s_, act, res)
     close_bf16(base, want)
     n = 0
-    for lsu in (0, 1):
+    halo_tma = k == 3 and s_ == 1 and cin == 64 and H >= 32 and W >= 32      # lsu = 2: one TMA box load per halo tile
+    for lsu in (0, 1, 2) if halo_tma else (0, 1):
         for ew in (0, 1, 2, 3, 4, 6):     # bit 0: per-warp epilogue, bit 1: fat epilogue (64-channel chunks), bit 2: resident weights
             for cps in (2, 3):
                 for bn in (-1, 64, 32):
                     got, _ = conv_case(ctx, B, H, W, cin, cout, k, s_, act, res, tune=(lsu, ew, cps, bn))
                     assert torch.equal(got, base), (lsu, ew, cps, bn, (got - base).abs().max().item())
                     n += 1
-    assert n == 72
+    assert n == (108 if halo_tma else 72)
 
 
 PAIR_SHAPES = [

@@ -214,12 +214,13 @@ extern "C" int y11_plan_autotune(y11_plan p, y11_stream s_, int reps) {
     std::vector<ConvTcTune> cands;
     const int bn0 = base.variant.bn_max;
     const long long tiles0 = (long long)base.p.tiles_w * base.p.tiles_h * base.p.tiles_n * base.p.n_tiles;
-    for (int lsu = base.lsu_eligible ? 1 : 0; lsu >= 0; --lsu)
+    for (int lsu = base.halo_tma_eligible ? 2 : base.lsu_eligible ? 1 : 0; lsu >= 0; --lsu)
       for (int ew = 0; ew <= 3; ++ew)  // bit 0: per-warp epilogue, bit 1: fat epilogue
         for (int cps = 3; cps >= 2; --cps) {
+          if (lsu == 1 && !base.lsu_eligible) continue;
           cands.push_back(ConvTcTune{lsu, ew, cps, -1});
           // few tiles (less than two waves of persistent CTAs): narrower N tiles spread the layer over more SMs
-          if (!(lsu && base.lsu_eligible) && bn0 >= 64 && tiles0 < 2ll * p->eng->num_sms * 3) {
+          if (lsu == 0 && bn0 >= 64 && tiles0 < 2ll * p->eng->num_sms * 3) {
             cands.push_back(ConvTcTune{lsu, ew, cps, bn0 / 2});
             if (bn0 == 256) cands.push_back(ConvTcTune{lsu, ew, cps, 64});
           } else if (bn0 == 256) {
@@ -227,7 +228,7 @@ extern "C" int y11_plan_autotune(y11_plan p, y11_stream s_, int reps) {
           }
           // ... and the other way round: 128x256 tiles for shorter-K layers whose heuristic tile is 128 wide (half the
           // activation re-reads from L2; the layers on 20x20 / 40x40 maps run at the L2 -> SM bandwidth cap)
-          if (bn0 == 128 && d->out.c % 256 == 0 && d->in.c % 64 == 0 && cps == 2 && !(lsu && base.lsu_eligible))
+          if (bn0 == 128 && d->out.c % 256 == 0 && d->in.c % 64 == 0 && cps == 2 && lsu == 0)
             cands.push_back(ConvTcTune{lsu, ew, 1, 256});
         }
     // resident weights (epi_warp bit 2) for single-N-tile TMA layers that walk several tiles per CTA

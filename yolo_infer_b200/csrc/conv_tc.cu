@@ -163,6 +163,24 @@ __device__ __forceinline__ void halo3_issue(uint32_t tmem_acc, uint32_t a_lo, ui
   }
 }
 
+// TMA-halo tile (cin = 64, round 2): the halo sits in the 128-byte-SWIZZLED K-major layout, one 128-byte row per halo pixel,
+// exactly as ONE TMA box load {64 ch, Tw+2, Th+2} writes it.  Tap (kh, kw) is the start address moved by (kh * 10 + kw) ROWS and the
+// 8-row groups follow at SBO = 10 rows = 1280 B - neither a multiple of the 1024-byte swizzle atom.  Measured on B200
+// (tools/halo_sw_probe.py): tcgen05.mma applies the 128-byte swizzle to the ABSOLUTE shared-memory address bits, so any
+// 128-byte-aligned start and any SBO that is a multiple of 128 B read what TMA wrote, with the descriptor's base-offset field left 0
+// (setting it to the start address's row phase gives wrong results).  Same K order (tap, then channels) as the other modes.
+template <int KK>
+__device__ __forceinline__ void halo3_issue_sw(uint32_t tmem_acc, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t b_step,
+                                               uint32_t idesc) {
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const uint32_t at = a_lo + (uint32_t)((tap / 3) * 10 + tap % 3) * 8u;  // 128-byte rows in 16-byte descriptor units
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) umma_lohi<false>(tmem_acc, at + 2u * kk, a_hi, b_lo + 2u * kk, b_hi, idesc, (tap | kk) ? 1u : 0u);
+    b_lo += b_step;
+  }
+}
+
 // 16 accumulator columns of one tile row: +bias, (+pre-activation term), SiLU, (+residual), convert, and the swizzled
 // 16-byte stores into the staging row at `dst`; `unit0` = index of the first 16-byte unit of these columns in the row.
 template <bool kQ>  // kQ: the e4m3 paths (dequantisation scale, e4m3 stores) are compiled in; false = the bf16 kernels, unchanged
@@ -293,7 +311,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar + 8 * s, p.halo ? 32 : 1);   // halo mode: every producer lane reports its own cp.async copies
+      mbar_init(full_bar + 8 * s, (p.halo && !p.halo_tma) ? 32 : 1);   // cp.async halo mode: every producer lane reports its own copies
       mbar_init(empty_bar + 8 * s, 1);
     }
     mbar_init(bres_bar, 1);
@@ -410,6 +428,21 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
       const __nv_bfloat16* org = in + ((size_t)n0 * p.Hin * p.Win + (size_t)h0 * p.Win + w0) * p.in_ct;
       mbar_wait(empty_bar + 8 * stage, phase ^ 1, p.err_flag, 101);
       if (lane == 0) TRACE(0, 1);
+      if (p.halo_tma) {
+        // the whole (Tw+2) x (Th+2) x 64-channel halo as ONE TMA box: 128-byte rows in the swizzled layout, zero fill outside the
+        // image - 180 rows per tile instead of 9 x 128 (tap-by-tap TMA mode) or 1440 16-byte cp.async copies
+        if (elect_one()) {
+          const uint32_t fb = full_bar + 8 * stage;
+          mbar_expect_tx(fb, (uint32_t)p.n_pos * 128u);
+          tma_load_4d(ring_base + stage * stage_bytes, &maps.a[0], fb, 0, w0 - 1, h0 - 1, n0);
+        }
+        __syncwarp();
+        if (lane == 0) TRACE(0, 2);
+        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+        const int nx = __shfl_sync(0xffffffffu, nx_raw, 0);
+        tile = nx < total_tiles ? nx : -1;
+        continue;
+      }
       const uint32_t dst = ring_base + stage * stage_bytes + (uint32_t)lane * 16u;
 #pragma unroll
       for (int i = 0; i < kMaxPos; ++i) {
@@ -535,7 +568,8 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
         if (elect_one()) {
           // 3x3: tap (kh, kw) = the halo tile shifted by kh rows of (Tw+2) = 10 pixels and kw pixels, in 16-byte units; the next
           // 16 channels = two 8-channel planes further (k_step) / +32 B in the weight row
-          if (mode == 2) halo3_issue<2>(tmem_acc, a_lo, a_hi, b_lo0, sw_hi, b_step, k_step, idesc);
+          if (p.halo_tma) halo3_issue_sw<4>(tmem_acc, (a_lo & 0x3FFFu) | (1u << 16), (p.a_sbo >> 4) | (1u << 14) | (2u << 29), b_lo0, sw_hi, b_step, idesc);
+          else if (mode == 2) halo3_issue<2>(tmem_acc, a_lo, a_hi, b_lo0, sw_hi, b_step, k_step, idesc);
           else if (mode == 4) halo3_issue<4>(tmem_acc, a_lo, a_hi, b_lo0, sw_hi, b_step, k_step, idesc);
           else if (mode == 1) halo3_issue<1>(tmem_acc, a_lo, a_hi, b_lo0, sw_hi, b_step, k_step, idesc);
           else if (p.pad) {
@@ -1201,12 +1235,21 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     // the L2 delivers chip-wide), and the halo mode moves a tenth of it; the heuristic default stays TMA above 40 KB
     static const size_t wmax = [] { const char* e = getenv("Y11_LSU_WMAX"); return (size_t)(e ? atoi(e) : 80) * 1024; }();
     const bool big = wbytes > 40 * 1024;
-    const bool fits = cout <= 128 && wbytes <= (tune.lsu == 1 ? wmax : (size_t)40 * 1024);
+    const bool fits = cout <= 128 && wbytes <= (tune.lsu >= 1 ? wmax : (size_t)40 * 1024);
     const bool k3 = k3e && (mode & 1), k1 = k1e && (mode & 2);
     L->lsu_eligible = (k3e || k1e) && cout <= 128 && wbytes <= wmax;
     (void)big;
     p.halo = (k1 || k3) && fits;
     p.pad = (p.halo && k3) ? 1 : 0;
+    // TMA-halo mode (tune.lsu == 2): 3x3 stride-1 layers with exactly one 128-byte channel chunk (cin = 64) and resident weights.
+    // Isolated, L2 flushed, batch 64 (tools/halo_sw_probe.py): 64 -> 64 on 80x80 46 us against 52-56 us for the cp.async halo, the
+    // tap-by-tap TMA mode and the CTA pair; 64 -> 32 35 against 43; 64 -> 64 on 40x40 21.5 against 23.5.  It is the heuristic's choice
+    // where it applies (Y11_HALO_TMA=0 removes it) and an autotuner candidate like the others (same K order: bit-identical results).
+    static const bool halo_tma_on = [] { const char* e = getenv("Y11_HALO_TMA"); return e ? atoi(e) != 0 : true; }();
+    const bool k3t = halo_tma_on && k3e && cin == 64 && cout <= 128 && wbytes <= wmax;
+    L->halo_tma_eligible = k3t;
+    if (tune.lsu == 2) Y11_REQUIRE(k3t, "conv_tc: the TMA-halo mode needs a 3x3 stride-1 layer with cin = 64 and <= %d KB of weights", (int)(wmax >> 10));
+    if (k3t && (tune.lsu == 2 || (tune.lsu < 0 && (mode & 1)))) { p.halo = 1; p.pad = 1; p.halo_tma = 1; }
   }
   if (p.halo && p.pad) { p.Tw = 8; p.Th = 16; p.Tn = 1; }
   else pick_tile(d->Wout, d->Hout, d->B, &p.Tw, &p.Th, &p.Tn);
@@ -1296,6 +1339,11 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     p.a_sbo = p.pad ? (uint32_t)(p.Tw + 2) * 16u : 128u;  // next 8 GEMM rows: next halo row (Tw = 8) / next 8 pixels
     if (const char* e = getenv("Y11_HALO_SWAP")) if (atoi(e)) std::swap(p.a_lbo, p.a_sbo);
     p.b_res_bytes = (uint32_t)(p.taps * p.chunks_per_tap) * p.b_slot;
+    if (p.halo_tma) {  // one 128-byte row per halo pixel; 8-row groups of the GEMM are one halo row (Tw + 2 pixels) apart
+      p.a_slot = ((uint32_t)p.n_pos * 128u + 1023u) & ~1023u;
+      p.a_lbo = 16u;
+      p.a_sbo = (uint32_t)(p.Tw + 2) * 128u;
+    }
     p.in = static_cast<const __nv_bfloat16*>(d->in.ptr) + d->in.c_off;
     p.in_ct = d->in.c_total; p.Hin = d->Hin; p.Win = d->Win;
     p.mg_ncg = ((1ull << 42) + (cin / 8) - 1) / (cin / 8);
@@ -1400,7 +1448,8 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   const size_t ct = d->in.c_total;
   const size_t ie = (size_t)in_esz;
   char* in_base = static_cast<char*>(d->in.ptr) + (size_t)d->in.c_off * ie;
-  const cuuint32_t box[4] = {(cuuint32_t)p.Cc, (cuuint32_t)p.Tw, (cuuint32_t)p.Th, (cuuint32_t)p.Tn};
+  const cuuint32_t box[4] = {(cuuint32_t)p.Cc, (cuuint32_t)(p.halo_tma ? p.Tw + 2 : p.Tw), (cuuint32_t)(p.halo_tma ? p.Th + 2 : p.Th),
+                             (cuuint32_t)p.Tn};
   const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const CUtensorMapDataType it = d->in_fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : bf;
   if (d->stride == 1) {
@@ -1469,7 +1518,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     const unsigned total_pairs = ((m_tiles + 1) / 2) * (unsigned)p.n_tiles;
     L->grid = 2u * std::min(total_pairs, (unsigned)((eng->num_sms / 2) * cps));
   }
-  L->variant = ConvTcTune{p.halo, p.epi_warp | (p.fat << 1) | (p.bres << 2) | (p.pair << 3), cps, bn};
+  L->variant = ConvTcTune{p.halo ? (p.halo_tma ? 2 : 1) : 0, p.epi_warp | (p.fat << 1) | (p.bres << 2) | (p.pair << 3), cps, bn};
   L->smem_bytes = kHeaderBytes + 1024u + p.b_res_bytes + (unsigned)stages * stage + staging;
   L->flops = 2.0 * d->B * d->Hout * d->Wout * (double)cout * cin * p.taps;
   (void)k_iters;
