@@ -390,7 +390,7 @@ def run_ours(args):
             for m, o, v in sorted(zip(per_op, net.ops, net.variants()), key=lambda r: -r[0]):
                 tf = o.flops / (m / 1e3) / 1e12 if m > 0 else 0
                 gb = o.bytes_algo / (m / 1e3) / 1e9 if m > 0 else 0
-                var = f"  [{('tma', 'lsu', 'halo-tma')[v[0]]} {'epiW' if v[1] & 1 else 'epiC'}{'-fat' if v[1] & 2 else ''}{'-bres' if v[1] & 4 else ''}{'-pair' if v[1] & 8 else ''} {v[2]}cta/SM BN{v[3]}]" if v[2] > 0 else ""
+                var = f"  [{('tma', 'lsu', 'halo-tma', 'halo-stream')[v[0]]} {'epiW' if v[1] & 1 else 'epiC'}{'-fat' if v[1] & 2 else ''}{'-bres' if v[1] & 4 else ''}{'-pair' if v[1] & 8 else ''} {v[2]}cta/SM BN{v[3]}]" if v[2] > 0 else ""
                 print(f"{m:8.4f} ms  {o.kind:9s} {o.name:28s} {tf:8.1f} TFLOP/s {gb:8.1f} GB/s(algo){var}", file=sys.stderr)
             print(f"network total {sum(per_op):.3f} ms; step {ms_step:.3f} ms", file=sys.stderr)
         if rank == 0:
@@ -527,7 +527,7 @@ def run_ours(args):
             for m, o, v in rows[:70]:
                 tf = o.flops / (m / 1e3) / 1e12 if m > 0 else 0
                 gb = o.bytes_algo / (m / 1e3) / 1e9 if m > 0 else 0
-                var = f"  [{('tma', 'lsu', 'halo-tma')[v[0]]} {'epiW' if v[1] & 1 else 'epiC'}{'-fat' if v[1] & 2 else ''}{'-bres' if v[1] & 4 else ''}{'-pair' if v[1] & 8 else ''} {v[2]}cta/SM BN{v[3]}]" if v[2] > 0 else ""
+                var = f"  [{('tma', 'lsu', 'halo-tma', 'halo-stream')[v[0]]} {'epiW' if v[1] & 1 else 'epiC'}{'-fat' if v[1] & 2 else ''}{'-bres' if v[1] & 4 else ''}{'-pair' if v[1] & 8 else ''} {v[2]}cta/SM BN{v[3]}]" if v[2] > 0 else ""
                 print(f"{m:8.4f} ms  {o.kind:9s} {o.name:28s} {tf:8.1f} TFLOP/s {gb:8.1f} GB/s(algo){var}", file=sys.stderr)
             print(f"network total {all_ms:.3f} ms; conv {conv_ms:.3f} ms; step {ms_step:.3f} ms", file=sys.stderr)
 

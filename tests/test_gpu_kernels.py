@@ -176,6 +176,9 @@ VARIANT_SHAPES = [
     (2, 32, 32, 64, 128, 3, 2, True, False),     # stride 2
     (2, 40, 36, 64, 64, 3, 1, True, True),       # TMA-halo eligible (3x3 stride 1, cin = 64): ragged tiles, residual
     (3, 32, 32, 64, 32, 3, 1, True, False),      # TMA-halo eligible, N = 32
+    (2, 40, 36, 128, 64, 3, 1, True, False),     # halo-stream: two 64-channel halo chunks, ragged tiles
+    (2, 32, 48, 128, 128, 3, 1, True, True),     # halo-stream, residual
+    (2, 32, 32, 64, 256, 3, 1, False, False),    # halo-stream, one chunk, two N tiles
 ]
 
 
@@ -187,15 +190,16 @@ def test_conv_launch_variants_are_bit_identical(ctx, shape):
     base, want = conv_case(ctx, B, H, W, cin, cout, k, s_, act, res)
     close_bf16(base, want)
     n = 0
-    halo_tma = k == 3 and s_ == 1 and cin == 64 and H >= 32 and W >= 32      # lsu = 2: one TMA box load per halo tile
-    for lsu in (0, 1, 2) if halo_tma else (0, 1):
+    halo_tma = k == 3 and s_ == 1 and cin == 64 and cout <= 64 and H >= 32 and W >= 32   # lsu = 2: one TMA box load per halo tile, resident weights
+    hstream = k == 3 and s_ == 1 and cin in (64, 128) and H >= 32 and W >= 32             # lsu = 3: TMA halo + streamed weights
+    for lsu in (0, 1) + ((2,) if halo_tma else ()) + ((3,) if hstream else ()):
         for ew in (0, 1, 2, 3, 4, 6):     # bit 0: per-warp epilogue, bit 1: fat epilogue (64-channel chunks), bit 2: resident weights
             for cps in (2, 3):
                 for bn in (-1, 64, 32):
                     got, _ = conv_case(ctx, B, H, W, cin, cout, k, s_, act, res, tune=(lsu, ew, cps, bn))
                     assert torch.equal(got, base), (lsu, ew, cps, bn, (got - base).abs().max().item())
                     n += 1
-    assert n == (108 if halo_tma else 72)
+    assert n == 72 + 36 * (int(halo_tma) + int(hstream))
 
 
 PAIR_SHAPES = [
@@ -343,12 +347,13 @@ def test_stem_reading_uint8_frames_equals_letterbox_then_stem(ctx, H, W):
 
 
 @pytest.mark.parametrize("act,res,H,W,c", [(True, False, 20, 28, 64), (False, True, 20, 28, 64), (True, True, 14, 20, 64),
-                                           # register kernel (maps narrower than 18 pixels or lower than 8 rows)
+                                           # register kernel (maps narrower than 18 pixels or lower than 8 rows, or narrower than 32 with <= 128 channels)
                                            (True, False, 1, 8, 64), (False, True, 7, 16, 64), (True, True, 20, 12, 128),
                                            # TMA-ring kernel (W >= 18, H >= 8: the three cases above and these; ragged tiles): 2/4/8-row groups, 80 channels
                                            # (surplus threads), two 128-channel chunks, residual, many tiles per CTA
                                            (True, False, 16, 32, 64), (False, True, 32, 48, 128), (True, True, 24, 64, 80),
-                                           (True, False, 16, 32, 256), (True, False, 8 * 20, 16 * 12, 32), (True, True, 40, 40, 128), (False, False, 20, 36, 64)])
+                                           (True, False, 16, 32, 256), (True, False, 8 * 20, 16 * 12, 32), (True, True, 40, 40, 128), (False, False, 20, 36, 64),
+                                           (True, True, 20, 20, 256)])
 def test_dwconv(ctx, act, res, H, W, c):
     g = torch.Generator().manual_seed(1)
     x = torch.randn(2, c, H, W, generator=g).to(ctx.dev).to(torch.bfloat16).float()

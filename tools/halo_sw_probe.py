@@ -56,3 +56,18 @@ if "time" in sys.argv:
     for tune in [(1, 0, -1, -1), (1, 2, 2, -1), (0, 0, -1, -1)]:
         timeit(64, 80, 80, 64, 32, tune, "P3 64->32")
         timeit(64, 40, 40, 64, 64, tune, "P4 64->64")
+
+if "stream" in sys.argv:
+    for (B, H, W, cin, cout, res) in [(2, 32, 40, 64, 64, False), (2, 40, 36, 128, 64, False), (2, 32, 48, 128, 128, True), (2, 32, 32, 64, 256, False)]:
+        for tune in [(3, 0, 2, -1), (3, 1, 2, -1), (3, 2, 2, -1)]:
+            got, want = conv_case(ctx, B, H, W, cin, cout, 3, 1, True, res, tune=tune)
+            base, _ = conv_case(ctx, B, H, W, cin, cout, 3, 1, True, res, tune=(0, 0, 2, -1))
+            print(f"STREAM B{B} {H}x{W} {cin}->{cout} res={res} tune={tune}: rel L2 {((got - want).norm() / want.norm()).item():.3g} bit-identical to tap mode: {torch.equal(got, base)}", flush=True)
+
+    def t3(B, H, W, cin, cout, tunes, label):
+        for tune in tunes:
+            timeit(B, H, W, cin, cout, tune, label)
+    t3(64, 80, 80, 128, 64, [(0, 0, -1, -1), (0, 8, 2, -1), (0, 10, 2, -1), (3, 0, 2, -1), (3, 2, 2, -1), (3, 0, 1, -1), (3, 1, 2, -1)], "cv2.0.0")
+    t3(64, 40, 40, 128, 64, [(0, 0, -1, -1), (0, 8, 2, -1), (3, 0, 2, -1), (3, 2, 2, -1)], "13.m.0.cv1")
+    t3(64, 40, 40, 64, 128, [(0, 0, -1, -1), (0, 8, 2, -1), (3, 0, 2, -1), (3, 2, 2, -1)], "13.m.0.cv2")
+    t3(64, 40, 40, 64, 64, [(0, 0, -1, -1), (2, 2, 2, -1), (3, 0, 2, -1), (3, 2, 2, -1)], "6.m.0.m.x")

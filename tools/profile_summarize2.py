@@ -85,7 +85,7 @@ def full_table(model, title, only=None):
     slim = [["layer"] + [c for c, _ in cols]]
     for o, d in zip(ops, data):
         v = o["variant"]
-        var = f"{('tma', 'lsu', 'halo-tma')[v[0]]} {'epiW' if v[1] & 1 else 'epiC'}{'-fat' if v[1] & 2 else ''}{'-bres' if v[1] & 4 else ''}{'-pair' if v[1] & 8 else ''} {v[2]}cta BN{v[3]}"
+        var = f"{('tma', 'lsu', 'halo-tma', 'halo-stream')[v[0]]} {'epiW' if v[1] & 1 else 'epiC'}{'-fat' if v[1] & 2 else ''}{'-bres' if v[1] & 4 else ''}{'-pair' if v[1] & 8 else ''} {v[2]}cta BN{v[3]}"
         us = float(d[idx["gpu__time_duration.sum"]])
         tf = o["flops"] / (us * 1e-6) / 1e12
         slim.append([o["name"]] + [d[idx[c]] for c, _ in cols])

@@ -231,6 +231,11 @@ extern "C" int y11_plan_autotune(y11_plan p, y11_stream s_, int reps) {
           if (bn0 == 128 && d->out.c % 256 == 0 && d->in.c % 64 == 0 && cps == 2 && lsu == 0)
             cands.push_back(ConvTcTune{lsu, ew, 1, 256});
         }
+    // halo-stream mode (lsu = 3): swizzled TMA halo + streamed weights for 3x3 stride-1 layers with 64 / 128 input channels
+    // (measured: 128 -> 64 on 80x80 73.7 us against 79.9 us for the CTA pair and 92 us tap by tap - with ONE halo tile buffer and
+    //  2 CTAs per SM; at 1 CTA per SM, which the fat epilogue's staging forces, it loses: 104 us; equal to the others on 40x40 maps)
+    if (base.hstream_eligible)
+      for (int ew = 0; ew <= 1; ++ew) cands.push_back(ConvTcTune{3, ew, 2, -1});
     // resident weights (epi_warp bit 2) for single-N-tile TMA layers that walk several tiles per CTA
     if (!base.p.halo && d->out.c == bn0 && tiles0 >= 4ll * p->eng->num_sms) {
       for (int ew = 4; ew <= 7; ++ew)

@@ -301,8 +301,10 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
   const uint32_t acce_bar = accf_bar + 16;                // 2 x 8 B  accumulator empty (epilogue -> MMA)
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_raw + 16 * kMaxStages + 48);
   // TMA mode : stages x [A tap box | B tap tile];  halo mode: [resident B, all taps] then stages x [A halo tile]
-  const uint32_t stage_bytes = (p.halo || p.bres) ? p.a_slot : p.a_slot + p.b_slot;
+  //            halo-stream mode: [2 tile buffers x cin/64 swizzled halo chunks] then stages x [B tap tile]
+  const uint32_t stage_bytes = p.hstream ? p.b_slot : (p.halo || p.bres) ? p.a_slot : p.a_slot + p.b_slot;
   const uint32_t ring_base = tiles_base + p.b_res_bytes;
+  const uint32_t hfull_bar = smem_base + 576, hempty_bar = smem_base + 592;  // halo-stream mode: 2 x halo tile full / empty
   const uint32_t staging_base = ring_base + p.stages * stage_bytes;  // 2 buffers x stg_bytes
   const uint32_t bres_bar = acce_bar + 16;               // halo mode: resident weights landed
 
@@ -315,6 +317,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
       mbar_init(empty_bar + 8 * s, 1);
     }
     mbar_init(bres_bar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(hfull_bar + 8 * a, 1); mbar_init(hempty_bar + 8 * a, 1); }
     for (int q = 0; q < kTileQ; ++q) {
       mbar_init(smem_base + kTqFullOff + 8 * q, 1);
       mbar_init(smem_base + kTqEmptyOff + 8 * q, 1 + kEpiWarps);  // consumers: the MMA warp + every epilogue warp
@@ -392,7 +395,47 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
     return nx;
   };
 
-  if (warp == 0 && p.halo) {
+  if (warp == 0 && p.hstream) {
+    // ------------------------------------------------------------------ halo-stream producer (converged warp, one elected lane issues)
+    // per tile: the cin/64 swizzled halo chunks of the tile into one of two tile buffers (one barrier), then the 9 x cin/64 weight
+    // tiles through the stage ring in the order the MMA warp consumes them (tap, then chunk)
+    const int nch = p.chunks_per_tap;
+    uint32_t stage = 0, phase = 0, qi = 0;
+    for (int tile = blockIdx.x; ; ++qi) {
+      tq_publish(qi, tile);
+      if (tile < 0) break;
+      const int nx_raw = tq_next(tile);
+      uint32_t t = tile, q;
+      q = fast_div(t, p.mg_ntiles); const int nt = t - q * p.n_tiles; t = q;
+      q = fast_div(t, p.mg_tw); const int w0 = (t - q * p.tiles_w) * p.Tw; t = q;
+      q = fast_div(t, p.mg_th); const int h0 = (t - q * p.tiles_h) * p.Th; t = q;
+      const int n0 = t * p.Tn;
+      const uint32_t hs = p.hbufs == 2 ? (qi & 1u) : 0u, hph = p.hbufs == 2 ? ((qi >> 1) & 1u) : (qi & 1u);
+      mbar_wait(hempty_bar + 8 * hs, hph ^ 1u, p.err_flag, 108);
+      if (lane == 0) TRACE(0, 1);
+      if (elect_one()) {
+        const uint32_t hb = hfull_bar + 8 * hs;
+        mbar_expect_tx(hb, (uint32_t)nch * (uint32_t)p.n_pos * 128u);
+        for (int c = 0; c < nch; ++c)
+          tma_load_4d(tiles_base + (hs * (uint32_t)nch + (uint32_t)c) * p.a_slot, &maps.a[0], hb, c * 64, w0 - 1, h0 - 1, n0);
+      }
+      __syncwarp();
+      if (lane == 0) TRACE(0, 2);
+      for (int tap = 0; tap < 9; ++tap)
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1, p.err_flag, 101);
+          if (elect_one()) {
+            const uint32_t fb = full_bar + 8 * stage;
+            mbar_expect_tx(fb, p.tx_bytes);
+            tma_load_2d(ring_base + stage * stage_bytes, &maps.b, fb, tap * p.cin + c * 64, nt * p.BN);
+          }
+          __syncwarp();
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+        }
+      const int nx = __shfl_sync(0xffffffffu, nx_raw, 0);
+      tile = nx < total_tiles ? nx : -1;
+    }
+  } else if (warp == 0 && p.halo) {
     // ------------------------------------------------------------------ LSU producer (whole warp, cp.async)
     if (lane == 0) {  // weights of all taps: loaded once, stay resident
       const int nb = p.taps * p.chunks_per_tap;
@@ -546,7 +589,48 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcMaps& maps, const ConvT
     // swizzled K-major descriptor (weights everywhere, activations in TMA mode): lo = addr>>4 | LBO(1)<<16, hi = SBO>>4 | version | layout
     const uint32_t sw_hi = (p.sbo >> 4) | (1u << 14) | (p.layout_type << 29);
     const uint32_t ring_lo0 = ((ring_base & 0x3FFFFu) >> 4) | (1u << 16);
-    if (p.halo) {
+    if (p.hstream) {
+      // halo-stream: A = the tile's swizzled halo chunks (tap = row offset of the start address, see halo3_issue_sw), B = one
+      // streamed weight tile per (tap, chunk) stage; K order (tap, chunk, 16-channel step) as in the tap-by-tap TMA mode
+      const uint32_t a_hi = (p.a_sbo >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t halo_lo0 = ((tiles_base & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t a_units = p.a_slot >> 4;
+      const int nch = p.chunks_per_tap;
+      for (;; ++ti) {
+        if (tq_take((uint32_t)ti) < 0) break;
+        const int as = ti & 1;
+        mbar_wait(acce_bar + 8 * as, ((ti >> 1) & 1) ^ 1, p.err_flag, 104);  // epilogue has drained this accumulator stage
+        if (lane == 0) TRACE(1, 1);
+        const uint32_t tmem_acc = tmem_base + as * acc_stride;
+        if (elect_one()) {
+          const uint32_t hs = p.hbufs == 2 ? ((uint32_t)ti & 1u) : 0u, hph = p.hbufs == 2 ? (((uint32_t)ti >> 1) & 1u) : ((uint32_t)ti & 1u);
+          mbar_wait(hfull_bar + 8 * hs, hph, p.err_flag, 109);
+          tc_fence_after();
+          const uint32_t h_lo = halo_lo0 + hs * (uint32_t)nch * a_units;
+          uint32_t st = stage, ph = phase;
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t toff = (uint32_t)((tap / 3) * 10 + tap % 3) * 8u;
+            for (int c = 0; c < nch; ++c) {
+              mbar_wait(full_bar + 8 * st, ph, p.err_flag, 102);
+              tc_fence_after();
+              const uint32_t at = h_lo + (uint32_t)c * a_units + toff;
+              const uint32_t b_lo = ring_lo0 + st * stage_units;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) umma_lohi<false>(tmem_acc, at + 2u * kk, a_hi, b_lo + 2u * kk, sw_hi, idesc, (tap | c | kk) ? 1u : 0u);
+              umma_commit(empty_bar + 8 * st);  // frees the weight slot once these MMAs retire
+              if (++st == n_stages) { st = 0; ph ^= 1; }
+            }
+          }
+          umma_commit(hempty_bar + 8 * hs);   // the halo tile buffer may be refilled
+          umma_commit(accf_bar + 8 * as);     // accumulator complete
+        }
+        __syncwarp();
+        if (lane == 0) TRACE(1, 3);
+        uint32_t adv = stage + (uint32_t)k_iters;
+        while (adv >= n_stages) { adv -= n_stages; phase ^= 1; }
+        stage = adv;
+      }
+    } else if (p.halo) {
       // un-swizzled activation tile: lo = addr>>4 | (LBO>>4)<<16, hi = SBO>>4 | version
       const uint32_t a_hi = (p.a_sbo >> 4) | (1u << 14);
       const uint32_t a_lo0 = ((ring_base & 0x3FFFFu) >> 4) | ((p.a_lbo >> 4) << 16);
@@ -1227,7 +1311,8 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     const int mode = tune.lsu >= 0 ? (tune.lsu ? 3 : 0) : (e ? atoi(e) : 3);  // bit 0: 3x3 halo tiles, bit 1: 1x1
     const size_t wbytes = (size_t)d->k * d->k * cin * cout * 2;
     const bool bf16_io = !d->in_fp8 && !d->out_fp8;   // the cp.async producer / un-swizzled layouts are bf16 only
-    const bool k3e = bf16_io && d->k == 3 && d->stride == 1 && cin <= 64 && d->Hout >= 32 && d->Wout >= 32;
+    const bool k3e_any = bf16_io && d->k == 3 && d->stride == 1 && d->Hout >= 32 && d->Wout >= 32;
+    const bool k3e = k3e_any && cin <= 64;
     const bool k1e = bf16_io && d->k == 1 && (cin <= 32 || (cin % 32 != 0 && cin <= 112));  // TMA rows would be 32-64 B
     // resident-weight budget: 40 KB keeps 2-3 CTAs per SM; up to Y11_LSU_WMAX KB (default 80: the 3x3 64->64 layers, 72 KB) the
     // mode is still OFFERED to the autotuner (1 CTA per SM, 4 halo stages) - those layers are bound by the L2->SM operand
@@ -1250,8 +1335,18 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     L->halo_tma_eligible = k3t;
     if (tune.lsu == 2) Y11_REQUIRE(k3t, "conv_tc: the TMA-halo mode needs a 3x3 stride-1 layer with cin = 64 and <= %d KB of weights", (int)(wmax >> 10));
     if (k3t && (tune.lsu == 2 || (tune.lsu < 0 && (mode & 1)))) { p.halo = 1; p.pad = 1; p.halo_tma = 1; }
+    // Halo-stream mode (tune.lsu == 3): the same swizzled TMA halo for cin = 64 or 128 (one or two 64-channel chunks per tile, two
+    // tile buffers) with the weights STREAMED per (tap, chunk) through the stage ring instead of resident - for the layers whose
+    // weights do not fit (64 -> 128, 128 -> 64, 128 -> 128: 147-295 KB).  Against the tap-by-tap TMA mode the activation tile crosses
+    // the L2 -> shared-memory path 1.4 instead of 9 times per output tile.
+    static const bool hstream_on = [] { const char* e = getenv("Y11_HALO_STREAM"); return e ? atoi(e) != 0 : true; }();
+    const bool k3s = hstream_on && k3e_any && (cin == 64 || cin == 128);
+    L->hstream_eligible = k3s;
+    if (tune.lsu == 3) Y11_REQUIRE(k3s, "conv_tc: the halo-stream mode needs a 3x3 stride-1 layer with cin = 64 or 128 on a map >= 32x32");
+    static const bool hstream_default = [] { const char* e = getenv("Y11_HALO_STREAM_DEFAULT"); return e ? atoi(e) != 0 : false; }();
+    if (k3s && !p.halo_tma && (tune.lsu == 3 || (tune.lsu < 0 && hstream_default))) { p.halo = 0; p.pad = 0; p.hstream = 1; }
   }
-  if (p.halo && p.pad) { p.Tw = 8; p.Th = 16; p.Tn = 1; }
+  if ((p.halo && p.pad) || p.hstream) { p.Tw = 8; p.Th = 16; p.Tn = 1; }
   else pick_tile(d->Wout, d->Hout, d->B, &p.Tw, &p.Th, &p.Tn);
   p.tiles_w = y11_ceil_div(d->Wout, p.Tw);
   p.tiles_h = y11_ceil_div(d->Hout, p.Th);
@@ -1273,11 +1368,13 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     if (mode && bn_cap >= 256 && cout % 256 == 0 && (cin * in_esz) % 128 == 0 && (k_total >= 1024 || forced)) bn = 256;
   }
   if (p.halo) bn = cout;
+  if (p.hstream && bn > 128) bn = 128;
   p.BN = bn;
   p.n_tiles = cout / bn;
   // K chunk per pipeline stage = one swizzle row: 128 / 64 / 32 bytes of channels
   if (d->in_fp8) p.Cc = (cin % 128 == 0) ? 128 : (cin % 64 == 0) ? 64 : 32;
   else p.Cc = (cin % 64 == 0) ? 64 : (cin % 32 == 0) ? 32 : 16;
+  if (p.hstream) p.Cc = 64;
   p.cin = cin;
   p.in_fp8 = d->in_fp8 ? 1 : 0;
   p.out_esz = out_esz;
@@ -1312,7 +1409,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   // every scale measured (they are shared-memory-bandwidth bound as single CTAs)
   static const bool pair_default = [] { const char* e = getenv("Y11_PAIR"); return e ? atoi(e) != 0 : true; }();
   const bool want_pair = tune.epi_warp >= 0 ? (tune.epi_warp & 8) != 0 : (pair_default && d->k == 3 && bn == 256);
-  p.pair = want_pair && !p.halo && !d->in_fp8 && !d->out_fp8 && !d->cscale && d->k != 2 &&
+  p.pair = want_pair && !p.halo && !p.hstream && !d->in_fp8 && !d->out_fp8 && !d->cscale && d->k != 2 &&
            bn >= 64 && bn % 32 == 0 && p.tiles_w * p.tiles_h * p.tiles_n >= 2;
   if (p.pair) p.b_slot = ((uint32_t)(bn / 2) * swz_bytes + 1023u) & ~1023u;
   // Resident weights in TMA mode: a layer with ONE N tile whose whole weight matrix is small keeps it in shared memory for
@@ -1326,7 +1423,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     const int nk = p.n_kt ? p.n_kt : p.taps * p.chunks_per_tap;
     const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
     // explicit variant (autotuner candidate / cached choice): bit 2 of epi_warp says it; heuristic otherwise
-    const bool fits = !p.halo && !p.pair && !d->in_fp8 && cout == bn;
+    const bool fits = !p.halo && !p.hstream && !p.pair && !d->in_fp8 && cout == bn;
     if (tune.epi_warp >= 0) p.bres = fits && (tune.epi_warp & 4) && (size_t)nk * p.b_slot <= (size_t)64 * 1024;
     else p.bres = fits && (size_t)nk * p.b_slot <= (size_t)bres_kb * 1024 && m_tiles >= 8ll * 3 * eng->num_sms;
     if (p.bres) p.b_res_bytes = (uint32_t)nk * p.b_slot;
@@ -1348,9 +1445,18 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     p.in_ct = d->in.c_total; p.Hin = d->Hin; p.Win = d->Win;
     p.mg_ncg = ((1ull << 42) + (cin / 8) - 1) / (cin / 8);
   }
+  if (p.hstream) {  // [2 tile buffers x cin/64 halo chunks of (Tw+2)(Th+2) 128-byte rows] in front of the ring of weight tiles
+    p.n_pos = (p.Tw + 2) * (p.Th + 2);
+    p.a_slot = ((uint32_t)p.n_pos * 128u + 1023u) & ~1023u;
+    p.a_lbo = 16u;
+    p.a_sbo = (uint32_t)(p.Tw + 2) * 128u;
+    p.hbufs = 2;
+    p.b_res_bytes = 2u * (uint32_t)p.chunks_per_tap * p.a_slot;
+  }
   p.tx_bytes = (uint32_t)(p.Tw * p.Th * p.Tn) * swz_bytes + (p.bres ? 0u : (uint32_t)(p.pair ? bn / 2 : bn) * swz_bytes);
+  if (p.hstream) p.tx_bytes = (uint32_t)bn * swz_bytes;
   const int k_iters = p.taps * p.chunks_per_tap;
-  const uint32_t stage = (p.halo || p.bres) ? p.a_slot : p.a_slot + p.b_slot;
+  const uint32_t stage = p.hstream ? p.b_slot : (p.halo || p.bres) ? p.a_slot : p.a_slot + p.b_slot;
   // Warp-independent epilogue: possible when the tile has exactly 128 rows and every 32-row quarter (one TMEM lane
   // quadrant) is itself a (qbw x qbh x qbn) box of pixels, so that each warp can TMA-store its own rows.
   int qbw = 0, qbh = 0, qbn = 0;
@@ -1418,12 +1524,22 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     while (cps > 1 && budget_of(cps) < fixed + 2 * stage) --cps;
     Y11_REQUIRE(budget_of(cps) >= fixed + 2 * stage, "conv_tc: halo tile does not fit in shared memory");
   }
+  uint32_t fixed_v = fixed;
+  if (p.hstream) {  // the halo tile buffers + at least four weight stages must fit; ONE tile buffer where two would cost a CTA slot
+    if (cps >= 2 && budget_of(2) < fixed + 4 * stage && budget_of(2) >= fixed - p.b_res_bytes / 2 + 4 * stage) {
+      p.hbufs = 1;
+      p.b_res_bytes /= 2;
+      fixed_v = fixed - p.b_res_bytes;
+    }
+    while (cps > 1 && budget_of(cps) < fixed_v + 4 * stage) --cps;
+    Y11_REQUIRE(budget_of(cps) >= fixed_v + 3 * stage, "conv_tc: halo-stream buffers do not fit in shared memory");
+  }
   if (p.bres) {  // resident weights + at least three activation stages must fit
     while (cps > 1 && budget_of(cps) < fixed + 3 * stage) --cps;
     Y11_REQUIRE(budget_of(cps) >= fixed + 2 * stage, "conv_tc: resident weights do not fit in shared memory");
   }
   const uint32_t budget = budget_of(cps);
-  int stages = budget > fixed ? (int)((budget - fixed) / stage) : 0;
+  int stages = budget > fixed_v ? (int)((budget - fixed_v) / stage) : 0;
   stages = std::max(2, std::min(stages, p.halo ? 6 : kMaxStages));
   p.stages = stages;
   p.tmem_cols = cols;
@@ -1448,7 +1564,8 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
   const size_t ct = d->in.c_total;
   const size_t ie = (size_t)in_esz;
   char* in_base = static_cast<char*>(d->in.ptr) + (size_t)d->in.c_off * ie;
-  const cuuint32_t box[4] = {(cuuint32_t)p.Cc, (cuuint32_t)(p.halo_tma ? p.Tw + 2 : p.Tw), (cuuint32_t)(p.halo_tma ? p.Th + 2 : p.Th),
+  const bool halo_box = p.halo_tma || p.hstream;
+  const cuuint32_t box[4] = {(cuuint32_t)p.Cc, (cuuint32_t)(halo_box ? p.Tw + 2 : p.Tw), (cuuint32_t)(halo_box ? p.Th + 2 : p.Th),
                              (cuuint32_t)p.Tn};
   const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const CUtensorMapDataType it = d->in_fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : bf;
@@ -1518,7 +1635,7 @@ int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* L, co
     const unsigned total_pairs = ((m_tiles + 1) / 2) * (unsigned)p.n_tiles;
     L->grid = 2u * std::min(total_pairs, (unsigned)((eng->num_sms / 2) * cps));
   }
-  L->variant = ConvTcTune{p.halo ? (p.halo_tma ? 2 : 1) : 0, p.epi_warp | (p.fat << 1) | (p.bres << 2) | (p.pair << 3), cps, bn};
+  L->variant = ConvTcTune{p.hstream ? 3 : p.halo ? (p.halo_tma ? 2 : 1) : 0, p.epi_warp | (p.fat << 1) | (p.bres << 2) | (p.pair << 3), cps, bn};
   L->smem_bytes = kHeaderBytes + 1024u + p.b_res_bytes + (unsigned)stages * stage + staging;
   L->flops = 2.0 * d->B * d->Hout * d->Wout * (double)cout * cin * p.taps;
   (void)k_iters;

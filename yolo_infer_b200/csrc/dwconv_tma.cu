@@ -200,8 +200,8 @@ bool dwconv_tma_eligible(const y11_dwconv_desc* d) {
   if (const char* e = getenv("Y11_DW_TMA")) if (!atoi(e)) return false;
   const int C = d->in.c;
   static const int min_w = [] { const char* e = getenv("Y11_DW_TMA_MINW"); return e ? atoi(e) : 18; }();  // 20x20 maps: 512 channels 29.8 -> 23.4 us, 128 channels equal (ragged 16x8 tiles)
-  if (d->W < min_w || d->W < kHaloW || d->H < (min_w < 32 ? kTH : 2 * kTH)) return false;
-  if (d->W < 32 && C <= 128) return false;  // 20x20 maps with one channel chunk: no faster than the register kernel (7.6 vs 7.8 us)  // ragged right/bottom tiles are fine: TMA zero-fills, stores are guarded
+  if (d->W < min_w || d->W < kHaloW || d->H < (min_w < 32 ? kTH : 2 * kTH)) return false;  // ragged right/bottom tiles are fine: TMA zero-fills, stores are guarded
+  if (d->W < 32 && C <= 128) return false;  // 20x20 maps with one channel chunk: no faster than the register kernel (7.6 vs 7.8 us)
   if (C % 8 != 0 || (C > 128 && C % 128 != 0)) return false;
   if (d->in.c_total % 8 != 0 || d->in.c_off % 8 != 0) return false;  // 16-byte aligned TMA base / strides
   return true;

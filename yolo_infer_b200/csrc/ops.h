@@ -92,6 +92,8 @@ struct ConvTcParams {
   int32_t in_ct, Hin, Win;
   uint32_t b_res_bytes; // resident weight region (all taps), loaded once per CTA
   uint32_t a_lbo, a_sbo;
+  int32_t hbufs;        // halo-stream mode: halo tile buffers (2, or 1 where that keeps two CTAs per SM)
+  int32_t hstream;      // halo-stream mode: swizzled TMA halo tiles (cin = 64 / 128, two tile buffers) + weights streamed per (tap, chunk)
   int32_t halo_tma;     // 3x3 halo tile in the 128-byte-swizzled layout (cin = 64), loaded by ONE TMA box per tile instead of cp.async
   // class-emit epilogue (Detect cv3.l.2 in single-label prediction, y11_plan_set_cls_emit): instead of storing the fp32 class
   // logits, every output row (= anchor) keeps the maximum logit and its class, and rows above the threshold are appended to the
@@ -108,7 +110,7 @@ struct ConvTcParams {
 // Per-layer launch variant.  -1 = the built-in heuristic (which an environment knob may override globally); the plan
 // autotuner (y11_plan_autotune) times the feasible combinations of a layer on its real buffers and keeps the fastest.
 struct ConvTcTune {
-  int32_t lsu;       // 0: tap-by-tap TMA producer; 1: cp.async (LSU) producer where eligible; 2: TMA-halo mode (3x3, cin = 64); -1: heuristic
+  int32_t lsu;       // 0: tap-by-tap TMA producer; 1: cp.async (LSU) producer where eligible; 2: TMA-halo mode (3x3, cin = 64, resident weights); 3: halo-stream mode (3x3, cin = 64 / 128, streamed weights); -1: heuristic
   int32_t epi_warp;  // bit 0: warp-independent epilogue, bit 1: fat epilogue (conv_tc_kernel_fat), bit 3: CTA-pair kernel (cta_group::2)
   int32_t cps;       // persistent CTAs per SM (1..4)
   int32_t bn_max;    // largest N tile to consider (16..256)
@@ -122,7 +124,7 @@ struct ConvTcLaunch {
   unsigned smem_bytes;
   double flops;
   ConvTcTune variant;  // what was actually used (resolved values)
-  int32_t lsu_eligible, epi_warp_possible, halo_tma_eligible;
+  int32_t lsu_eligible, epi_warp_possible, halo_tma_eligible, hstream_eligible;
 };
 
 int conv_tc_prepare(y11_engine* eng, const y11_conv_desc* d, ConvTcLaunch* out, const ConvTcTune* tune = nullptr);
