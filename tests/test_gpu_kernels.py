@@ -347,13 +347,13 @@ def test_stem_reading_uint8_frames_equals_letterbox_then_stem(ctx, H, W):
 
 
 @pytest.mark.parametrize("act,res,H,W,c", [(True, False, 20, 28, 64), (False, True, 20, 28, 64), (True, True, 14, 20, 64),
-                                           # register kernel (maps narrower than 18 pixels or lower than 8 rows, or narrower than 32 with <= 128 channels)
+                                           # register kernel (maps narrower than 18 pixels or lower than 8 rows, or narrower than 32 with < 512 channels)
                                            (True, False, 1, 8, 64), (False, True, 7, 16, 64), (True, True, 20, 12, 128),
                                            # TMA-ring kernel (W >= 18, H >= 8: the three cases above and these; ragged tiles): 2/4/8-row groups, 80 channels
                                            # (surplus threads), two 128-channel chunks, residual, many tiles per CTA
                                            (True, False, 16, 32, 64), (False, True, 32, 48, 128), (True, True, 24, 64, 80),
                                            (True, False, 16, 32, 256), (True, False, 8 * 20, 16 * 12, 32), (True, True, 40, 40, 128), (False, False, 20, 36, 64),
-                                           (True, True, 20, 20, 256)])
+                                           (True, True, 20, 20, 256), (True, True, 20, 20, 512)])
 def test_dwconv(ctx, act, res, H, W, c):
     g = torch.Generator().manual_seed(1)
     x = torch.randn(2, c, H, W, generator=g).to(ctx.dev).to(torch.bfloat16).float()

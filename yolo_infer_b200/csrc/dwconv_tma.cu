@@ -199,9 +199,11 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 bool dwconv_tma_eligible(const y11_dwconv_desc* d) {
   if (const char* e = getenv("Y11_DW_TMA")) if (!atoi(e)) return false;
   const int C = d->in.c;
-  static const int min_w = [] { const char* e = getenv("Y11_DW_TMA_MINW"); return e ? atoi(e) : 18; }();  // 20x20 maps: 512 channels 29.8 -> 23.4 us, 128 channels equal (ragged 16x8 tiles)
+  static const int min_w = [] { const char* e = getenv("Y11_DW_TMA_MINW"); return e ? atoi(e) : 18; }();
   if (d->W < min_w || d->W < kHaloW || d->H < (min_w < 32 ? kTH : 2 * kTH)) return false;  // ragged right/bottom tiles are fine: TMA zero-fills, stores are guarded
-  if (d->W < 32 && C <= 128) return false;  // 20x20 maps with one channel chunk: no faster than the register kernel (7.6 vs 7.8 us)
+  // maps narrower than 32 pixels (ragged 16x8 tiles): only with >= 4 channel chunks - 512 channels on 20x20 29.8 -> 23.4 us, but 128
+  // channels equal (7.6 vs 7.8 us) and the 256-channel Attention.pe (strided view, residual) slower in the network (34 vs 29 us)
+  if (d->W < 32 && C < 512) return false;
   if (C % 8 != 0 || (C > 128 && C % 128 != 0)) return false;
   if (d->in.c_total % 8 != 0 || d->in.c_off % 8 != 0) return false;  // 16-byte aligned TMA base / strides
   return true;
