@@ -203,3 +203,26 @@ def test_compact_space_to_depth_packing_equals_the_3x3_stride2_conv():
         # only the blocks a tap can touch carry weights: 9 of the 16 (tap, block) pairs
         nz = (w2.view(pc.c2, 4, c, 2, 2).abs().sum((0, 2)) > 0).sum().item()
         assert nz == 9
+
+
+def test_uint8_to_unit_float_through_the_mantissa_trick_is_the_rounded_quotient():
+    """The stem's uint8 path (csrc/conv_simt.cu, stem_kernel<., true>) converts a byte b to b/255 as one fused multiply-add on the
+    float 2^23 + b (PRMT puts the byte into the mantissa of 0x4B000000): fma(2^23 + b, r, -(2^23 * r)) with r = fp32(1/255).  The
+    product of two 24-bit significands is exact in float64, so the fused result is RN_fp32(b * r) - the value letterbox_kernel's
+    __fmul_rn((float)b, r) produces - and its bf16 rounding equals the bf16 rounding of the exact fp32 quotient b / 255."""
+    import numpy as np
+    r = np.float32(1.0) / np.float32(255.0)
+    c = np.float32(-8388608.0) * r                                   # exact: a power-of-two multiple of r
+    assert float(c) == -8388608.0 * float(r)
+    b = np.arange(256, dtype=np.uint32)
+    v = (np.uint32(0x4B000000) | b).view(np.float32)                 # what PRMT builds: 2^23 + b
+    assert np.array_equal(v, (8388608.0 + b).astype(np.float32))
+    fused = (v.astype(np.float64) * np.float64(r) + np.float64(c)).astype(np.float32)   # one rounding, like fma.rn
+    plain = b.astype(np.float32) * r                                 # __fmul_rn((float)b, r)
+    assert np.array_equal(fused.view(np.uint32), plain.view(np.uint32))
+
+    def bf16_bits(x):                                                # round-to-nearest-even truncation of fp32 to bf16
+        u = x.view(np.uint32).astype(np.uint64)
+        return ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint32)
+    quotient = b.astype(np.float32) / np.float32(255.0)
+    assert np.array_equal(bf16_bits(plain), bf16_bits(quotient))
